@@ -1,0 +1,274 @@
+"""Generate the committed golden fixtures by running the REFERENCE's own code in this container.
+
+Run once here (``python tests/golden/make_golden.py``); /root/reference does not exist on the GPU box, so
+tests only ever read the ``.npz`` files this script writes.  Nothing from the reference is copied: its files
+are imported *where they lie* through ``sys.modules`` shims (recipe: SURVEY.md Appendix A).
+
+Fixtures (all inputs are re-derivable from seeds through ``sessd_b200.synth`` / the ``*_random_state`` helpers,
+so only outputs -- or their hashes when large -- are stored):
+  voxel_cases.npz      reference numba voxeliser (point_cloud_ops_v2.py) on 7 seeded / edge-case clouds
+  iou_cases.npz        reference iou3d_cpu.cpp (compiled in place -> oracle/_ref): overlap / IoU matrices
+  anchors_assign.npz   reference AnchorGeneratorRange + TargetAssigner.assign_v2 (12 seeded GT boxes)
+  decode_case.npz      reference box_torch_ops.second_box_decode
+  ssfa_head_case.npz   reference SSFA + Head modules (rpn_v1.py, mg_head_sessd.py) with seeded state dicts
+  vfe_case.npz         reference VoxelFeatureExtractorV3
+"""
+import hashlib
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "se-ssd_b200"))
+
+from sessd_b200 import synth  # noqa: E402
+from oracle import bev_ref, build as obuild, cpu as ocpu  # noqa: E402
+
+
+def _pkg(name):
+    m = types.ModuleType(name)
+    m.__path__ = [os.path.join(REF, *name.split("."))]
+    sys.modules[name] = m
+    return m
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    for k, v in attrs.items():
+        setattr(m, k, v)
+    sys.modules[name] = m
+    return m
+
+
+def _load(name, rel):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules[name] = m
+    spec.loader.exec_module(m)
+    return m
+
+
+def sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), np.uint8)
+
+
+# --------------------------------------------------------------------------------------------
+def voxel_cases():
+    """(name, points, max_points, max_voxels) -- also imported by the tests to rebuild inputs."""
+    rng = np.random.default_rng(123)
+    cases = []
+    cases.append(("uniform2k", synth.uniform_cloud(1, 2000), 5, 20000))
+    cases.append(("uniform20k", synth.uniform_cloud(0, 20000), 5, 20000))
+    cases.append(("ring20k", synth.ring_cloud(0, 20000), 5, 20000))
+    # max_voxels cut: the loop breaks at the first NEW voxel beyond the cap and drops all later points
+    cases.append(("cut300", synth.uniform_cloud(2, 5000), 5, 300))
+    # many points per voxel (> max_points) + duplicates: clustered cloud
+    ctr = rng.uniform([5, -10, -2], [40, 10, 0], (40, 3))
+    p = ctr[rng.integers(0, 40, 6000)] + rng.normal(0, 0.04, (6000, 3))
+    cases.append(("clustered", np.concatenate([p, rng.uniform(0, 1, (6000, 1))], 1).astype(np.float32), 5, 20000))
+    # out-of-range points and exact boundary values
+    q = synth.uniform_cloud(3, 3000)
+    q[::7, 0] = -0.01
+    q[1::11, 1] = 40.0
+    q[2::13, 2] = 1.0
+    q[3::17, 0] = 70.4
+    q[4::19] = np.float32([0.0, -40.0, -3.0, 0.5])
+    q[5::23, 0] = np.nextafter(np.float32(70.4), np.float32(0))
+    cases.append(("edges", q, 5, 20000))
+    cases.append(("clustered_mp3_cut", cases[4][1][:4000].copy(), 3, 500))
+    cases.append(("empty", np.zeros((0, 4), np.float32), 5, 20000))
+    return cases
+
+
+def gen_voxel():
+    pc = _load("pc_v2_ref", "det3d/ops/point_cloud/point_cloud_ops_v2.py")
+    out = {}
+    for name, pts, mp, mv in voxel_cases():
+        v, c, n = pc.points_to_voxel(pts, np.float32(synth.VOXEL_SIZE), np.float32(synth.PC_RANGE), mp, True, mv)
+        ov, oc, on = ocpu.points_to_voxel(pts, synth.VOXEL_SIZE, synth.PC_RANGE, mp, mv)
+        assert (v == ov).all() and (c == oc).all() and (n == on).all(), name
+        out[name + "_coors"] = c.astype(np.int32)
+        out[name + "_num"] = n.astype(np.int32)
+        out[name + "_voxels_sha"] = sha(v)
+        out[name + "_points_sha"] = sha(pts)
+        if v.shape[0] <= 2500:
+            out[name + "_voxels"] = v
+        print("voxel", name, v.shape)
+    np.savez_compressed(os.path.join(HERE, "voxel_cases.npz"), **out)
+
+
+# --------------------------------------------------------------------------------------------
+def iou_inputs():
+    b1, _ = synth.random_boxes(11, 160, spread=0.25)     # dense scene -> many overlaps
+    b2, _ = synth.random_boxes(12, 120, spread=0.25)
+    # add exact duplicates, shared edges, zero-size and axis-aligned boxes
+    b2[:10] = b1[:10]
+    b2[10:15, :2] = b1[10:15, :2] + np.float32([1.6, 0.0]); b2[10:15, 3:7] = b1[10:15, 3:7]
+    b1[20, 3] = 0.0
+    b1[21:25, 6] = np.float32([0.0, np.pi / 2, -np.pi / 2, np.pi])
+    return b1, b2
+
+
+def gen_iou():
+    ref = obuild.load_ref() or (obuild.build_ref() and obuild.load_ref())
+    b1, b2 = iou_inputs()
+    a5, c5 = ocpu.boxes3d_to_bev(b1), ocpu.boxes3d_to_bev(b2)
+    ov = torch.zeros(len(a5), len(c5))
+    iou = torch.zeros(len(a5), len(c5))
+    ref.boxes_overlap_bev_cpu(torch.from_numpy(a5), torch.from_numpy(c5), ov)
+    ref.boxes_iou_bev_cpu(torch.from_numpy(a5), torch.from_numpy(c5), iou)
+    assert (ocpu.boxes_overlap_bev(a5, c5) == ov.numpy()).all()
+    assert (ocpu.boxes_iou_bev(a5, c5) == iou.numpy()).all()
+    np.savez_compressed(os.path.join(HERE, "iou_cases.npz"), overlap=ov.numpy(), iou=iou.numpy())
+    print("iou", ov.shape, float(ov.max()), int((ov > 0).sum()))
+
+
+# --------------------------------------------------------------------------------------------
+def install_det3d_shims():
+    for p in ("det3d", "det3d.core", "det3d.core.bbox", "det3d.core.anchor", "det3d.ops", "det3d.ops.nms",
+              "det3d.models", "det3d.models.necks", "det3d.models.bbox_heads", "det3d.models.readers",
+              "det3d.torchie", "det3d.utils", "det3d.core.iou3d", "det3d.core.sampler", "det3d.models.losses"):
+        _pkg(p)
+    _stub("spconv")
+    _stub("spconv.utils", rbbox_iou=None, rbbox_intersection=None)
+    _stub("det3d.ops.nms.nms_cpu", rotate_nms_cc=None, rotate_weighted_nms_cc=None)
+    _stub("det3d.ops.nms.nms_gpu", nms_gpu=None, rotate_iou_gpu=None, rotate_nms_gpu=None)
+    _stub("matplotlib")
+    _stub("matplotlib.pyplot")
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    _orig_meshgrid = np.meshgrid
+    np.meshgrid = lambda *a, **k: list(_orig_meshgrid(*a, **k))   # box_np_ops.py:814 item-assigns into it
+
+    class _Reg:
+        def register_module(self, cls):
+            return cls
+
+    reg = _Reg()
+    _stub("det3d.models.registry", READERS=reg, BACKBONES=reg, NECKS=reg, HEADS=reg, LOSSES=reg, DETECTORS=reg)
+    _stub("det3d.torchie.cnn", constant_init=None, kaiming_init=None, xavier_init=None)
+    _stub("det3d.torchie.trainer", load_checkpoint=None)
+    _stub("det3d.models.builder", build_loss=None)
+    sys.modules["det3d.models"].builder = sys.modules["det3d.models.builder"]
+    _stub("det3d.models.losses.metrics")
+    sys.modules["det3d.models.losses"].metrics = sys.modules["det3d.models.losses.metrics"]
+    sys.modules["det3d.models.losses"].accuracy = None
+    _stub("det3d.core.iou3d.iou3d_utils")
+    sys.modules["det3d.core.iou3d"].iou3d_utils = sys.modules["det3d.core.iou3d.iou3d_utils"]
+    _stub("det3d.core.sampler.preprocess")
+    sys.modules["det3d.core.sampler"].preprocess = sys.modules["det3d.core.sampler.preprocess"]
+    # real norm builder needs syncbn/dist: provide the two norm types the config uses (norm.py:60-111)
+    from torch import nn
+
+    def build_norm_layer(cfg, num_features, postfix=""):
+        cfg = dict(cfg)
+        t = cfg.pop("type")
+        cfg.setdefault("eps", 1e-5)
+        layer = {"BN": nn.BatchNorm2d, "BN1d": nn.BatchNorm1d}[t](num_features, **cfg)
+        return "bn" + str(postfix), layer
+
+    misc = _load("det3d.models.utils.misc", "det3d/models/utils/misc.py")
+    _stub("det3d.models.utils", Empty=misc.Empty, GroupNorm=misc.GroupNorm, Sequential=misc.Sequential,
+          change_default_args=misc.change_default_args, build_norm_layer=build_norm_layer,
+          get_paddings_indicator=misc.get_paddings_indicator)
+    sys.modules["det3d.models"].utils = sys.modules["det3d.models.utils"]
+
+
+def gen_anchors_assign():
+    bn = _load("det3d.core.bbox.box_np_ops", "det3d/core/bbox/box_np_ops.py")
+    sys.modules["det3d.core.bbox"].box_np_ops = bn
+    bt = _load("det3d.core.bbox.box_torch_ops", "det3d/core/bbox/box_torch_ops.py")
+    sys.modules["det3d.core.bbox"].box_torch_ops = bt
+    rs = _load("det3d.core.bbox.region_similarity", "det3d/core/bbox/region_similarity.py")
+    bc = _load("det3d.core.bbox.box_coders", "det3d/core/bbox/box_coders.py")
+    ag_mod = _load("det3d.core.anchor.anchor_generator", "det3d/core/anchor/anchor_generator.py")
+    _load("det3d.core.anchor.target_ops_v2", "det3d/core/anchor/target_ops_v2.py")
+    ta_mod = _load("det3d.core.anchor.target_assigner", "det3d/core/anchor/target_assigner.py")
+    ag = ag_mod.AnchorGeneratorRange(anchor_ranges=[0, -40.0, -1.0, 70.4, 40.0, -1.0], sizes=[1.6, 3.9, 1.56],
+                                     rotations=[0, 1.57], velocities=None, class_name="Car",
+                                     match_threshold=0.6, unmatch_threshold=0.45)
+    ta = ta_mod.TargetAssigner(box_coder=bc.GroundBox3dCoderTorch(linear_dim=False, vec_encode=False, n_dim=7),
+                               anchor_generators=[ag], region_similarity_calculator=rs.NearestIouSimilarity(),
+                               positive_fraction=None, sample_size=512)
+    ad = ta.generate_anchors_dict([1, 200, 176])
+    anchors = ad["Car"]["anchors"]
+    gt, _ = synth.random_boxes(21, 12)
+    gt[:, 2] = -1.0
+    res = ta.assign_v2(ad, gt, None, gt_classes=np.ones(12, np.int32), gt_names=np.array(["Car"] * 12),
+                       enable_similar_type=True)
+    from oracle import anchors as oa
+    mine = oa.create_anchors_3d_range()
+    assert (mine.reshape(-1, 7) == anchors.reshape(-1, 7)).all()
+    om = oa.assign_targets(anchors.reshape(-1, 7), gt)
+    assert (om["labels"] == res["labels"]).all()
+    assert np.array_equal(om["bbox_targets"], res["bbox_targets"])
+    pos = np.nonzero(res["labels"] > 0)[0]
+    np.savez_compressed(os.path.join(HERE, "anchors_assign.npz"),
+                        anchors_sha=sha(anchors), anchors_head=anchors.reshape(-1, 7)[:704].copy(),
+                        anchors_tail=anchors.reshape(-1, 7)[-704:].copy(),
+                        labels=res["labels"].astype(np.int8), pos_idx=pos.astype(np.int32),
+                        pos_targets=res["bbox_targets"][pos], weights_sum=np.float64(res["bbox_outside_weights"].sum()))
+    print("anchors", anchors.shape, "pos", len(pos), "neg", int((res["labels"] == 0).sum()))
+    # decode fixture from the reference torch op
+    g = torch.Generator().manual_seed(5)
+    enc = torch.randn(2048, 7, generator=g) * 0.3
+    anc = torch.from_numpy(anchors.reshape(-1, 7)[::34][:2048].copy())
+    dec = bt.second_box_decode(enc, anc)
+    assert torch.equal(dec, bev_ref.box_decode(enc, anc))
+    np.savez_compressed(os.path.join(HERE, "decode_case.npz"), decoded=dec.numpy())
+    print("decode", dec.shape)
+
+
+def gen_models():
+    import logging
+
+    rpn = _load("det3d.models.necks.rpn_v1", "det3d/models/necks/rpn_v1.py")
+    ssfa = rpn.SSFA(layer_nums=[5], ds_layer_strides=[1], ds_num_filters=[128], us_layer_strides=[1],
+                    us_num_filters=[128], num_input_features=128, norm_cfg=None, logger=logging.getLogger("RPN"))
+    sd = bev_ref.ssfa_random_state(7)
+    missing = ssfa.load_state_dict(sd, strict=True)
+    print("ssfa load:", missing)
+    ssfa.eval()
+    g = torch.Generator().manual_seed(8)
+    x = torch.relu(torch.randn(1, 128, 24, 16, generator=g))
+    with torch.no_grad():
+        y = ssfa(x)
+        y_or = bev_ref.ssfa_forward(x, sd)
+    err = float((y - y_or).abs().max() / y.abs().max())
+    print("ssfa ref vs oracle rel err", err)
+    assert err < 1e-5
+    # Head (mg_head_sessd.py:195-230)
+    mg = _load("det3d.models.bbox_heads.mg_head_sessd", "det3d/models/bbox_heads/mg_head_sessd.py")
+    head = mg.Head(128, 14, 2, use_dir=True, num_dir=4, header=False)
+    hsd = bev_ref.head_random_state(9, prefix="")
+    head.load_state_dict(hsd, strict=True)
+    with torch.no_grad():
+        h = head(y)
+    h_or = bev_ref.head_forward(y, hsd, prefix="")
+    for k in h:
+        assert torch.allclose(h[k], h_or[k], rtol=1e-5, atol=1e-6), k
+    np.savez_compressed(os.path.join(HERE, "ssfa_head_case.npz"), ssfa_out=y.numpy(),
+                        **{k: v.numpy() for k, v in h.items()})
+    # VFE V3
+    ve = _load("det3d.models.readers.voxel_encoder", "det3d/models/readers/voxel_encoder.py")
+    vfe = ve.VoxelFeatureExtractorV3(num_input_features=4)
+    pts = synth.uniform_cloud(1, 2000)
+    v, c, n = ocpu.points_to_voxel(pts, synth.VOXEL_SIZE, synth.PC_RANGE, 5, 20000)
+    m = vfe(torch.from_numpy(v), torch.from_numpy(n))
+    assert torch.equal(m, bev_ref.vfe_mean(torch.from_numpy(v), torch.from_numpy(n)))
+    np.savez_compressed(os.path.join(HERE, "vfe_case.npz"), mean=m.numpy())
+    print("vfe", m.shape)
+
+
+if __name__ == "__main__":
+    gen_voxel()
+    gen_iou()
+    install_det3d_shims()
+    gen_anchors_assign()
+    gen_models()
