@@ -1,0 +1,217 @@
+/*
+ * sessd_b200.h -- C ABI of the B200-native SE-SSD per-frame LiDAR hot path
+ *                 (voxelise -> sparse 3-D conv encoder -> BEV neck/head -> rotated IoU / NMS).
+ *
+ * Conventions (all entry points):
+ *   - plain C types only; device pointers are owned by the caller (torch's allocator in the Python host);
+ *   - every call takes an explicit `stream` (a cudaStream_t passed as void*), launches asynchronously on it
+ *     and performs NO hidden synchronisation or allocation, so a whole frame can be captured in a CUDA graph;
+ *   - data-dependent sizes (voxel / active-site / candidate counts) live in DEVICE memory: kernels take
+ *     `const int* d_count` plus a host-side capacity and are launched as persistent grids sized from the SM count;
+ *   - return value 0 on success, negative SESSD_E* on argument / capacity errors, positive cudaError_t otherwise
+ *     (no exit(), unlike the reference's CHECK_ERROR macro, det3d/core/iou3d/src/iou3d.cpp:13-21).
+ *
+ * Each function cites the reference interface (file:line under Vegeta2020/SE-SSD) it replaces.
+ */
+#ifndef SESSD_B200_H
+#define SESSD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SESSD_OK 0
+#define SESSD_EINVAL (-1)
+#define SESSD_ECAPACITY (-2)
+#define SESSD_EWORKSPACE (-3)
+
+/* library / build information: returns e.g. "sessd_b200 0.1 sm_100a" */
+const char *sessd_version(void);
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches claim) */
+long long sessd_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * V1/V2/V4 + R1: voxeliser.
+ * Replaces det3d/core/input/voxel_generator.py:10-32 (VoxelGenerator.generate) ->
+ * det3d/ops/point_cloud/point_cloud_ops_v2.py:120-194 (points_to_voxel) and :9-62 (numba kernel),
+ * batched over frames in the wire format of det3d/torchie/parallel/collate.py:154-218 (concatenated
+ * voxels, coordinates with a leading batch column), with the per-voxel mean of
+ * det3d/models/readers/voxel_encoder.py:205-210 (VoxelFeatureExtractorV3) fused into the same pass.
+ * Results are bit-identical to the sequential reference loop (voxel id = rank of the voxel's first point in
+ * input order; first max_points points kept in input order; everything after the first point that would open
+ * voxel #max_voxels is dropped).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    float voxel_size[3];      /* x, y, z */
+    float range_min[3];       /* x, y, z */
+    float range_max[3];
+    int grid[3];              /* x, y, z cells = round((max-min)/voxel_size) in fp32 (voxel_generator.py:15-16) */
+    int max_points;           /* per voxel (config: 5) */
+    int max_voxels;           /* per frame (config: 20000) */
+    int num_feat;             /* floats per point (4) */
+} sessd_voxel_cfg;
+
+size_t sessd_voxelize_workspace_bytes(int max_total_points, int batch, const sessd_voxel_cfg *cfg);
+
+/* d_points [max_total_points, num_feat] f32; d_frame_off [batch+1] i32 (device; frame f owns points
+ * [off[f], off[f+1])); outputs: d_voxels [batch*max_voxels, max_points, num_feat] (zero padded),
+ * d_coors [batch*max_voxels, 4] i32 (b, z, y, x), d_num_points [batch*max_voxels] i32,
+ * d_mean [batch*max_voxels, num_feat] f32 (nullable), d_num_voxels [batch+1] i32 (per frame; last = total). */
+int sessd_voxelize(const float *d_points, const int *d_frame_off, int batch, int max_total_points,
+                   const sessd_voxel_cfg *cfg, float *d_voxels, int *d_coors, int *d_num_points, float *d_mean,
+                   int *d_num_voxels, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Host-buffer convenience for the numpy-level API (VoxelGenerator.generate): one frame, host in / host out,
+ * allocation + H2D + D2H inside, synchronous.  Returns the voxel count (>=0) or a negative error. */
+int sessd_voxelize_host(const float *h_points, int num_points, const sessd_voxel_cfg *cfg, float *h_voxels,
+                        int *h_coors_zyx /*[max_voxels,3]*/, int *h_num_points);
+
+/* ------------------------------------------------------------------------------------------------
+ * S3: rulebook ("indice pairs") construction.  Replaces spconv 1.x's indice-pair builders that
+ * det3d/models/backbones/scn.py:106-149,182-183 trigger (4 SubM keys + 4 strided convs per forward).
+ * The rulebook is kept output-major: nbr[o, k] = input row feeding output o through kernel offset k, or -1.
+ * The canonical spconv form (per offset: pairs sorted by output index) is sessd_rulebook_pairs().
+ *
+ * An "index" is either a hash table over given coordinates (any row order: the voxeliser's first-appearance
+ * order at level 0) or a rank bitmap (rows in ascending linear index: what strided convs emit).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int batch;
+    int shape[3];     /* D, H, W  (z, y, x) */
+} sessd_grid;
+
+/* hash index: table of `capacity` (power of two >= 2*max_rows) 64-bit slots */
+size_t sessd_hash_bytes(int max_rows, int *capacity_out);
+int sessd_hash_build(const int *d_coors /*[n,4] b,z,y,x*/, const int *d_n, int max_rows, sessd_grid grid,
+                     uint64_t *d_table, int capacity, void *stream);
+
+/* rank bitmap index: uint2 {bits, exclusive prefix popcount} per 32 cells; + scan scratch */
+size_t sessd_bitmap_words(sessd_grid grid);
+size_t sessd_scan_scratch_bytes(size_t n_items);
+
+/* SubM rulebook over an index: nbr [max_rows, kvol] */
+int sessd_subm_rulebook(const int *d_coors, const int *d_n, int max_rows, sessd_grid grid, const int ksize[3],
+                        int index_kind /*0 hash, 1 bitmap*/, const void *d_index, int hash_capacity,
+                        int *d_nbr, void *stream);
+
+/* Strided sparse conv rulebook: marks reachable outputs in d_out_bitmap (zeroed by the call), ranks them
+ * (ascending linear index == canonical order), emits out coords + count and the [max_out, kvol] nbr table. */
+int sessd_strided_rulebook(const int *d_in_coors, const int *d_n_in, int max_in, sessd_grid in_grid,
+                           int in_index_kind, const void *d_in_index, int in_hash_capacity,
+                           const int ksize[3], const int stride[3], const int padding[3],
+                           sessd_grid out_grid, void *d_out_bitmap /*uint2[words]*/, void *d_scan_scratch,
+                           int *d_out_coors, int *d_n_out, int max_out, int *d_nbr, int *d_status, void *stream);
+
+/* canonical spconv-style pairs from a nbr table: pairs_in/out [kvol, max_rows], pair_num [kvol] */
+size_t sessd_rulebook_pairs_workspace_bytes(int max_rows, int kvol);
+int sessd_rulebook_pairs(const int *d_nbr, const int *d_n_out, int max_rows, int kvol, int *d_pairs_in,
+                         int *d_pairs_out, int *d_pair_num, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * S4/S5: sparse convolution (gather -> GEMM -> fused BN(eval)+ReLU epilogue, output-stationary) and dense().
+ * Replaces spconv.SubMConv3d / SparseConv3d forward + BatchNorm1d + ReLU (scn.py:106-149) and
+ * SparseConvTensor.dense() + view (scn.py:184-187).
+ * weight layout [kvol, Cin, Cout] (== spconv 1.x [kz,ky,kx,Cin,Cout] flattened); scale/shift = folded BN
+ * (scale = gamma/sqrt(var+eps), shift = beta - mean*scale), nullable => identity; relu flag.
+ * ------------------------------------------------------------------------------------------------ */
+int sessd_spconv_forward(const float *d_in_feat, int cin, const int *d_nbr, int kvol, const int *d_n_out,
+                         int max_out, const float *d_weight, int cout, const float *d_scale, const float *d_shift,
+                         int relu, float *d_out_feat, void *stream);
+
+/* dense(): out NHWC [batch, H, W, C*D] with channel index c*D + d (zero-filled by the call) */
+int sessd_sparse_to_dense(const float *d_feat, const int *d_coors, const int *d_n, int max_rows, int channels,
+                          sessd_grid grid, float *d_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * N1/H1: BEV neck (SSFA) + head.  Replaces the cuDNN conv/deconv + BatchNorm2d + ReLU blocks of
+ * det3d/models/necks/rpn_v1.py:135-235 and the four 1x1 convs of
+ * det3d/models/bbox_heads/mg_head_sessd.py:202-230.  Activations are NHWC fp32.
+ * One call = one tap-list convolution:  out[b, oy*os+py, ox*os+px, :] =
+ *    epilogue( sum_t in[b, oy*is + dy[t], ox*is + dx[t], :] @ W[t] )   (zero outside the input)
+ * with epilogue y = acc*scale + shift (nullable), optional ReLU, optional residual add AFTER the ReLU
+ * (rpn_v1.py:225: deconv_block_0(x_trans_1) + x_trans_0).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int batch, in_h, in_w, cin;       /* input tensor  [batch, in_h, in_w, cin]  */
+    int out_h, out_w, cout;           /* output tensor [batch, out_h, out_w, cout] */
+    int grid_h, grid_w;               /* output positions computed by this call (per batch) */
+    int in_stride;                    /* is */
+    int out_stride, out_off_y, out_off_x;   /* os, py, px */
+    int ntaps;
+    int tap_dy[16], tap_dx[16];
+    int relu;
+} sessd_conv_desc;
+
+int sessd_bev_conv(const float *d_in, const float *d_weight /*[ntaps, cin, cout]*/, const float *d_scale,
+                   const float *d_shift, const float *d_residual /*nullable, same shape as out*/, float *d_out,
+                   const sessd_conv_desc *desc, void *stream);
+
+/* SSFA tail (rpn_v1.py:229-233): w_k = BN(conv1x1_{128->1}(x_k)); softmax over the pair; weighted sum */
+int sessd_ssfa_fuse(const float *d_x0, const float *d_x1, const float *d_w0 /*[C]*/, const float *d_w1,
+                    float s0, float t0, float s1, float t1, int num_pixels, int channels, float *d_out,
+                    void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * P1/P2/P3: decode -> sigmoid -> threshold -> IoU-rectified score -> top-k -> rotated NMS -> direction fix ->
+ * range mask, all on device, no host round trip.  Replaces MultiGroupHead.predict / get_task_detections
+ * (mg_head_sessd.py:893-1057), box_torch_ops.second_box_decode (:81-147), box_torch_ops.rotate_nms (:527-548),
+ * nms_cpu.py:37-48 and nms_cpu.h:72-168.
+ * head layout per pixel: [box 2x7 | cls 2 | dir 2x2 | iou 2] = 22 floats, row stride head_stride (22, or 24 when the
+ * fused 128->22 head GEMM pads its output to a multiple of 4 channels).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int batch;
+    int num_anchors;           /* per frame (70400) */
+    int anchors_per_loc;       /* 2 */
+    int head_stride;           /* floats per pixel row of d_head (>= 22) */
+    float score_thresh;        /* 0.3 */
+    int nms_pre_max;           /* 1000 */
+    int nms_post_max;          /* 100 */
+    float nms_iou_thresh;      /* 0.01 */
+    int nms_ge;                /* 1: suppress when iou >= thr (nms_cpu.h:155); 0: iou > thr (iou3d nms_kernel) */
+    float post_range[6];       /* 0,-40,-5,70.4,40,5 */
+    float direction_offset;    /* 0 */
+    int use_frustum;           /* apply the calib frustum filter (mg_head_sessd.py:1024-1030) */
+} sessd_post_cfg;
+
+size_t sessd_postprocess_workspace_bytes(const sessd_post_cfg *cfg);
+
+/* d_head [batch, num_anchors/apl, head_stride]; d_anchors [num_anchors, 7] (shared by all frames);
+ * d_frustum [batch, 6, 4] plane (a,b,c,d) per surface (nullable unless use_frustum);
+ * outputs: d_boxes [batch, post_max, 7], d_scores [batch, post_max], d_labels [batch, post_max] i32,
+ * d_count [batch] i32, d_aux [batch, 4] i32 (candidates, pre-NMS count, NMS-selected count, reserved),
+ * d_sel_anchor [batch, post_max] i32 (anchor index of each NMS-selected box, before frustum/range masks). */
+int sessd_postprocess(const float *d_head, const float *d_anchors, const float *d_frustum,
+                      const sessd_post_cfg *cfg, float *d_boxes, float *d_scores, int *d_labels, int *d_count,
+                      int *d_aux, int *d_sel_anchor, void *workspace, size_t workspace_bytes, void *stream);
+
+/* stand-alone rotated NMS on [n,5] (x,y,w,l,r) + scores: box_torch_ops.rotate_nms semantics
+ * (top-k pre_max by score, greedy, keep <= post_max); d_keep [post_max] i32 indices into the input */
+size_t sessd_rotate_nms_workspace_bytes(int max_boxes, int pre_max);
+int sessd_rotate_nms(const float *d_boxes5, const float *d_scores, const int *d_n, int max_boxes, int pre_max,
+                     int post_max, float iou_thresh, int ge, int *d_keep, int *d_num_keep, void *workspace,
+                     size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * I1/I2: the iou3d_cuda extension.  Replaces det3d/core/iou3d/src/iou3d.cpp:34-281 (+ iou3d_kernel.cu
+ * :270-365): same box layouts ([x1,y1,x2,y2,ry] / [x1,y1,z1,x2,y2,z2,ry]), caller-allocated outputs.
+ * NMS variants take boxes already sorted by descending score (iou3d_utils.py:254-306) and do the greedy
+ * reduction ON DEVICE (the reference copies the N x N/64 mask to the host, iou3d.cpp:131-158).
+ * ------------------------------------------------------------------------------------------------ */
+int sessd_boxes_overlap_bev(const float *d_a, int n, const float *d_b, int m, float *d_out, void *stream);
+int sessd_boxes_aligned_overlap_bev(const float *d_a, const float *d_b, int n, float *d_out, void *stream);
+int sessd_boxes_iou_bev(const float *d_a, int n, const float *d_b, int m, float *d_out, void *stream);
+int sessd_boxes_iou3d(const float *d_a, int n, const float *d_b, int m, float *d_out, void *stream);
+size_t sessd_nms_workspace_bytes(int n);
+/* mode 0: rotated BEV (nms_gpu), 1: 3-D (nms_3d_gpu), 2: axis-aligned (nms_normal_gpu);
+ * d_keep [n] int64 (device), d_num_keep [1] i32 (device) */
+int sessd_nms_sorted(const float *d_boxes, int n, float thresh, int mode, long long *d_keep, int *d_num_keep,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

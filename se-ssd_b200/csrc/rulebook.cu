@@ -1,0 +1,313 @@
+// rulebook.cu -- sparse-convolution rulebook ("indice pairs") construction on B200.
+//
+// Replaces the indice-pair builders of spconv 1.x that det3d/models/backbones/scn.py:106-149,182-183 triggers
+// (one per SubM indice_key + one per strided SparseConv3d = 8 builds per forward).  spconv builds per-offset pair
+// lists with global atomic counters (nondeterministic order).  Here the rulebook is OUTPUT-MAJOR and deterministic:
+//     nbr[o, k] = row of the input voxel at  pos_o * stride - pad + k   (or -1),
+// which is exactly what the output-stationary gather-GEMM in spconv.cu consumes (no scatter-add, no atomics on
+// features), and from which the canonical spconv form (per offset, pairs sorted by output index) follows by an
+// ordered compaction (sessd_rulebook_pairs: warp ballots + shared-memory histogram).
+//
+// Two coordinate indices:
+//   * hash   : 64-bit open addressing over linear cell index -> row, for coordinates given in arbitrary order
+//              (level 0: the voxeliser's first-appearance order);
+//   * bitmap : one bit per cell + exclusive popcount prefix per 32-cell word (uint2).  A strided conv marks its
+//              reachable outputs in the bitmap; ranking the bits yields the output rows in ascending linear index
+//              -- the canonical order -- without any sort, and the same structure answers lookups with ONE 8-byte
+//              read (bit test + popc).  Level-1..4 bitmaps are 3 MB ... 18 KB per frame: L2 resident.
+// HBM traffic per build: reads 16 B/input row, writes 4*kvol B/output row (nbr) + 16 B/output row (coords); the
+// bitmap/hash probes hit L2.  All counts are device-resident (d_n), grids are persistent.
+#include "common.cuh"
+
+namespace sessd {
+
+struct GridDims { int B, D, H, W; };
+
+__device__ __forceinline__ unsigned long long lin_index(GridDims g, int b, int z, int y, int x) {
+    return (((unsigned long long)b * g.D + z) * g.H + y) * g.W + x;
+}
+
+struct HashIndex {
+    const unsigned long long *tbl;
+    int mask;
+    __device__ __forceinline__ int find(unsigned long long lin) const { return hash_lookup(tbl, mask, lin); }
+};
+
+struct BitmapIndex {
+    const uint2 *words;
+    __device__ __forceinline__ int find(unsigned long long lin) const {
+        const uint2 e = __ldg(&words[lin >> 5]);
+        const unsigned int bit = (unsigned int)lin & 31u;
+        if (!((e.x >> bit) & 1u)) return -1;
+        return (int)e.y + __popc(e.x & ((1u << bit) - 1u));
+    }
+};
+
+__global__ void __launch_bounds__(256) hash_build_kernel(const int4 *__restrict__ coors, const int *__restrict__ d_n, int max_rows,
+                                                         GridDims g, unsigned long long *tbl, int mask) {
+    const int n = min(*d_n, max_rows);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 c = coors[i];
+        hash_insert_min(tbl, mask, lin_index(g, c.x, c.y, c.z, c.w), (unsigned int)i);
+    }
+}
+
+// nbr table: one thread per (output row, kernel offset), k fastest (coalesced 4-byte stores)
+template <class Index>
+__global__ void __launch_bounds__(256) nbr_kernel(const int4 *__restrict__ out_coors, const int *__restrict__ d_n_out, int max_out,
+                                                  GridDims gin, Index index, int kd, int kh, int kw, int sd, int sh, int sw,
+                                                  int pd, int ph, int pw, int *__restrict__ nbr) {
+    const int kvol = kd * kh * kw;
+    const long long total = (long long)min(*d_n_out, max_out) * kvol;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int o = (int)(t / kvol);
+        const int k = (int)(t - (long long)o * kvol);
+        const int a = k / (kh * kw), r = k - a * (kh * kw), bb = r / kw, c = r - bb * kw;
+        const int4 oc = __ldg(&out_coors[o]);
+        const int z = oc.y * sd - pd + a, y = oc.z * sh - ph + bb, x = oc.w * sw - pw + c;
+        int res = -1;
+        if (z >= 0 && z < gin.D && y >= 0 && y < gin.H && x >= 0 && x < gin.W) res = index.find(lin_index(gin, oc.x, z, y, x));
+        nbr[t] = res;
+    }
+}
+
+// strided conv, step 1: mark every reachable output cell
+__global__ void __launch_bounds__(256) mark_outputs_kernel(const int4 *__restrict__ in_coors, const int *__restrict__ d_n_in, int max_in,
+                                                           GridDims gout, int kd, int kh, int kw, int sd, int sh, int sw,
+                                                           int pd, int ph, int pw, uint2 *bitmap) {
+    const int kvol = kd * kh * kw;
+    const long long total = (long long)min(*d_n_in, max_in) * kvol;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t / kvol);
+        const int k = (int)(t - (long long)i * kvol);
+        const int a = k / (kh * kw), r = k - a * (kh * kw), bb = r / kw, c = r - bb * kw;
+        const int4 ic = __ldg(&in_coors[i]);
+        const int nz = ic.y + pd - a, ny = ic.z + ph - bb, nx = ic.w + pw - c;
+        if (nz < 0 || ny < 0 || nx < 0) continue;
+        if (nz % sd || ny % sh || nx % sw) continue;
+        const int z = nz / sd, y = ny / sh, x = nx / sw;
+        if (z >= gout.D || y >= gout.H || x >= gout.W) continue;
+        const unsigned long long lin = lin_index(gout, ic.x, z, y, x);
+        unsigned int *w = &bitmap[lin >> 5].x;
+        const unsigned int bit = 1u << ((unsigned int)lin & 31u);
+        if (!(*(volatile unsigned int *)w & bit)) atomicOr(w, bit);
+    }
+}
+
+struct PopcLoad {
+    const uint2 *words;
+    __device__ __forceinline__ int operator()(long long i) const { return __popc(words[i].x); }
+};
+struct PrefixStore {
+    uint2 *words;
+    __device__ __forceinline__ void operator()(long long i, int ex, int) const { words[i].y = (unsigned int)ex; }
+};
+
+// strided conv, step 3: emit output coordinates in ascending linear index, clamp the count
+__global__ void __launch_bounds__(256) enumerate_kernel(const uint2 *__restrict__ bitmap, long long nwords, GridDims gout,
+                                                        const int *__restrict__ d_total, int max_out, int4 *__restrict__ out_coors,
+                                                        int *__restrict__ d_n_out, int *__restrict__ d_status) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const int tot = *d_total;
+        *d_n_out = tot < max_out ? tot : max_out;
+        if (tot > max_out && d_status) atomicOr(d_status, 1);
+    }
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (long long)gridDim.x * blockDim.x) {
+        const uint2 e = bitmap[w];
+        unsigned int bits = e.x;
+        int pos = (int)e.y;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (pos < max_out) {
+                unsigned long long lin = (unsigned long long)w * 32 + b;
+                const int x = (int)(lin % gout.W); lin /= gout.W;
+                const int y = (int)(lin % gout.H); lin /= gout.H;
+                const int z = (int)(lin % gout.D); lin /= gout.D;
+                out_coors[pos] = make_int4((int)lin, z, y, x);
+            }
+            ++pos;
+        }
+    }
+}
+
+// canonical pairs: per kernel offset, (in, out) sorted by out.  Pass 1 histogram, pass 2 ordered write.
+constexpr int kPairRows = 256;
+
+__global__ void __launch_bounds__(kPairRows) pair_count_kernel(const int *__restrict__ nbr, const int *__restrict__ d_n, int max_rows,
+                                                               int kvol, int *__restrict__ block_counts /*[nblocks, kvol]*/) {
+    extern __shared__ int s_hist[];   // [kvol]
+    const int n = min(*d_n, max_rows);
+    const int base = blockIdx.x * kPairRows;
+    if (base >= n) return;
+    for (int k = threadIdx.x; k < kvol; k += blockDim.x) s_hist[k] = 0;
+    __syncthreads();
+    const int o = base + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    for (int k = 0; k < kvol; ++k) {
+        const bool f = (o < n) && (nbr[(size_t)o * kvol + k] >= 0);
+        const unsigned int bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0 && bal) atomicAdd(&s_hist[k], __popc(bal));
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < kvol; k += blockDim.x) block_counts[(size_t)blockIdx.x * kvol + k] = s_hist[k];
+}
+
+__global__ void __launch_bounds__(32) pair_offsets_kernel(const int *__restrict__ d_n, int max_rows, int kvol,
+                                                          int *__restrict__ block_counts, int *__restrict__ pair_num) {
+    // one warp per kernel offset: exclusive scan of the per-block counts (serial over block chunks of 32)
+    const int n = min(*d_n, max_rows);
+    const int nblk = (n + kPairRows - 1) / kPairRows;
+    const int k = blockIdx.x;
+    const int lane = threadIdx.x;
+    int carry = 0;
+    for (int b0 = 0; b0 < nblk; b0 += 32) {
+        const int b = b0 + lane;
+        const int v = (b < nblk) ? block_counts[(size_t)b * kvol + k] : 0;
+        const int incl = warp_incl_scan(v, lane);
+        if (b < nblk) block_counts[(size_t)b * kvol + k] = carry + incl - v;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) pair_num[k] = carry;
+}
+
+__global__ void __launch_bounds__(kPairRows) pair_write_kernel(const int *__restrict__ nbr, const int *__restrict__ d_n, int max_rows,
+                                                               int kvol, const int *__restrict__ block_offsets,
+                                                               int *__restrict__ pairs_in, int *__restrict__ pairs_out) {
+    __shared__ int s_warp[kPairRows / 32];
+    const int n = min(*d_n, max_rows);
+    const int base = blockIdx.x * kPairRows;
+    if (base >= n) return;
+    const int o = base + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = 0; k < kvol; ++k) {
+        const int src = (o < n) ? nbr[(size_t)o * kvol + k] : -1;
+        const bool f = src >= 0;
+        const unsigned int bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        int woff = 0;
+        for (int w2 = 0; w2 < warp; ++w2) woff += s_warp[w2];
+        if (f) {
+            const int pos = block_offsets[(size_t)blockIdx.x * kvol + k] + woff + __popc(bal & ((1u << lane) - 1u));
+            pairs_in[(size_t)k * max_rows + pos] = src;
+            pairs_out[(size_t)k * max_rows + pos] = o;
+        }
+        __syncthreads();
+    }
+}
+
+static GridDims to_dims(sessd_grid g) { GridDims d; d.B = g.batch; d.D = g.shape[0]; d.H = g.shape[1]; d.W = g.shape[2]; return d; }
+
+}  // namespace sessd
+
+using namespace sessd;
+
+extern "C" size_t sessd_hash_bytes(int max_rows, int *capacity_out) {
+    int cap = 1024;
+    while (cap < 2 * max_rows) cap <<= 1;
+    if (capacity_out) *capacity_out = cap;
+    return sizeof(unsigned long long) * (size_t)cap;
+}
+
+extern "C" int sessd_hash_build(const int *d_coors, const int *d_n, int max_rows, sessd_grid grid, uint64_t *d_table, int capacity,
+                                void *stream) {
+    if (!d_coors || !d_n || !d_table || max_rows < 1 || capacity < 2 * max_rows || (capacity & (capacity - 1))) return SESSD_EINVAL;
+    if ((long long)max_rows >= (1ll << kHashValBits)) return SESSD_ECAPACITY;
+    const unsigned long long cells = (unsigned long long)grid.batch * grid.shape[0] * grid.shape[1] * grid.shape[2];
+    if (cells >= (1ull << (64 - kHashValBits))) return SESSD_ECAPACITY;
+    cudaStream_t st = (cudaStream_t)stream;
+    SESSD_CUDA_TRY(cudaMemsetAsync(d_table, 0xff, sizeof(unsigned long long) * (size_t)capacity, st));
+    SESSD_LAUNCH(hash_build_kernel, persistent_grid(max_rows, 256), 256, 0, st, (const int4 *)d_coors, d_n, max_rows, to_dims(grid),
+                 (unsigned long long *)d_table, capacity - 1);
+    return last_error();
+}
+
+extern "C" size_t sessd_bitmap_words(sessd_grid grid) {
+    const unsigned long long cells = (unsigned long long)grid.batch * grid.shape[0] * grid.shape[1] * grid.shape[2];
+    return (size_t)((cells + 31) / 32);
+}
+
+extern "C" size_t sessd_scan_scratch_bytes(size_t n_items) { return scan_scratch_bytes((long long)n_items) + 256; }
+
+extern "C" int sessd_subm_rulebook(const int *d_coors, const int *d_n, int max_rows, sessd_grid grid, const int ksize[3],
+                                   int index_kind, const void *d_index, int hash_capacity, int *d_nbr, void *stream) {
+    if (!d_coors || !d_n || !d_index || !d_nbr || max_rows < 1 || !ksize) return SESSD_EINVAL;
+    const int kd = ksize[0], kh = ksize[1], kw = ksize[2];
+    if (kd < 1 || kh < 1 || kw < 1 || !(kd & 1) || !(kh & 1) || !(kw & 1)) return SESSD_EINVAL;
+    const GridDims g = to_dims(grid);
+    const int grid_sz = persistent_grid((long long)max_rows * kd * kh * kw, 256);
+    if (index_kind == 0) {
+        HashIndex idx{(const unsigned long long *)d_index, hash_capacity - 1};
+        SESSD_LAUNCH((nbr_kernel<HashIndex>), grid_sz, 256, 0, stream, (const int4 *)d_coors, d_n, max_rows, g, idx, kd, kh, kw, 1, 1, 1,
+                     kd / 2, kh / 2, kw / 2, d_nbr);
+    } else if (index_kind == 1) {
+        BitmapIndex idx{(const uint2 *)d_index};
+        SESSD_LAUNCH((nbr_kernel<BitmapIndex>), grid_sz, 256, 0, stream, (const int4 *)d_coors, d_n, max_rows, g, idx, kd, kh, kw, 1, 1, 1,
+                     kd / 2, kh / 2, kw / 2, d_nbr);
+    } else {
+        return SESSD_EINVAL;
+    }
+    return last_error();
+}
+
+extern "C" int sessd_strided_rulebook(const int *d_in_coors, const int *d_n_in, int max_in, sessd_grid in_grid, int in_index_kind,
+                                      const void *d_in_index, int in_hash_capacity, const int ksize[3], const int stride[3],
+                                      const int padding[3], sessd_grid out_grid, void *d_out_bitmap, void *d_scan_scratch,
+                                      int *d_out_coors, int *d_n_out, int max_out, int *d_nbr, int *d_status, void *stream) {
+    if (!d_in_coors || !d_n_in || !d_in_index || !d_out_bitmap || !d_scan_scratch || !d_out_coors || !d_n_out || !d_nbr || !ksize ||
+        !stride || !padding || max_in < 1 || max_out < 1)
+        return SESSD_EINVAL;
+    for (int j = 0; j < 3; ++j) {
+        if (ksize[j] < 1 || stride[j] < 1 || padding[j] < 0) return SESSD_EINVAL;
+        if (out_grid.shape[j] != (in_grid.shape[j] + 2 * padding[j] - ksize[j]) / stride[j] + 1) return SESSD_EINVAL;
+    }
+    if (out_grid.batch != in_grid.batch) return SESSD_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const GridDims gi = to_dims(in_grid), go = to_dims(out_grid);
+    const size_t words = sessd_bitmap_words(out_grid);
+    if (words >= (1ull << 31)) return SESSD_ECAPACITY;
+    uint2 *bm = (uint2 *)d_out_bitmap;
+    const int kvol = ksize[0] * ksize[1] * ksize[2];
+    SESSD_CUDA_TRY(cudaMemsetAsync(bm, 0, sizeof(uint2) * words, st));
+    SESSD_LAUNCH(mark_outputs_kernel, persistent_grid((long long)max_in * kvol, 256), 256, 0, st, (const int4 *)d_in_coors, d_n_in,
+                 max_in, go, ksize[0], ksize[1], ksize[2], stride[0], stride[1], stride[2], padding[0], padding[1], padding[2], bm);
+    int *scratch = (int *)d_scan_scratch;
+    int *d_total = scratch;                    // first int: total; tile sums follow (256-byte offset)
+    PopcLoad ld{bm};
+    PrefixStore stf{bm};
+    device_scan(ld, stf, nullptr, (long long)words, (long long)words, scratch + 64, d_total, st);
+    SESSD_LAUNCH(enumerate_kernel, persistent_grid((long long)words, 256), 256, 0, st, bm, (long long)words, go, d_total, max_out,
+                 (int4 *)d_out_coors, d_n_out, d_status);
+    const int grid_sz = persistent_grid((long long)max_out * kvol, 256);
+    if (in_index_kind == 0) {
+        HashIndex idx{(const unsigned long long *)d_in_index, in_hash_capacity - 1};
+        SESSD_LAUNCH((nbr_kernel<HashIndex>), grid_sz, 256, 0, st, (const int4 *)d_out_coors, d_n_out, max_out, gi, idx, ksize[0], ksize[1],
+                     ksize[2], stride[0], stride[1], stride[2], padding[0], padding[1], padding[2], d_nbr);
+    } else if (in_index_kind == 1) {
+        BitmapIndex idx{(const uint2 *)d_in_index};
+        SESSD_LAUNCH((nbr_kernel<BitmapIndex>), grid_sz, 256, 0, st, (const int4 *)d_out_coors, d_n_out, max_out, gi, idx, ksize[0], ksize[1],
+                     ksize[2], stride[0], stride[1], stride[2], padding[0], padding[1], padding[2], d_nbr);
+    } else {
+        return SESSD_EINVAL;
+    }
+    return last_error();
+}
+
+extern "C" size_t sessd_rulebook_pairs_workspace_bytes(int max_rows, int kvol) {
+    if (max_rows < 1 || kvol < 1) return 0;
+    return sizeof(int) * (size_t)div_up(max_rows, kPairRows) * kvol;
+}
+
+extern "C" int sessd_rulebook_pairs(const int *d_nbr, const int *d_n_out, int max_rows, int kvol, int *d_pairs_in, int *d_pairs_out,
+                                    int *d_pair_num, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!d_nbr || !d_n_out || !d_pairs_in || !d_pairs_out || !d_pair_num || max_rows < 1 || kvol < 1 || kvol > 1024) return SESSD_EINVAL;
+    if (!workspace || workspace_bytes < sessd_rulebook_pairs_workspace_bytes(max_rows, kvol)) return SESSD_EWORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nblk = div_up(max_rows, kPairRows);
+    int *block_counts = (int *)workspace;   // per-block histograms -> exclusive offsets
+    SESSD_LAUNCH(pair_count_kernel, nblk, kPairRows, sizeof(int) * kvol, st, d_nbr, d_n_out, max_rows, kvol, block_counts);
+    SESSD_LAUNCH(pair_offsets_kernel, kvol, 32, 0, st, d_n_out, max_rows, kvol, block_counts, d_pair_num);
+    SESSD_LAUNCH(pair_write_kernel, nblk, kPairRows, 0, st, d_nbr, d_n_out, max_rows, kvol, block_counts, d_pairs_in, d_pairs_out);
+    return last_error();
+}

@@ -1,0 +1,265 @@
+"""Tensor-level wrappers over the C ABI (PyTorch supplies device memory and streams only).
+
+Every function launches asynchronously on ``torch.cuda.current_stream()`` and never synchronises; data-dependent
+row counts stay on the device as int32 tensors (``n`` arguments), buffers are capacity sized.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, Grid, PostCfg, VoxelCfg, check, lib
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _cuda(t, dtype, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise ValueError("%s must be a contiguous CUDA %s tensor" % (name, dtype))
+    return t
+
+
+def _i3(v):
+    return (C.c_int * 3)(*[int(x) for x in v])
+
+
+def make_grid(batch, shape_dhw):
+    g = Grid()
+    g.batch = int(batch)
+    g.shape[0], g.shape[1], g.shape[2] = [int(v) for v in shape_dhw]
+    return g
+
+
+# ------------------------------------------------------------------------------------------------ voxeliser
+def make_voxel_cfg(voxel_size, pc_range, max_points, max_voxels, num_feat=4):
+    cfg = VoxelCfg()
+    vs = np.asarray(voxel_size, np.float32)
+    rg = np.asarray(pc_range, np.float32)
+    grid = np.round((rg[3:] - rg[:3]) / vs).astype(np.int64)      # voxel_generator.py:15-16
+    for j in range(3):
+        cfg.voxel_size[j] = float(vs[j])
+        cfg.range_min[j] = float(rg[j])
+        cfg.range_max[j] = float(rg[3 + j])
+        cfg.grid[j] = int(grid[j])
+    cfg.max_points, cfg.max_voxels, cfg.num_feat = int(max_points), int(max_voxels), int(num_feat)
+    return cfg
+
+
+class VoxelBuffers:
+    """Capacity-sized outputs + workspace of the batched voxeliser (reused across frames / graph replays)."""
+
+    def __init__(self, cfg, batch, max_total_points, device, with_mean=True):
+        self.cfg, self.batch, self.max_total_points = cfg, batch, max_total_points
+        nv = batch * cfg.max_voxels
+        self.voxels = torch.empty((nv, cfg.max_points, cfg.num_feat), dtype=torch.float32, device=device)
+        self.coors = torch.empty((nv, 4), dtype=torch.int32, device=device)
+        self.num_points = torch.empty((nv,), dtype=torch.int32, device=device)
+        self.mean = torch.empty((nv, cfg.num_feat), dtype=torch.float32, device=device) if with_mean else None
+        self.num_voxels = torch.zeros((batch + 1,), dtype=torch.int32, device=device)
+        ws = lib.sessd_voxelize_workspace_bytes(max_total_points, batch, C.byref(cfg))
+        self.ws = torch.empty((ws,), dtype=torch.uint8, device=device)
+
+
+def voxelize(points, frame_off, buf):
+    """points [P,F] f32 cuda (P <= buf.max_total_points), frame_off [B+1] i32 cuda -> fills buf."""
+    _cuda(points, torch.float32, "points")
+    _cuda(frame_off, torch.int32, "frame_off")
+    if points.shape[0] > buf.max_total_points or points.shape[1] != buf.cfg.num_feat or frame_off.numel() != buf.batch + 1:
+        raise ValueError("voxelize: shape/capacity mismatch")
+    rc = lib.sessd_voxelize(_p(points), _p(frame_off), buf.batch, buf.max_total_points, C.byref(buf.cfg), _p(buf.voxels),
+                            _p(buf.coors), _p(buf.num_points), _p(buf.mean), _p(buf.num_voxels), _p(buf.ws), buf.ws.numel(), _st())
+    check(rc, "sessd_voxelize")
+    return buf
+
+
+def voxelize_host(points_np, cfg):
+    """numpy in / numpy out single-frame path (VoxelGenerator.generate)."""
+    pts = np.ascontiguousarray(points_np, np.float32)
+    if pts.ndim != 2 or pts.shape[1] != cfg.num_feat:
+        raise ValueError("points must be [N,%d]" % cfg.num_feat)
+    voxels = np.zeros((cfg.max_voxels, cfg.max_points, cfg.num_feat), np.float32)
+    coors = np.zeros((cfg.max_voxels, 3), np.int32)
+    num = np.zeros((cfg.max_voxels,), np.int32)
+    m = lib.sessd_voxelize_host(pts.ctypes.data_as(C.c_void_p), pts.shape[0], C.byref(cfg), voxels.ctypes.data_as(C.c_void_p),
+                                coors.ctypes.data_as(C.c_void_p), num.ctypes.data_as(C.c_void_p))
+    if m < 0:
+        raise _lib.SessdError("sessd_voxelize_host failed (%d)" % m)
+    return voxels[:m].copy(), coors[:m].copy(), num[:m].copy()
+
+
+# ------------------------------------------------------------------------------------------------ rulebook
+def hash_capacity(max_rows):
+    cap = C.c_int(0)
+    lib.sessd_hash_bytes(int(max_rows), C.byref(cap))
+    return cap.value
+
+
+def hash_build(coors, n, max_rows, grid, table=None):
+    cap = hash_capacity(max_rows)
+    if table is None:
+        table = torch.empty((cap,), dtype=torch.int64, device=coors.device)
+    check(lib.sessd_hash_build(_p(coors), _p(n), int(max_rows), grid, _p(table), cap, _st()), "sessd_hash_build")
+    return table
+
+
+def bitmap_alloc(grid, device):
+    words = lib.sessd_bitmap_words(grid)
+    bitmap = torch.empty((words, 2), dtype=torch.int32, device=device)
+    scratch = torch.empty((lib.sessd_scan_scratch_bytes(words),), dtype=torch.uint8, device=device)
+    return bitmap, scratch
+
+
+def subm_rulebook(coors, n, max_rows, grid, ksize, index_kind, index, nbr=None):
+    kvol = int(ksize[0] * ksize[1] * ksize[2])
+    if nbr is None:
+        nbr = torch.empty((max_rows, kvol), dtype=torch.int32, device=coors.device)
+    cap = index.numel() if index_kind == 0 else 0
+    check(lib.sessd_subm_rulebook(_p(coors), _p(n), int(max_rows), grid, _i3(ksize), int(index_kind), _p(index), cap, _p(nbr), _st()),
+          "sessd_subm_rulebook")
+    return nbr
+
+
+def strided_rulebook(in_coors, n_in, max_in, in_grid, in_index_kind, in_index, ksize, stride, padding, out_grid, bitmap,
+                     scratch, out_coors, n_out, max_out, nbr, status):
+    cap = in_index.numel() if in_index_kind == 0 else 0
+    check(lib.sessd_strided_rulebook(_p(in_coors), _p(n_in), int(max_in), in_grid, int(in_index_kind), _p(in_index), cap, _i3(ksize),
+                                     _i3(stride), _i3(padding), out_grid, _p(bitmap), _p(scratch), _p(out_coors), _p(n_out),
+                                     int(max_out), _p(nbr), _p(status), _st()), "sessd_strided_rulebook")
+
+
+def rulebook_pairs(nbr, n, max_rows, kvol):
+    dev = nbr.device
+    pin = torch.full((kvol, max_rows), -1, dtype=torch.int32, device=dev)
+    pout = torch.full((kvol, max_rows), -1, dtype=torch.int32, device=dev)
+    num = torch.zeros((kvol,), dtype=torch.int32, device=dev)
+    ws = torch.empty((lib.sessd_rulebook_pairs_workspace_bytes(int(max_rows), int(kvol)),), dtype=torch.uint8, device=dev)
+    check(lib.sessd_rulebook_pairs(_p(nbr), _p(n), int(max_rows), int(kvol), _p(pin), _p(pout), _p(num), _p(ws), ws.numel(), _st()),
+          "sessd_rulebook_pairs")
+    return pin, pout, num
+
+
+# ------------------------------------------------------------------------------------------------ sparse conv
+def spconv_forward(in_feat, nbr, n_out, max_out, weight, scale, shift, relu, out=None):
+    """in_feat [*,Cin]; nbr [max_out,kvol]; weight [kvol,Cin,Cout]; scale/shift [Cout] or None."""
+    kvol, cin, cout = weight.shape
+    if out is None:
+        out = torch.empty((max_out, cout), dtype=torch.float32, device=in_feat.device)
+    check(lib.sessd_spconv_forward(_p(in_feat), int(cin), _p(nbr), int(kvol), _p(n_out), int(max_out), _p(weight), int(cout),
+                                   _p(scale), _p(shift), int(bool(relu)), _p(out), _st()), "sessd_spconv_forward")
+    return out
+
+
+def sparse_to_dense(feat, coors, n, max_rows, grid, out=None):
+    c = feat.shape[1]
+    d, h, w = grid.shape[0], grid.shape[1], grid.shape[2]
+    if out is None:
+        out = torch.empty((grid.batch, h, w, c * d), dtype=torch.float32, device=feat.device)
+    check(lib.sessd_sparse_to_dense(_p(feat), _p(coors), _p(n), int(max_rows), int(c), grid, _p(out), _st()), "sessd_sparse_to_dense")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ BEV convs
+def conv_desc(batch, in_hw, cin, out_hw, cout, grid_hw, taps, in_stride=1, out_stride=1, out_off=(0, 0), relu=True):
+    d = ConvDesc()
+    d.batch, d.in_h, d.in_w, d.cin = int(batch), int(in_hw[0]), int(in_hw[1]), int(cin)
+    d.out_h, d.out_w, d.cout = int(out_hw[0]), int(out_hw[1]), int(cout)
+    d.grid_h, d.grid_w = int(grid_hw[0]), int(grid_hw[1])
+    d.in_stride, d.out_stride, d.out_off_y, d.out_off_x = int(in_stride), int(out_stride), int(out_off[0]), int(out_off[1])
+    d.ntaps = len(taps)
+    for t, (dy, dx) in enumerate(taps):
+        d.tap_dy[t], d.tap_dx[t] = int(dy), int(dx)
+    d.relu = int(bool(relu))
+    return d
+
+
+def bev_conv(x, weight, scale, shift, residual, out, desc):
+    check(lib.sessd_bev_conv(_p(x), _p(weight), _p(scale), _p(shift), _p(residual), _p(out), C.byref(desc), _st()), "sessd_bev_conv")
+    return out
+
+
+def ssfa_fuse(x0, x1, w0, w1, s0, t0, s1, t1, out):
+    npix = x0.numel() // x0.shape[-1]
+    check(lib.sessd_ssfa_fuse(_p(x0), _p(x1), _p(w0), _p(w1), float(s0), float(t0), float(s1), float(t1), int(npix), int(x0.shape[-1]),
+                              _p(out), _st()), "sessd_ssfa_fuse")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ post-processing
+def make_post_cfg(batch, num_anchors=70400, anchors_per_loc=2, head_stride=24, score_thresh=0.3, nms_pre_max=1000, nms_post_max=100,
+                  nms_iou_thresh=0.01, nms_ge=True, post_range=(0, -40.0, -5.0, 70.4, 40.0, 5.0), direction_offset=0.0,
+                  use_frustum=False):
+    c = PostCfg()
+    c.batch, c.num_anchors, c.anchors_per_loc, c.head_stride = int(batch), int(num_anchors), int(anchors_per_loc), int(head_stride)
+    c.score_thresh, c.nms_pre_max, c.nms_post_max = float(score_thresh), int(nms_pre_max), int(nms_post_max)
+    c.nms_iou_thresh, c.nms_ge = float(nms_iou_thresh), int(bool(nms_ge))
+    for j in range(6):
+        c.post_range[j] = float(post_range[j])
+    c.direction_offset, c.use_frustum = float(direction_offset), int(bool(use_frustum))
+    return c
+
+
+class PostBuffers:
+    def __init__(self, cfg, device):
+        self.cfg = cfg
+        b, p = cfg.batch, cfg.nms_post_max
+        self.boxes = torch.zeros((b, p, 7), dtype=torch.float32, device=device)
+        self.scores = torch.zeros((b, p), dtype=torch.float32, device=device)
+        self.labels = torch.zeros((b, p), dtype=torch.int32, device=device)
+        self.count = torch.zeros((b,), dtype=torch.int32, device=device)
+        self.aux = torch.zeros((b, 4), dtype=torch.int32, device=device)
+        self.sel_anchor = torch.zeros((b, p), dtype=torch.int32, device=device)
+        self.ws = torch.empty((lib.sessd_postprocess_workspace_bytes(C.byref(cfg)),), dtype=torch.uint8, device=device)
+
+
+def postprocess(head, anchors, frustum_planes, buf):
+    check(lib.sessd_postprocess(_p(head), _p(anchors), _p(frustum_planes), C.byref(buf.cfg), _p(buf.boxes), _p(buf.scores), _p(buf.labels),
+                                _p(buf.count), _p(buf.aux), _p(buf.sel_anchor), _p(buf.ws), buf.ws.numel(), _st()), "sessd_postprocess")
+    return buf
+
+
+def rotate_nms(boxes5, scores, n, max_boxes, pre_max, post_max, iou_thresh, ge=True):
+    dev = boxes5.device
+    keep = torch.empty((post_max,), dtype=torch.int32, device=dev)
+    num = torch.zeros((1,), dtype=torch.int32, device=dev)
+    ws = torch.empty((lib.sessd_rotate_nms_workspace_bytes(int(max_boxes), int(pre_max)),), dtype=torch.uint8, device=dev)
+    check(lib.sessd_rotate_nms(_p(boxes5), _p(scores), _p(n), int(max_boxes), int(pre_max), int(post_max), float(iou_thresh),
+                               int(bool(ge)), _p(keep), _p(num), _p(ws), ws.numel(), _st()), "sessd_rotate_nms")
+    return keep, num
+
+
+# ------------------------------------------------------------------------------------------------ iou3d family
+def boxes_overlap_bev(a, b, out):
+    check(lib.sessd_boxes_overlap_bev(_p(a), a.shape[0], _p(b), b.shape[0], _p(out), _st()), "sessd_boxes_overlap_bev")
+    return out
+
+
+def boxes_aligned_overlap_bev(a, b, out):
+    check(lib.sessd_boxes_aligned_overlap_bev(_p(a), _p(b), a.shape[0], _p(out), _st()), "sessd_boxes_aligned_overlap_bev")
+    return out
+
+
+def boxes_iou_bev(a, b, out):
+    check(lib.sessd_boxes_iou_bev(_p(a), a.shape[0], _p(b), b.shape[0], _p(out), _st()), "sessd_boxes_iou_bev")
+    return out
+
+
+def boxes_iou3d(a, b, out):
+    check(lib.sessd_boxes_iou3d(_p(a), a.shape[0], _p(b), b.shape[0], _p(out), _st()), "sessd_boxes_iou3d")
+    return out
+
+
+def nms_sorted(boxes, thresh, mode):
+    n = boxes.shape[0]
+    dev = boxes.device
+    keep = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)
+    num = torch.zeros((1,), dtype=torch.int32, device=dev)
+    ws = torch.empty((lib.sessd_nms_workspace_bytes(n),), dtype=torch.uint8, device=dev)
+    check(lib.sessd_nms_sorted(_p(boxes), n, float(thresh), int(mode), _p(keep), _p(num), _p(ws), ws.numel(), _st()), "sessd_nms_sorted")
+    return keep, num

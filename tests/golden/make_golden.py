@@ -31,6 +31,9 @@ sys.path.insert(0, os.path.join(ROOT, "se-ssd_b200"))
 from sessd_b200 import synth  # noqa: E402
 from oracle import bev_ref, build as obuild, cpu as ocpu  # noqa: E402
 
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from cases import iou_inputs, sha, voxel_cases  # noqa: E402  (seeded inputs shared with the tests)
+
 
 def _pkg(name):
     m = types.ModuleType(name)
@@ -55,38 +58,7 @@ def _load(name, rel):
     return m
 
 
-def sha(a):
-    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), np.uint8)
-
-
 # --------------------------------------------------------------------------------------------
-def voxel_cases():
-    """(name, points, max_points, max_voxels) -- also imported by the tests to rebuild inputs."""
-    rng = np.random.default_rng(123)
-    cases = []
-    cases.append(("uniform2k", synth.uniform_cloud(1, 2000), 5, 20000))
-    cases.append(("uniform20k", synth.uniform_cloud(0, 20000), 5, 20000))
-    cases.append(("ring20k", synth.ring_cloud(0, 20000), 5, 20000))
-    # max_voxels cut: the loop breaks at the first NEW voxel beyond the cap and drops all later points
-    cases.append(("cut300", synth.uniform_cloud(2, 5000), 5, 300))
-    # many points per voxel (> max_points) + duplicates: clustered cloud
-    ctr = rng.uniform([5, -10, -2], [40, 10, 0], (40, 3))
-    p = ctr[rng.integers(0, 40, 6000)] + rng.normal(0, 0.04, (6000, 3))
-    cases.append(("clustered", np.concatenate([p, rng.uniform(0, 1, (6000, 1))], 1).astype(np.float32), 5, 20000))
-    # out-of-range points and exact boundary values
-    q = synth.uniform_cloud(3, 3000)
-    q[::7, 0] = -0.01
-    q[1::11, 1] = 40.0
-    q[2::13, 2] = 1.0
-    q[3::17, 0] = 70.4
-    q[4::19] = np.float32([0.0, -40.0, -3.0, 0.5])
-    q[5::23, 0] = np.nextafter(np.float32(70.4), np.float32(0))
-    cases.append(("edges", q, 5, 20000))
-    cases.append(("clustered_mp3_cut", cases[4][1][:4000].copy(), 3, 500))
-    cases.append(("empty", np.zeros((0, 4), np.float32), 5, 20000))
-    return cases
-
-
 def gen_voxel():
     pc = _load("pc_v2_ref", "det3d/ops/point_cloud/point_cloud_ops_v2.py")
     out = {}
@@ -105,17 +77,6 @@ def gen_voxel():
 
 
 # --------------------------------------------------------------------------------------------
-def iou_inputs():
-    b1, _ = synth.random_boxes(11, 160, spread=0.25)     # dense scene -> many overlaps
-    b2, _ = synth.random_boxes(12, 120, spread=0.25)
-    # add exact duplicates, shared edges, zero-size and axis-aligned boxes
-    b2[:10] = b1[:10]
-    b2[10:15, :2] = b1[10:15, :2] + np.float32([1.6, 0.0]); b2[10:15, 3:7] = b1[10:15, 3:7]
-    b1[20, 3] = 0.0
-    b1[21:25, 6] = np.float32([0.0, np.pi / 2, -np.pi / 2, np.pi])
-    return b1, b2
-
-
 def gen_iou():
     ref = obuild.load_ref() or (obuild.build_ref() and obuild.load_ref())
     b1, b2 = iou_inputs()

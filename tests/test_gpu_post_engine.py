@@ -1,0 +1,123 @@
+"""Device post-processing and the whole-frame engine vs the CPU oracle (predict glue of mg_head_sessd.py:893-1057)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _synthetic_head(seed, batch=1, n_pos=600, hw=(200, 176)):
+    """Head output [B,H,W,24] that yields ~n_pos candidates over threshold with overlapping boxes."""
+    rng = np.random.default_rng(seed)
+    h = np.zeros((batch, hw[0], hw[1], 24), np.float32)
+    h[..., 0:14] = rng.normal(0, 0.25, h[..., 0:14].shape)
+    h[..., 14:16] = rng.normal(-4.0, 0.5, h[..., 14:16].shape)
+    h[..., 16:20] = rng.normal(0, 1, h[..., 16:20].shape)
+    h[..., 20:22] = rng.uniform(-0.5, 1.0, h[..., 20:22].shape)
+    for b in range(batch):
+        ys = rng.integers(0, hw[0], n_pos)
+        xs = rng.integers(0, hw[1], n_pos)
+        rs = rng.integers(0, 2, n_pos)
+        h[b, ys, xs, 14 + rs] = rng.uniform(-0.8, 4.0, n_pos)   # sigmoid in (0.31, 0.98)
+    return h
+
+
+def _oracle_frame(h, anchors, **kw):
+    from oracle import bev_ref
+    flat = torch.from_numpy(h.reshape(-1, 24))
+    enc = flat[:, 0:14].reshape(-1, 7)
+    cls = flat[:, 14:16].reshape(-1)
+    dirs = flat[:, 16:20].reshape(-1, 2)
+    iou = flat[:, 20:22].reshape(-1)
+    return bev_ref.predict_frame(enc, cls, dirs, iou, torch.from_numpy(anchors), return_aux=True, **kw)
+
+
+@pytest.mark.parametrize("seed,n_pos", [(0, 0), (1, 40), (2, 600), (3, 3000)])
+def test_postprocess_matches_oracle(seed, n_pos):
+    from sessd_b200 import ops, weights
+    anchors = weights.kitti_car_anchors()
+    batch = 2
+    h = _synthetic_head(seed, batch, n_pos)
+    cfg = ops.make_post_cfg(batch=batch, head_stride=24)
+    buf = ops.PostBuffers(cfg, "cuda")
+    ops.postprocess(torch.from_numpy(h).cuda(), torch.from_numpy(anchors).cuda(), None, buf)
+    torch.cuda.synchronize()
+    for b in range(batch):
+        boxes, scores, labels, aux = _oracle_frame(h[b], anchors)
+        k = int(buf.count[b].item())
+        assert int(buf.aux[b, 0].item()) == aux["n_candidates"]
+        if "nms_selected_anchor" in aux:
+            sel = aux["nms_selected_anchor"].numpy()
+            got_sel = buf.sel_anchor[b, : len(sel)].cpu().numpy()
+            assert np.array_equal(got_sel, sel), "NMS keep set differs"
+        assert k == boxes.shape[0]
+        np.testing.assert_allclose(buf.boxes[b, :k].cpu().numpy(), boxes.numpy(), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(buf.scores[b, :k].cpu().numpy(), scores.numpy(), rtol=1e-4, atol=1e-7)
+
+
+def test_postprocess_frustum_and_gt_mode():
+    from oracle import bev_ref
+    from sessd_b200 import ops, weights
+    anchors = weights.kitti_car_anchors()
+    h = _synthetic_head(5, 1, 500)
+    # a synthetic convex frustum: the half space x < 35 plus five far-away planes (normals point outwards: sign<0 inside)
+    planes = np.array([[1, 0, 0, -35.0], [-1, 0, 0, -1.0], [0, 1, 0, -100.0], [0, -1, 0, -100.0], [0, 0, 1, -50.0], [0, 0, -1, -50.0]],
+                      np.float32)[None]
+    cfg = ops.make_post_cfg(batch=1, head_stride=24, use_frustum=True)
+    buf = ops.PostBuffers(cfg, "cuda")
+    ops.postprocess(torch.from_numpy(h).cuda(), torch.from_numpy(anchors).cuda(), torch.from_numpy(planes).cuda(), buf)
+    torch.cuda.synchronize()
+    boxes, scores, _l, _aux = _oracle_frame(h[0], anchors)
+    keep = boxes[:, 0] < 35.0
+    k = int(buf.count[0].item())
+    assert k == int(keep.sum())
+    np.testing.assert_allclose(buf.boxes[0, :k].cpu().numpy(), boxes[keep].numpy(), rtol=1e-4, atol=1e-5)
+
+
+def _full_oracle(cloud, sd, anchors):
+    """CPU oracle of the whole frame: voxelise -> VFE -> SpMiddleFHD -> SSFA -> head -> predict."""
+    from oracle import bev_ref, cpu as ocpu, spconv_ref as S
+    from sessd_b200 import synth, weights
+    layers, ssfa, head = weights.split_detector_state(sd)
+    v, c, n = ocpu.points_to_voxel(cloud, synth.VOXEL_SIZE, synth.PC_RANGE, 5, 20000)
+    feat = bev_ref.vfe_mean(torch.from_numpy(v), torch.from_numpy(n)).numpy()
+    coors = np.concatenate([np.zeros((len(c), 1), np.int32), c], 1)
+    params = [{k: l[k].numpy() for k in ("weight", "gamma", "beta", "mean", "var")} for l in layers]
+    dense = S.spmiddle_forward(feat, coors, 1, (1408, 1600, 40), params, np.float32)
+    x = torch.from_numpy(dense.astype(np.float32))
+    neck = bev_ref.ssfa_forward(x, ssfa)
+    hd = bev_ref.head_forward(neck, head)
+    enc = hd["box_preds"].reshape(-1, 7)
+    cls = hd["cls_preds"].reshape(-1)
+    dirs = hd["dir_cls_preds"].reshape(-1, 2)
+    iou = hd["iou_preds"].reshape(-1)
+    out = bev_ref.predict_frame(enc, cls, dirs, iou, torch.from_numpy(anchors), return_aux=True)
+    return hd, out, len(c)
+
+
+def test_engine_end_to_end_matches_cpu_oracle():
+    from sessd_b200 import synth, weights
+    from sessd_b200.engine import FrameEngine
+    sd = weights.random_detector_state(11, cls_bias=-3.0)
+    anchors = weights.kitti_car_anchors()
+    clouds = [synth.ring_cloud(21, 20000), synth.ring_cloud(22, 18000)]
+    eng = FrameEngine(batch=2, max_points_per_frame=20000)
+    eng.load_weights(*weights.split_detector_state(sd), anchors)
+    eager = eng.infer(clouds)
+    eng.capture()
+    graph = eng.infer(clouds)
+    graph2 = eng.infer(clouds[::-1])[::-1]
+    head_gpu = eng.neck.buf["head"].cpu().numpy()      # holds the reversed batch now
+    for f, cloud in enumerate(clouds):
+        hd, (boxes, scores, _labels, aux), nvox = _full_oracle(cloud, sd, anchors)
+        for res in (eager[f], graph[f], graph2[f]):
+            assert res["num_voxels"] == nvox
+            assert res["num_candidates"] == aux["n_candidates"]
+            assert res["box3d_lidar"].shape[0] == boxes.shape[0]
+            np.testing.assert_allclose(res["box3d_lidar"], boxes.numpy(), rtol=1e-4, atol=1e-4)
+            np.testing.assert_allclose(res["scores"], scores.numpy(), rtol=1e-4, atol=1e-6)
+        # raw head maps within 1e-4 relative
+        hg = head_gpu[1 - f]
+        for sl, key in ((slice(0, 14), "box_preds"), (slice(14, 16), "cls_preds"), (slice(16, 20), "dir_cls_preds"), (slice(20, 22), "iou_preds")):
+            ref = hd[key][0].numpy()
+            assert np.abs(hg[..., sl] - ref).max() / np.abs(ref).max() < 1e-4, key

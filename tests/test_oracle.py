@@ -1,0 +1,166 @@
+"""CPU: the oracle restatements against the committed golden vectors produced by the REFERENCE's own code
+(tests/golden/make_golden.py) -- this is what pins the oracle."""
+import os
+
+import numpy as np
+import torch
+
+from cases import iou_inputs, sha, voxel_cases
+
+
+def test_oracle_voxeliser_equals_reference_golden(golden_dir):
+    from oracle import cpu as ocpu
+    from sessd_b200 import synth
+    g = np.load(os.path.join(golden_dir, "voxel_cases.npz"))
+    for name, pts, mp, mv in voxel_cases():
+        assert (sha(pts) == g[name + "_points_sha"]).all()
+        v, c, n = ocpu.points_to_voxel(pts, synth.VOXEL_SIZE, synth.PC_RANGE, mp, mv)
+        assert np.array_equal(c, g[name + "_coors"]) and np.array_equal(n, g[name + "_num"])
+        assert (sha(v) == g[name + "_voxels_sha"]).all()
+    # semantic edge cases of the sequential loop
+    assert g["cut300_coors"].shape[0] == 300 and g["clustered_num"].max() == 5 and g["empty_coors"].shape[0] == 0
+
+
+def test_oracle_rotated_iou_equals_reference_golden_bit_exact(golden_dir):
+    from oracle import cpu as ocpu
+    g = np.load(os.path.join(golden_dir, "iou_cases.npz"))
+    b1, b2 = iou_inputs()
+    a5, c5 = ocpu.boxes3d_to_bev(b1), ocpu.boxes3d_to_bev(b2)
+    assert np.array_equal(ocpu.boxes_overlap_bev(a5, c5), g["overlap"])
+    assert np.array_equal(ocpu.boxes_iou_bev(a5, c5), g["iou"])
+
+
+def test_oracle_matches_compiled_reference_when_present():
+    """oracle/_ref (reference iou3d_cpu.cpp compiled in place) travels with the repo; compare live if loadable."""
+    from oracle import build as obuild, cpu as ocpu
+    from sessd_b200 import synth
+    ref = obuild.load_ref()
+    if ref is None:
+        return
+    b, _ = synth.random_boxes(99, 150, spread=0.2)
+    a5 = ocpu.boxes3d_to_bev(b)
+    out = torch.zeros(150, 150)
+    ref.boxes_iou_bev_cpu(torch.from_numpy(a5), torch.from_numpy(a5), out)
+    assert np.array_equal(out.numpy(), ocpu.boxes_iou_bev(a5, a5))
+
+
+def test_oracle_anchors_and_assigner_equal_reference_golden(golden_dir):
+    from oracle import anchors as oa
+    from sessd_b200 import synth
+    g = np.load(os.path.join(golden_dir, "anchors_assign.npz"))
+    anc = oa.create_anchors_3d_range().reshape(-1, 7)
+    assert (sha(anc) == g["anchors_sha"]).all()
+    assert np.array_equal(anc[:704], g["anchors_head"]) and np.array_equal(anc[-704:], g["anchors_tail"])
+    gt, _ = synth.random_boxes(21, 12)
+    gt[:, 2] = -1.0
+    res = oa.assign_targets(anc, gt)
+    assert np.array_equal(res["labels"].astype(np.int8), g["labels"])
+    pos = np.nonzero(res["labels"] > 0)[0]
+    assert np.array_equal(pos, g["pos_idx"])
+    assert np.array_equal(res["bbox_targets"][pos], g["pos_targets"])
+    assert float(res["bbox_outside_weights"].sum()) == float(g["weights_sum"])
+
+
+def test_oracle_decode_ssfa_head_vfe_equal_reference_golden(golden_dir):
+    from oracle import anchors as oa, bev_ref, cpu as ocpu
+    from sessd_b200 import synth
+    g = np.load(os.path.join(golden_dir, "decode_case.npz"))
+    gen = torch.Generator().manual_seed(5)
+    enc = torch.randn(2048, 7, generator=gen) * 0.3
+    anc = torch.from_numpy(oa.create_anchors_3d_range().reshape(-1, 7)[::34][:2048].copy())
+    assert np.array_equal(bev_ref.box_decode(enc, anc).numpy(), g["decoded"])
+    np.testing.assert_allclose(ocpu.box_decode(enc.numpy(), anc.numpy()), g["decoded"], rtol=2e-6, atol=1e-6)
+    g2 = np.load(os.path.join(golden_dir, "ssfa_head_case.npz"))
+    x = torch.relu(torch.randn(1, 128, 24, 16, generator=torch.Generator().manual_seed(8)))
+    y = bev_ref.ssfa_forward(x, bev_ref.ssfa_random_state(7))
+    np.testing.assert_allclose(y.numpy(), g2["ssfa_out"], rtol=1e-5, atol=1e-6)
+    h = bev_ref.head_forward(y, bev_ref.head_random_state(9, prefix=""), prefix="")
+    for k in ("box_preds", "cls_preds", "dir_cls_preds", "iou_preds"):
+        np.testing.assert_allclose(h[k].numpy(), g2[k], rtol=1e-5, atol=1e-6)
+    g3 = np.load(os.path.join(golden_dir, "vfe_case.npz"))
+    v, _c, n = ocpu.points_to_voxel(synth.uniform_cloud(1, 2000), synth.VOXEL_SIZE, synth.PC_RANGE, 5, 20000)
+    assert np.array_equal(bev_ref.vfe_mean(torch.from_numpy(v), torch.from_numpy(n)).numpy(), g3["mean"])
+
+
+def test_oracle_sparse_shapes_match_reference_comments():
+    """scn.py:113,122,134,146 pin the output-shape rule; SURVEY.md 8(d) pins the active-site / pair counts."""
+    from oracle import cpu as ocpu, spconv_ref as S
+    from sessd_b200 import synth
+    v, c, n = ocpu.points_to_voxel(synth.uniform_cloud(0, 20000), synth.VOXEL_SIZE, synth.PC_RANGE, 5, 20000)
+    cur = np.concatenate([np.zeros((len(c), 1), np.int32), c], 1)
+    shape = (41, 1600, 1408)
+    counts, pairs, shapes = [], [], []
+    for kind, _ci, _co, ks, st, pd, _key in S.SPMIDDLE_FHD_LAYERS:
+        if kind != "spconv":
+            continue
+        oc, oshape = S.strided_out_coors(cur, shape, ks, st, pd)
+        pairs.append(int((S.neighbor_table(cur, shape, oc, ks, st, pd) >= 0).sum()))
+        cur, shape = oc, oshape
+        counts.append(len(oc))
+        shapes.append(oshape)
+    assert shapes == [(21, 800, 704), (11, 400, 352), (5, 200, 176), (2, 200, 176)]
+    assert counts == [67955, 103374, 85774, 52169]
+    assert pairs == [68148, 228309, 323785, 104137]
+
+
+def test_rotate_nms_second_opinion_exact_polygon_clip():
+    """The oracle swaps boost::geometry for iou3d_cpu arithmetic (boost is absent): cross-check the keep set against
+    an exact fp64 convex-polygon clip.  Differences are only allowed for pairs within 1e-4 of the threshold."""
+    from oracle import cpu as ocpu
+    from sessd_b200 import synth
+
+    def corners(b):
+        x, y, w, l, r = [float(v) for v in b]
+        c, s = np.cos(r), np.sin(r)
+        pts = np.array([[-w / 2, -l / 2], [-w / 2, l / 2], [w / 2, l / 2], [w / 2, -l / 2]])
+        return np.stack([pts[:, 0] * c + pts[:, 1] * s + x, -pts[:, 0] * s + pts[:, 1] * c + y], 1)
+
+    def area(p):
+        return 0.5 * abs(np.dot(p[:, 0], np.roll(p[:, 1], -1)) - np.dot(p[:, 1], np.roll(p[:, 0], -1))) if len(p) >= 3 else 0.0
+
+    def cross2(u, v):
+        return u[0] * v[1] - u[1] * v[0]
+
+    def clip(subj, clipper):
+        out = subj
+        sign = np.sign(cross2(clipper[1] - clipper[0], clipper[2] - clipper[1]))
+        for i in range(4):
+            a, b = clipper[i], clipper[(i + 1) % 4]
+            inp, out = out, []
+            if len(inp) == 0:
+                break
+            for j in range(len(inp)):
+                p, q = inp[j], inp[(j + 1) % len(inp)]
+                sp = sign * cross2(b - a, p - a)
+                sq = sign * cross2(b - a, q - a)
+                if sp >= 0:
+                    out.append(p)
+                if sp * sq < 0:
+                    t = sp / (sp - sq)
+                    out.append(p + t * (q - p))
+            out = np.array(out) if len(out) else np.zeros((0, 2))
+        return out
+
+    boxes, scores = synth.random_boxes(5, 400, spread=0.3)
+    b5 = boxes[:, [0, 1, 3, 4, 6]].astype(np.float64)
+    order = np.argsort(-scores, kind="stable")
+    cs = [corners(b) for b in b5]
+    dead = np.zeros(len(b5), bool)
+    keep = []
+    near = False
+    for ii, i in enumerate(order):
+        if dead[i]:
+            continue
+        keep.append(i)
+        for j in order[ii + 1:]:
+            if dead[j]:
+                continue
+            inter = area(clip(cs[i], cs[j]))
+            iou = inter / (b5[i, 2] * b5[i, 3] + b5[j, 2] * b5[j, 3] - inter)
+            near |= abs(iou - 0.01) < 1e-4
+            if iou >= 0.01:
+                dead[j] = True
+    dets = np.concatenate([b5[order], scores[order, None]], 1).astype(np.float32)
+    ref = order[ocpu.rotate_nms_cc(dets, 0.01, ge=True)]
+    if not near:
+        assert np.array_equal(np.array(keep), ref)
