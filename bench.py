@@ -135,6 +135,17 @@ def run_reference(args):
     layers_np = [{k: l[k].numpy() for k in ("weight", "gamma", "beta", "mean", "var")} for l in layers]
     anchors = weights.kitti_car_anchors()
     clouds = [make_cloud(args.cloud, s) for s in range(min(args.pool, 4))]
+    # same calibration rule as the GPU arm (FrameEngine.calibrate_cls_bias): ~400 anchors over the score threshold
+    from oracle import bev_ref, cpu as ocpu, spconv_ref as S
+    from sessd_b200 import synth
+    v, c, n = ocpu.points_to_voxel(clouds[0], synth.VOXEL_SIZE, synth.PC_RANGE, 5, 20000)
+    dense = S.spmiddle_forward(bev_ref.vfe_mean(torch.from_numpy(v), torch.from_numpy(n)).numpy(),
+                               np.concatenate([np.zeros((len(c), 1), np.int32), c], 1), 1, (1408, 1600, 40), layers_np, np.float32)
+    with torch.no_grad():
+        lg = bev_ref.head_forward(bev_ref.ssfa_forward(torch.from_numpy(dense.astype(np.float32)), ssfa), head)["cls_preds"].reshape(-1)
+    top = torch.topk(lg, 402).values
+    head = dict(head)
+    head["tasks.0.conv_cls.bias"] = head["tasks.0.conv_cls.bias"] + float(np.log(0.3 / 0.7) - 0.5 * (top[400] + top[401]))
     for i in range(args.warmup):
         cpu_frame_oracle(clouds[i % len(clouds)], layers_np, ssfa, head, anchors, cores)
     t0 = time.perf_counter()
@@ -178,9 +189,15 @@ def run_ours(args):
     clouds = [make_cloud(args.cloud, rank + world * j) for j in range(args.pool)]
     maxpts = max(c.shape[0] for c in clouds)
     engines = []
+    shift = None
     for _ in range(S):
         e = FrameEngine(batch=1, max_points_per_frame=maxpts, device=dev)
         e.load_weights(layers, ssfa, head, anchors)
+        if shift is None:
+            shift = e.calibrate_cls_bias([make_cloud(args.cloud, 0)], 400)    # ~400 candidates / frame, like a trained model
+            head = dict(head)
+            head["tasks.0.conv_cls.bias"] = head["tasks.0.conv_cls.bias"] + shift
+            e.load_weights(layers, ssfa, head, anchors)
         engines.append(e)
     # device-resident pool for the `value` loop
     pool = torch.zeros((args.pool, maxpts, 4), dtype=torch.float32, device=dev)
@@ -287,7 +304,7 @@ def run_ours(args):
                 "config": {"workload": WORKLOAD % args.cloud, "frames_per_step_per_gpu": F, "streams": S, "batch": 1,
                            "parallelism": "frame-sharded x%d, no collective" % world,
                            "l2": "no explicit flush: per-frame activation working set (~0.4 GB) exceeds the 126 MB L2; inputs rotate over %d clouds" % args.pool,
-                           "weights": "seeded random init (cls bias -3.0 => trained-like candidate counts)"},
+                           "weights": "seeded random init; cls bias calibrated to ~400 candidates/frame (trained-like)"},
                 "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": h2d[0] // args.steps, "d2h_bytes_per_step": d2h[0] // args.steps},
                 "gpu_launches": int(launches_full) * F * args.steps,

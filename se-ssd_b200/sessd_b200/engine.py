@@ -56,6 +56,22 @@ class FrameEngine:
         assert self.anchors.shape[0] == self.pcfg.num_anchors
         self.graph = None
 
+    def calibrate_cls_bias(self, clouds, target_candidates=400):
+        """Random-init weights put ~0 % or ~50 % of the anchors over the 0.3 score threshold.  Shift the classification
+        bias so that ~`target_candidates` anchors per frame pass, which is what a trained SE-SSD produces on a KITTI frame
+        (hundreds of candidates, tens of detections).  Returns the shift; deterministic for a given seed / cloud."""
+        import math
+        self.stage(clouds)
+        with torch.cuda.stream(self.stream):
+            self._step_body()
+        self.stream.synchronize()
+        logits = self.neck.buf["head"][..., 14:16].reshape(-1)
+        k = min(int(target_candidates) * self.batch, logits.numel() - 1)
+        kth = torch.topk(logits, k + 1).values[-2:].mean()
+        shift = float(math.log(self.pcfg.score_thresh / (1.0 - self.pcfg.score_thresh)) - kth.item())
+        self.neck.params["head"][1][14:16] += shift
+        return shift
+
     # ---------------------------------------------------------------------------------------------- device pipeline
     def _device_pipeline(self):
         """All launches of one batch of frames on the current stream (capturable)."""
