@@ -149,6 +149,13 @@ int sessd_bev_conv(const float *d_in, const float *d_weight /*[ntaps, cin, cout]
                    const float *d_shift, const float *d_residual /*nullable, same shape as out*/, float *d_out,
                    const sessd_conv_desc *desc, void *stream);
 
+/* Tensor-core variant (tcgen05 + TMEM + TMA, 3xTF32 split for fp32-level accuracy): same contract, in_stride must be 1.
+ * d_weight_split [2 (hi|lo)][ntaps][cout_pad][cin]: hi = weights truncated to tf32, lo = w - hi; cout_pad is a multiple of the
+ * N tile (128; 32 when cout <= 32). */
+int sessd_bev_conv_tc(const float *d_in, const float *d_weight_split, int cout_pad, const float *d_scale,
+                      const float *d_shift, const float *d_residual, float *d_out, const sessd_conv_desc *desc,
+                      void *stream);
+
 /* SSFA tail (rpn_v1.py:229-233): w_k = BN(conv1x1_{128->1}(x_k)); softmax over the pair; weighted sum */
 int sessd_ssfa_fuse(const float *d_x0, const float *d_x1, const float *d_w0 /*[C]*/, const float *d_w1,
                     float s0, float t0, float s1, float t1, int num_pixels, int channels, float *d_out,

@@ -1,0 +1,355 @@
+// bevconv_tc.cu -- BEV neck/head convolutions on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), fp32-accurate
+// through the 3xTF32 split:   a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi,   a_hi = tf32(a), a_lo = a - a_hi  (exact in fp32).
+//
+// Same contract as bev_conv_kernel (bevconv.cu): tap-list implicit GEMM over NHWC activations with a fused
+// BatchNorm(eval)+ReLU(+residual) epilogue; replaces the cuDNN conv / deconv + BN + ReLU triplets of
+// det3d/models/necks/rpn_v1.py:135-210 and the head convs of det3d/models/bbox_heads/mg_head_sessd.py:202-230.
+// Single-pass TF32 (10-bit mantissa; what cuDNN silently uses on sm_80+) cannot hold the 1e-4 parity bar through 13
+// stacked layers -- and truncation is biased on post-ReLU activations -- hence three tensor-core products per tile.
+//
+// Tiling: one CTA = one 8x16 output-pixel patch (M = 128) x one 128-wide (or 32-wide, head) slice of Cout.
+//   K loop over (tap, 32-channel chunk): BK = 32 tf32 = one 128-byte swizzle row.
+//   A tile  : the input patch shifted by the tap offset is a plain 4-D TMA box {32 ch, 16 x, 8 y, 1 image} of the NHWC
+//             tensor; out-of-range coordinates (conv padding, deconv fringe, partial tiles) are zero-filled by TMA.
+//   B tiles : pre-split weights [plane hi|lo][tap][Cout][Cin] (K-major), box {32, N, 1, 1}.
+//   All tiles land in the canonical K-major SWIZZLE_128B layout that tcgen05.mma descriptors address directly.
+// Warp roles (192 threads): w0 TMA producer | w1 TMEM alloc + MMA issuer | w2..w5 split a -> (a_hi, a_lo) in smem, then
+// epilogue (TMEM -> registers -> BN/ReLU/residual -> global).  3-stage mbarrier pipeline:
+//   full[s] (TMA bytes landed) -> split[s] (a_hi/a_lo written, fence.proxy.async) -> 12 x tcgen05.mma (M128 N128 K8)
+//   -> tcgen05.commit -> empty[s];  last commit -> acc_full -> epilogue.
+// Every mbarrier wait is bounded (trap on timeout) so a descriptor mistake aborts the kernel instead of hanging the GPU.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace sessd {
+
+constexpr int kTcStages = 3;
+constexpr int kTcBM = 128;                 // pixels per tile: 8 rows x 16 cols
+constexpr int kTcTileH = 8, kTcTileW = 16;
+constexpr int kTcBK = 32;                  // tf32 elements per K chunk (128 bytes)
+constexpr int kTcTileBytes = kTcBM * kTcBK * 4;   // 16 KB
+constexpr int kTcStageBytes = 4 * kTcTileBytes;   // A_hi (in place), A_lo, B_hi, B_lo
+constexpr int kTcThreads = 192;
+constexpr int kTcSmemBytes = kTcStages * kTcStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+struct TcParams {
+    int batch, in_h, in_w, cin;
+    int out_h, out_w, cout;
+    int grid_h, grid_w;
+    int out_stride, out_off_y, out_off_x;
+    int ntaps;
+    int tap_dy[16], tap_dx[16];
+    int relu;
+    int n_tile;          // 128 or 32: UMMA N and rows of each B tile
+    int tiles_x, tiles_y;
+};
+
+// ---------------------------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: 2 s of wall clock, then trap (the host sees a launch failure instead of a hung GPU)
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (true) {
+        for (int i = 0; i < 64; ++i)
+            if (mbar_try_wait(bar, parity)) return;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 2000000000ull) __trap();
+    }
+}
+
+__device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by ONE thread
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (= 1024 B: 8 rows x 128 B)
+//   [46,48) version=1 (Blackwell) | [49,52) base_offset=0 | [61,64) layout_type=2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) /*C=F32*/ | (2u << 7) /*A=TF32*/ | (2u << 10) /*B=TF32*/ | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                    const __grid_constant__ CUtensorMap map_b,
+                                                                    const float *__restrict__ scale, const float *__restrict__ shift,
+                                                                    const float *__restrict__ resid, float *__restrict__ out, TcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *tiles = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B atoms: 1024 B
+    uint64_t *bars = (uint64_t *)(tiles + kTcStages * kTcStageBytes);
+    uint64_t *full = bars, *split = bars + kTcStages, *empty = bars + 2 * kTcStages, *acc_full = bars + 3 * kTcStages;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 3 * kTcStages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile coordinates
+    int t = blockIdx.x;
+    const int tx = t % p.tiles_x; t /= p.tiles_x;
+    const int ty = t % p.tiles_y;
+    const int b = t / p.tiles_y;
+    const int oy0 = ty * kTcTileH, ox0 = tx * kTcTileW;
+    const int n0 = blockIdx.y * p.n_tile;
+    const int kchunks = p.cin / kTcBK;
+    const int steps = p.ntaps * kchunks;
+    const uint32_t b_tile_bytes = (uint32_t)p.n_tile * kTcBK * 4;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 128); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM: 128 lanes x 128 fp32 columns for the accumulator
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int it = 0; it < steps; ++it) {
+                const int s = it % kTcStages;
+                const uint32_t ph = (it / kTcStages) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                const int tap = it / kchunks, c0 = (it - tap * kchunks) * kTcBK;
+                unsigned char *st = tiles + s * kTcStageBytes;
+                mbar_expect_tx(&full[s], kTcTileBytes + 2 * b_tile_bytes);
+                tma_load_4d(st, &map_a, &full[s], c0, ox0 + p.tap_dx[tap], oy0 + p.tap_dy[tap], b);
+                tma_load_4d(st + 2 * kTcTileBytes, &map_b, &full[s], c0, n0, tap, 0);
+                tma_load_4d(st + 3 * kTcTileBytes, &map_b, &full[s], c0, n0, tap, 1);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = make_idesc_tf32(kTcBM, p.n_tile);
+        for (int it = 0; it < steps; ++it) {
+            const int s = it % kTcStages;
+            const uint32_t ph = (it / kTcStages) & 1;
+            mbar_wait(&full[s], ph);
+            mbar_wait(&split[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a_hi = smem_u32(tiles + s * kTcStageBytes);
+                const uint32_t a_lo = a_hi + kTcTileBytes, b_hi = a_hi + 2 * kTcTileBytes, b_lo = a_hi + 3 * kTcTileBytes;
+#pragma unroll
+                for (int k = 0; k < kTcBK / 8; ++k) {          // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle row
+                    const uint32_t ko = k * 32;
+                    const uint64_t dah = make_sw128_desc(a_hi + ko), dal = make_sw128_desc(a_lo + ko);
+                    const uint64_t dbh = make_sw128_desc(b_hi + ko), dbl = make_sw128_desc(b_lo + ko);
+                    tc_mma_tf32(tmem_base, dal, dbh, idesc, (it | k) != 0);   // small terms first
+                    tc_mma_tf32(tmem_base, dah, dbl, idesc, 1);
+                    tc_mma_tf32(tmem_base, dah, dbh, idesc, 1);
+                }
+                tc_commit(&empty[s]);                             // smem stage reusable once these MMAs retire
+                if (it == steps - 1) tc_commit(acc_full);         // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== split warps (then epilogue) =====================
+        const int tid = threadIdx.x - 64;   // 0..127
+        for (int it = 0; it < steps; ++it) {
+            const int s = it % kTcStages;
+            const uint32_t ph = (it / kTcStages) & 1;
+            mbar_wait(&full[s], ph);
+            float4 *a = reinterpret_cast<float4 *>(tiles + s * kTcStageBytes);
+            float4 *lo = reinterpret_cast<float4 *>(tiles + s * kTcStageBytes + kTcTileBytes);
+#pragma unroll
+            for (int j = 0; j < kTcTileBytes / 16 / 128; ++j) {    // 8 x 16-byte chunks per thread; layout agnostic
+                const int i = tid + j * 128;
+                const float4 v = a[i];
+                float4 h, l;
+                h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+                h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+                h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+                h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                a[i] = h;
+                lo[i] = l;
+            }
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to tcgen05 (async proxy)
+            mbar_arrive(&split[s]);
+        }
+        // ---- epilogue: TMEM -> registers -> BN/ReLU/residual -> global ----
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;                     // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;                // accumulator row == pixel within the patch
+        const int gy = oy0 + r / kTcTileW, gx = ox0 + r % kTcTileW;
+        const bool pix_ok = gy < p.grid_h && gx < p.grid_w;
+        const size_t opix = (((size_t)b * p.out_h + (size_t)gy * p.out_stride + p.out_off_y) * p.out_w + (size_t)gx * p.out_stride + p.out_off_x);
+        for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (!pix_ok) continue;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const int n = n0 + c0 + j;
+                if (n >= p.cout) break;
+                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (scale) sc = *reinterpret_cast<const float4 *>(scale + n);
+                if (shift) sh = *reinterpret_cast<const float4 *>(shift + n);
+                float4 o;
+                o.x = fmaf(__uint_as_float(v[j + 0]), sc.x, sh.x); o.y = fmaf(__uint_as_float(v[j + 1]), sc.y, sh.y);
+                o.z = fmaf(__uint_as_float(v[j + 2]), sc.z, sh.z); o.w = fmaf(__uint_as_float(v[j + 3]), sc.w, sh.w);
+                if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                const size_t off = opix * p.cout + n;
+                if (resid) {
+                    const float4 rr = *reinterpret_cast<const float4 *>(resid + off);
+                    o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                }
+                *reinterpret_cast<float4 *>(out + off) = o;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(128) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static int encode_4d(CUtensorMap *m, const void *base, const cuuint64_t dims[4], const cuuint32_t box[4]) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return SESSD_EINVAL;
+    cuuint64_t strides[3] = {dims[0] * 4, dims[0] * dims[1] * 4, dims[0] * dims[1] * dims[2] * 4};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 700 + (int)r;
+}
+
+}  // namespace sessd
+
+using namespace sessd;
+
+// Tensor-core variant of sessd_bev_conv.  d_weight_split: [2 (hi, lo)][ntaps][cout_pad][cin] with cout_pad a multiple of the N tile
+// (128, or 32 when cout <= 32); hi = tf32-truncated weights, lo = w - hi.  in_stride must be 1.
+extern "C" int sessd_bev_conv_tc(const float *d_in, const float *d_weight_split, int cout_pad, const float *d_scale, const float *d_shift,
+                                 const float *d_residual, float *d_out, const sessd_conv_desc *desc, void *stream) {
+    if (!d_in || !d_weight_split || !d_out || !desc) return SESSD_EINVAL;
+    const sessd_conv_desc &d = *desc;
+    const int n_tile = d.cout <= 32 ? 32 : 128;
+    if (d.batch < 1 || d.cin < kTcBK || d.cin % kTcBK || d.cout < 4 || d.cout % 4 || d.ntaps < 1 || d.ntaps > 16 || d.in_stride != 1 ||
+        d.out_stride < 1 || d.grid_h < 1 || d.grid_w < 1 || cout_pad % n_tile || cout_pad < d.cout)
+        return SESSD_EINVAL;
+    if ((d.grid_h - 1) * d.out_stride + d.out_off_y >= d.out_h || (d.grid_w - 1) * d.out_stride + d.out_off_x >= d.out_w) return SESSD_EINVAL;
+    CUtensorMap map_a, map_b;
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)d.in_w, (cuuint64_t)d.in_h, (cuuint64_t)d.batch};
+        const cuuint32_t box[4] = {kTcBK, kTcTileW, kTcTileH, 1};
+        int rc = encode_4d(&map_a, d_in, dims, box);
+        if (rc) return rc;
+    }
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)cout_pad, (cuuint64_t)d.ntaps, 2};
+        const cuuint32_t box[4] = {kTcBK, (cuuint32_t)n_tile, 1, 1};
+        int rc = encode_4d(&map_b, d_weight_split, dims, box);
+        if (rc) return rc;
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        SESSD_CUDA_TRY(cudaFuncSetAttribute(bev_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+        attr_done = true;
+    }
+    TcParams p;
+    p.batch = d.batch; p.in_h = d.in_h; p.in_w = d.in_w; p.cin = d.cin;
+    p.out_h = d.out_h; p.out_w = d.out_w; p.cout = d.cout;
+    p.grid_h = d.grid_h; p.grid_w = d.grid_w;
+    p.out_stride = d.out_stride; p.out_off_y = d.out_off_y; p.out_off_x = d.out_off_x;
+    p.ntaps = d.ntaps;
+    for (int t = 0; t < 16; ++t) { p.tap_dy[t] = d.tap_dy[t]; p.tap_dx[t] = d.tap_dx[t]; }
+    p.relu = d.relu;
+    p.n_tile = n_tile;
+    p.tiles_x = div_up(d.grid_w, kTcTileW);
+    p.tiles_y = div_up(d.grid_h, kTcTileH);
+    dim3 grid(p.tiles_x * p.tiles_y * d.batch, cout_pad / n_tile);
+    SESSD_LAUNCH(bev_conv_tc_kernel, grid, kTcThreads, kTcSmemBytes, stream, map_a, map_b, d_scale, d_shift, d_residual, d_out, p);
+    return last_error();
+}

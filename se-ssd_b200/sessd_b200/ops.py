@@ -184,6 +184,27 @@ def bev_conv(x, weight, scale, shift, residual, out, desc):
     return out
 
 
+def split_tf32(w):
+    """w -> (hi, lo): hi = w truncated to tf32 (13 low mantissa bits cleared), lo = w - hi (exact in fp32)."""
+    hi = (w.contiguous().view(torch.int32) & -8192).view(torch.float32)
+    return hi, w - hi
+
+
+def pack_weight_tc(wp, cout_pad):
+    """[taps, Cin, Cout] (SIMT packing) -> [2, taps, cout_pad, Cin] K-major hi/lo planes for sessd_bev_conv_tc."""
+    taps, cin, cout = wp.shape
+    wt = torch.zeros((taps, cout_pad, cin), dtype=torch.float32, device=wp.device)
+    wt[:, :cout] = wp.permute(0, 2, 1)
+    hi, lo = split_tf32(wt)
+    return torch.stack([hi, lo], 0).contiguous()
+
+
+def bev_conv_tc(x, weight_split, scale, shift, residual, out, desc):
+    check(lib.sessd_bev_conv_tc(_p(x), _p(weight_split), int(weight_split.shape[2]), _p(scale), _p(shift), _p(residual), _p(out),
+                                C.byref(desc), _st()), "sessd_bev_conv_tc")
+    return out
+
+
 def ssfa_fuse(x0, x1, w0, w1, s0, t0, s1, t1, out):
     npix = x0.numel() // x0.shape[-1]
     check(lib.sessd_ssfa_fuse(_p(x0), _p(x1), _p(w0), _p(w1), float(s0), float(t0), float(s1), float(t1), int(npix), int(x0.shape[-1]),

@@ -164,8 +164,10 @@ class SSFARunner:
 
     HEAD_STRIDE = 24
 
-    def __init__(self, batch, hw=(200, 176), device="cuda"):
+    def __init__(self, batch, hw=(200, 176), device="cuda", use_tc=True):
+        """use_tc: tcgen05 3xTF32 tensor-core convs (default); False = the fp32 SIMT baseline kernels."""
         self.batch, self.h, self.w, self.device = batch, int(hw[0]), int(hw[1]), torch.device(device)
+        self.use_tc = bool(use_tc)
         h, w, h2, w2 = self.h, self.w, self.h // 2, self.w // 2
         z = lambda hh, ww, c: torch.zeros((batch, hh, ww, c), dtype=torch.float32, device=self.device)  # noqa: E731
         self.buf = dict(b0a=z(h, w, 128), b0b=z(h, w, 128), x0=z(h, w, 128), b1a=z(h2, w2, 256), b1b=z(h2, w2, 256),
@@ -188,8 +190,13 @@ class SSFARunner:
                           ("trans_0.0", 0), ("trans_1.0", 0), ("conv_0.0", 1), ("conv_1.0", 1)):
             wp, taps = _pack_conv(g(name + ".weight"))
             P[name] = (wp, [(dy - pad, dx - pad) for dy, dx in taps]) + bn(name)
+            if self.use_tc and name != "bottom_up_block_1.0":      # the stride-2 conv stays on the SIMT kernel
+                P[name + ":tc"] = ops.pack_weight_tc(wp, -(-wp.shape[2] // 128) * 128)
         for name in ("deconv_block_0.0", "deconv_block_1.0"):
-            P[name] = (_deconv_classes(g(name + ".weight")),) + bn(name)
+            classes = _deconv_classes(g(name + ".weight"))
+            P[name] = (classes,) + bn(name)
+            if self.use_tc:
+                P[name + ":tc"] = [ops.pack_weight_tc(wp, 128) for _py, _px, wp, _t in classes]
         for name in ("w_0.0", "w_1.0"):
             sc, sh = bn(name)
             P[name] = (g(name + ".weight").reshape(-1).contiguous(), float(sc[0]), float(sh[0]))
@@ -201,18 +208,26 @@ class SSFARunner:
             hb[o:o + c] = head_sd[head_prefix + nm + ".bias"].to(dev, torch.float32)
             o += c
         P["head"] = (hw.contiguous(), hb.contiguous())
+        if self.use_tc:
+            P["head:tc"] = ops.pack_weight_tc(hw, 32)
         self.params = P
 
     def _conv(self, name, x, out, in_hw, out_hw, cin, cout, stride=1, relu=True):
         wp, taps, sc, sh = self.params[name]
         d = ops.conv_desc(self.batch, in_hw, cin, out_hw, cout, out_hw, taps, in_stride=stride, relu=relu)
+        if (name + ":tc") in self.params:
+            return ops.bev_conv_tc(x, self.params[name + ":tc"], sc, sh, None, out, d)
         return ops.bev_conv(x, wp, sc, sh, None, out, d)
 
     def _deconv(self, name, x, out, in_hw, out_hw, cin, cout, residual=None):
         classes, sc, sh = self.params[name]
-        for py, px, wp, taps in classes:
+        tc = self.params.get(name + ":tc")
+        for ci, (py, px, wp, taps) in enumerate(classes):
             d = ops.conv_desc(self.batch, in_hw, cin, out_hw, cout, in_hw, taps, in_stride=1, out_stride=2, out_off=(py, px), relu=True)
-            ops.bev_conv(x, wp, sc, sh, residual, out, d)
+            if tc is not None:
+                ops.bev_conv_tc(x, tc[ci], sc, sh, residual, out, d)
+            else:
+                ops.bev_conv(x, wp, sc, sh, residual, out, d)
         return out
 
     def forward(self, x):
@@ -242,4 +257,6 @@ class SSFARunner:
         hw, hb = self.params["head"]
         H = (self.h, self.w)
         d = ops.conv_desc(self.batch, H, 128, H, self.HEAD_STRIDE, H, [(0, 0)], relu=False)
+        if "head:tc" in self.params:
+            return ops.bev_conv_tc(x, self.params["head:tc"], None, hb, None, self.buf["head"], d)
         return ops.bev_conv(x, hw, None, hb, None, self.buf["head"], d)

@@ -14,7 +14,8 @@ def _rel(a, b):
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
 
 
-def test_ssfa_and_head_match_reference_golden(golden_dir):
+@pytest.mark.parametrize("use_tc", [False, True], ids=["simt", "tcgen05"])
+def test_ssfa_and_head_match_reference_golden(golden_dir, use_tc):
     from oracle import bev_ref
     from sessd_b200.runners import SSFARunner
     g = np.load(os.path.join(golden_dir, "ssfa_head_case.npz"))
@@ -22,7 +23,7 @@ def test_ssfa_and_head_match_reference_golden(golden_dir):
     hsd = bev_ref.head_random_state(9, prefix="tasks.0.")
     gen = torch.Generator().manual_seed(8)
     x = torch.relu(torch.randn(1, 128, 24, 16, generator=gen))
-    r = SSFARunner(1, (24, 16), "cuda")
+    r = SSFARunner(1, (24, 16), "cuda", use_tc=use_tc)
     r.load_state(sd, hsd)
     out, head = r.forward(x.permute(0, 2, 3, 1).contiguous().cuda())
     torch.cuda.synchronize()
@@ -39,7 +40,8 @@ def test_ssfa_and_head_match_reference_golden(golden_dir):
     assert _rel(h[..., 20:22], g["iou_preds"]) < TOL
 
 
-def test_ssfa_intermediates_match_oracle_fp64_batch2():
+@pytest.mark.parametrize("use_tc", [False, True], ids=["simt", "tcgen05"])
+def test_ssfa_intermediates_match_oracle_fp64_batch2(use_tc):
     from oracle import bev_ref
     from sessd_b200.runners import SSFARunner
     sd = bev_ref.ssfa_random_state(17)
@@ -48,7 +50,7 @@ def test_ssfa_intermediates_match_oracle_fp64_batch2():
     x = torch.relu(torch.randn(2, 128, 40, 48, generator=gen))
     trace = {}
     ref = bev_ref.ssfa_forward(x.double(), {k: v.double() if v.is_floating_point() else v for k, v in sd.items()}, trace)
-    r = SSFARunner(2, (40, 48), "cuda")
+    r = SSFARunner(2, (40, 48), "cuda", use_tc=use_tc)
     r.load_state(sd, hsd)
     out, _ = r.forward(x.permute(0, 2, 3, 1).contiguous().cuda())
     torch.cuda.synchronize()
@@ -56,3 +58,43 @@ def test_ssfa_intermediates_match_oracle_fp64_batch2():
         got = r.buf[mine].permute(0, 3, 1, 2).cpu().numpy()
         assert _rel(got, trace[theirs].numpy()) < 2e-5, mine
     assert _rel(out.permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("use_tc", [False, True], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("cin,cout,k,hw", [(128, 128, 3, (21, 37)), (256, 256, 3, (9, 50)), (128, 128, 1, (8, 16)), (256, 256, 1, (13, 17)),
+                                           (128, 24, 1, (20, 33))])
+def test_single_conv_vs_fp64(use_tc, cin, cout, k, hw):
+    """One tap-list conv incl. partial 8x16 tiles, BN scale/shift, ReLU and residual, against an fp64 torch conv."""
+    import torch.nn.functional as F
+    from sessd_b200 import ops
+    from sessd_b200.runners import _pack_conv
+    g = torch.Generator().manual_seed(cin + cout + k)
+    b = 2
+    x = torch.randn(b, cin, hw[0], hw[1], generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    sc = 1.0 + 0.1 * torch.randn(cout, generator=g)
+    sh = 0.1 * torch.randn(cout, generator=g)
+    res = torch.randn(b, cout, hw[0], hw[1], generator=g)
+    ref = F.relu(F.conv2d(x.double(), w.double(), None, 1, k // 2) * sc.double().view(1, -1, 1, 1) + sh.double().view(1, -1, 1, 1)) + res.double()
+    wp, taps = _pack_conv(w)
+    taps = [(dy - k // 2, dx - k // 2) for dy, dx in taps]
+    xd = x.permute(0, 2, 3, 1).contiguous().cuda()
+    rd = res.permute(0, 2, 3, 1).contiguous().cuda()
+    out = torch.zeros((b, hw[0], hw[1], cout), device="cuda")
+    d = ops.conv_desc(b, hw, cin, hw, cout, hw, taps, relu=True)
+    if use_tc:
+        ops.bev_conv_tc(xd, ops.pack_weight_tc(wp.cuda(), 32 if cout <= 32 else -(-cout // 128) * 128), sc.cuda(), sh.cuda(), rd, out, d)
+    else:
+        ops.bev_conv(xd, wp.cuda(), sc.cuda(), sh.cuda(), rd, out, d)
+    torch.cuda.synchronize()
+    got = out.permute(0, 3, 1, 2).cpu().double()
+    err = float((got - ref).abs().max() / ref.abs().max())
+    assert err < 3e-6, err
+
+
+def test_tf32_split_is_exact():
+    from sessd_b200 import ops
+    w = torch.randn(4096, generator=torch.Generator().manual_seed(1))
+    hi, lo = ops.split_tf32(w)
+    assert torch.equal(hi + lo, w)
+    assert int((hi.view(torch.int32) & 8191).abs().max()) == 0
