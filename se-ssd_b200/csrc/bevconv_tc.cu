@@ -17,6 +17,11 @@
 // epilogue (TMEM -> registers -> BN/ReLU/residual -> global).  3-stage mbarrier pipeline:
 //   full[s] (TMA bytes landed) -> split[s] (a_hi/a_lo written, fence.proxy.async) -> 12 x tcgen05.mma (M128 N128 K8)
 //   -> tcgen05.commit -> empty[s];  last commit -> acc_full -> epilogue.
+// Accumulation: tcgen05.mma adds into its fp32 TMEM accumulator with truncation (measured: ~2^-24 of the accumulator magnitude
+// per instruction, biased, i.e. growing LINEARLY with the number of accumulation steps -- 1.6e-5 relative after the 432
+// instructions of a 3x3x128 tile).  So the K loop is spread round-robin over THREE "main" accumulators (a_hi*b_hi) plus ONE
+// accumulator for the small cross terms (a_lo*b_hi + a_hi*b_lo, 2^-10 smaller), 4 x 128 = all 512 TMEM columns, and the
+// epilogue adds the four partial sums in round-to-nearest fp32.  Result: ~1.5e-6 relative per layer.
 // Every mbarrier wait is bounded (trap on timeout) so a descriptor mistake aborts the kernel instead of hanging the GPU.
 #include <cuda.h>
 
@@ -166,8 +171,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
         mbar_init(acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    if (warp == 1) {   // TMEM: 128 lanes x 128 fp32 columns for the accumulator
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(128) : "memory");
+    if (warp == 1) {   // TMEM: 128 lanes x 512 fp32 columns = 3 main partial accumulators + 1 cross-term accumulator
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
     tc_fence_before();
@@ -207,9 +212,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
                     const uint32_t ko = k * 32;
                     const uint64_t dah = make_sw128_desc(a_hi + ko), dal = make_sw128_desc(a_lo + ko);
                     const uint64_t dbh = make_sw128_desc(b_hi + ko), dbl = make_sw128_desc(b_lo + ko);
-                    tc_mma_tf32(tmem_base, dal, dbh, idesc, (it | k) != 0);   // small terms first
-                    tc_mma_tf32(tmem_base, dah, dbl, idesc, 1);
-                    tc_mma_tf32(tmem_base, dah, dbh, idesc, 1);
+                    const uint32_t acc_small = tmem_base + 3 * (uint32_t)p.n_tile;
+                    const uint32_t acc_main = tmem_base + (uint32_t)(it % 3) * (uint32_t)p.n_tile;
+                    tc_mma_tf32(acc_small, dal, dbh, idesc, (it | k) != 0);
+                    tc_mma_tf32(acc_small, dah, dbl, idesc, 1);
+                    tc_mma_tf32(acc_main, dah, dbh, idesc, (it >= 3 || k != 0) ? 1u : 0u);
                 }
                 tc_commit(&empty[s]);                             // smem stage reusable once these MMAs retire
                 if (it == steps - 1) tc_commit(acc_full);         // accumulator complete
@@ -248,9 +255,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
         const int gy = oy0 + r / kTcTileW, gx = ox0 + r % kTcTileW;
         const bool pix_ok = gy < p.grid_h && gx < p.grid_w;
         const size_t opix = (((size_t)b * p.out_h + (size_t)gy * p.out_stride + p.out_off_y) * p.out_w + (size_t)gx * p.out_stride + p.out_off_x);
+        const int nmain = steps < 3 ? steps : 3;     // main accumulators that were written at least once
         for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            uint32_t v[32], u[32];
+            const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            tmem_ld_32x32b_x32(lane_base, v);                                       // main 0
+            tmem_ld_32x32b_x32(lane_base + 3 * (uint32_t)p.n_tile, u);              // cross terms
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+            for (int m = 1; m < nmain; ++m) {
+                tmem_ld_32x32b_x32(lane_base + (uint32_t)m * (uint32_t)p.n_tile, u);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+            }
             if (!pix_ok) continue;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -275,7 +292,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(128) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 

@@ -89,7 +89,7 @@ def test_single_conv_vs_fp64(use_tc, cin, cout, k, hw):
     torch.cuda.synchronize()
     got = out.permute(0, 3, 1, 2).cpu().double()
     err = float((got - ref).abs().max() / ref.abs().max())
-    assert err < 3e-6, err
+    assert err < 5e-6, err
 
 
 def test_tf32_split_is_exact():
