@@ -1,0 +1,169 @@
+"""MultiGroupHead (SE-SSD variant) -- inference half (reference: det3d/models/bbox_heads/mg_head_sessd.py:195-230, 379-523,
+893-1057).  Same constructor signature / parameter names (``tasks.0.conv_box`` ...).
+
+* ``forward``  : the four 1x1 convs are ONE 128 -> 22 tensor-core GEMM writing NHWC directly (the reference launches 4 convs + 4
+  permute copies); the returned dict has the reference's keys and shapes.
+* ``predict``  : decode -> sigmoid -> threshold -> IoU-rectified score -> top-k -> rotated NMS -> frustum filter -> direction fix
+  -> range mask in five kernels with no host round trip (sessd_postprocess); the reference syncs to the host twice per frame
+  (box_torch_ops.py:536, mg_head_sessd.py:1026) and clips polygons on one CPU thread.
+* ``loss``     : training is a "next" row; raises NotImplementedError."""
+import logging
+
+import numpy as np
+import torch
+from torch import nn
+
+from det3d.core.bbox.geometry import frustum_planes
+from sessd_b200 import ops
+from sessd_b200.runners import HeadRunner
+
+from ..builder import build_loss
+from ..registry import HEADS
+
+
+@HEADS.register_module
+class Head(nn.Module):
+    def __init__(self, num_input, num_pred, num_cls, use_dir=False, num_dir=0, header=True, name="", focal_loss_init=False, **kwargs):
+        super().__init__(**kwargs)
+        self.use_dir = use_dir
+        self.conv_box = nn.Conv2d(num_input, num_pred, 1)
+        self.conv_cls = nn.Conv2d(num_input, num_cls, 1)
+        self.conv_iou = nn.Conv2d(num_input, 2, 1)
+        self.trans_conv = None
+        if self.use_dir:
+            self.conv_dir = nn.Conv2d(num_input, num_dir, 1)
+        self._runner = None
+        self._runner_key = None
+        self._weights_key = None
+
+    def packed_forward(self, x):
+        """x logical NCHW [B,128,H,W] -> packed NHWC [B,H,W,24] = [box 14 | cls 2 | dir 4 | iou 2 | pad 2]."""
+        if not (self.use_dir and self.conv_box.out_channels == 14 and self.conv_cls.out_channels == 2 and self.conv_dir.out_channels == 4):
+            raise NotImplementedError("the fused head kernel is built for the car head: 2 anchors x (7 box, 1 cls, 2 dir, 1 iou)")
+        b, c, h, w = x.shape
+        key = (b, h, w, str(x.device))
+        if self._runner is None or self._runner_key != key:
+            self._runner = HeadRunner(b, (h, w), x.device)
+            self._runner_key, self._weights_key = key, None
+        wkey = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if wkey != self._weights_key:
+            self._runner.load_state({k: v.detach() for k, v in self.state_dict().items()}, prefix="")
+            self._weights_key = wkey
+        return self._runner.forward(x.detach().float().permute(0, 2, 3, 1).contiguous())
+
+    def forward(self, x):
+        packed = self.packed_forward(x)
+        ret = {"box_preds": packed[..., 0:14].contiguous(), "cls_preds": packed[..., 14:16].contiguous()}
+        if self.use_dir:
+            ret["dir_cls_preds"] = packed[..., 16:20].contiguous()
+        ret["iou_preds"] = packed[..., 20:22].contiguous()
+        ret["_packed"] = packed            # private: lets predict() skip re-packing
+        return ret
+
+
+@HEADS.register_module
+class MultiGroupHead(nn.Module):
+    def __init__(self, mode="3d", in_channels=[128, ], norm_cfg=None, tasks=[], weights=[], num_classes=[1, ], box_coder=None,
+                 with_cls=True, with_reg=True, reg_class_agnostic=False, encode_background_as_zeros=True,
+                 loss_norm=dict(type="NormByNumPositives", pos_cls_weight=1.0, neg_cls_weight=1.0, ),
+                 loss_cls=dict(type="SigmoidFocalLoss", alpha=0.25, gamma=2.0, loss_weight=1.0, ), use_sigmoid_score=True,
+                 loss_bbox=dict(type="WeightedSmoothL1Loss", sigma=3.0, code_weights=[1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0], codewise=True,
+                                loss_weight=2.0, ),
+                 encode_rad_error_by_sin=True,
+                 loss_aux=dict(type="WeightedSoftmaxClassificationLoss", name="direction_classifier", loss_weight=0.2, ),
+                 direction_offset=0.0, name="rpn", logger=None, ):
+        super().__init__()
+        assert with_cls or with_reg
+        num_classes = [len(t["class_names"]) for t in tasks]
+        self.class_names = [t["class_names"] for t in tasks]
+        self.num_anchor_per_locs = [2 * n for n in num_classes]
+        self.box_coder = box_coder
+        self.with_cls, self.with_reg, self.in_channels, self.num_classes = with_cls, with_reg, in_channels, num_classes
+        self.reg_class_agnostic, self.encode_rad_error_by_sin = reg_class_agnostic, encode_rad_error_by_sin
+        self.encode_background_as_zeros, self.use_sigmoid_score = encode_background_as_zeros, use_sigmoid_score
+        self.box_n_dim = self.box_coder.n_dim
+        self.loss_cls = build_loss(loss_cls)
+        self.loss_reg = build_loss(loss_bbox)
+        if loss_aux is not None:
+            self.loss_aux = build_loss(loss_aux)
+        self.loss_norm = loss_norm
+        self.logger = logger or logging.getLogger("MultiGroupHead")
+        self.use_direction_classifier = loss_aux is not None
+        if loss_aux:
+            self.direction_offset = direction_offset
+        self.bev_only = mode == "bev"
+        self.tasks = nn.ModuleList()
+        num_preds, num_dirs = [], []
+        for num_c, num_a in zip(num_classes, self.num_anchor_per_locs):
+            num_cls = num_a * num_c if encode_background_as_zeros else num_a * (num_c + 1)
+            num_pred = num_a * (self.box_n_dim - 2 if self.bev_only else self.box_n_dim)
+            num_dir = num_a * 2 if self.use_direction_classifier else None
+            num_preds.append(num_pred)
+            num_dirs.append(num_dir)
+            self.tasks.append(Head(in_channels, num_pred, num_cls, use_dir=self.use_direction_classifier, num_dir=num_dir, header=False))
+        self.logger.info("num_classes: %s, num_preds: %s, num_dirs: %s" % (num_classes, num_preds, num_dirs))
+        self.logger.info("Finish MultiGroupHead Initialization")
+        self.post_center_range = [0, -40.0, -5.0, 70.4, 40.0, 5.0]      # reference hard-codes this (:484)
+        self.thresh = 0.3                                                # and this (:486)
+        self._post = None
+        self._post_key = None
+
+    def init_weights(self, pretrained=None):
+        if pretrained is not None:
+            raise NotImplementedError("load checkpoints with load_state_dict")
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+
+    def forward(self, x):
+        return [task(x) for task in self.tasks]
+
+    def loss(self, example, preds_dicts, preds_ema=None, **kwargs):
+        raise NotImplementedError("MultiGroupHead.loss: the SE-SSD training step (consistency + ODIoU losses) is a 'next' row")
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def predict(self, example, preds_dicts, test_cfg, **kwargs):
+        if len(preds_dicts) != 1:
+            raise NotImplementedError("the fused post-processing is built for the single-task (car) head")
+        preds = preds_dicts[0]
+        anchors = example["anchors"][0]
+        batch = int(anchors.shape[0])
+        anc = anchors[0].reshape(-1, self.box_n_dim).float().contiguous()
+        if not anc.is_cuda:
+            anc = anc.cuda()
+        packed = preds.get("_packed")
+        if packed is None:
+            b, h, w, _ = preds["box_preds"].shape
+            packed = torch.zeros((b, h, w, 24), dtype=torch.float32, device=preds["box_preds"].device)
+            packed[..., 0:14], packed[..., 14:16] = preds["box_preds"], preds["cls_preds"]
+            packed[..., 16:20], packed[..., 20:22] = preds["dir_cls_preds"], preds["iou_preds"]
+        nms = test_cfg.nms if hasattr(test_cfg, "nms") else test_cfg["nms"]
+        if test_cfg["score_threshold"] <= 0.0:
+            raise NotImplementedError("score_threshold must be positive (the reference path thresholds before NMS)")
+        frustum = None
+        calib = example.get("calib") if isinstance(example, dict) else None
+        if calib is not None and "frustum" in calib:
+            fr = calib["frustum"]
+            fr = fr.cpu().numpy() if isinstance(fr, torch.Tensor) else np.asarray(fr)
+            planes = np.stack([frustum_planes(fr[i])[0] for i in range(batch)], 0)          # [B, 6, 4]
+            frustum = torch.from_numpy(np.ascontiguousarray(planes, np.float32)).to(packed.device)
+        key = (batch, int(anc.shape[0]), float(self.thresh), int(nms["nms_pre_max_size"]), int(nms["nms_post_max_size"]),
+               float(nms["nms_iou_threshold"]), frustum is not None, str(packed.device))
+        if self._post is None or self._post_key != key:
+            cfg = ops.make_post_cfg(batch=batch, num_anchors=int(anc.shape[0]), anchors_per_loc=self.num_anchor_per_locs[0],
+                                    head_stride=24, score_thresh=self.thresh, nms_pre_max=nms["nms_pre_max_size"],
+                                    nms_post_max=nms["nms_post_max_size"], nms_iou_thresh=nms["nms_iou_threshold"], nms_ge=True,
+                                    post_range=self.post_center_range, direction_offset=getattr(self, "direction_offset", 0.0),
+                                    use_frustum=frustum is not None)
+            self._post, self._post_key = ops.PostBuffers(cfg, packed.device), key
+        buf = ops.postprocess(packed.contiguous(), anc, frustum, self._post)
+        counts = buf.count.cpu().tolist()                       # the one host sync of the frame
+        meta = example.get("metadata", [None] * batch)
+        out = []
+        for i in range(batch):
+            k = counts[i]
+            out.append({"box3d_lidar": buf.boxes[i, :k].clone(), "scores": buf.scores[i, :k].clone(),
+                        "label_preds": buf.labels[i, :k].long(), "metadata": meta[i]})
+        return out

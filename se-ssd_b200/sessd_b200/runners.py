@@ -159,6 +159,40 @@ def _deconv_classes(w):
     return out
 
 
+def pack_head(head_sd, prefix, device, stride=24):
+    """Four 1x1 head convs (mg_head_sessd.py:202-215) -> one [1,128,stride] GEMM weight + bias, channel layout
+    [box 14 | cls 2 | dir 4 | iou 2 | zero pad]."""
+    hw = torch.zeros((1, 128, stride), dtype=torch.float32, device=device)
+    hb = torch.zeros((stride,), dtype=torch.float32, device=device)
+    o = 0
+    for nm, c in (("conv_box", 14), ("conv_cls", 2), ("conv_dir", 4), ("conv_iou", 2)):
+        hw[0, :, o:o + c] = head_sd[prefix + nm + ".weight"].to(device, torch.float32).reshape(c, 128).t()
+        hb[o:o + c] = head_sd[prefix + nm + ".bias"].to(device, torch.float32)
+        o += c
+    return hw.contiguous(), hb.contiguous()
+
+
+class HeadRunner:
+    """The fused head GEMM alone (MultiGroupHead.forward)."""
+
+    def __init__(self, batch, hw, device="cuda", use_tc=True, stride=24):
+        self.batch, self.h, self.w, self.stride, self.use_tc = batch, int(hw[0]), int(hw[1]), stride, use_tc
+        self.out = torch.zeros((batch, self.h, self.w, stride), dtype=torch.float32, device=device)
+        self.device = torch.device(device)
+        self.w_simt = self.w_tc = self.bias = None
+
+    def load_state(self, head_sd, prefix=""):
+        self.w_simt, self.bias = pack_head(head_sd, prefix, self.device, self.stride)
+        self.w_tc = ops.pack_weight_tc(self.w_simt, 32) if self.use_tc else None
+
+    def forward(self, x):
+        H = (self.h, self.w)
+        d = ops.conv_desc(self.batch, H, 128, H, self.stride, H, [(0, 0)], relu=False)
+        if self.w_tc is not None:
+            return ops.bev_conv_tc(x, self.w_tc, None, self.bias, None, self.out, d)
+        return ops.bev_conv(x, self.w_simt, None, self.bias, None, self.out, d)
+
+
 class SSFARunner:
     """SSFA neck (rpn_v1.py:220-235) + the fused 128->22(+2 pad) head GEMM (mg_head_sessd.py:202-230)."""
 
@@ -175,7 +209,7 @@ class SSFARunner:
                         o0=z(h, w, 128), o1=z(h, w, 128), out=z(h, w, 128), head=z(h, w, self.HEAD_STRIDE))
         self.params = None
 
-    def load_state(self, ssfa_sd, head_sd, head_prefix="tasks.0."):
+    def load_state(self, ssfa_sd, head_sd=None, head_prefix="tasks.0."):
         dev = self.device
         g = lambda k: ssfa_sd[k].to(dev, torch.float32)   # noqa: E731
         P = {}
@@ -200,16 +234,11 @@ class SSFARunner:
         for name in ("w_0.0", "w_1.0"):
             sc, sh = bn(name)
             P[name] = (g(name + ".weight").reshape(-1).contiguous(), float(sc[0]), float(sh[0]))
-        hw = torch.zeros((1, 128, self.HEAD_STRIDE), dtype=torch.float32, device=dev)
-        hb = torch.zeros((self.HEAD_STRIDE,), dtype=torch.float32, device=dev)
-        o = 0
-        for nm, c in (("conv_box", 14), ("conv_cls", 2), ("conv_dir", 4), ("conv_iou", 2)):
-            hw[0, :, o:o + c] = head_sd[head_prefix + nm + ".weight"].to(dev, torch.float32).reshape(c, 128).t()
-            hb[o:o + c] = head_sd[head_prefix + nm + ".bias"].to(dev, torch.float32)
-            o += c
-        P["head"] = (hw.contiguous(), hb.contiguous())
-        if self.use_tc:
-            P["head:tc"] = ops.pack_weight_tc(hw, 32)
+        if head_sd is not None:
+            hw, hb = pack_head(head_sd, head_prefix, dev, self.HEAD_STRIDE)
+            P["head"] = (hw, hb)
+            if self.use_tc:
+                P["head:tc"] = ops.pack_weight_tc(hw, 32)
         self.params = P
 
     def _conv(self, name, x, out, in_hw, out_hw, cin, cout, stride=1, relu=True):
@@ -250,6 +279,8 @@ class SSFARunner:
         w0, s0, t0 = self.params["w_0.0"]
         w1, s1, t1 = self.params["w_1.0"]
         ops.ssfa_fuse(b["o0"], b["o1"], w0, w1, s0, t0, s1, t1, b["out"])
+        if "head" not in self.params:
+            return b["out"], None
         self.head(b["out"])
         return b["out"], b["head"]
 

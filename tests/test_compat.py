@@ -1,0 +1,192 @@
+"""Drop-in boundary: the det3d / spconv / iou3d_cuda API surface.  CPU part: config + registries + builders;
+GPU part: VoxelNet.forward(example, return_loss=False) through the reference's own pipeline transforms and collate format."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUR_CFG = os.path.join(ROOT, "examples", "second", "configs", "config.py")
+REF_CFG = "/root/reference/examples/second/configs/config.py"
+
+
+def _build(cfg_path):
+    from det3d.models import build_detector
+    from det3d.torchie import Config
+    cfg = Config.fromfile(cfg_path)
+    model = build_detector(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg)
+    return cfg, model
+
+
+@pytest.mark.parametrize("path", [OUR_CFG, REF_CFG], ids=["repo-config", "reference-config-unchanged"])
+def test_config_loads_and_detector_builds(path):
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present on this machine")
+    cfg, model = _build(path)
+    assert cfg.model.type == "VoxelNet" and cfg.test_cfg.nms.nms_iou_threshold == 0.01
+    assert cfg.assigner.out_size_factor == 8
+    from sessd_b200 import weights
+    sd = weights.random_detector_state(0)
+    missing = model.load_state_dict(sd, strict=True)          # reference state-dict key names
+    assert not missing.missing_keys and not missing.unexpected_keys
+    n_params = sum(p.numel() for p in model.parameters())
+    assert 3.7e6 < n_params < 3.9e6                            # ~3.8 M parameters
+
+
+def test_registry_semantics():
+    from det3d.models.registry import BACKBONES
+    from det3d.utils import Registry, build_from_cfg
+    with pytest.raises(KeyError):
+        build_from_cfg(dict(type="NoSuchBackbone"), BACKBONES)
+    r = Registry("x")
+
+    @r.register_module
+    class A(object):
+        def __init__(self, v=1):
+            self.v = v
+
+    with pytest.raises(KeyError):
+        r.register_module(A)                                   # duplicates are an error, like the reference
+    assert build_from_cfg(dict(type="A"), r, dict(v=3)).v == 3
+    with pytest.raises(TypeError):
+        r.register_module(3)
+
+
+def test_anchor_assigner_pipeline_matches_reference_golden(golden_dir):
+    """AssignTarget (config #1, CPU): anchors + labels + regression targets equal the reference's assign_v2 output."""
+    from det3d.datasets.pipelines import AssignTarget
+    from det3d.torchie import Config
+    from sessd_b200 import synth
+    cfg = Config.fromfile(OUR_CFG)
+    at = AssignTarget(cfg=cfg.train_cfg.assigner)
+    gt, _ = synth.random_boxes(21, 12)
+    gt[:, 2] = -1.0
+    res = dict(mode="train", labeled=True, lidar=dict(annotations=dict(gt_boxes=gt.copy(), gt_classes=np.ones(12, np.int32),
+                                                                            gt_names=np.array(["Car"] * 12))))
+    res, _ = at(res, None)
+    g = np.load(os.path.join(golden_dir, "anchors_assign.npz"))
+    t = res["lidar"]["targets"]
+    assert np.array_equal(t["anchors"][0][:704], g["anchors_head"])
+    assert np.array_equal(t["labels"][0].astype(np.int8), g["labels"])
+    pos = np.nonzero(t["labels"][0] > 0)[0]
+    assert np.array_equal(pos, g["pos_idx"]) and np.array_equal(t["reg_targets"][0][pos], g["pos_targets"])
+
+
+def _example_from_clouds(cfg, clouds):
+    from det3d.datasets.pipelines import AssignTarget, Reformat, Voxelization
+    from det3d.torchie.parallel import collate_kitti
+    tf = [Voxelization(cfg=cfg.voxel_generator), AssignTarget(cfg=cfg.train_cfg.assigner), Reformat()]
+    frames = []
+    for i, c in enumerate(clouds):
+        res = dict(mode="val", metadata=dict(token=i), lidar=dict(points=c))
+        for t in tf:
+            res, _ = t(res, None)
+        frames.append(res)
+    return collate_kitti(frames)
+
+
+@pytest.mark.gpu
+def test_voxelnet_dropin_matches_oracle_and_engine():
+    from sessd_b200 import synth, weights
+    from test_gpu_post_engine import _calibrated_state, _full_oracle
+    cfg, model = _build(OUR_CFG)
+    anchors = weights.kitti_car_anchors()
+    clouds = [synth.ring_cloud(31, 20000), synth.ring_cloud(32, 15000)]
+    sd = _calibrated_state(5, clouds[0], anchors)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    example = _example_from_clouds(cfg, clouds)
+    assert example["coordinates"].shape[1] == 4 and example["anchors"][0].shape == (2, 70400, 7)
+    dev = {k: (v.cuda() if isinstance(v, torch.Tensor) else [t.cuda() for t in v] if k == "anchors" else v) for k, v in example.items()}
+    with torch.no_grad():
+        dets = model(dev, return_loss=False)
+    assert len(dets) == 2
+    for f, cloud in enumerate(clouds):
+        _hd, (boxes, scores, _l, aux), _nv = _full_oracle(cloud, sd, anchors)
+        assert boxes.shape[0] > 3
+        d = dets[f]
+        assert d["metadata"]["token"] == f and d["label_preds"].dtype == torch.int64
+        assert d["box3d_lidar"].shape[0] == boxes.shape[0]
+        np.testing.assert_allclose(d["box3d_lidar"].cpu().numpy(), boxes.numpy(), rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(d["scores"].cpu().numpy(), scores.numpy(), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_spconv_module_api_matches_oracle():
+    """spconv.SparseConvTensor / SubMConv3d / SparseConv3d / SparseSequential / dense() used stand-alone."""
+    import spconv
+    from oracle import cpu as ocpu, spconv_ref as S
+    from sessd_b200 import synth
+    from torch import nn
+    v, c, n = ocpu.points_to_voxel(synth.ring_cloud(9, 5000), synth.VOXEL_SIZE, synth.PC_RANGE, 5, 20000)
+    coors = np.concatenate([np.zeros((len(c), 1), np.int32), c], 1).astype(np.int32)
+    feat = (v.sum(1) / n[:, None]).astype(np.float32)
+    torch.manual_seed(0)
+    net = spconv.SparseSequential(spconv.SubMConv3d(4, 16, 3, bias=False, indice_key="k0"), nn.ReLU(),
+                                  spconv.SparseConv3d(16, 32, 3, 2, padding=1, bias=True)).cuda()
+    x = spconv.SparseConvTensor(torch.from_numpy(feat).cuda(), torch.from_numpy(coors).cuda(), [41, 1600, 1408], 1)
+    y = net(x)
+    w0 = net[0].weight.detach().cpu().numpy().reshape(27, 4, 16)
+    w1 = net[2].weight.detach().cpu().numpy().reshape(27, 16, 32)
+    nbr0 = S.neighbor_table(coors, (41, 1600, 1408), coors, (3, 3, 3), (1, 1, 1), (1, 1, 1))
+    f0 = np.maximum(S.conv_from_nbr(feat, nbr0, w0), 0)
+    oc, osh = S.strided_out_coors(coors, (41, 1600, 1408), (3, 3, 3), (2, 2, 2), (1, 1, 1))
+    nbr1 = S.neighbor_table(coors, (41, 1600, 1408), oc, (3, 3, 3), (2, 2, 2), (1, 1, 1))
+    f1 = S.conv_from_nbr(f0, nbr1, w1) + net[2].bias.detach().cpu().numpy()[None]
+    assert y.spatial_shape == list(osh) and np.array_equal(y.indices.cpu().numpy(), oc)
+    assert np.abs(y.features.cpu().numpy() - f1).max() / np.abs(f1).max() < 1e-5
+    dense = y.dense()
+    assert tuple(dense.shape) == (1, 32, 21, 800, 704)
+    assert float(dense.abs().sum()) == pytest.approx(float(y.features.abs().sum()), rel=1e-4)
+
+
+@pytest.mark.gpu
+def test_iou3d_utils_api():
+    from det3d.core.iou3d import iou3d_utils
+    from oracle import cpu as ocpu
+    from sessd_b200 import synth
+    import iou3d_cuda
+    b1, s1 = synth.random_boxes(3, 200, spread=0.3)
+    b2, _ = synth.random_boxes(4, 150, spread=0.3)
+    a, b = torch.from_numpy(b1).cuda(), torch.from_numpy(b2).cuda()
+    iou = iou3d_utils.boxes_iou_bev_gpu(a, b)
+    ref = ocpu.boxes_iou_bev(ocpu.boxes3d_to_bev(b1), ocpu.boxes3d_to_bev(b2))
+    np.testing.assert_allclose(iou.cpu().numpy(), ref, rtol=2e-5, atol=2e-5)
+    i3 = iou3d_utils.boxes_iou3d_gpu(a, b)
+    assert i3.shape == (200, 150) and float(i3.max()) <= 1.0 + 1e-5
+    al = iou3d_utils.boxes_aligned_iou3d_gpu(a[:150], b)
+    np.testing.assert_allclose(al.cpu().numpy()[:, 0], np.diag(i3.cpu().numpy()[:150]), rtol=1e-4, atol=1e-5)
+    keep = iou3d_utils.nms_gpu(a, torch.from_numpy(s1).cuda(), 0.1)
+    order = np.argsort(-s1, kind="stable")
+    bev = torch.zeros(200, 5)
+    bev[:, 0], bev[:, 1] = torch.from_numpy(b1[:, 0] - b1[:, 4] / 2), torch.from_numpy(b1[:, 2] - b1[:, 3] / 2)   # rect=True layout
+    bev[:, 2], bev[:, 3] = torch.from_numpy(b1[:, 0] + b1[:, 4] / 2), torch.from_numpy(b1[:, 2] + b1[:, 3] / 2)
+    bev[:, 4] = torch.from_numpy(b1[:, 6])
+    ref_keep = order[ocpu.nms_sorted(bev.numpy()[order], 0.1, 0)]
+    assert np.array_equal(keep.cpu().numpy(), ref_keep)
+    with pytest.raises(RuntimeError):
+        iou3d_cuda.boxes_iou_bev_gpu(torch.zeros(2, 5), torch.zeros(2, 5).cuda(), torch.zeros(2, 2).cuda())
+
+
+@pytest.mark.gpu
+def test_voxel_generator_and_rotate_nms_api(golden_dir):
+    from cases import sha
+    from det3d.core.bbox import box_torch_ops
+    from det3d.core.input.voxel_generator import VoxelGenerator
+    from det3d.ops.nms.nms_cpu import rotate_nms_cc
+    from oracle import cpu as ocpu
+    from sessd_b200 import synth
+    vg = VoxelGenerator([0.05, 0.05, 0.1], [0, -40.0, -3.0, 70.4, 40.0, 1.0], 5, 20000)
+    assert list(vg.grid_size) == [1408, 1600, 40]
+    v, c, n = vg.generate(synth.uniform_cloud(0, 20000))
+    g = np.load(os.path.join(golden_dir, "voxel_cases.npz"))
+    assert np.array_equal(c, g["uniform20k_coors"]) and (sha(v) == g["uniform20k_voxels_sha"]).all() and c.dtype == np.int32
+    boxes, scores = synth.random_boxes(8, 600, spread=0.3)
+    b5 = boxes[:, [0, 1, 3, 4, 6]]
+    sel = box_torch_ops.rotate_nms(torch.from_numpy(b5).cuda(), torch.from_numpy(scores).cuda(), 1000, 100, 0.01)
+    order = np.lexsort((np.arange(600), -scores.astype(np.float64)))
+    ref = order[ocpu.rotate_nms_cc(np.concatenate([b5[order], scores[order, None]], 1), 0.01)[:100]]
+    assert sel.dtype == torch.int64 and np.array_equal(sel.cpu().numpy(), ref)
+    lst = rotate_nms_cc(np.concatenate([b5, scores[:, None]], 1), 0.01)
+    assert isinstance(lst, list) and lst[:100] == list(ref)
