@@ -121,6 +121,12 @@ int sessd_spconv_forward(const float *d_in_feat, int cin, const int *d_nbr, int 
                          int max_out, const float *d_weight, int cout, const float *d_scale, const float *d_shift,
                          int relu, float *d_out_feat, void *stream);
 
+/* Tensor-core variant (tcgen05, 3xTF32) for (Cin, Cout) in {(32,32), (32,64), (64,64)}: d_weight_split is
+ * [2 (hi|lo)][kvol][Cout][Cin] (K-major), hi = tf32-truncated weights, lo = w - hi. */
+int sessd_spconv_forward_tc(const float *d_in_feat, int cin, const int *d_nbr, int kvol, const int *d_n_out,
+                            int max_out, const float *d_weight_split, int cout, const float *d_scale,
+                            const float *d_shift, int relu, float *d_out_feat, void *stream);
+
 /* dense(): out NHWC [batch, H, W, C*D] with channel index c*D + d (zero-filled by the call) */
 int sessd_sparse_to_dense(const float *d_feat, const int *d_coors, const int *d_n, int max_rows, int channels,
                           sessd_grid grid, float *d_out, void *stream);

@@ -35,6 +35,7 @@ struct PostWs {
     float *sbox;                   // [B, K, 7] decoded boxes
     float *sbev;                   // [B, K, 5]
     float *ssu;                    // [B, K, 4] stand-up AABB
+    RotBox *srot;                  // [B, K] corners + trig precomputed once per box
     float *sscore;                 // [B, K]
     int *sdir;                     // [B, K]
     unsigned long long *mask;      // [B, K, K/64]
@@ -55,6 +56,7 @@ static PostWs post_carve(void *base, int batch, int anchors, int k) {
     w.sbox = (float *)take(sizeof(float) * (size_t)batch * k * 7);
     w.sbev = (float *)take(sizeof(float) * (size_t)batch * k * 5);
     w.ssu = (float *)take(sizeof(float) * (size_t)batch * k * 4);
+    w.srot = (RotBox *)take(sizeof(RotBox) * (size_t)batch * k);
     w.sscore = (float *)take(sizeof(float) * (size_t)batch * k);
     w.sdir = (int *)take(sizeof(int) * (size_t)batch * k);
     w.mask = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)batch * k * cb);
@@ -190,6 +192,7 @@ __global__ void __launch_bounds__(128) post_prepare_kernel(const float *__restri
 #pragma unroll
         for (int j = 0; j < 7; ++j) w.sbox[o * 7 + j] = box[j];
         nms_geometry(box, w.sbev + o * 5, w.ssu + o * 4);
+        w.srot[o] = rot_prepare(w.sbev[o * 5], w.sbev[o * 5 + 1], w.sbev[o * 5 + 2], w.sbev[o * 5 + 3], w.sbev[o * 5 + 4]);
         w.sscore[o] = key_score(key);
         const float *d = h + 7 * apl + apl + 2 * r;
         w.sdir[o] = (d[1] > d[0]) ? 1 : 0;                           // torch.max(dim=-1)[1]: first max wins
@@ -203,6 +206,8 @@ __global__ void __launch_bounds__(128) nms_prepare_kernel(const float *__restric
         const float *q = boxes5 + (size_t)src * 5;
         float box[7] = {q[0], q[1], 0.f, q[2], q[3], 0.f, q[4]};
         nms_geometry(box, w.sbev + (size_t)i * 5, w.ssu + (size_t)i * 4);
+        const float *bv = w.sbev + (size_t)i * 5;
+        w.srot[i] = rot_prepare(bv[0], bv[1], bv[2], bv[3], bv[4]);
     }
 }
 
@@ -221,40 +226,52 @@ __device__ __forceinline__ float standup_iou_pos(const float *bn, const float *q
     return 0.f;
 }
 
-__global__ void __launch_bounds__(64) post_mask_kernel(PostWs w, int K, float thresh, int ge) {
+// one CTA per 64x64 tile of the upper triangle; 512 threads = 8 rows x 64 columns per pass, bits gathered with warp ballots
+constexpr int kMaskThreads = 512;
+__global__ void __launch_bounds__(kMaskThreads) post_mask_kernel(PostWs w, int K, float thresh, int ge) {
     const int b = blockIdx.z;
     const int rb = blockIdx.y, cb = blockIdx.x;
     if (cb < rb) return;
     const int m = min(w.ncand[b], K);
     if (rb * 64 >= m || cb * 64 >= m) return;
     const int col_blocks = (K + 63) / 64;
-    __shared__ float s_bev[64 * 5];
-    __shared__ float s_su[64 * 4];
-    const int ncol = min(m - cb * 64, 64);
+    __shared__ RotBox s_col[64];
+    __shared__ RotBox s_row[64];
+    __shared__ float s_csu[64 * 4];
+    __shared__ float s_rsu[64 * 4];
+    const int ncol = min(m - cb * 64, 64), nrow = min(m - rb * 64, 64);
     const size_t fb = (size_t)b * K;
-    if ((int)threadIdx.x < ncol) {
-        const size_t j = fb + cb * 64 + threadIdx.x;
+    if ((int)threadIdx.x < 64) {
+        const int t = threadIdx.x;
+        if (t < ncol) {
+            s_col[t] = w.srot[fb + cb * 64 + t];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) s_bev[threadIdx.x * 5 + k] = w.sbev[j * 5 + k];
+            for (int k = 0; k < 4; ++k) s_csu[t * 4 + k] = w.ssu[(fb + cb * 64 + t) * 4 + k];
+        }
+    } else if (threadIdx.x < 128) {
+        const int t = threadIdx.x - 64;
+        if (t < nrow) {
+            s_row[t] = w.srot[fb + rb * 64 + t];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) s_su[threadIdx.x * 4 + k] = w.ssu[j * 4 + k];
+            for (int k = 0; k < 4; ++k) s_rsu[t * 4 + k] = w.ssu[(fb + rb * 64 + t) * 4 + k];
+        }
     }
     __syncthreads();
-    const int i = rb * 64 + threadIdx.x;
-    if (i >= m) return;
-    float me[5], su[4];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) me[k] = w.sbev[(fb + i) * 5 + k];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) su[k] = w.ssu[(fb + i) * 4 + k];
-    unsigned long long bits = 0;
-    const int start = (rb == cb) ? threadIdx.x + 1 : 0;
-    for (int j = start; j < ncol; ++j) {
-        if (standup_iou_pos(su, s_su + j * 4) <= 0.0f) continue;    // nms_cpu.h:104-105
-        const float v = rot_iou_bev(me, s_bev + j * 5);
-        if (ge ? (v >= thresh) : (v > thresh)) bits |= 1ull << j;
+    const int j = threadIdx.x & 63;           // column within the tile
+    const int half = j >> 5;                  // which 32-bit half of the 64-bit mask word this warp produces
+    for (int r0 = 0; r0 < 64; r0 += kMaskThreads / 64) {
+        const int r = r0 + (threadIdx.x >> 6);
+        bool hit = false;
+        if (r < nrow && j < ncol && (rb != cb || j > r)) {
+            if (standup_iou_pos(s_rsu + r * 4, s_csu + j * 4) > 0.0f) {            // nms_cpu.h:104-105
+                const float v = rot_iou_bev_pre(s_row[r], s_col[j]);
+                hit = ge ? (v >= thresh) : (v > thresh);
+            }
+        }
+        const unsigned int bits = __ballot_sync(0xffffffffu, hit);
+        if ((threadIdx.x & 31) == 0 && r < nrow)
+            reinterpret_cast<unsigned int *>(w.mask + (fb + rb * 64 + r) * col_blocks + cb)[half] = bits;
     }
-    w.mask[(fb + i) * col_blocks + cb] = bits;
 }
 
 // 5. finalize ------------------------------------------------------------------------------------------------
@@ -423,7 +440,7 @@ extern "C" int sessd_postprocess(const float *d_head, const float *d_anchors, co
     SESSD_LAUNCH(post_prepare_kernel, g3, 128, 0, st, d_head, d_anchors, *cfg, w);
     const int cb = (K + 63) / 64;
     dim3 g4(cb, cb, B);
-    SESSD_LAUNCH(post_mask_kernel, g4, 64, 0, st, w, K, cfg->nms_iou_thresh, cfg->nms_ge);
+    SESSD_LAUNCH(post_mask_kernel, g4, kMaskThreads, 0, st, w, K, cfg->nms_iou_thresh, cfg->nms_ge);
     const size_t sm = finalize_smem(K, P);
     if (sm > 48 * 1024) SESSD_CUDA_TRY(cudaFuncSetAttribute(post_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     SESSD_LAUNCH(post_finalize_kernel, B, 256, sm, st, w, *cfg, d_frustum, d_boxes, d_scores, d_labels, d_count, d_aux, d_sel_anchor);
@@ -450,7 +467,7 @@ extern "C" int sessd_rotate_nms(const float *d_boxes5, const float *d_scores, co
     SESSD_LAUNCH(nms_prepare_kernel, div_up(pre_max, 128), 128, 0, st, d_boxes5, pre_max, w);
     const int cb = (pre_max + 63) / 64;
     dim3 g4(cb, cb, 1);
-    SESSD_LAUNCH(post_mask_kernel, g4, 64, 0, st, w, pre_max, iou_thresh, ge);
+    SESSD_LAUNCH(post_mask_kernel, g4, kMaskThreads, 0, st, w, pre_max, iou_thresh, ge);
     const size_t sm = finalize_smem(pre_max, post_max);
     if (sm > 48 * 1024) SESSD_CUDA_TRY(cudaFuncSetAttribute(nms_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     SESSD_LAUNCH(nms_finalize_kernel, 1, 256, sm, st, w, pre_max, post_max, d_keep, d_num_keep);

@@ -120,6 +120,80 @@ __device__ inline float rot_overlap(float ax1, float ay1, float ax2, float ay2, 
     return fabsf(area) / 2.0f;
 }
 
+// ---- precomputed form: corners + trig evaluated once per box (bit-identical to rot_overlap: same expressions; uses
+// cosf(-x) == cosf(x) and sinf(-x) == -sinf(x), which hold exactly for CUDA's implementations) ----------------------------
+struct RotBox {
+    float x1, y1, x2, y2;
+    float c, s;          // cos / sin of the angle
+    P2 corner[4];        // rotated corners, same order as the reference
+};
+
+__device__ __forceinline__ RotBox rot_prepare(float x1, float y1, float x2, float y2, float ang) {
+    RotBox b;
+    b.x1 = x1; b.y1 = y1; b.x2 = x2; b.y2 = y2;
+    b.c = cosf(ang); b.s = sinf(ang);
+    const P2 ctr = {(x1 + x2) / 2, (y1 + y2) / 2};
+    const P2 raw[4] = {{x1, y1}, {x2, y1}, {x2, y2}, {x1, y2}};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) b.corner[k] = rb_spin(ctr, b.c, b.s, raw[k]);
+    return b;
+}
+
+__device__ inline float rot_overlap_pre(const RotBox &a, const RotBox &b) {
+    P2 A[5], B[5];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { A[k] = a.corner[k]; B[k] = b.corner[k]; }
+    A[4] = A[0]; B[4] = B[0];
+    P2 poly[24];
+    float ang[24];
+    P2 ctr = {0.f, 0.f};
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            P2 x;
+            if (rb_seg_cross(A[i + 1], A[i], B[j + 1], B[j], x)) {
+                ctr.x = ctr.x + x.x; ctr.y = ctr.y + x.y;
+                if (cnt < 24) poly[cnt++] = x;
+            }
+        }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (rb_inside(a.x1, a.y1, a.x2, a.y2, a.c, -a.s, B[k])) {
+            ctr.x = ctr.x + B[k].x; ctr.y = ctr.y + B[k].y;
+            if (cnt < 24) poly[cnt++] = B[k];
+        }
+        if (rb_inside(b.x1, b.y1, b.x2, b.y2, b.c, -b.s, A[k])) {
+            ctr.x = ctr.x + A[k].x; ctr.y = ctr.y + A[k].y;
+            if (cnt < 24) poly[cnt++] = A[k];
+        }
+    }
+    if (cnt < 3) return 0.f;
+    ctr.x /= cnt; ctr.y /= cnt;
+    for (int k = 0; k < cnt; ++k) ang[k] = atan2f(poly[k].y - ctr.y, poly[k].x - ctr.x);
+    for (int j = 0; j < cnt - 1; ++j)
+        for (int i = 0; i < cnt - j - 1; ++i)
+            if (ang[i] > ang[i + 1]) {
+                P2 t = poly[i]; poly[i] = poly[i + 1]; poly[i + 1] = t;
+                float ta = ang[i]; ang[i] = ang[i + 1]; ang[i + 1] = ta;
+            }
+    float area = 0.f;
+    for (int k = 0; k < cnt - 1; ++k) {
+        const float ux = poly[k].x - poly[0].x, uy = poly[k].y - poly[0].y;
+        const float vx = poly[k + 1].x - poly[0].x, vy = poly[k + 1].y - poly[0].y;
+        area += ux * vy - uy * vx;
+    }
+    return fabsf(area) / 2.0f;
+}
+
+__device__ __forceinline__ float rot_iou_bev_pre(const RotBox &a, const RotBox &b) {
+    const float sa = (a.x2 - a.x1) * (a.y2 - a.y1);
+    const float sb = (b.x2 - b.x1) * (b.y2 - b.y1);
+    const float so = rot_overlap_pre(a, b);
+    return so / fmaxf(sa + sb - so, kRotEps);
+}
+
 __device__ __forceinline__ float rot_overlap5(const float *a, const float *b) {
     return rot_overlap(a[0], a[1], a[2], a[3], a[4], b[0], b[1], b[2], b[3], b[4]);
 }

@@ -29,7 +29,7 @@ class FrameEngine:
         self.d_points = torch.zeros((self.max_points, 4), dtype=torch.float32, device=dev)
         self.d_off = torch.zeros((self.batch + 1,), dtype=torch.int32, device=dev)
         self.vox = ops.VoxelBuffers(self.vcfg, self.batch, self.max_points, dev, with_mean=True)
-        self.middle = SpMiddleRunner(self.batch, self.batch * max_voxels, self.grid_xyz, 4, dev, growth=growth)
+        self.middle = SpMiddleRunner(self.batch, self.batch * max_voxels, self.grid_xyz, 4, dev, growth=growth, use_tc=use_tc)
         self.neck = SSFARunner(self.batch, (self.grid_xyz[1] // 8, self.grid_xyz[0] // 8), dev, use_tc=use_tc)
         self.anchors = None
         pk = dict(batch=self.batch, head_stride=SSFARunner.HEAD_STRIDE)

@@ -156,6 +156,14 @@ def spconv_forward(in_feat, nbr, n_out, max_out, weight, scale, shift, relu, out
     return out
 
 
+def spconv_forward_tc(in_feat, nbr, n_out, max_out, weight_split, scale, shift, relu, out):
+    """weight_split [2, kvol, Cout, Cin] from pack_weight_tc(weight [kvol,Cin,Cout], Cout)."""
+    _two, kvol, cout, cin = weight_split.shape
+    check(lib.sessd_spconv_forward_tc(_p(in_feat), int(cin), _p(nbr), int(kvol), _p(n_out), int(max_out), _p(weight_split), int(cout),
+                                      _p(scale), _p(shift), int(bool(relu)), _p(out), _st()), "sessd_spconv_forward_tc")
+    return out
+
+
 def sparse_to_dense(feat, coors, n, max_rows, grid, out=None):
     c = feat.shape[1]
     d, h, w = grid.shape[0], grid.shape[1], grid.shape[2]

@@ -48,8 +48,10 @@ class SpMiddleRunner:
     GROWTH = (1.0, 4.0, 6.0, 5.0, 3.0)
 
     def __init__(self, batch, max_voxels_total, input_shape_xyz=(1408, 1600, 40), num_input_features=4, device="cuda",
-                 growth=None):
+                 growth=None, use_tc=True):
+        """use_tc: run the Cin >= 32 layers on the tcgen05 tensor cores (3xTF32); False = fp32 SIMT baseline for all layers."""
         self.batch, self.device = batch, torch.device(device)
+        self.use_tc = bool(use_tc)
         self.cin0 = num_input_features
         shape = (int(input_shape_xyz[2]) + 1, int(input_shape_xyz[1]), int(input_shape_xyz[0]))   # scn.py:179
         growth = growth or self.GROWTH
@@ -105,7 +107,9 @@ class SpMiddleRunner:
             w = torch.as_tensor(l["weight"], dtype=torch.float32, device=self.device)
             assert tuple(w.shape) == (*p["ks"], p["cin"], p["cout"]), (w.shape, p)
             sc, sh = fold_bn(*[torch.as_tensor(l[k], device=self.device) for k in ("gamma", "beta", "mean", "var")])
-            self.weights.append((w.reshape(-1, p["cin"], p["cout"]).contiguous(), sc, sh))
+            wp = w.reshape(-1, p["cin"], p["cout"]).contiguous()
+            tc = ops.pack_weight_tc(wp, p["cout"]) if (self.use_tc and p["cin"] >= 32) else None
+            self.weights.append((wp, sc, sh, tc))
 
     def forward(self, feat0, coors0, n0):
         """feat0 [cap0, Cin] f32, coors0 [cap0,4] i32 (b,z,y,x), n0 [1] i32 (device).  Returns dense NHWC."""
@@ -129,8 +133,11 @@ class SpMiddleRunner:
                                      p["pd"], lout["grid"], lout["index"], lout["scratch"], lout["coors"], lout["n"], lout["cap"],
                                      p["nbr"], self.status)
                 n_out, cap_out = lout["n"], lout["cap"]
-            w, sc, sh = self.weights[li]
-            x = ops.spconv_forward(x, p["nbr"], n_out, cap_out, w, sc, sh, True, self.feats[li])
+            w, sc, sh, tc = self.weights[li]
+            if tc is not None:
+                x = ops.spconv_forward_tc(x, p["nbr"], n_out, cap_out, tc, sc, sh, True, self.feats[li])
+            else:
+                x = ops.spconv_forward(x, p["nbr"], n_out, cap_out, w, sc, sh, True, self.feats[li])
         last = self.levels[-1]
         return ops.sparse_to_dense(x, last["coors"], last["n"], last["cap"], last["grid"], self.dense)
 
