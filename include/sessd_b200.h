@@ -155,12 +155,16 @@ int sessd_bev_conv(const float *d_in, const float *d_weight /*[ntaps, cin, cout]
                    const float *d_shift, const float *d_residual /*nullable, same shape as out*/, float *d_out,
                    const sessd_conv_desc *desc, void *stream);
 
-/* Tensor-core variant (tcgen05 + TMEM + TMA, 3xTF32 split for fp32-level accuracy): same contract, in_stride must be 1.
+/* Tensor-core variant (tcgen05 + TMEM + TMA, 3xTF32 split for fp32-level accuracy): same contract (in_stride 1 or 2).
  * d_weight_split [2 (hi|lo)][ntaps][cout_pad][cin]: hi = weights truncated to tf32, lo = w - hi; cout_pad is a multiple of the
  * N tile (128; 32 when cout <= 32). */
 int sessd_bev_conv_tc(const float *d_in, const float *d_weight_split, int cout_pad, const float *d_scale,
                       const float *d_shift, const float *d_residual, float *d_out, const sessd_conv_desc *desc,
                       void *stream);
+
+/* tunable of sessd_bev_conv_tc: CTAs per thread-block cluster sharing the weight tiles through TMA multicast (1, 2 or 4) */
+void sessd_set_conv_cluster(int ctas_per_cluster);
+int sessd_get_conv_cluster(void);
 
 /* SSFA tail (rpn_v1.py:229-233): w_k = BN(conv1x1_{128->1}(x_k)); softmax over the pair; weighted sum */
 int sessd_ssfa_fuse(const float *d_x0, const float *d_x1, const float *d_w0 /*[C]*/, const float *d_w1,

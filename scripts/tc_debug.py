@@ -48,3 +48,29 @@ xs = torch.randn(1, 16, 32, c, generator=g)
 o = run(xs, eye, c, [(1, -1)])
 ref = torch.zeros_like(xs); ref[:, :-1, 1:] = xs[:, 1:, :-1]
 print("A5 tap shift: max err =", float((o - ref).abs().max()))
+
+# A6: cluster multicast of the weight tiles (2 / 4 CTAs per cluster) and the strided-TMA stride-2 conv
+import torch.nn.functional as F
+xs = torch.randn(2, 37, 45, c, generator=g)
+w3 = torch.randn(128, c, 3, 3, generator=g) * (2.0 / (c * 9)) ** 0.5
+ref = F.conv2d(xs.permute(0, 3, 1, 2).double(), w3.double(), None, 1, 1).permute(0, 2, 3, 1)
+wp3 = w3.permute(2, 3, 1, 0).reshape(9, c, 128).contiguous()
+taps = [(dy - 1, dx - 1) for dy in range(3) for dx in range(3)]
+for cs in (1, 2, 4):
+    ops.set_conv_cluster(cs)
+    try:
+        o = run(xs, wp3, 128, taps)
+        print("A6 cluster=%d conv3x3: max rel err =" % cs, float((o.double() - ref).abs().max() / ref.abs().max()))
+    except Exception as e:
+        print("A6 cluster=%d FAILED:" % cs, repr(e)[:200]); break
+ops.set_conv_cluster(1)
+ref2 = F.conv2d(xs.permute(0, 3, 1, 2).double(), w3.double(), None, 2, 1).permute(0, 2, 3, 1)
+b_, h2, w2 = ref2.shape[0], ref2.shape[1], ref2.shape[2]
+out = torch.full((b_, h2, w2, 128), -777.0, device="cuda")
+d = ops.conv_desc(b_, (37, 45), c, (h2, w2), 128, (h2, w2), taps, in_stride=2, relu=False)
+try:
+    ops.bev_conv_tc(xs.cuda(), ops.pack_weight_tc(wp3.cuda(), 128), None, None, None, out, d)
+    torch.cuda.synchronize()
+    print("A7 stride-2 conv (strided TMA): max rel err =", float((out.cpu().double() - ref2).abs().max() / ref2.abs().max()))
+except Exception as e:
+    print("A7 stride-2 FAILED:", repr(e)[:200])

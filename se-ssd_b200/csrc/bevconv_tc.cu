@@ -45,10 +45,12 @@ struct TcParams {
     int tap_dy[16], tap_dx[16];
     int relu;
     int n_tile;          // 128 or 32: UMMA N and rows of each B tile
+    int in_stride;       // 1 or 2 (strided TMA box for the stride-2 conv)
     int tiles_x, tiles_y;
 };
 
 // ---------------------------------------------------------------------------------------------------------------- kernel
+template <int CS>   // CTAs per cluster sharing (multicasting) the weight tiles
 __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                     const __grid_constant__ CUtensorMap map_b,
                                                                     const float *__restrict__ scale, const float *__restrict__ shift,
@@ -71,8 +73,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
     const int steps = p.ntaps * kchunks;
     const uint32_t b_tile_bytes = (uint32_t)p.n_tile * kTcBK * 4;
 
+    const uint32_t crank = (CS > 1) ? cluster_cta_rank() : 0u;
+    constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 128); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 128); mbar_init(&empty[s], CS); }
         mbar_init(acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -82,6 +86,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
     }
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();        // peers' barriers must be initialised before any multicast / remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -95,9 +100,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
                 const int tap = it / kchunks, c0 = (it - tap * kchunks) * kTcBK;
                 unsigned char *st = tiles + s * kTcStageBytes;
                 mbar_expect_tx(&full[s], kTcTileBytes + 2 * b_tile_bytes);
-                tma_load_4d(st, &map_a, &full[s], c0, ox0 + p.tap_dx[tap], oy0 + p.tap_dy[tap], b);
-                tma_load_4d(st + 2 * kTcTileBytes, &map_b, &full[s], c0, n0, tap, 0);
-                tma_load_4d(st + 3 * kTcTileBytes, &map_b, &full[s], c0, n0, tap, 1);
+                tma_load_4d(st, &map_a, &full[s], c0, ox0 * p.in_stride + p.tap_dx[tap], oy0 * p.in_stride + p.tap_dy[tap], b);
+                if (CS == 1) {
+                    tma_load_4d(st + 2 * kTcTileBytes, &map_b, &full[s], c0, n0, tap, 0);
+                    tma_load_4d(st + 3 * kTcTileBytes, &map_b, &full[s], c0, n0, tap, 1);
+                } else {
+                    // this CTA fetches rows [crank*n/CS, (crank+1)*n/CS) of both weight planes and multicasts them to the cluster
+                    const int rows = p.n_tile / CS;
+                    const uint32_t so = crank * (uint32_t)rows * 128u;
+                    tma_load_4d_mc(st + 2 * kTcTileBytes + so, &map_b, &full[s], c0, n0 + (int)crank * rows, tap, 0, kMask);
+                    tma_load_4d_mc(st + 3 * kTcTileBytes + so, &map_b, &full[s], c0, n0 + (int)crank * rows, tap, 1, kMask);
+                }
             }
         }
     } else if (warp == 1) {
@@ -123,7 +136,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
                     tc_mma_tf32(acc_small, dah, dbl, idesc, 1);
                     tc_mma_tf32(acc_main, dah, dbh, idesc, (it >= 3 || k != 0) ? 1u : 0u);
                 }
-                tc_commit(&empty[s]);                             // smem stage reusable once these MMAs retire
+                if (CS == 1) tc_commit(&empty[s]);                // smem stage reusable once these MMAs retire
+                else tc_commit_mc(&empty[s], kMask);              // ... in every CTA of the cluster (peers multicast into it)
                 if (it == steps - 1) tc_commit(acc_full);         // accumulator complete
             }
             __syncwarp();
@@ -158,7 +172,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
         const int q = warp & 3;                     // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;                // accumulator row == pixel within the patch
         const int gy = oy0 + r / kTcTileW, gx = ox0 + r % kTcTileW;
-        const bool pix_ok = gy < p.grid_h && gx < p.grid_w;
+        const bool pix_ok = b < p.batch && gy < p.grid_h && gx < p.grid_w;
         const size_t opix = (((size_t)b * p.out_h + (size_t)gy * p.out_stride + p.out_off_y) * p.out_w + (size_t)gx * p.out_stride + p.out_off_x);
         const int nmain = steps < 3 ? steps : 3;     // main accumulators that were written at least once
         for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
@@ -196,10 +210,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
     }
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();        // nobody exits while a peer may still multicast into / arrive on this CTA
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
+
+static int g_conv_cluster = 1;
 
 }  // namespace sessd
 
@@ -212,26 +229,31 @@ extern "C" int sessd_bev_conv_tc(const float *d_in, const float *d_weight_split,
     if (!d_in || !d_weight_split || !d_out || !desc) return SESSD_EINVAL;
     const sessd_conv_desc &d = *desc;
     const int n_tile = d.cout <= 32 ? 32 : 128;
-    if (d.batch < 1 || d.cin < kTcBK || d.cin % kTcBK || d.cout < 4 || d.cout % 4 || d.ntaps < 1 || d.ntaps > 16 || d.in_stride != 1 ||
+    if (d.batch < 1 || d.cin < kTcBK || d.cin % kTcBK || d.cout < 4 || d.cout % 4 || d.ntaps < 1 || d.ntaps > 16 || d.in_stride < 1 || d.in_stride > 2 ||
         d.out_stride < 1 || d.grid_h < 1 || d.grid_w < 1 || cout_pad % n_tile || cout_pad < d.cout)
         return SESSD_EINVAL;
     if ((d.grid_h - 1) * d.out_stride + d.out_off_y >= d.out_h || (d.grid_w - 1) * d.out_stride + d.out_off_x >= d.out_w) return SESSD_EINVAL;
+    const int cs = (g_conv_cluster == 4 || g_conv_cluster == 2) ? g_conv_cluster : 1;
     CUtensorMap map_a, map_b;
     {
         const cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)d.in_w, (cuuint64_t)d.in_h, (cuuint64_t)d.batch};
-        const cuuint32_t box[4] = {kTcBK, kTcTileW, kTcTileH, 1};
-        int rc = encode_map_4d(&map_a, d_in, dims, box);
+        // stride-2 conv: the box TRAVERSES 2x the tile extent with element stride 2 => still 16 x 8 pixels land in smem
+        const cuuint32_t box[4] = {kTcBK, (cuuint32_t)(kTcTileW * d.in_stride), (cuuint32_t)(kTcTileH * d.in_stride), 1};
+        const cuuint32_t estr[4] = {1, (cuuint32_t)d.in_stride, (cuuint32_t)d.in_stride, 1};
+        int rc = encode_map_4d(&map_a, d_in, dims, box, estr);
         if (rc) return rc;
     }
     {
         const cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)cout_pad, (cuuint64_t)d.ntaps, 2};
-        const cuuint32_t box[4] = {kTcBK, (cuuint32_t)n_tile, 1, 1};
+        const cuuint32_t box[4] = {kTcBK, (cuuint32_t)(n_tile / cs), 1, 1};
         int rc = encode_map_4d(&map_b, d_weight_split, dims, box);
         if (rc) return rc;
     }
     static bool attr_done = false;
     if (!attr_done) {
-        SESSD_CUDA_TRY(cudaFuncSetAttribute(bev_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+        SESSD_CUDA_TRY(cudaFuncSetAttribute(bev_conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+        SESSD_CUDA_TRY(cudaFuncSetAttribute(bev_conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+        SESSD_CUDA_TRY(cudaFuncSetAttribute(bev_conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
         attr_done = true;
     }
     TcParams p;
@@ -243,9 +265,30 @@ extern "C" int sessd_bev_conv_tc(const float *d_in, const float *d_weight_split,
     for (int t = 0; t < 16; ++t) { p.tap_dy[t] = d.tap_dy[t]; p.tap_dx[t] = d.tap_dx[t]; }
     p.relu = d.relu;
     p.n_tile = n_tile;
+    p.in_stride = d.in_stride;
     p.tiles_x = div_up(d.grid_w, kTcTileW);
     p.tiles_y = div_up(d.grid_h, kTcTileH);
-    dim3 grid(p.tiles_x * p.tiles_y * d.batch, cout_pad / n_tile);
-    SESSD_LAUNCH(bev_conv_tc_kernel, grid, kTcThreads, kTcSmemBytes, stream, map_a, map_b, d_scale, d_shift, d_residual, d_out, p);
+    const int tiles = p.tiles_x * p.tiles_y * d.batch;
+    dim3 grid(div_up(tiles, cs) * cs, cout_pad / n_tile);     // padded tiles decode to image index >= batch: TMA zero-fills, stores masked
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = kTcSmemBytes;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e;
+    if (cs == 4) e = cudaLaunchKernelEx(&cfg, bev_conv_tc_kernel<4>, map_a, map_b, d_scale, d_shift, d_residual, d_out, p);
+    else if (cs == 2) e = cudaLaunchKernelEx(&cfg, bev_conv_tc_kernel<2>, map_a, map_b, d_scale, d_shift, d_residual, d_out, p);
+    else e = cudaLaunchKernelEx(&cfg, bev_conv_tc_kernel<1>, map_a, map_b, d_scale, d_shift, d_residual, d_out, p);
+    ++g_launches;
+    if (e != cudaSuccess) return (int)e;
     return last_error();
 }
+
+// tunable: CTAs per cluster that share (TMA-multicast) the weight tiles of sessd_bev_conv_tc: 1, 2 or 4
+extern "C" void sessd_set_conv_cluster(int cs) { sessd::g_conv_cluster = cs; }
+extern "C" int sessd_get_conv_cluster(void) { return sessd::g_conv_cluster; }

@@ -50,11 +50,40 @@ __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
+// multicast variant: the box lands at the same CTA-relative smem offset of every CTA in cta_mask and performs complete_tx on the
+// mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_4d_mc(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3,
+                                               uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+        : "memory");
+}
+
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// commit that arrives on the barrier at the same offset in every CTA of cta_mask (releases a multicast-filled stage cluster-wide)
+__device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
 }
 
 // D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by ONE thread
@@ -117,11 +146,13 @@ static inline EncodeTiledFn get_tensor_map_encoder() {
 }
 
 // fp32 4-D tiled tensor map, SWIZZLE_128B, zero OOB fill; dims / box innermost first
-static inline int encode_map_4d(CUtensorMap *m, const void *base, const cuuint64_t dims[4], const cuuint32_t box[4]) {
+static inline int encode_map_4d(CUtensorMap *m, const void *base, const cuuint64_t dims[4], const cuuint32_t box[4],
+                                const cuuint32_t *elem_strides = nullptr) {
     EncodeTiledFn enc = get_tensor_map_encoder();
     if (!enc) return SESSD_EINVAL;
     cuuint64_t strides[3] = {dims[0] * 4, dims[0] * dims[1] * 4, dims[0] * dims[1] * dims[2] * 4};
     cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (elem_strides) for (int i = 0; i < 4; ++i) estr[i] = elem_strides[i];
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : 700 + (int)r;

@@ -213,6 +213,11 @@ def bev_conv_tc(x, weight_split, scale, shift, residual, out, desc):
     return out
 
 
+def set_conv_cluster(n):
+    """CTAs per cluster sharing weight tiles via TMA multicast in bev_conv_tc (1, 2 or 4)."""
+    lib.sessd_set_conv_cluster(int(n))
+
+
 def ssfa_fuse(x0, x1, w0, w1, s0, t0, s1, t1, out):
     npix = x0.numel() // x0.shape[-1]
     check(lib.sessd_ssfa_fuse(_p(x0), _p(x1), _p(w0), _p(w1), float(s0), float(t0), float(s1), float(t1), int(npix), int(x0.shape[-1]),

@@ -205,6 +205,8 @@ class SSFARunner:
 
     HEAD_STRIDE = 24
 
+    TC_STRIDE2 = True     # run the stride-2 conv through the strided-TMA tensor-core path as well
+
     def __init__(self, batch, hw=(200, 176), device="cuda", use_tc=True):
         """use_tc: tcgen05 3xTF32 tensor-core convs (default); False = the fp32 SIMT baseline kernels."""
         self.batch, self.h, self.w, self.device = batch, int(hw[0]), int(hw[1]), torch.device(device)
@@ -231,7 +233,7 @@ class SSFARunner:
                           ("trans_0.0", 0), ("trans_1.0", 0), ("conv_0.0", 1), ("conv_1.0", 1)):
             wp, taps = _pack_conv(g(name + ".weight"))
             P[name] = (wp, [(dy - pad, dx - pad) for dy, dx in taps]) + bn(name)
-            if self.use_tc and name != "bottom_up_block_1.0":      # the stride-2 conv stays on the SIMT kernel
+            if self.use_tc and (self.TC_STRIDE2 or name != "bottom_up_block_1.0"):
                 P[name + ":tc"] = ops.pack_weight_tc(wp, -(-wp.shape[2] // 128) * 128)
         for name in ("deconv_block_0.0", "deconv_block_1.0"):
             classes = _deconv_classes(g(name + ".weight"))
