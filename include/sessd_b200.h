@@ -162,9 +162,18 @@ int sessd_bev_conv_tc(const float *d_in, const float *d_weight_split, int cout_p
                       const float *d_shift, const float *d_residual, float *d_out, const sessd_conv_desc *desc,
                       void *stream);
 
+/* ConvTranspose2d(k3, s2, p1, op1) + BN + ReLU (+ residual) in one launch (four output-parity classes as blockIdx.z);
+ * d_weight_split [2][9][cout_pad][cin], tap = ky*3+kx of W[cin][cout][ky][kx]; output [batch, 2*in_h, 2*in_w, cout] NHWC
+ * (rpn_v1.py:183-195). */
+int sessd_bev_deconv_tc(const float *d_in, const float *d_weight_split, int cout_pad, const float *d_scale,
+                        const float *d_shift, const float *d_residual, float *d_out, int batch, int in_h, int in_w,
+                        int cin, int cout, int relu, void *stream);
+
 /* tunable of sessd_bev_conv_tc: CTAs per thread-block cluster sharing the weight tiles through TMA multicast (1, 2 or 4) */
 void sessd_set_conv_cluster(int ctas_per_cluster);
 int sessd_get_conv_cluster(void);
+/* profiling experiments only: bit mask of pipeline stages to skip inside bev_conv_tc (results are garbage when non-zero) */
+void sessd_set_conv_ablate(int mask);
 
 /* SSFA tail (rpn_v1.py:229-233): w_k = BN(conv1x1_{128->1}(x_k)); softmax over the pair; weighted sum */
 int sessd_ssfa_fuse(const float *d_x0, const float *d_x1, const float *d_w0 /*[C]*/, const float *d_w1,

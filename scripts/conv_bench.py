@@ -35,3 +35,21 @@ bench("conv1x1 128->128 @200x176", 128, 128, (200, 176), (200, 176), [(0, 0)])
 bench("conv1x1 256->256 @100x88", 256, 256, (100, 88), (100, 88), [(0, 0)])
 bench("deconv class(4 taps) 256->128", 256, 128, (100, 88), (100, 88), [(0, 0), (0, 1), (1, 0), (1, 1)])
 bench("head 128->24 @200x176", 128, 24, (200, 176), (200, 176), [(0, 0)])
+
+print("--- ablations on conv3x3 128->128 @200x176 (cluster 1): 1=no split, 2=hi*hi only, 4=no TMA reloads")
+from sessd_b200._lib import lib
+ops.set_conv_cluster(1)
+x = torch.randn(1, 200, 176, 128, device="cuda"); wp = torch.randn(9, 128, 128, device="cuda") * 0.05
+wt = ops.pack_weight_tc(wp, 128); out = torch.zeros(1, 200, 176, 128, device="cuda")
+d = ops.conv_desc(1, (200, 176), 128, (200, 176), 128, (200, 176), t3, relu=True)
+flush = torch.empty(64 * 1024 * 1024, device="cuda")
+for mode in (0, 1, 2, 4, 3, 5, 6, 7):
+    lib.sessd_set_conv_ablate(mode)
+    ts = []
+    for i in range(8):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); ops.bev_conv_tc(x, wt, None, None, None, out, d); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    print("ablate=%d  %.1f us" % (mode, float(np.median(ts[2:])) * 1000))
+lib.sessd_set_conv_ablate(0)

@@ -40,12 +40,16 @@ struct TcParams {
     int batch, in_h, in_w, cin;
     int out_h, out_w, cout;
     int grid_h, grid_w;
-    int out_stride, out_off_y, out_off_x;
-    int ntaps;
-    int tap_dy[16], tap_dx[16];
+    int out_stride;
+    // up to 4 "classes" per launch (blockIdx.z): a plain conv is one class; ConvTranspose2d(k3,s2,p1,op1) is its 4 output-parity
+    // classes with 1/2/2/4 taps each, all reading the same input and the same 9-tap weight tensor
+    int nclass;
+    int cls_ntaps[4], cls_off_y[4], cls_off_x[4];
+    int tap_dy[4][9], tap_dx[4][9], tap_w[4][9];
     int relu;
     int n_tile;          // 128 or 32: UMMA N and rows of each B tile
     int in_stride;       // 1 or 2 (strided TMA box for the stride-2 conv)
+    int ablate;          // timing experiments only (results become garbage): 1 skip the hi/lo split, 2 hi*hi product only, 4 no TMA reloads
     int tiles_x, tiles_y;
 };
 
@@ -69,8 +73,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
     const int b = t / p.tiles_y;
     const int oy0 = ty * kTcTileH, ox0 = tx * kTcTileW;
     const int n0 = blockIdx.y * p.n_tile;
+    const int cls = blockIdx.z;
     const int kchunks = p.cin / kTcBK;
-    const int steps = p.ntaps * kchunks;
+    const int steps = p.cls_ntaps[cls] * kchunks;
     const uint32_t b_tile_bytes = (uint32_t)p.n_tile * kTcBK * 4;
 
     const uint32_t crank = (CS > 1) ? cluster_cta_rank() : 0u;
@@ -99,17 +104,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
                 mbar_wait(&empty[s], ph ^ 1);
                 const int tap = it / kchunks, c0 = (it - tap * kchunks) * kTcBK;
                 unsigned char *st = tiles + s * kTcStageBytes;
+                if ((p.ablate & 4) && it >= kTcStages) { mbar_arrive(&full[s]); continue; }
                 mbar_expect_tx(&full[s], kTcTileBytes + 2 * b_tile_bytes);
-                tma_load_4d(st, &map_a, &full[s], c0, ox0 * p.in_stride + p.tap_dx[tap], oy0 * p.in_stride + p.tap_dy[tap], b);
+                const int wtap = p.tap_w[cls][tap];
+                tma_load_4d(st, &map_a, &full[s], c0, ox0 * p.in_stride + p.tap_dx[cls][tap], oy0 * p.in_stride + p.tap_dy[cls][tap], b);
                 if (CS == 1) {
-                    tma_load_4d(st + 2 * kTcTileBytes, &map_b, &full[s], c0, n0, tap, 0);
-                    tma_load_4d(st + 3 * kTcTileBytes, &map_b, &full[s], c0, n0, tap, 1);
+                    tma_load_4d(st + 2 * kTcTileBytes, &map_b, &full[s], c0, n0, wtap, 0);
+                    tma_load_4d(st + 3 * kTcTileBytes, &map_b, &full[s], c0, n0, wtap, 1);
                 } else {
                     // this CTA fetches rows [crank*n/CS, (crank+1)*n/CS) of both weight planes and multicasts them to the cluster
                     const int rows = p.n_tile / CS;
                     const uint32_t so = crank * (uint32_t)rows * 128u;
-                    tma_load_4d_mc(st + 2 * kTcTileBytes + so, &map_b, &full[s], c0, n0 + (int)crank * rows, tap, 0, kMask);
-                    tma_load_4d_mc(st + 3 * kTcTileBytes + so, &map_b, &full[s], c0, n0 + (int)crank * rows, tap, 1, kMask);
+                    tma_load_4d_mc(st + 2 * kTcTileBytes + so, &map_b, &full[s], c0, n0 + (int)crank * rows, wtap, 0, kMask);
+                    tma_load_4d_mc(st + 3 * kTcTileBytes + so, &map_b, &full[s], c0, n0 + (int)crank * rows, wtap, 1, kMask);
                 }
             }
         }
@@ -132,8 +139,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
                     const uint64_t dbh = make_sw128_desc(b_hi + ko), dbl = make_sw128_desc(b_lo + ko);
                     const uint32_t acc_small = tmem_base + 3 * (uint32_t)p.n_tile;
                     const uint32_t acc_main = tmem_base + (uint32_t)(it % 3) * (uint32_t)p.n_tile;
-                    tc_mma_tf32(acc_small, dal, dbh, idesc, (it | k) != 0);
-                    tc_mma_tf32(acc_small, dah, dbl, idesc, 1);
+                    if (!(p.ablate & 2)) {
+                        tc_mma_tf32(acc_small, dal, dbh, idesc, (it | k) != 0);
+                        tc_mma_tf32(acc_small, dah, dbl, idesc, 1);
+                    }
                     tc_mma_tf32(acc_main, dah, dbh, idesc, (it >= 3 || k != 0) ? 1u : 0u);
                 }
                 if (CS == 1) tc_commit(&empty[s]);                // smem stage reusable once these MMAs retire
@@ -151,6 +160,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
             mbar_wait(&full[s], ph);
             float4 *a = reinterpret_cast<float4 *>(tiles + s * kTcStageBytes);
             float4 *lo = reinterpret_cast<float4 *>(tiles + s * kTcStageBytes + kTcTileBytes);
+            if (p.ablate & 1) { mbar_arrive(&split[s]); continue; }
 #pragma unroll
             for (int j = 0; j < kTcTileBytes / 16 / 128; ++j) {    // 8 x 16-byte chunks per thread; layout agnostic
                 const int i = tid + j * 128;
@@ -173,7 +183,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
         const int r = q * 32 + lane;                // accumulator row == pixel within the patch
         const int gy = oy0 + r / kTcTileW, gx = ox0 + r % kTcTileW;
         const bool pix_ok = b < p.batch && gy < p.grid_h && gx < p.grid_w;
-        const size_t opix = (((size_t)b * p.out_h + (size_t)gy * p.out_stride + p.out_off_y) * p.out_w + (size_t)gx * p.out_stride + p.out_off_x);
+        const size_t opix = (((size_t)b * p.out_h + (size_t)gy * p.out_stride + p.cls_off_y[cls]) * p.out_w + (size_t)gx * p.out_stride + p.cls_off_x[cls]);
         const int nmain = steps < 3 ? steps : 3;     // main accumulators that were written at least once
         for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
             uint32_t v[32], u[32];
@@ -217,36 +227,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
 }
 
 static int g_conv_cluster = 1;
+static int g_conv_ablate = 0;
 
 }  // namespace sessd
 
 using namespace sessd;
 
-// Tensor-core variant of sessd_bev_conv.  d_weight_split: [2 (hi, lo)][ntaps][cout_pad][cin] with cout_pad a multiple of the N tile
-// (128, or 32 when cout <= 32); hi = tf32-truncated weights, lo = w - hi.  in_stride must be 1.
-extern "C" int sessd_bev_conv_tc(const float *d_in, const float *d_weight_split, int cout_pad, const float *d_scale, const float *d_shift,
-                                 const float *d_residual, float *d_out, const sessd_conv_desc *desc, void *stream) {
-    if (!d_in || !d_weight_split || !d_out || !desc) return SESSD_EINVAL;
-    const sessd_conv_desc &d = *desc;
-    const int n_tile = d.cout <= 32 ? 32 : 128;
-    if (d.batch < 1 || d.cin < kTcBK || d.cin % kTcBK || d.cout < 4 || d.cout % 4 || d.ntaps < 1 || d.ntaps > 16 || d.in_stride < 1 || d.in_stride > 2 ||
-        d.out_stride < 1 || d.grid_h < 1 || d.grid_w < 1 || cout_pad % n_tile || cout_pad < d.cout)
-        return SESSD_EINVAL;
-    if ((d.grid_h - 1) * d.out_stride + d.out_off_y >= d.out_h || (d.grid_w - 1) * d.out_stride + d.out_off_x >= d.out_w) return SESSD_EINVAL;
+static int launch_tc(const float *d_in, const float *d_w, int w_taps, int cout_pad, const float *d_scale, const float *d_shift,
+                     const float *d_residual, float *d_out, TcParams &p, void *stream) {
+    const int n_tile = p.cout <= 32 ? 32 : 128;
+    if (cout_pad % n_tile || cout_pad < p.cout) return SESSD_EINVAL;
     const int cs = (g_conv_cluster == 4 || g_conv_cluster == 2) ? g_conv_cluster : 1;
     CUtensorMap map_a, map_b;
     {
-        const cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)d.in_w, (cuuint64_t)d.in_h, (cuuint64_t)d.batch};
+        const cuuint64_t dims[4] = {(cuuint64_t)p.cin, (cuuint64_t)p.in_w, (cuuint64_t)p.in_h, (cuuint64_t)p.batch};
         // stride-2 conv: the box TRAVERSES 2x the tile extent with element stride 2 => still 16 x 8 pixels land in smem
-        const cuuint32_t box[4] = {kTcBK, (cuuint32_t)(kTcTileW * d.in_stride), (cuuint32_t)(kTcTileH * d.in_stride), 1};
-        const cuuint32_t estr[4] = {1, (cuuint32_t)d.in_stride, (cuuint32_t)d.in_stride, 1};
+        const cuuint32_t box[4] = {kTcBK, (cuuint32_t)(kTcTileW * p.in_stride), (cuuint32_t)(kTcTileH * p.in_stride), 1};
+        const cuuint32_t estr[4] = {1, (cuuint32_t)p.in_stride, (cuuint32_t)p.in_stride, 1};
         int rc = encode_map_4d(&map_a, d_in, dims, box, estr);
         if (rc) return rc;
     }
     {
-        const cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)cout_pad, (cuuint64_t)d.ntaps, 2};
+        const cuuint64_t dims[4] = {(cuuint64_t)p.cin, (cuuint64_t)cout_pad, (cuuint64_t)w_taps, 2};
         const cuuint32_t box[4] = {kTcBK, (cuuint32_t)(n_tile / cs), 1, 1};
-        int rc = encode_map_4d(&map_b, d_weight_split, dims, box);
+        int rc = encode_map_4d(&map_b, d_w, dims, box);
         if (rc) return rc;
     }
     static bool attr_done = false;
@@ -256,20 +260,12 @@ extern "C" int sessd_bev_conv_tc(const float *d_in, const float *d_weight_split,
         SESSD_CUDA_TRY(cudaFuncSetAttribute(bev_conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
         attr_done = true;
     }
-    TcParams p;
-    p.batch = d.batch; p.in_h = d.in_h; p.in_w = d.in_w; p.cin = d.cin;
-    p.out_h = d.out_h; p.out_w = d.out_w; p.cout = d.cout;
-    p.grid_h = d.grid_h; p.grid_w = d.grid_w;
-    p.out_stride = d.out_stride; p.out_off_y = d.out_off_y; p.out_off_x = d.out_off_x;
-    p.ntaps = d.ntaps;
-    for (int t = 0; t < 16; ++t) { p.tap_dy[t] = d.tap_dy[t]; p.tap_dx[t] = d.tap_dx[t]; }
-    p.relu = d.relu;
     p.n_tile = n_tile;
-    p.in_stride = d.in_stride;
-    p.tiles_x = div_up(d.grid_w, kTcTileW);
-    p.tiles_y = div_up(d.grid_h, kTcTileH);
-    const int tiles = p.tiles_x * p.tiles_y * d.batch;
-    dim3 grid(div_up(tiles, cs) * cs, cout_pad / n_tile);     // padded tiles decode to image index >= batch: TMA zero-fills, stores masked
+    p.ablate = g_conv_ablate;
+    p.tiles_x = div_up(p.grid_w, kTcTileW);
+    p.tiles_y = div_up(p.grid_h, kTcTileH);
+    const int tiles = p.tiles_x * p.tiles_y * p.batch;
+    dim3 grid(div_up(tiles, cs) * cs, cout_pad / n_tile, p.nclass);   // padded tiles decode to image index >= batch: masked
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(kTcThreads);
@@ -289,6 +285,65 @@ extern "C" int sessd_bev_conv_tc(const float *d_in, const float *d_weight_split,
     return last_error();
 }
 
+// Tensor-core variant of sessd_bev_conv.  d_weight_split: [2 (hi, lo)][ntaps][cout_pad][cin] with cout_pad a multiple of the N tile
+// (128, or 32 when cout <= 32); hi = tf32-truncated weights, lo = w - hi.
+extern "C" int sessd_bev_conv_tc(const float *d_in, const float *d_weight_split, int cout_pad, const float *d_scale, const float *d_shift,
+                                 const float *d_residual, float *d_out, const sessd_conv_desc *desc, void *stream) {
+    if (!d_in || !d_weight_split || !d_out || !desc) return SESSD_EINVAL;
+    const sessd_conv_desc &d = *desc;
+    if (d.batch < 1 || d.cin < kTcBK || d.cin % kTcBK || d.cout < 4 || d.cout % 4 || d.ntaps < 1 || d.ntaps > 9 || d.in_stride < 1 || d.in_stride > 2 ||
+        d.out_stride < 1 || d.grid_h < 1 || d.grid_w < 1)
+        return SESSD_EINVAL;
+    if ((d.grid_h - 1) * d.out_stride + d.out_off_y >= d.out_h || (d.grid_w - 1) * d.out_stride + d.out_off_x >= d.out_w) return SESSD_EINVAL;
+    TcParams p = {};
+    p.batch = d.batch; p.in_h = d.in_h; p.in_w = d.in_w; p.cin = d.cin;
+    p.out_h = d.out_h; p.out_w = d.out_w; p.cout = d.cout;
+    p.grid_h = d.grid_h; p.grid_w = d.grid_w;
+    p.out_stride = d.out_stride;
+    p.relu = d.relu;
+    p.in_stride = d.in_stride;
+    p.nclass = 1;
+    p.cls_ntaps[0] = d.ntaps; p.cls_off_y[0] = d.out_off_y; p.cls_off_x[0] = d.out_off_x;
+    for (int t = 0; t < d.ntaps; ++t) { p.tap_dy[0][t] = d.tap_dy[t]; p.tap_dx[0][t] = d.tap_dx[t]; p.tap_w[0][t] = t; }
+    return launch_tc(d_in, d_weight_split, d.ntaps, cout_pad, d_scale, d_shift, d_residual, d_out, p, stream);
+}
+
+// ConvTranspose2d(kernel 3, stride 2, padding 1, output_padding 1) + BN + ReLU (+ residual) in ONE launch: the four output-parity
+// classes (1/2/2/4 taps, no multiplications by the zero-stuffed grid) run as blockIdx.z over the same input and the same weight tensor.
+// d_weight_split: [2][9][cout_pad][cin] with tap index ky*3+kx of the transposed-conv kernel W[cin][cout][ky][kx].
+// Output is [batch, 2*in_h, 2*in_w, cout] NHWC.   (det3d/models/necks/rpn_v1.py:183-195)
+extern "C" int sessd_bev_deconv_tc(const float *d_in, const float *d_weight_split, int cout_pad, const float *d_scale, const float *d_shift,
+                                   const float *d_residual, float *d_out, int batch, int in_h, int in_w, int cin, int cout, int relu,
+                                   void *stream) {
+    if (!d_in || !d_weight_split || !d_out || batch < 1 || in_h < 1 || in_w < 1 || cin < kTcBK || cin % kTcBK || cout < 4 || cout % 4) return SESSD_EINVAL;
+    TcParams p = {};
+    p.batch = batch; p.in_h = in_h; p.in_w = in_w; p.cin = cin;
+    p.out_h = 2 * in_h; p.out_w = 2 * in_w; p.cout = cout;
+    p.grid_h = in_h; p.grid_w = in_w;
+    p.out_stride = 2;
+    p.relu = relu;
+    p.in_stride = 1;
+    p.nclass = 4;
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+            const int c = py * 2 + px;
+            p.cls_off_y[c] = py; p.cls_off_x[c] = px;
+            // out[2y+py] receives in[y+dy] * W[ky] with 2y+py = 2(y+dy) - 1 + ky:  py=0 -> (ky=1,dy=0);  py=1 -> (ky=0,dy=1), (ky=2,dy=0)
+            const int kys[2] = {py == 0 ? 1 : 0, 2}, dys[2] = {py == 0 ? 0 : 1, 0}, ny = py == 0 ? 1 : 2;
+            const int kxs[2] = {px == 0 ? 1 : 0, 2}, dxs[2] = {px == 0 ? 0 : 1, 0}, nx = px == 0 ? 1 : 2;
+            int t = 0;
+            for (int a = 0; a < ny; ++a)
+                for (int b = 0; b < nx; ++b) {
+                    p.tap_dy[c][t] = dys[a]; p.tap_dx[c][t] = dxs[b]; p.tap_w[c][t] = kys[a] * 3 + kxs[b];
+                    ++t;
+                }
+            p.cls_ntaps[c] = t;
+        }
+    return launch_tc(d_in, d_weight_split, 9, cout_pad, d_scale, d_shift, d_residual, d_out, p, stream);
+}
+
 // tunable: CTAs per cluster that share (TMA-multicast) the weight tiles of sessd_bev_conv_tc: 1, 2 or 4
 extern "C" void sessd_set_conv_cluster(int cs) { sessd::g_conv_cluster = cs; }
 extern "C" int sessd_get_conv_cluster(void) { return sessd::g_conv_cluster; }
+// negative values select timing-ablation modes of the conv kernel (profiling experiments only)
+extern "C" void sessd_set_conv_ablate(int m) { sessd::g_conv_ablate = m; }

@@ -61,8 +61,10 @@ SIGNATURES = {
     "sessd_sparse_to_dense": (_i, [_vp, _vp, _vp, _i, _i, Grid, _vp, _vp]),
     "sessd_bev_conv": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(ConvDesc), _vp]),
     "sessd_bev_conv_tc": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, C.POINTER(ConvDesc), _vp]),
+    "sessd_bev_deconv_tc": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "sessd_set_conv_cluster": (None, [_i]),
     "sessd_get_conv_cluster": (_i, []),
+    "sessd_set_conv_ablate": (None, [_i]),
     "sessd_ssfa_fuse": (_i, [_vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _i, _vp, _vp]),
     "sessd_postprocess_workspace_bytes": (_sz, [C.POINTER(PostCfg)]),
     "sessd_postprocess": (_i, [_vp, _vp, _vp, C.POINTER(PostCfg), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -213,6 +213,15 @@ def bev_conv_tc(x, weight_split, scale, shift, residual, out, desc):
     return out
 
 
+def bev_deconv_tc(x, weight_split, scale, shift, residual, out, relu=True):
+    """ConvTranspose2d(k3,s2,p1,op1)+BN+ReLU(+residual): x [B,H,W,Cin] -> out [B,2H,2W,Cout]; weight_split from
+    pack_weight_tc(W.permute(2,3,0,1).reshape(9,Cin,Cout), cout_pad)."""
+    b, h, w, cin = x.shape
+    check(lib.sessd_bev_deconv_tc(_p(x), _p(weight_split), int(weight_split.shape[2]), _p(scale), _p(shift), _p(residual), _p(out),
+                                  int(b), int(h), int(w), int(cin), int(out.shape[-1]), int(bool(relu)), _st()), "sessd_bev_deconv_tc")
+    return out
+
+
 def set_conv_cluster(n):
     """CTAs per cluster sharing weight tiles via TMA multicast in bev_conv_tc (1, 2 or 4)."""
     lib.sessd_set_conv_cluster(int(n))

@@ -238,8 +238,9 @@ class SSFARunner:
         for name in ("deconv_block_0.0", "deconv_block_1.0"):
             classes = _deconv_classes(g(name + ".weight"))
             P[name] = (classes,) + bn(name)
-            if self.use_tc:
-                P[name + ":tc"] = [ops.pack_weight_tc(wp, 128) for _py, _px, wp, _t in classes]
+            if self.use_tc:     # one launch for the four parity classes: plain 9-tap packing of W[cin][cout][ky][kx]
+                wd = g(name + ".weight")
+                P[name + ":tc"] = ops.pack_weight_tc(wd.permute(2, 3, 0, 1).reshape(9, wd.shape[0], wd.shape[1]).contiguous(), 128)
         for name in ("w_0.0", "w_1.0"):
             sc, sh = bn(name)
             P[name] = (g(name + ".weight").reshape(-1).contiguous(), float(sc[0]), float(sh[0]))
@@ -260,12 +261,11 @@ class SSFARunner:
     def _deconv(self, name, x, out, in_hw, out_hw, cin, cout, residual=None):
         classes, sc, sh = self.params[name]
         tc = self.params.get(name + ":tc")
-        for ci, (py, px, wp, taps) in enumerate(classes):
+        if tc is not None:
+            return ops.bev_deconv_tc(x, tc, sc, sh, residual, out, relu=True)
+        for py, px, wp, taps in classes:
             d = ops.conv_desc(self.batch, in_hw, cin, out_hw, cout, in_hw, taps, in_stride=1, out_stride=2, out_off=(py, px), relu=True)
-            if tc is not None:
-                ops.bev_conv_tc(x, tc[ci], sc, sh, residual, out, d)
-            else:
-                ops.bev_conv(x, wp, sc, sh, residual, out, d)
+            ops.bev_conv(x, wp, sc, sh, residual, out, d)
         return out
 
     def forward(self, x):

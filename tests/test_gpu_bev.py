@@ -98,3 +98,25 @@ def test_tf32_split_is_exact():
     hi, lo = ops.split_tf32(w)
     assert torch.equal(hi + lo, w)
     assert int((hi.view(torch.int32) & 8191).abs().max()) == 0
+
+
+@pytest.mark.parametrize("hw", [(13, 17), (100, 88)])
+def test_deconv_single_launch_vs_fp64(hw):
+    """ConvTranspose2d(k3,s2,p1,op1)+BN+ReLU+residual as one 4-class tensor-core launch."""
+    import torch.nn.functional as F
+    from sessd_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    b, cin, cout = 2, 256, 128
+    x = torch.randn(b, cin, hw[0], hw[1], generator=g)
+    w = torch.randn(cin, cout, 3, 3, generator=g) * (2.0 / (cin * 2.25)) ** 0.5
+    sc = 1.0 + 0.1 * torch.randn(cout, generator=g)
+    sh = 0.1 * torch.randn(cout, generator=g)
+    res = torch.randn(b, cout, 2 * hw[0], 2 * hw[1], generator=g)
+    ref = F.relu(F.conv_transpose2d(x.double(), w.double(), None, 2, 1, output_padding=1) * sc.double().view(1, -1, 1, 1)
+                 + sh.double().view(1, -1, 1, 1)) + res.double()
+    wt = ops.pack_weight_tc(w.permute(2, 3, 0, 1).reshape(9, cin, cout).contiguous().cuda(), 128)
+    out = torch.zeros((b, 2 * hw[0], 2 * hw[1], cout), device="cuda")
+    ops.bev_deconv_tc(x.permute(0, 2, 3, 1).contiguous().cuda(), wt, sc.cuda(), sh.cuda(), res.permute(0, 2, 3, 1).contiguous().cuda(), out)
+    torch.cuda.synchronize()
+    got = out.permute(0, 3, 1, 2).cpu().double()
+    assert float((got - ref).abs().max() / ref.abs().max()) < 5e-6
