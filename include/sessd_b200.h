@@ -172,8 +172,12 @@ int sessd_bev_deconv_tc(const float *d_in, const float *d_weight_split, int cout
 /* tunable of sessd_bev_conv_tc: CTAs per thread-block cluster sharing the weight tiles through TMA multicast (1, 2 or 4) */
 void sessd_set_conv_cluster(int ctas_per_cluster);
 int sessd_get_conv_cluster(void);
+/* 1: A operand staged in shared memory, 2: A operand staged in tensor memory (less smem traffic) */
+void sessd_set_conv_variant(int variant);
 /* profiling experiments only: bit mask of pipeline stages to skip inside bev_conv_tc (results are garbage when non-zero) */
 void sessd_set_conv_ablate(int mask);
+/* profiling experiments only: device buffer [ctas][8] int64 receiving per-CTA globaltimer stamps of bev_conv_tc (NULL = off) */
+void sessd_set_conv_debug_buffer(void *d_buf);
 
 /* SSFA tail (rpn_v1.py:229-233): w_k = BN(conv1x1_{128->1}(x_k)); softmax over the pair; weighted sum */
 int sessd_ssfa_fuse(const float *d_x0, const float *d_x1, const float *d_w0 /*[C]*/, const float *d_w1,

@@ -28,6 +28,11 @@ def bench(name, cin, cout, hw_in, hw_out, taps, stride=1, reps=10):
     print("%-34s GF=%6.2f  us: cs1=%6.1f cs2=%6.1f cs4=%6.1f   TF/s(best)=%6.1f" % (name, fl / 1e9, res[1], res[2], res[4], fl / min(res.values()) / 1e6))
 
 t3 = [(dy - 1, dx - 1) for dy in range(3) for dx in range(3)]
+from sessd_b200._lib import lib
+import sys as _s
+variant = int(_s.argv[1]) if len(_s.argv) > 1 else 1
+lib.sessd_set_conv_variant(variant)
+print("=== conv variant", variant)
 bench("conv3x3 128->128 @200x176", 128, 128, (200, 176), (200, 176), t3)
 bench("conv3x3 s2 128->256 -> 100x88", 128, 256, (200, 176), (100, 88), t3, stride=2)
 bench("conv3x3 256->256 @100x88", 256, 256, (100, 88), (100, 88), t3)
@@ -37,7 +42,6 @@ bench("deconv class(4 taps) 256->128", 256, 128, (100, 88), (100, 88), [(0, 0), 
 bench("head 128->24 @200x176", 128, 24, (200, 176), (200, 176), [(0, 0)])
 
 print("--- ablations on conv3x3 128->128 @200x176 (cluster 1): 1=no split, 2=hi*hi only, 4=no TMA reloads")
-from sessd_b200._lib import lib
 ops.set_conv_cluster(1)
 x = torch.randn(1, 200, 176, 128, device="cuda"); wp = torch.randn(9, 128, 128, device="cuda") * 0.05
 wt = ops.pack_weight_tc(wp, 128); out = torch.zeros(1, 200, 176, 128, device="cuda")
@@ -53,3 +57,26 @@ for mode in (0, 1, 2, 4, 3, 5, 6, 7):
         ts.append(a.elapsed_time(b))
     print("ablate=%d  %.1f us" % (mode, float(np.median(ts[2:])) * 1000))
 lib.sessd_set_conv_ablate(0)
+
+print("--- per-CTA timeline (globaltimer ns): setup, first TMA, mainloop, epilogue")
+import ctypes
+for name, cin, cout, hw, taps in (("conv3x3 128->128 @200x176", 128, 128, (200, 176), t3), ("conv1x1 128->128 @200x176", 128, 128, (200, 176), [(0, 0)])):
+    x = torch.randn(1, hw[0], hw[1], cin, device="cuda"); wp = torch.randn(len(taps), cin, cout, device="cuda") * 0.05
+    wt = ops.pack_weight_tc(wp, 128); out = torch.zeros(1, hw[0], hw[1], cout, device="cuda")
+    d = ops.conv_desc(1, hw, cin, hw, cout, hw, taps, relu=True)
+    dbg = torch.zeros((400, 8), dtype=torch.int64, device="cuda")
+    for i in range(2):
+        ops.bev_conv_tc(x, wt, None, None, None, out, d)
+    torch.cuda.synchronize()
+    lib.sessd_set_conv_debug_buffer(ctypes.c_void_p(dbg.data_ptr()))
+    ops.bev_conv_tc(x, wt, None, None, None, out, d)
+    torch.cuda.synchronize()
+    lib.sessd_set_conv_debug_buffer(ctypes.c_void_p(0))
+    t = dbg[:275].cpu().numpy().astype(np.float64)
+    t0 = t[:, 0].min()
+    print(name, "kernel span %.1f us" % ((t[:, 4].max() - t0) / 1000))
+    for lbl, a, b in (("setup", 0, 1), ("first TMA", 1, 2), ("mainloop", 2, 3), ("epilogue", 3, 4), ("CTA total", 0, 4)):
+        dt = (t[:, b] - t[:, a]) / 1000
+        print("   %-10s median %.2f us  (min %.2f max %.2f)" % (lbl, np.median(dt), dt.min(), dt.max()))
+    st = (t[:, 0] - t0) / 1000
+    print("   CTA start times: first wave <1us: %d, later: median %.1f us" % (int((st < 1).sum()), float(np.median(st[st >= 1])) if (st >= 1).any() else 0))

@@ -49,6 +49,7 @@ struct TcParams {
     int relu;
     int n_tile;          // 128 or 32: UMMA N and rows of each B tile
     int in_stride;       // 1 or 2 (strided TMA box for the stride-2 conv)
+    long long *dbg;      // optional [ctas][8] globaltimer stamps (profiling experiments)
     int ablate;          // timing experiments only (results become garbage): 1 skip the hi/lo split, 2 hi*hi product only, 4 no TMA reloads
     int tiles_x, tiles_y;
 };
@@ -66,6 +67,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
     uint32_t *tmem_slot = (uint32_t *)(bars + 3 * kTcStages + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto stamp = [&](int slot) {
+        if (p.dbg) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            p.dbg[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + slot] = (long long)t;
+        }
+    };
+    if (threadIdx.x == 0) stamp(0);
     // tile coordinates
     int t = blockIdx.x;
     const int tx = t % p.tiles_x; t /= p.tiles_x;
@@ -94,6 +103,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
     if (CS > 1) cluster_sync_all();        // peers' barriers must be initialised before any multicast / remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) stamp(1);                      // setup done (barriers, TMEM alloc)
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -127,6 +137,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
             const int s = it % kTcStages;
             const uint32_t ph = (it / kTcStages) & 1;
             mbar_wait(&full[s], ph);
+            if (it == 0 && lane == 0) stamp(2);            // first TMA stage landed
             mbar_wait(&split[s], ph);
             tc_fence_after();
             if (lane == 0) {
@@ -179,6 +190,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
         // ---- epilogue: TMEM -> registers -> BN/ReLU/residual -> global ----
         mbar_wait(acc_full, 0);
         tc_fence_after();
+        if (threadIdx.x == 64) stamp(3);            // accumulators complete
         const int q = warp & 3;                     // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;                // accumulator row == pixel within the patch
         const int gy = oy0 + r / kTcTileW, gx = ox0 + r % kTcTileW;
@@ -220,14 +232,183 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) stamp(4);        // epilogue done
     if (CS > 1) cluster_sync_all();        // nobody exits while a peer may still multicast into / arrive on this CTA
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
+
+// ================================================================================================================
+// Variant 2: A operand in TENSOR MEMORY.  Timeline measurements of the variant above (profiles/) show the main loop is bound by
+// shared-memory bandwidth (128 B/clk/SM): per k-step the tensor core fetches 12 x (4 KB A + 4 KB B) of operands from smem, the
+// split warps read 16 KB and write 32 KB, TMA writes 48 KB => 192 KB => ~1500 clk, measured 1540.  Here the split warps write
+// a_hi / a_lo straight into TMEM (tcgen05.st) and the MMAs take A from TMEM, so smem only carries the TMA writes (48 KB), one read of
+// the raw A tile (16 KB) and the B operand fetches (48 KB): 112 KB per k-step.  Stages shrink to 48 KB => 4 stages.
+// TMEM columns: [0,N) main0 | [N,2N) main1 | [2N,3N) cross terms | [384,448) A slot 0 (hi 32 | lo 32) | [448,512) A slot 1.
+// ================================================================================================================
+constexpr int kV2Stages = 4;
+constexpr int kV2StageBytes = 3 * kTcTileBytes;        // A raw, B_hi, B_lo
+constexpr int kV2SmemBytes = kV2Stages * kV2StageBytes + 1024 + 256;
+constexpr uint32_t kV2ACol = 384;
+
+__global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                     const __grid_constant__ CUtensorMap map_b,
+                                                                     const float *__restrict__ scale, const float *__restrict__ shift,
+                                                                     const float *__restrict__ resid, float *__restrict__ out, TcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *tiles = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = (uint64_t *)(tiles + kV2Stages * kV2StageBytes);
+    uint64_t *full = bars, *split = bars + kV2Stages, *empty = bars + 2 * kV2Stages, *a_free = bars + 3 * kV2Stages;   // a_free[2]
+    uint64_t *acc_full = bars + 3 * kV2Stages + 2;
+    uint32_t *tmem_slot = (uint32_t *)(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int t = blockIdx.x;
+    const int tx = t % p.tiles_x; t /= p.tiles_x;
+    const int ty = t % p.tiles_y;
+    const int b = t / p.tiles_y;
+    const int oy0 = ty * kTcTileH, ox0 = tx * kTcTileW;
+    const int n0 = blockIdx.y * p.n_tile;
+    const int cls = blockIdx.z;
+    const int kchunks = p.cin / kTcBK;
+    const int steps = p.cls_ntaps[cls] * kchunks;
+    const uint32_t b_tile_bytes = (uint32_t)p.n_tile * kTcBK * 4;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kV2Stages; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 128); mbar_init(&empty[s], 1); }
+        mbar_init(&a_free[0], 1); mbar_init(&a_free[1], 1);
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < steps; ++it) {
+                const int s = it % kV2Stages;
+                const uint32_t ph = (it / kV2Stages) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                const int tap = it / kchunks, c0 = (it - tap * kchunks) * kTcBK;
+                const int wtap = p.tap_w[cls][tap];
+                unsigned char *st = tiles + s * kV2StageBytes;
+                mbar_expect_tx(&full[s], kTcTileBytes + 2 * b_tile_bytes);
+                tma_load_4d(st, &map_a, &full[s], c0, ox0 * p.in_stride + p.tap_dx[cls][tap], oy0 * p.in_stride + p.tap_dy[cls][tap], b);
+                tma_load_4d(st + kTcTileBytes, &map_b, &full[s], c0, n0, wtap, 0);
+                tma_load_4d(st + 2 * kTcTileBytes, &map_b, &full[s], c0, n0, wtap, 1);
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = make_idesc_tf32(kTcBM, p.n_tile);
+        const uint32_t acc_cross = tmem_base + 2 * (uint32_t)p.n_tile;
+        for (int it = 0; it < steps; ++it) {
+            const int s = it % kV2Stages;
+            const uint32_t ph = (it / kV2Stages) & 1;
+            mbar_wait(&full[s], ph);
+            mbar_wait(&split[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t b_hi = smem_u32(tiles + s * kV2StageBytes) + kTcTileBytes, b_lo = b_hi + kTcTileBytes;
+                const uint32_t a_hi = tmem_base + kV2ACol + (uint32_t)(it & 1) * 64u, a_lo = a_hi + 32u;
+                const uint32_t acc_main = tmem_base + (uint32_t)(it & 1) * (uint32_t)p.n_tile;
+#pragma unroll
+                for (int k = 0; k < kTcBK / 8; ++k) {
+                    const uint64_t dbh = make_sw128_desc(b_hi + k * 32), dbl = make_sw128_desc(b_lo + k * 32);
+                    tc_mma_tf32_ts(acc_cross, a_lo + k * 8, dbh, idesc, (it | k) != 0);
+                    tc_mma_tf32_ts(acc_cross, a_hi + k * 8, dbl, idesc, 1);
+                    tc_mma_tf32_ts(acc_main, a_hi + k * 8, dbh, idesc, (it >= 2 || k != 0) ? 1u : 0u);
+                }
+                tc_commit(&empty[s]);
+                tc_commit(&a_free[it & 1]);
+                if (it == steps - 1) tc_commit(acc_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;                 // the tile row (TMEM lane) this thread owns
+        for (int it = 0; it < steps; ++it) {
+            const int s = it % kV2Stages;
+            const uint32_t ph = (it / kV2Stages) & 1;
+            mbar_wait(&full[s], ph);
+            const unsigned char *a = tiles + s * kV2StageBytes + r * 128;
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {            // row r of the SWIZZLE_128B tile: logical chunk c sits at chunk c ^ (r & 7)
+                const float4 v = *reinterpret_cast<const float4 *>(a + ((c ^ (r & 7)) << 4));
+                const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t h = __float_as_uint(x[e]) & 0xFFFFE000u;
+                    hi[c * 4 + e] = h;
+                    lo[c * 4 + e] = __float_as_uint(x[e] - __uint_as_float(h));
+                }
+            }
+            // the A slot (it & 1) was last read by the MMAs of step it-2
+            if (it >= 2) mbar_wait(&a_free[it & 1], ((it >> 1) - 1) & 1);
+            tc_fence_after();
+            const uint32_t a_hi = tmem_base + ((uint32_t)(q * 32) << 16) + kV2ACol + (uint32_t)(it & 1) * 64u;
+            tmem_st_32x32b_x32(a_hi, hi);
+            tmem_st_32x32b_x32(a_hi + 32u, lo);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&split[s]);
+        }
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int gy = oy0 + r / kTcTileW, gx = ox0 + r % kTcTileW;
+        const bool pix_ok = b < p.batch && gy < p.grid_h && gx < p.grid_w;
+        const size_t opix = (((size_t)b * p.out_h + (size_t)gy * p.out_stride + p.cls_off_y[cls]) * p.out_w + (size_t)gx * p.out_stride + p.cls_off_x[cls]);
+        for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+            uint32_t v[32], u[32];
+            const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            tmem_ld_32x32b_x32(lane_base, v);
+            tmem_ld_32x32b_x32(lane_base + 2 * (uint32_t)p.n_tile, u);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+            if (steps > 1) {
+                tmem_ld_32x32b_x32(lane_base + (uint32_t)p.n_tile, u);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+            }
+            if (!pix_ok) continue;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const int n = n0 + c0 + j;
+                if (n >= p.cout) break;
+                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (scale) sc = *reinterpret_cast<const float4 *>(scale + n);
+                if (shift) sh = *reinterpret_cast<const float4 *>(shift + n);
+                float4 o;
+                o.x = fmaf(__uint_as_float(v[j + 0]), sc.x, sh.x); o.y = fmaf(__uint_as_float(v[j + 1]), sc.y, sh.y);
+                o.z = fmaf(__uint_as_float(v[j + 2]), sc.z, sh.z); o.w = fmaf(__uint_as_float(v[j + 3]), sc.w, sh.w);
+                if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                const size_t off = opix * p.cout + n;
+                if (resid) {
+                    const float4 rr = *reinterpret_cast<const float4 *>(resid + off);
+                    o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                }
+                *reinterpret_cast<float4 *>(out + off) = o;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+static int g_conv_variant = 1;     // 1: A operand from shared memory (kernel above), 2: A operand from tensor memory
 static int g_conv_cluster = 1;
 static int g_conv_ablate = 0;
+static long long *g_conv_dbg = nullptr;
 
 }  // namespace sessd
 
@@ -237,7 +418,7 @@ static int launch_tc(const float *d_in, const float *d_w, int w_taps, int cout_p
                      const float *d_residual, float *d_out, TcParams &p, void *stream) {
     const int n_tile = p.cout <= 32 ? 32 : 128;
     if (cout_pad % n_tile || cout_pad < p.cout) return SESSD_EINVAL;
-    const int cs = (g_conv_cluster == 4 || g_conv_cluster == 2) ? g_conv_cluster : 1;
+    const int cs = (g_conv_variant == 2) ? 1 : (g_conv_cluster == 4 || g_conv_cluster == 2) ? g_conv_cluster : 1;
     CUtensorMap map_a, map_b;
     {
         const cuuint64_t dims[4] = {(cuuint64_t)p.cin, (cuuint64_t)p.in_w, (cuuint64_t)p.in_h, (cuuint64_t)p.batch};
@@ -262,6 +443,7 @@ static int launch_tc(const float *d_in, const float *d_w, int w_taps, int cout_p
     }
     p.n_tile = n_tile;
     p.ablate = g_conv_ablate;
+    p.dbg = g_conv_dbg;
     p.tiles_x = div_up(p.grid_w, kTcTileW);
     p.tiles_y = div_up(p.grid_h, kTcTileH);
     const int tiles = p.tiles_x * p.tiles_y * p.batch;
@@ -277,7 +459,14 @@ static int launch_tc(const float *d_in, const float *d_w, int w_taps, int cout_p
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e;
-    if (cs == 4) e = cudaLaunchKernelEx(&cfg, bev_conv_tc_kernel<4>, map_a, map_b, d_scale, d_shift, d_residual, d_out, p);
+    if (g_conv_variant == 2) {
+        static bool attr2 = false;
+        if (!attr2) { SESSD_CUDA_TRY(cudaFuncSetAttribute(bev_conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kV2SmemBytes)); attr2 = true; }
+        cfg.gridDim = dim3(tiles, cout_pad / n_tile, p.nclass);
+        cfg.dynamicSmemBytes = kV2SmemBytes;
+        attr[0].val.clusterDim.x = 1;
+        e = cudaLaunchKernelEx(&cfg, bev_conv_tc2_kernel, map_a, map_b, d_scale, d_shift, d_residual, d_out, p);
+    } else if (cs == 4) e = cudaLaunchKernelEx(&cfg, bev_conv_tc_kernel<4>, map_a, map_b, d_scale, d_shift, d_residual, d_out, p);
     else if (cs == 2) e = cudaLaunchKernelEx(&cfg, bev_conv_tc_kernel<2>, map_a, map_b, d_scale, d_shift, d_residual, d_out, p);
     else e = cudaLaunchKernelEx(&cfg, bev_conv_tc_kernel<1>, map_a, map_b, d_scale, d_shift, d_residual, d_out, p);
     ++g_launches;
@@ -346,4 +535,6 @@ extern "C" int sessd_bev_deconv_tc(const float *d_in, const float *d_weight_spli
 extern "C" void sessd_set_conv_cluster(int cs) { sessd::g_conv_cluster = cs; }
 extern "C" int sessd_get_conv_cluster(void) { return sessd::g_conv_cluster; }
 // negative values select timing-ablation modes of the conv kernel (profiling experiments only)
+extern "C" void sessd_set_conv_variant(int v) { sessd::g_conv_variant = v; }
 extern "C" void sessd_set_conv_ablate(int m) { sessd::g_conv_ablate = m; }
+extern "C" void sessd_set_conv_debug_buffer(void *d_buf) { sessd::g_conv_dbg = (long long *)d_buf; }

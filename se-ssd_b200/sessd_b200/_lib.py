@@ -65,6 +65,8 @@ SIGNATURES = {
     "sessd_set_conv_cluster": (None, [_i]),
     "sessd_get_conv_cluster": (_i, []),
     "sessd_set_conv_ablate": (None, [_i]),
+    "sessd_set_conv_variant": (None, [_i]),
+    "sessd_set_conv_debug_buffer": (None, [_vp]),
     "sessd_ssfa_fuse": (_i, [_vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _i, _vp, _vp]),
     "sessd_postprocess_workspace_bytes": (_sz, [C.POINTER(PostCfg)]),
     "sessd_postprocess": (_i, [_vp, _vp, _vp, C.POINTER(PostCfg), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
