@@ -176,6 +176,9 @@ int sessd_get_conv_cluster(void);
 void sessd_set_conv_variant(int variant);
 /* profiling experiments only: bit mask of pipeline stages to skip inside bev_conv_tc (results are garbage when non-zero) */
 void sessd_set_conv_ablate(int mask);
+/* profiling aid: sustained tcgen05.mma kind::tf32 rate (M=128, N=n) of one CTA per SM; mode bit0 = A from TMEM, bit1 = two rotating
+ * accumulators; d_out[0..2] = issue cycles, cycles to retire, ns */
+int sessd_mma_probe(int n, int iters, int mode, long long *d_out, void *stream);
 /* profiling experiments only: device buffer [ctas][8] int64 receiving per-CTA globaltimer stamps of bev_conv_tc (NULL = off) */
 void sessd_set_conv_debug_buffer(void *d_buf);
 

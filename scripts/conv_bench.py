@@ -64,7 +64,7 @@ for name, cin, cout, hw, taps in (("conv3x3 128->128 @200x176", 128, 128, (200, 
     x = torch.randn(1, hw[0], hw[1], cin, device="cuda"); wp = torch.randn(len(taps), cin, cout, device="cuda") * 0.05
     wt = ops.pack_weight_tc(wp, 128); out = torch.zeros(1, hw[0], hw[1], cout, device="cuda")
     d = ops.conv_desc(1, hw, cin, hw, cout, hw, taps, relu=True)
-    dbg = torch.zeros((400, 8), dtype=torch.int64, device="cuda")
+    dbg = torch.zeros((1024, 8), dtype=torch.int64, device="cuda")
     for i in range(2):
         ops.bev_conv_tc(x, wt, None, None, None, out, d)
     torch.cuda.synchronize()
@@ -80,3 +80,11 @@ for name, cin, cout, hw, taps in (("conv3x3 128->128 @200x176", 128, 128, (200, 
         print("   %-10s median %.2f us  (min %.2f max %.2f)" % (lbl, np.median(dt), dt.min(), dt.max()))
     st = (t[:, 0] - t0) / 1000
     print("   CTA start times: first wave <1us: %d, later: median %.1f us" % (int((st < 1).sum()), float(np.median(st[st >= 1])) if (st >= 1).any() else 0))
+
+    if variant == 1:
+        tr = dbg.view(-1)[4096:4096 + 36 * 8].cpu().numpy().reshape(36, 8).astype(np.float64)
+        base = tr[0, 0]
+        print("   step trace CTA0 (us since first producer issue): P=producer got empty, Cf=conv got full, Cd=conv done, Mf=mma got full, Ms=mma got split, Mi=mma issued")
+        for it in list(range(0, min(12, len(taps) * (cin // 32)))):
+            r = (tr[it, :6] - base) / 1000
+            print("   it=%2d  P=%6.2f Cf=%6.2f Cd=%6.2f Mf=%6.2f Ms=%6.2f Mi=%6.2f" % (it, r[0], r[1], r[2], r[3], r[4], r[5]))

@@ -74,6 +74,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
             p.dbg[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + slot] = (long long)t;
         }
     };
+    auto trace = [&](int it, int slot) {
+        if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it < 128) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            p.dbg[4096 + it * 8 + slot] = (long long)t;
+        }
+    };
     if (threadIdx.x == 0) stamp(0);
     // tile coordinates
     int t = blockIdx.x;
@@ -112,6 +119,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
                 const int s = it % kTcStages;
                 const uint32_t ph = (it / kTcStages) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
+                trace(it, 0);
                 const int tap = it / kchunks, c0 = (it - tap * kchunks) * kTcBK;
                 unsigned char *st = tiles + s * kTcStageBytes;
                 if ((p.ablate & 4) && it >= kTcStages) { mbar_arrive(&full[s]); continue; }
@@ -138,8 +146,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
             const uint32_t ph = (it / kTcStages) & 1;
             mbar_wait(&full[s], ph);
             if (it == 0 && lane == 0) stamp(2);            // first TMA stage landed
+            if (lane == 0) trace(it, 3);
             mbar_wait(&split[s], ph);
             tc_fence_after();
+            if (lane == 0) trace(it, 4);
             if (lane == 0) {
                 const uint32_t a_hi = smem_u32(tiles + s * kTcStageBytes);
                 const uint32_t a_lo = a_hi + kTcTileBytes, b_hi = a_hi + 2 * kTcTileBytes, b_lo = a_hi + 3 * kTcTileBytes;
@@ -156,6 +166,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
                     }
                     tc_mma_tf32(acc_main, dah, dbh, idesc, (it >= 3 || k != 0) ? 1u : 0u);
                 }
+                trace(it, 5);
                 if (CS == 1) tc_commit(&empty[s]);                // smem stage reusable once these MMAs retire
                 else tc_commit_mc(&empty[s], kMask);              // ... in every CTA of the cluster (peers multicast into it)
                 if (it == steps - 1) tc_commit(acc_full);         // accumulator complete
@@ -171,6 +182,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
             mbar_wait(&full[s], ph);
             float4 *a = reinterpret_cast<float4 *>(tiles + s * kTcStageBytes);
             float4 *lo = reinterpret_cast<float4 *>(tiles + s * kTcStageBytes + kTcTileBytes);
+            if (tid == 0) trace(it, 1);
             if (p.ablate & 1) { mbar_arrive(&split[s]); continue; }
 #pragma unroll
             for (int j = 0; j < kTcTileBytes / 16 / 128; ++j) {    // 8 x 16-byte chunks per thread; layout agnostic
@@ -185,6 +197,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
                 lo[i] = l;
             }
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to tcgen05 (async proxy)
+            if (tid == 0) trace(it, 2);
             mbar_arrive(&split[s]);
         }
         // ---- epilogue: TMEM -> registers -> BN/ReLU/residual -> global ----
@@ -246,7 +259,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
 // split warps read 16 KB and write 32 KB, TMA writes 48 KB => 192 KB => ~1500 clk, measured 1540.  Here the split warps write
 // a_hi / a_lo straight into TMEM (tcgen05.st) and the MMAs take A from TMEM, so smem only carries the TMA writes (48 KB), one read of
 // the raw A tile (16 KB) and the B operand fetches (48 KB): 112 KB per k-step.  Stages shrink to 48 KB => 4 stages.
-// TMEM columns: [0,N) main0 | [N,2N) main1 | [2N,3N) cross terms | [384,448) A slot 0 (hi 32 | lo 32) | [448,512) A slot 1.
+// Issue-rate measurements (scripts/mma_probe.py, profiles/): a tf32 tcgen05.mma with K=8 costs ~96 clk for any N <= 128, 138 clk for N=256
+// (A from TMEM).  So the two products sharing a_hi are issued as ONE N=2n instruction against the concatenated weight tile
+// [b_hi ; b_lo] (the planes sit back to back in smem; odd steps load them in the order [b_lo ; b_hi]):
+//   even step: D=[main0|cross] += a_hi x [b_hi;b_lo]      odd step: D=[cross|main1] += a_hi x [b_lo;b_hi]      + cross += a_lo x b_hi (N=n)
+// i.e. 138 + 96 = 234 clk per k-sub-step instead of 3 x 107.
+// TMEM columns: [0,N) main0 | [N,2N) cross terms | [2N,3N) main1 | [384,448) A slot 0 (hi 32 | lo 32) | [448,512) A slot 1.
 // ================================================================================================================
 constexpr int kV2Stages = 4;
 constexpr int kV2StageBytes = 3 * kTcTileBytes;        // A raw, B_hi, B_lo
@@ -302,13 +320,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc2_kernel(const __gri
                 unsigned char *st = tiles + s * kV2StageBytes;
                 mbar_expect_tx(&full[s], kTcTileBytes + 2 * b_tile_bytes);
                 tma_load_4d(st, &map_a, &full[s], c0, ox0 * p.in_stride + p.tap_dx[cls][tap], oy0 * p.in_stride + p.tap_dy[cls][tap], b);
-                tma_load_4d(st + kTcTileBytes, &map_b, &full[s], c0, n0, wtap, 0);
-                tma_load_4d(st + 2 * kTcTileBytes, &map_b, &full[s], c0, n0, wtap, 1);
+                // weight planes back to back as one 2n-row K-major tile: [b_hi ; b_lo] on even steps, [b_lo ; b_hi] on odd steps
+                const uint32_t hi_off = (it & 1) ? b_tile_bytes : 0u, lo_off = (it & 1) ? 0u : b_tile_bytes;
+                tma_load_4d(st + kTcTileBytes + hi_off, &map_b, &full[s], c0, n0, wtap, 0);
+                tma_load_4d(st + kTcTileBytes + lo_off, &map_b, &full[s], c0, n0, wtap, 1);
             }
         }
     } else if (warp == 1) {
-        const uint32_t idesc = make_idesc_tf32(kTcBM, p.n_tile);
-        const uint32_t acc_cross = tmem_base + 2 * (uint32_t)p.n_tile;
+        const uint32_t idesc1 = make_idesc_tf32(kTcBM, p.n_tile), idesc2 = make_idesc_tf32(kTcBM, 2 * p.n_tile);
+        const uint32_t acc_main0 = tmem_base, acc_cross = tmem_base + (uint32_t)p.n_tile, acc_main1 = tmem_base + 2 * (uint32_t)p.n_tile;
         for (int it = 0; it < steps; ++it) {
             const int s = it % kV2Stages;
             const uint32_t ph = (it / kV2Stages) & 1;
@@ -316,15 +336,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc2_kernel(const __gri
             mbar_wait(&split[s], ph);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t b_hi = smem_u32(tiles + s * kV2StageBytes) + kTcTileBytes, b_lo = b_hi + kTcTileBytes;
+                const uint32_t b_cat = smem_u32(tiles + s * kV2StageBytes) + kTcTileBytes;     // [hi;lo] (even) or [lo;hi] (odd)
+                const uint32_t b_hi = b_cat + ((it & 1) ? b_tile_bytes : 0u);
                 const uint32_t a_hi = tmem_base + kV2ACol + (uint32_t)(it & 1) * 64u, a_lo = a_hi + 32u;
-                const uint32_t acc_main = tmem_base + (uint32_t)(it & 1) * (uint32_t)p.n_tile;
 #pragma unroll
                 for (int k = 0; k < kTcBK / 8; ++k) {
-                    const uint64_t dbh = make_sw128_desc(b_hi + k * 32), dbl = make_sw128_desc(b_lo + k * 32);
-                    tc_mma_tf32_ts(acc_cross, a_lo + k * 8, dbh, idesc, (it | k) != 0);
-                    tc_mma_tf32_ts(acc_cross, a_hi + k * 8, dbl, idesc, 1);
-                    tc_mma_tf32_ts(acc_main, a_hi + k * 8, dbh, idesc, (it >= 2 || k != 0) ? 1u : 0u);
+                    const uint64_t dcat = make_sw128_desc(b_cat + k * 32), dbh = make_sw128_desc(b_hi + k * 32);
+                    if (!(it & 1)) {
+                        // [main0 | cross] (+)= a_hi x [b_hi ; b_lo]; the very first instruction overwrites (zero-initialises) both halves
+                        tc_mma_tf32_ts(acc_main0, a_hi + k * 8, dcat, idesc2, (it | k) != 0);
+                    } else if (it == 1 && k == 0) {
+                        // main1 is written for the first time here (overwrite) while cross must accumulate: two N=n instructions once
+                        tc_mma_tf32_ts(acc_cross, a_hi + k * 8, dcat, idesc1, 1);                                  // x b_lo
+                        tc_mma_tf32_ts(acc_main1, a_hi + k * 8, dbh, idesc1, 0);                                   // x b_hi
+                    } else {
+                        tc_mma_tf32_ts(acc_cross, a_hi + k * 8, dcat, idesc2, 1);                                  // [cross | main1] += a_hi x [b_lo ; b_hi]
+                    }
+                    tc_mma_tf32_ts(acc_cross, a_lo + k * 8, dbh, idesc1, 1);                                       // cross += a_lo x b_hi
                 }
                 tc_commit(&empty[s]);
                 tc_commit(&a_free[it & 1]);
@@ -370,12 +398,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc2_kernel(const __gri
         for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
             uint32_t v[32], u[32];
             const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            tmem_ld_32x32b_x32(lane_base, v);
-            tmem_ld_32x32b_x32(lane_base + 2 * (uint32_t)p.n_tile, u);
+            tmem_ld_32x32b_x32(lane_base, v);                                  // main0
+            tmem_ld_32x32b_x32(lane_base + (uint32_t)p.n_tile, u);             // cross terms
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
             if (steps > 1) {
-                tmem_ld_32x32b_x32(lane_base + (uint32_t)p.n_tile, u);
+                tmem_ld_32x32b_x32(lane_base + 2 * (uint32_t)p.n_tile, u);     // main1
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
             }

@@ -64,6 +64,7 @@ SIGNATURES = {
     "sessd_bev_deconv_tc": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "sessd_set_conv_cluster": (None, [_i]),
     "sessd_get_conv_cluster": (_i, []),
+    "sessd_mma_probe": (_i, [_i, _i, _i, _vp, _vp]),
     "sessd_set_conv_ablate": (None, [_i]),
     "sessd_set_conv_variant": (None, [_i]),
     "sessd_set_conv_debug_buffer": (None, [_vp]),
