@@ -13,7 +13,7 @@ def bench(name, cin, cout, hw_in, hw_out, taps, stride=1, reps=10):
     d = ops.conv_desc(1, hw_in, cin, hw_out, cout, hw_out, taps, in_stride=stride, relu=True)
     flush = torch.empty(64 * 1024 * 1024, device="cuda")
     res = {}
-    for cs in (1, 2, 4):
+    for cs in (1, 2, 4, 8):
         ops.set_conv_cluster(cs)
         for _ in range(2):
             ops.bev_conv_tc(x, wt, None, None, None, out, d)
@@ -25,7 +25,7 @@ def bench(name, cin, cout, hw_in, hw_out, taps, stride=1, reps=10):
             ts.append(a.elapsed_time(b))
         res[cs] = float(np.median(ts)) * 1000
     fl = 2.0 * hw_out[0] * hw_out[1] * cin * cout * len(taps)
-    print("%-34s GF=%6.2f  us: cs1=%6.1f cs2=%6.1f cs4=%6.1f   TF/s(best)=%6.1f" % (name, fl / 1e9, res[1], res[2], res[4], fl / min(res.values()) / 1e6))
+    print("%-34s GF=%6.2f  us: cs1=%6.1f cs2=%6.1f cs4=%6.1f cs8=%6.1f  TF/s(best)=%6.1f" % (name, fl / 1e9, res[1], res[2], res[4], res[8], fl / min(res.values()) / 1e6))
 
 t3 = [(dy - 1, dx - 1) for dy in range(3) for dx in range(3)]
 from sessd_b200._lib import lib
@@ -43,11 +43,12 @@ bench("head 128->24 @200x176", 128, 24, (200, 176), (200, 176), [(0, 0)])
 
 print("--- ablations on conv3x3 128->128 @200x176 (cluster 1): 1=no split, 2=hi*hi only, 4=no TMA reloads")
 ops.set_conv_cluster(1)
+lib.sessd_set_conv_variant(variant)
 x = torch.randn(1, 200, 176, 128, device="cuda"); wp = torch.randn(9, 128, 128, device="cuda") * 0.05
 wt = ops.pack_weight_tc(wp, 128); out = torch.zeros(1, 200, 176, 128, device="cuda")
 d = ops.conv_desc(1, (200, 176), 128, (200, 176), 128, (200, 176), t3, relu=True)
 flush = torch.empty(64 * 1024 * 1024, device="cuda")
-for mode in (0, 1, 2, 4, 3, 5, 6, 7):
+for mode in ((0, 4) if variant == 2 else (0, 1, 2, 4, 7)):
     lib.sessd_set_conv_ablate(mode)
     ts = []
     for i in range(8):

@@ -270,8 +270,9 @@ constexpr int kV2Stages = 4;
 constexpr int kV2StageBytes = 3 * kTcTileBytes;        // A raw, B_hi, B_lo
 constexpr int kV2SmemBytes = kV2Stages * kV2StageBytes + 1024 + 256;
 constexpr uint32_t kV2ACol = 384;
+constexpr int kV2Threads = 320;                         // w0 TMA, w1 MMA, w2-5 split group 0 (+ epilogue), w6-9 split group 1
 
-__global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
+__global__ void __launch_bounds__(kV2Threads, 1) bev_conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                      const __grid_constant__ CUtensorMap map_b,
                                                                      const float *__restrict__ scale, const float *__restrict__ shift,
                                                                      const float *__restrict__ resid, float *__restrict__ out, TcParams p) {
@@ -318,6 +319,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc2_kernel(const __gri
                 const int tap = it / kchunks, c0 = (it - tap * kchunks) * kTcBK;
                 const int wtap = p.tap_w[cls][tap];
                 unsigned char *st = tiles + s * kV2StageBytes;
+                if ((p.ablate & 4) && it >= kV2Stages) { mbar_arrive(&full[s]); continue; }
                 mbar_expect_tx(&full[s], kTcTileBytes + 2 * b_tile_bytes);
                 tma_load_4d(st, &map_a, &full[s], c0, ox0 * p.in_stride + p.tap_dx[cls][tap], oy0 * p.in_stride + p.tap_dy[cls][tap], b);
                 // weight planes back to back as one 2n-row K-major tile: [b_hi ; b_lo] on even steps, [b_lo ; b_hi] on odd steps
@@ -363,7 +365,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc2_kernel(const __gri
     } else {
         const int q = warp & 3;
         const int r = q * 32 + lane;                 // the tile row (TMEM lane) this thread owns
-        for (int it = 0; it < steps; ++it) {
+        const int grp = (warp - 2) >> 2;             // two split groups alternate k-steps (group g owns TMEM A slot g)
+        for (int it = grp; it < steps; it += 2) {
             const int s = it % kV2Stages;
             const uint32_t ph = (it / kV2Stages) & 1;
             mbar_wait(&full[s], ph);
@@ -390,6 +393,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc2_kernel(const __gri
             tc_fence_before();
             mbar_arrive(&split[s]);
         }
+        if (grp == 0) {
         mbar_wait(acc_full, 0);
         tc_fence_after();
         const int gy = oy0 + r / kTcTileW, gx = ox0 + r % kTcTileW;
@@ -427,6 +431,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc2_kernel(const __gri
                 *reinterpret_cast<float4 *>(out + off) = o;
             }
         }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -446,7 +451,7 @@ static int launch_tc(const float *d_in, const float *d_w, int w_taps, int cout_p
                      const float *d_residual, float *d_out, TcParams &p, void *stream) {
     const int n_tile = p.cout <= 32 ? 32 : 128;
     if (cout_pad % n_tile || cout_pad < p.cout) return SESSD_EINVAL;
-    const int cs = (g_conv_variant == 2) ? 1 : (g_conv_cluster == 4 || g_conv_cluster == 2) ? g_conv_cluster : 1;
+    const int cs = (g_conv_variant == 2) ? 1 : (g_conv_cluster == 8 || g_conv_cluster == 4 || g_conv_cluster == 2) ? g_conv_cluster : 1;
     CUtensorMap map_a, map_b;
     {
         const cuuint64_t dims[4] = {(cuuint64_t)p.cin, (cuuint64_t)p.in_w, (cuuint64_t)p.in_h, (cuuint64_t)p.batch};
@@ -467,6 +472,7 @@ static int launch_tc(const float *d_in, const float *d_w, int w_taps, int cout_p
         SESSD_CUDA_TRY(cudaFuncSetAttribute(bev_conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
         SESSD_CUDA_TRY(cudaFuncSetAttribute(bev_conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
         SESSD_CUDA_TRY(cudaFuncSetAttribute(bev_conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+        SESSD_CUDA_TRY(cudaFuncSetAttribute(bev_conv_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
         attr_done = true;
     }
     p.n_tile = n_tile;
@@ -492,9 +498,11 @@ static int launch_tc(const float *d_in, const float *d_w, int w_taps, int cout_p
         if (!attr2) { SESSD_CUDA_TRY(cudaFuncSetAttribute(bev_conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kV2SmemBytes)); attr2 = true; }
         cfg.gridDim = dim3(tiles, cout_pad / n_tile, p.nclass);
         cfg.dynamicSmemBytes = kV2SmemBytes;
+        cfg.blockDim = dim3(kV2Threads);
         attr[0].val.clusterDim.x = 1;
         e = cudaLaunchKernelEx(&cfg, bev_conv_tc2_kernel, map_a, map_b, d_scale, d_shift, d_residual, d_out, p);
-    } else if (cs == 4) e = cudaLaunchKernelEx(&cfg, bev_conv_tc_kernel<4>, map_a, map_b, d_scale, d_shift, d_residual, d_out, p);
+    } else if (cs == 8) e = cudaLaunchKernelEx(&cfg, bev_conv_tc_kernel<8>, map_a, map_b, d_scale, d_shift, d_residual, d_out, p);
+    else if (cs == 4) e = cudaLaunchKernelEx(&cfg, bev_conv_tc_kernel<4>, map_a, map_b, d_scale, d_shift, d_residual, d_out, p);
     else if (cs == 2) e = cudaLaunchKernelEx(&cfg, bev_conv_tc_kernel<2>, map_a, map_b, d_scale, d_shift, d_residual, d_out, p);
     else e = cudaLaunchKernelEx(&cfg, bev_conv_tc_kernel<1>, map_a, map_b, d_scale, d_shift, d_residual, d_out, p);
     ++g_launches;
