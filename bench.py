@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--streams", type=int, default=4)
     ap.add_argument("--cloud", default="ring", choices=["ring", "uniform"])
     ap.add_argument("--pool", type=int, default=16, help="distinct synthetic frames per rank")
+    ap.add_argument("--quick", action="store_true", help="skip the e2e / roofline / cpu_baseline legs (tuning runs)")
     return ap.parse_args()
 
 
@@ -255,6 +256,13 @@ def run_ours(args):
     ms_value = timed(step_device, args.steps)
     clocks = sampler.stop()
     value = world * F * args.steps / (ms_value / 1000.0)
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "value": value, "streams": S, "frames_per_step": F, "ms_per_frame": ms_value / args.steps / F}))
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
 
     # ---- e2e: host buffers through the public engine API -----------------------------------------------------------
     h2d = [0]

@@ -88,3 +88,21 @@ for variant in (1, 2):
         print('variant', variant, 'FAILED:', repr(e)[:300])
         break
 _L.sessd_set_conv_variant(1)
+
+# E1: which rounding does the tensor core apply to raw fp32 bits fed as tf32?  (variant 1, A_hi left raw)
+print("========== E1: raw fp32 as tf32 operand")
+import torch.nn.functional as F
+g = torch.Generator().manual_seed(3)
+xs = torch.rand(1, 32, 32, 128, generator=g) + 0.5          # positive data: truncation bias would show up clearly
+w3 = torch.randn(128, 128, 3, 3, generator=g) * (2.0 / (128 * 9)) ** 0.5
+ref = F.conv2d(xs.permute(0, 3, 1, 2).double(), w3.double(), None, 1, 1).permute(0, 2, 3, 1)
+wp3 = w3.permute(2, 3, 1, 0).reshape(9, 128, 128).contiguous()
+taps = [(dy - 1, dx - 1) for dy in range(3) for dx in range(3)]
+for mode, name in ((0, "hi written back (reference)"), (8, "raw hi, lo = a - trunc(a)"), (16, "raw hi, lo = a - rna(a)")):
+    _L.sessd_set_conv_ablate(mode)
+    out = torch.zeros(1, 32, 32, 128, device="cuda")
+    d = ops.conv_desc(1, (32, 32), 128, (32, 32), 128, (32, 32), taps, relu=False)
+    ops.bev_conv_tc(xs.cuda(), ops.pack_weight_tc(wp3.cuda(), 128), None, None, None, out, d)
+    torch.cuda.synchronize()
+    print("E1 %-32s max rel err = %.3e" % (name, float((out.cpu().double() - ref).abs().max() / ref.abs().max())))
+_L.sessd_set_conv_ablate(0)

@@ -189,11 +189,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
                 const int i = tid + j * 128;
                 const float4 v = a[i];
                 float4 h, l;
-                h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-                h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-                h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-                h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-                a[i] = h;
+                if (p.ablate & 16) {        // experiment: does the tensor core round tf32 operands to nearest?
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=f"(h.x) : "f"(v.x)); asm("cvt.rna.tf32.f32 %0, %1;" : "=f"(h.y) : "f"(v.y));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=f"(h.z) : "f"(v.z)); asm("cvt.rna.tf32.f32 %0, %1;" : "=f"(h.w) : "f"(v.w));
+                } else {
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                }
+                l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+                if (!(p.ablate & 24)) a[i] = h;     // modes 8 / 16 leave the RAW fp32 value as the "hi" operand
                 lo[i] = l;
             }
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to tcgen05 (async proxy)
