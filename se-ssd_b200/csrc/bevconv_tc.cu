@@ -190,8 +190,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) bev_conv_tc_kernel(const __grid
                 const float4 v = a[i];
                 float4 h, l;
                 if (p.ablate & 16) {        // experiment: does the tensor core round tf32 operands to nearest?
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=f"(h.x) : "f"(v.x)); asm("cvt.rna.tf32.f32 %0, %1;" : "=f"(h.y) : "f"(v.y));
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=f"(h.z) : "f"(v.z)); asm("cvt.rna.tf32.f32 %0, %1;" : "=f"(h.w) : "f"(v.w));
+                    uint32_t u0, u1, u2, u3;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u0) : "f"(v.x)); asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u1) : "f"(v.y));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u2) : "f"(v.z)); asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u3) : "f"(v.w));
+                    h.x = __uint_as_float(u0); h.y = __uint_as_float(u1); h.z = __uint_as_float(u2); h.w = __uint_as_float(u3);
                 } else {
                     h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
                     h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
