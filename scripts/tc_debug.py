@@ -79,7 +79,7 @@ def suite():
         print("A7 stride-2 FAILED:", repr(e)[:200])
 
 
-for variant in (1, 2):
+for variant in (1, 2, 3):
     print('========== conv variant', variant)
     _L.sessd_set_conv_variant(variant)
     try:

@@ -444,6 +444,181 @@ __global__ void __launch_bounds__(kV2Threads, 1) bev_conv_tc2_kernel(const __gri
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
+
+// ================================================================================================================
+// Variant 3 (hybrid): measured facts (scripts/tc_debug.py E1, scripts/mma_probe.py, per-step traces in profiles/):
+//   * the tensor core TRUNCATES raw fp32 bits to tf32, so a_hi needs no copy at all: the raw TMA tile IS the a_hi operand;
+//   * variants 1/2 run at ~0.8 us per k-step although their MMA issue time is 0.70 / 0.51 us: the ring is too shallow for the round trip
+//     MMA retire -> empty -> TMA (~1 us) -> split -> MMA (variant 1: 3 x 64 KB stages; variant 2: only 2 TMEM slots for a_hi|a_lo).
+// Here only a_lo goes to TMEM (32 columns per step => FOUR slots next to the three accumulators), a_hi products are SS-form with the
+// concatenated [b_hi;b_lo] tile (N = 2n), stages are 48 KB => four stages: 4 steps of work in flight.
+// ================================================================================================================
+constexpr int kV3Stages = 4;
+constexpr int kV3StageBytes = 3 * kTcTileBytes;        // A raw, B_hi, B_lo
+constexpr int kV3SmemBytes = kV3Stages * kV3StageBytes + 1024 + 256;
+constexpr uint32_t kV3ACol = 384;
+constexpr int kV3Threads = 320;                         // w0 TMA, w1 MMA, w2-5 split group 0 (+ epilogue), w6-9 split group 1
+
+__global__ void __launch_bounds__(kV3Threads, 1) bev_conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                     const __grid_constant__ CUtensorMap map_b,
+                                                                     const float *__restrict__ scale, const float *__restrict__ shift,
+                                                                     const float *__restrict__ resid, float *__restrict__ out, TcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *tiles = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = (uint64_t *)(tiles + kV3Stages * kV3StageBytes);
+    uint64_t *full = bars, *split = bars + kV3Stages, *empty = bars + 2 * kV3Stages, *a_free = bars + 3 * kV3Stages;   // a_free[4]
+    uint64_t *acc_full = bars + 3 * kV3Stages + 4;
+    uint32_t *tmem_slot = (uint32_t *)(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int t = blockIdx.x;
+    const int tx = t % p.tiles_x; t /= p.tiles_x;
+    const int ty = t % p.tiles_y;
+    const int b = t / p.tiles_y;
+    const int oy0 = ty * kTcTileH, ox0 = tx * kTcTileW;
+    const int n0 = blockIdx.y * p.n_tile;
+    const int cls = blockIdx.z;
+    const int kchunks = p.cin / kTcBK;
+    const int steps = p.cls_ntaps[cls] * kchunks;
+    const uint32_t b_tile_bytes = (uint32_t)p.n_tile * kTcBK * 4;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kV3Stages; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 128); mbar_init(&empty[s], 1); }
+        for (int q4 = 0; q4 < 4; ++q4) mbar_init(&a_free[q4], 1);
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < steps; ++it) {
+                const int s = it % kV3Stages;
+                const uint32_t ph = (it / kV3Stages) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                const int tap = it / kchunks, c0 = (it - tap * kchunks) * kTcBK;
+                const int wtap = p.tap_w[cls][tap];
+                unsigned char *st = tiles + s * kV3StageBytes;
+                if ((p.ablate & 4) && it >= kV3Stages) { mbar_arrive(&full[s]); continue; }
+                mbar_expect_tx(&full[s], kTcTileBytes + 2 * b_tile_bytes);
+                tma_load_4d(st, &map_a, &full[s], c0, ox0 * p.in_stride + p.tap_dx[cls][tap], oy0 * p.in_stride + p.tap_dy[cls][tap], b);
+                // weight planes back to back as one 2n-row K-major tile: [b_hi ; b_lo] on even steps, [b_lo ; b_hi] on odd steps
+                const uint32_t hi_off = (it & 1) ? b_tile_bytes : 0u, lo_off = (it & 1) ? 0u : b_tile_bytes;
+                tma_load_4d(st + kTcTileBytes + hi_off, &map_b, &full[s], c0, n0, wtap, 0);
+                tma_load_4d(st + kTcTileBytes + lo_off, &map_b, &full[s], c0, n0, wtap, 1);
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc1 = make_idesc_tf32(kTcBM, p.n_tile), idesc2 = make_idesc_tf32(kTcBM, 2 * p.n_tile);
+        const uint32_t acc_main0 = tmem_base, acc_cross = tmem_base + (uint32_t)p.n_tile, acc_main1 = tmem_base + 2 * (uint32_t)p.n_tile;
+        for (int it = 0; it < steps; ++it) {
+            const int s = it % kV3Stages;
+            const uint32_t ph = (it / kV3Stages) & 1;
+            mbar_wait(&full[s], ph);
+            mbar_wait(&split[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t b_cat = smem_u32(tiles + s * kV3StageBytes) + kTcTileBytes;     // [hi;lo] (even) or [lo;hi] (odd)
+                const uint32_t b_hi = b_cat + ((it & 1) ? b_tile_bytes : 0u);
+                const uint32_t a_raw = smem_u32(tiles + s * kV3StageBytes);                     // raw fp32: the tensor core truncates to tf32 == a_hi
+                const uint32_t a_lo = tmem_base + kV3ACol + (uint32_t)(it & 3) * 32u;
+#pragma unroll
+                for (int k = 0; k < kTcBK / 8; ++k) {
+                    const uint64_t dcat = make_sw128_desc(b_cat + k * 32), dbh = make_sw128_desc(b_hi + k * 32);
+                    const uint64_t da = make_sw128_desc(a_raw + k * 32);
+                    if (!(it & 1)) {
+                        tc_mma_tf32(acc_main0, da, dcat, idesc2, (it | k) != 0);         // [main0 | cross] (+)= a_hi x [b_hi ; b_lo]
+                    } else if (it == 1 && k == 0) {
+                        tc_mma_tf32(acc_cross, da, dcat, idesc1, 1);                     // cross += a_hi x b_lo
+                        tc_mma_tf32(acc_main1, da, dbh, idesc1, 0);                      // main1  = a_hi x b_hi (first write)
+                    } else {
+                        tc_mma_tf32(acc_cross, da, dcat, idesc2, 1);                     // [cross | main1] += a_hi x [b_lo ; b_hi]
+                    }
+                    tc_mma_tf32_ts(acc_cross, a_lo + k * 8, dbh, idesc1, 1);             // cross += a_lo x b_hi   (a_lo from TMEM)
+                }
+                tc_commit(&empty[s]);
+                tc_commit(&a_free[it & 3]);
+                if (it == steps - 1) tc_commit(acc_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;                 // the tile row (TMEM lane) this thread owns
+        const int grp = (warp - 2) >> 2;             // two split groups alternate k-steps (group g owns TMEM A slot g)
+        for (int it = grp; it < steps; it += 2) {
+            const int s = it % kV3Stages;
+            const uint32_t ph = (it / kV3Stages) & 1;
+            mbar_wait(&full[s], ph);
+            const unsigned char *a = tiles + s * kV3StageBytes + r * 128;
+            uint32_t lo[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {            // row r of the SWIZZLE_128B tile: logical chunk c sits at chunk c ^ (r & 7)
+                const float4 v = *reinterpret_cast<const float4 *>(a + ((c ^ (r & 7)) << 4));
+                const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) lo[c * 4 + e] = __float_as_uint(x[e] - __uint_as_float(__float_as_uint(x[e]) & 0xFFFFE000u));
+            }
+            // the a_lo slot (it & 3) was last read by the MMAs of step it-4
+            if (it >= 4) mbar_wait(&a_free[it & 3], ((it >> 2) - 1) & 1);
+            tc_fence_after();
+            tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + kV3ACol + (uint32_t)(it & 3) * 32u, lo);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&split[s]);
+        }
+        if (grp == 0) {
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int gy = oy0 + r / kTcTileW, gx = ox0 + r % kTcTileW;
+        const bool pix_ok = b < p.batch && gy < p.grid_h && gx < p.grid_w;
+        const size_t opix = (((size_t)b * p.out_h + (size_t)gy * p.out_stride + p.cls_off_y[cls]) * p.out_w + (size_t)gx * p.out_stride + p.cls_off_x[cls]);
+        for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+            uint32_t v[32], u[32];
+            const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            tmem_ld_32x32b_x32(lane_base, v);                                  // main0
+            tmem_ld_32x32b_x32(lane_base + (uint32_t)p.n_tile, u);             // cross terms
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+            if (steps > 1) {
+                tmem_ld_32x32b_x32(lane_base + 2 * (uint32_t)p.n_tile, u);     // main1
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+            }
+            if (!pix_ok) continue;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const int n = n0 + c0 + j;
+                if (n >= p.cout) break;
+                float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (scale) sc = *reinterpret_cast<const float4 *>(scale + n);
+                if (shift) sh = *reinterpret_cast<const float4 *>(shift + n);
+                float4 o;
+                o.x = fmaf(__uint_as_float(v[j + 0]), sc.x, sh.x); o.y = fmaf(__uint_as_float(v[j + 1]), sc.y, sh.y);
+                o.z = fmaf(__uint_as_float(v[j + 2]), sc.z, sh.z); o.w = fmaf(__uint_as_float(v[j + 3]), sc.w, sh.w);
+                if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                const size_t off = opix * p.cout + n;
+                if (resid) {
+                    const float4 rr = *reinterpret_cast<const float4 *>(resid + off);
+                    o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                }
+                *reinterpret_cast<float4 *>(out + off) = o;
+            }
+        }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
 static int g_conv_variant = 1;     // 1: A operand from shared memory (kernel above), 2: A operand from tensor memory
 static int g_conv_cluster = 1;
 static int g_conv_ablate = 0;
@@ -457,7 +632,7 @@ static int launch_tc(const float *d_in, const float *d_w, int w_taps, int cout_p
                      const float *d_residual, float *d_out, TcParams &p, void *stream) {
     const int n_tile = p.cout <= 32 ? 32 : 128;
     if (cout_pad % n_tile || cout_pad < p.cout) return SESSD_EINVAL;
-    const int cs = (g_conv_variant == 2) ? 1 : (g_conv_cluster == 8 || g_conv_cluster == 4 || g_conv_cluster == 2) ? g_conv_cluster : 1;
+    const int cs = (g_conv_variant >= 2) ? 1 : (g_conv_cluster == 8 || g_conv_cluster == 4 || g_conv_cluster == 2) ? g_conv_cluster : 1;
     CUtensorMap map_a, map_b;
     {
         const cuuint64_t dims[4] = {(cuuint64_t)p.cin, (cuuint64_t)p.in_w, (cuuint64_t)p.in_h, (cuuint64_t)p.batch};
@@ -499,7 +674,15 @@ static int launch_tc(const float *d_in, const float *d_w, int w_taps, int cout_p
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e;
-    if (g_conv_variant == 2) {
+    if (g_conv_variant == 3) {
+        static bool attr3 = false;
+        if (!attr3) { SESSD_CUDA_TRY(cudaFuncSetAttribute(bev_conv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kV3SmemBytes)); attr3 = true; }
+        cfg.gridDim = dim3(tiles, cout_pad / n_tile, p.nclass);
+        cfg.dynamicSmemBytes = kV3SmemBytes;
+        cfg.blockDim = dim3(kV3Threads);
+        attr[0].val.clusterDim.x = 1;
+        e = cudaLaunchKernelEx(&cfg, bev_conv_tc3_kernel, map_a, map_b, d_scale, d_shift, d_residual, d_out, p);
+    } else if (g_conv_variant == 2) {
         static bool attr2 = false;
         if (!attr2) { SESSD_CUDA_TRY(cudaFuncSetAttribute(bev_conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kV2SmemBytes)); attr2 = true; }
         cfg.gridDim = dim3(tiles, cout_pad / n_tile, p.nclass);
