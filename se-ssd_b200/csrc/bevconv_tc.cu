@@ -23,6 +23,8 @@
 // accumulator for the small cross terms (a_lo*b_hi + a_hi*b_lo, 2^-10 smaller), 4 x 128 = all 512 TMEM columns, and the
 // epilogue adds the four partial sums in round-to-nearest fp32.  Result: ~1.5e-6 relative per layer.
 // Every mbarrier wait is bounded (trap on timeout) so a descriptor mistake aborts the kernel instead of hanging the GPU.
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace sessd {
@@ -516,24 +518,35 @@ __global__ void __launch_bounds__(kV3Threads, 1) bev_conv_tc3_kernel(const __gri
             }
         }
     } else if (warp == 1) {
+        // The MMA stream is issued by ONE thread: its scalar instruction count per tcgen05.mma is the real ceiling (measured: ~100 clk per
+        // MMA with per-instruction descriptor construction).  So: 4-stage ring fully unrolled (stage == it & 3, and with four stages
+        // the parity of `it` equals the parity of the stage), descriptors precomputed per stage, only "+ 2k" on the low word per k sub-step.
         const uint32_t idesc1 = make_idesc_tf32(kTcBM, p.n_tile), idesc2 = make_idesc_tf32(kTcBM, 2 * p.n_tile);
         const uint32_t acc_main0 = tmem_base, acc_cross = tmem_base + (uint32_t)p.n_tile, acc_main1 = tmem_base + 2 * (uint32_t)p.n_tile;
-        for (int it = 0; it < steps; ++it) {
-            const int s = it % kV3Stages;
+        const uint64_t desc_hi = ((uint64_t)(((1024u >> 4)) | (1u << 14) | (2u << 29))) << 32;          // SBO | version | SWIZZLE_128B
+        const uint32_t tiles_lo = ((smem_u32(tiles) >> 4) & 0x3FFFu) | (1u << 16);                        // start address field + LBO
+        const uint32_t b_rows_lo = b_tile_bytes >> 4;
+        uint64_t dA[kV3Stages], dCat[kV3Stages], dBhi[kV3Stages];
+        uint32_t aLo[kV3Stages];
+#pragma unroll
+        for (int sgi = 0; sgi < kV3Stages; ++sgi) {
+            const uint32_t st_lo = tiles_lo + (uint32_t)sgi * (kV3StageBytes >> 4);
+            dA[sgi] = desc_hi | st_lo;
+            dCat[sgi] = desc_hi | (st_lo + (kTcTileBytes >> 4));
+            dBhi[sgi] = desc_hi | (st_lo + (kTcTileBytes >> 4) + ((sgi & 1) ? b_rows_lo : 0u));
+            aLo[sgi] = tmem_base + kV3ACol + (uint32_t)sgi * 32u;
+        }
+        auto issue = [&](auto stage_c, int it) {
+            constexpr int S = decltype(stage_c)::value;
             const uint32_t ph = (it / kV3Stages) & 1;
-            mbar_wait(&full[s], ph);
-            mbar_wait(&split[s], ph);
+            mbar_wait(&full[S], ph);
+            mbar_wait(&split[S], ph);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t b_cat = smem_u32(tiles + s * kV3StageBytes) + kTcTileBytes;     // [hi;lo] (even) or [lo;hi] (odd)
-                const uint32_t b_hi = b_cat + ((it & 1) ? b_tile_bytes : 0u);
-                const uint32_t a_raw = smem_u32(tiles + s * kV3StageBytes);                     // raw fp32: the tensor core truncates to tf32 == a_hi
-                const uint32_t a_lo = tmem_base + kV3ACol + (uint32_t)(it & 3) * 32u;
 #pragma unroll
                 for (int k = 0; k < kTcBK / 8; ++k) {
-                    const uint64_t dcat = make_sw128_desc(b_cat + k * 32), dbh = make_sw128_desc(b_hi + k * 32);
-                    const uint64_t da = make_sw128_desc(a_raw + k * 32);
-                    if (!(it & 1)) {
+                    const uint64_t da = dA[S] + 2 * k, dcat = dCat[S] + 2 * k, dbh = dBhi[S] + 2 * k;
+                    if ((S & 1) == 0) {
                         tc_mma_tf32(acc_main0, da, dcat, idesc2, (it | k) != 0);         // [main0 | cross] (+)= a_hi x [b_hi ; b_lo]
                     } else if (it == 1 && k == 0) {
                         tc_mma_tf32(acc_cross, da, dcat, idesc1, 1);                     // cross += a_hi x b_lo
@@ -541,13 +554,19 @@ __global__ void __launch_bounds__(kV3Threads, 1) bev_conv_tc3_kernel(const __gri
                     } else {
                         tc_mma_tf32(acc_cross, da, dcat, idesc2, 1);                     // [cross | main1] += a_hi x [b_lo ; b_hi]
                     }
-                    tc_mma_tf32_ts(acc_cross, a_lo + k * 8, dbh, idesc1, 1);             // cross += a_lo x b_hi   (a_lo from TMEM)
+                    tc_mma_tf32_ts(acc_cross, aLo[S] + k * 8, dbh, idesc1, 1);           // cross += a_lo x b_hi   (a_lo from TMEM)
                 }
-                tc_commit(&empty[s]);
-                tc_commit(&a_free[it & 3]);
+                tc_commit(&empty[S]);
+                tc_commit(&a_free[S]);
                 if (it == steps - 1) tc_commit(acc_full);
             }
             __syncwarp();
+        };
+        for (int it = 0; it < steps; it += kV3Stages) {
+            issue(std::integral_constant<int, 0>{}, it);
+            if (it + 1 < steps) issue(std::integral_constant<int, 1>{}, it + 1);
+            if (it + 2 < steps) issue(std::integral_constant<int, 2>{}, it + 2);
+            if (it + 3 < steps) issue(std::integral_constant<int, 3>{}, it + 3);
         }
     } else {
         const int q = warp & 3;

@@ -8,10 +8,11 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, int iters, int
     extern __shared__ unsigned char smem_raw[];
     unsigned char *tiles = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t bar;
+    __shared__ uint64_t dummy[4];
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<float *>(tiles)[i] = 0.001f * (i & 255);
-    if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); for (int q = 0; q < 4; ++q) mbar_init(&dummy[q], 1 << 20); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
@@ -32,6 +33,9 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, int iters, int
             const uint32_t acc = (mode & 2) ? tmem + (uint32_t)((i & 1) * n) : tmem;      // rotate between two accumulators
             if (mode & 1) tc_mma_tf32_ts(acc, tmem + 448 + (i & 3) * 8, make_sw128_desc(b + k), idesc, 1);
             else tc_mma_tf32(acc, make_sw128_desc(a + k), make_sw128_desc(b + k), idesc, 1);
+            if ((mode & 4) && (i % 12) == 11) tc_commit(&dummy[(i / 12) & 3]);               // a commit per "k-step" (never completes a phase)
+            if ((mode & 8) && (i % 12) == 11) { tc_commit(&dummy[(i / 12) & 3]); tc_commit(&dummy[((i / 12) + 1) & 3]); }
+            if ((mode & 16) && (i % 12) == 11) { mbar_try_wait(&dummy[0], 1); tc_fence_after(); __syncwarp(0x1); }
         }
         tc_commit(&bar);
         long long c1 = clock64();
