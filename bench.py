@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=32)
-    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--streams", type=int, default=8)
     ap.add_argument("--cloud", default="ring", choices=["ring", "uniform"])
     ap.add_argument("--pool", type=int, default=16, help="distinct synthetic frames per rank")
     ap.add_argument("--quick", action="store_true", help="skip the e2e / roofline / cpu_baseline legs (tuning runs)")

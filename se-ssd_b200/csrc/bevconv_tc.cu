@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) bev_conv_tc3_kernel(const __gri
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
-static int g_conv_variant = 1;     // 1: A operand from shared memory (kernel above), 2: A operand from tensor memory
+static int g_conv_variant = 3;     // 1: A operand from shared memory, 2: A operand from tensor memory, 3: hybrid (default, fastest)
 static int g_conv_cluster = 1;
 static int g_conv_ablate = 0;
 static long long *g_conv_dbg = nullptr;

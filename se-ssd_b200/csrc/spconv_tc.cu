@@ -14,6 +14,8 @@
 // Offsets with no neighbour inside the tile are skipped (bitmask built while staging the tile's nbr rows).
 // Epilogue: 4 warps read the four TMEM accumulators, add them in RN fp32, apply folded BN + ReLU, store the row once.
 // No scatter-add, no atomics on features, no intermediate gather/scatter buffers.
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace sessd {
@@ -179,35 +181,51 @@ __global__ void __launch_bounds__(kStThreads, 1) spconv_tc_kernel(const float *_
         }
     } else if (warp == 8) {
         // ===================== MMA issuer =====================
+        // single issuing thread: keep its scalar work per tcgen05.mma minimal (descriptors precomputed per stage, ring unrolled)
         const uint32_t idesc = make_idesc_tf32(kStBM, COUT);
-        for (int j = 0; j < nact; ++j) {
-            const int s = j % C::kStages;
+        const uint64_t desc_hi = ((uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29))) << 32;      // SBO | version | SWIZZLE_128B
+        const uint32_t tiles_lo = ((smem_u32(tiles) >> 4) & 0x3FFFu) | (1u << 16);
+        uint64_t dAh[C::kStages], dAl[C::kStages], dBh[C::kStages], dBl[C::kStages];
+#pragma unroll
+        for (int sgi = 0; sgi < C::kStages; ++sgi) {
+            const uint32_t st_lo = tiles_lo + (uint32_t)sgi * (C::kStage >> 4);
+            dAh[sgi] = desc_hi | st_lo;
+            dAl[sgi] = desc_hi | (st_lo + (C::kATile >> 4));
+            dBh[sgi] = desc_hi | (st_lo + (2 * C::kATile >> 4));
+            dBl[sgi] = desc_hi | (st_lo + ((2 * C::kATile + C::kBTile) >> 4));
+        }
+        const uint32_t acc_small = tmem_base + 3 * COUT;
+        auto issue = [&](auto stage_c, int j) {
+            constexpr int S = decltype(stage_c)::value;
             const uint32_t ph = (j / C::kStages) & 1;
-            mbar_wait(&full_a[s], ph);
-            mbar_wait(&full_b[s], ph);
+            mbar_wait(&full_a[S], ph);
+            mbar_wait(&full_b[S], ph);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t a_hi = smem_u32(tiles + s * C::kStage);
-                const uint32_t a_lo = a_hi + C::kATile, b_hi = a_hi + 2 * C::kATile, b_lo = b_hi + C::kBTile;
-                const uint32_t acc_small = tmem_base + 3 * COUT;
                 const uint32_t acc_main = tmem_base + (uint32_t)(j % 3) * COUT;
 #pragma unroll
                 for (int kb = 0; kb < C::kKblk; ++kb) {
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
-                        const uint32_t ao = kb * (kStBM * 128) + kk * 32, bo = kb * (COUT * 128) + kk * 32;
-                        const uint64_t dah = make_sw128_desc(a_hi + ao), dal = make_sw128_desc(a_lo + ao);
-                        const uint64_t dbh = make_sw128_desc(b_hi + bo), dbl = make_sw128_desc(b_lo + bo);
+                        const uint32_t ao = (uint32_t)(kb * (kStBM * 128) + kk * 32) >> 4, bo = (uint32_t)(kb * (COUT * 128) + kk * 32) >> 4;
                         const bool first = (kb | kk) == 0;
-                        tc_mma_tf32(acc_small, dal, dbh, idesc, (j != 0 || !first) ? 1u : 0u);
-                        tc_mma_tf32(acc_small, dah, dbl, idesc, 1u);
-                        tc_mma_tf32(acc_main, dah, dbh, idesc, (j >= 3 || !first) ? 1u : 0u);
+                        tc_mma_tf32(acc_small, dAl[S] + ao, dBh[S] + bo, idesc, (j != 0 || !first) ? 1u : 0u);
+                        tc_mma_tf32(acc_small, dAh[S] + ao, dBl[S] + bo, idesc, 1u);
+                        tc_mma_tf32(acc_main, dAh[S] + ao, dBh[S] + bo, idesc, (j >= 3 || !first) ? 1u : 0u);
                     }
                 }
-                tc_commit(&empty[s]);
+                tc_commit(&empty[S]);
                 if (j == nact - 1) tc_commit(acc_full);
             }
             __syncwarp();
+        };
+        for (int j = 0; j < nact; j += C::kStages) {
+            issue(std::integral_constant<int, 0>{}, j);
+            if (j + 1 < nact) issue(std::integral_constant<int, 1>{}, j + 1);
+            if constexpr (C::kStages == 4) {
+                if (j + 2 < nact) issue(std::integral_constant<int, 2>{}, j + 2);
+                if (j + 3 < nact) issue(std::integral_constant<int, 3>{}, j + 3);
+            }
         }
         if (nact == 0 && lane == 0) mbar_arrive(acc_full);     // isolated tile: nothing to accumulate
     } else {
