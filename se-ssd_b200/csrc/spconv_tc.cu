@@ -9,8 +9,10 @@
 //     split every value into tf32 hi / lo parts in registers and store both into shared memory directly in the canonical
 //     K-major SWIZZLE_128B layout (chunk ^= row & 7) that the UMMA descriptors address;
 //   * the TMA warp streams the pre-split weight tiles W_hi[k], W_lo[k] ([Cout][Cin], K-major) for the stage;
-//   * the MMA warp issues Cin/8 x 3 tcgen05.mma (M128 x N=Cout x K8): a_hi*b_hi into one of three round-robin main
-//     accumulators, the two cross terms into a fourth (see bevconv_tc.cu on why: TMEM accumulation truncates).
+//   * the MMA warp issues, per 8-channel sub-step, ONE N=2*Cout tcgen05.mma of a_hi against the concatenated [b_hi ; b_lo] tile
+//     (main and a_hi*b_lo cross term in adjacent TMEM columns) plus one N=Cout MMA for a_lo*b_hi; even / odd offsets alternate between
+//     [main0 | cross] and [cross | main1] (weights loaded as [b_lo ; b_hi] on odd steps) so that no accumulator sees more than half of
+//     the (truncating) TMEM accumulation steps -- see bevconv_tc.cu.
 // Offsets with no neighbour inside the tile are skipped (bitmask built while staging the tile's nbr rows).
 // Epilogue: 4 warps read the four TMEM accumulators, add them in RN fp32, apply folded BN + ReLU, store the row once.
 // No scatter-add, no atomics on features, no intermediate gather/scatter buffers.
@@ -146,13 +148,13 @@ __global__ void __launch_bounds__(kStThreads, 1) spconv_tc_kernel(const float *_
             tc_fence_after();
             const int q = warp & 3;
             const int r = q * 32 + lane;
-            const int nmain = nact < 3 ? nact : 3;
+            const int nmain = nact < 2 ? nact : 2;
             for (int c0 = 0; c0 < COUT; c0 += 32) {
                 uint32_t acc[32], u[32];
                 const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
                 if (nact > 0) {
                     tmem_ld_32x32b_x32(lane_base, acc);
-                    tmem_ld_32x32b_x32(lane_base + 3 * COUT, u);
+                    tmem_ld_32x32b_x32(lane_base + COUT, u);                      // cross terms
 #pragma unroll
                     for (int i = 0; i < 32; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(u[i]));
                 } else {
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(kStThreads, 1) spconv_tc_kernel(const float *_
                     for (int i = 0; i < 32; ++i) acc[i] = 0u;
                 }
                 for (int m = 1; m < nmain; ++m) {
-                    tmem_ld_32x32b_x32(lane_base + m * COUT, u);
+                    tmem_ld_32x32b_x32(lane_base + 2 * m * COUT, u);             // main1
 #pragma unroll
                     for (int i = 0; i < 32; ++i) acc[i] = __float_as_uint(__uint_as_float(acc[i]) + __uint_as_float(u[i]));
                 }
@@ -191,10 +193,11 @@ __global__ void __launch_bounds__(kStThreads, 1) spconv_tc_kernel(const float *_
             const uint32_t st_lo = tiles_lo + (uint32_t)sgi * (C::kStage >> 4);
             dAh[sgi] = desc_hi | st_lo;
             dAl[sgi] = desc_hi | (st_lo + (C::kATile >> 4));
-            dBh[sgi] = desc_hi | (st_lo + (2 * C::kATile >> 4));
-            dBl[sgi] = desc_hi | (st_lo + ((2 * C::kATile + C::kBTile) >> 4));
+            dBh[sgi] = desc_hi | (st_lo + ((2 * C::kATile + ((sgi & 1) ? COUT * 128 : 0)) >> 4));   // b_hi rows inside the [X;Y] block
+            dBl[sgi] = desc_hi | (st_lo + (2 * C::kATile >> 4));                                       // the concatenated 2*Cout-row tile
         }
-        const uint32_t acc_small = tmem_base + 3 * COUT;
+        const uint32_t idesc2 = make_idesc_tf32(kStBM, 2 * COUT);
+        const uint32_t acc_main0 = tmem_base, acc_cross = tmem_base + COUT, acc_main1 = tmem_base + 2 * COUT;
         auto issue = [&](auto stage_c, int j) {
             constexpr int S = decltype(stage_c)::value;
             const uint32_t ph = (j / C::kStages) & 1;
@@ -202,16 +205,21 @@ __global__ void __launch_bounds__(kStThreads, 1) spconv_tc_kernel(const float *_
             mbar_wait(&full_b[S], ph);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t acc_main = tmem_base + (uint32_t)(j % 3) * COUT;
 #pragma unroll
                 for (int kb = 0; kb < C::kKblk; ++kb) {
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
-                        const uint32_t ao = (uint32_t)(kb * (kStBM * 128) + kk * 32) >> 4, bo = (uint32_t)(kb * (COUT * 128) + kk * 32) >> 4;
+                        const uint32_t ao = (uint32_t)(kb * (kStBM * 128) + kk * 32) >> 4, bo = (uint32_t)(kb * (2 * COUT * 128) + kk * 32) >> 4;
                         const bool first = (kb | kk) == 0;
-                        tc_mma_tf32(acc_small, dAl[S] + ao, dBh[S] + bo, idesc, (j != 0 || !first) ? 1u : 0u);
-                        tc_mma_tf32(acc_small, dAh[S] + ao, dBl[S] + bo, idesc, 1u);
-                        tc_mma_tf32(acc_main, dAh[S] + ao, dBh[S] + bo, idesc, (j >= 3 || !first) ? 1u : 0u);
+                        if ((S & 1) == 0) {
+                            tc_mma_tf32(acc_main0, dAh[S] + ao, dBl[S] + bo, idesc2, (j != 0 || !first) ? 1u : 0u);   // [main0|cross] (+)= a_hi x [b_hi;b_lo]
+                        } else if (j == 1 && first) {
+                            tc_mma_tf32(acc_cross, dAh[S] + ao, dBl[S] + bo, idesc, 1u);                             // cross += a_hi x b_lo
+                            tc_mma_tf32(acc_main1, dAh[S] + ao, dBh[S] + bo, idesc, 0u);                             // main1  = a_hi x b_hi
+                        } else {
+                            tc_mma_tf32(acc_cross, dAh[S] + ao, dBl[S] + bo, idesc2, 1u);                            // [cross|main1] += a_hi x [b_lo;b_hi]
+                        }
+                        tc_mma_tf32(acc_cross, dAl[S] + ao, dBh[S] + bo, idesc, 1u);                                 // cross += a_lo x b_hi
                     }
                 }
                 tc_commit(&empty[S]);
@@ -240,8 +248,10 @@ __global__ void __launch_bounds__(kStThreads, 1) spconv_tc_kernel(const float *_
                 mbar_expect_tx(&full_b[s], 2 * C::kBTile);
 #pragma unroll
                 for (int kb = 0; kb < C::kKblk; ++kb) {
-                    tma_load_4d(b_hi + kb * (COUT * 128), &map_w, &full_b[s], kb * 32, 0, k, 0);
-                    tma_load_4d(b_hi + C::kBTile + kb * (COUT * 128), &map_w, &full_b[s], kb * 32, 0, k, 1);
+                    // per K block one 2*Cout-row tile: [b_hi ; b_lo] on even steps, [b_lo ; b_hi] on odd steps
+                    unsigned char *blk = b_hi + kb * (2 * COUT * 128);
+                    tma_load_4d(blk + ((j & 1) ? COUT * 128 : 0), &map_w, &full_b[s], kb * 32, 0, k, 0);
+                    tma_load_4d(blk + ((j & 1) ? 0 : COUT * 128), &map_w, &full_b[s], kb * 32, 0, k, 1);
                 }
             }
         }
