@@ -169,6 +169,22 @@ int sessd_bev_deconv_tc(const float *d_in, const float *d_weight_split, int cout
                         const float *d_shift, const float *d_residual, float *d_out, int batch, int in_h, int in_w,
                         int cin, int cout, int relu, void *stream);
 
+/* fp16-split tensor-core variant (tcgen05 kind::f16, A operand in tensor memory, one halo patch per channel chunk): same contract as
+ * sessd_bev_conv_tc for in_stride == 1, cin % 64 == 0 and tap lists whose reach fits a 10x18-pixel patch (else SESSD_EINVAL: use
+ * sessd_bev_conv_tc).  Every fp32 operand is represented exactly-scaled as fp16 hi + fp16 lo (>= 22 significand bits, same as 3xTF32).
+ * d_weight_h2: __half [2 (hi|lo)][ntaps][cout_pad][cin] of 2^e[n]*w (per output channel n; max |2^e w| in [2^10, 2^11));
+ * d_scale (required) = folded BN scale * 2^-e[n].
+ * d_amax_in  (nullable): device scalar >= max|in| -- selects the activation scaling 2^s; NULL = no scaling (|in| must stay < 65504).
+ * d_amax_out (nullable): device scalar, atomically raised to max|out| (the next layer's d_amax_in); zero it once per frame. */
+int sessd_bev_conv_h2(const float *d_in, const void *d_weight_h2, int cout_pad, const float *d_scale,
+                      const float *d_shift, const float *d_residual, float *d_out, const sessd_conv_desc *desc,
+                      const float *d_amax_in, float *d_amax_out, void *stream);
+int sessd_bev_deconv_h2(const float *d_in, const void *d_weight_h2, int cout_pad, const float *d_scale,
+                        const float *d_shift, const float *d_residual, float *d_out, int batch, int in_h, int in_w,
+                        int cin, int cout, int relu, const float *d_amax_in, float *d_amax_out, void *stream);
+/* *d_amax = max(*d_amax, max_i |d_x[i]|)  (for tensors produced by kernels without an abs-max epilogue) */
+int sessd_absmax(const float *d_x, long long n, float *d_amax, void *stream);
+
 /* tunable of sessd_bev_conv_tc: CTAs per thread-block cluster sharing the weight tiles through TMA multicast (1, 2 or 4) */
 void sessd_set_conv_cluster(int ctas_per_cluster);
 int sessd_get_conv_cluster(void);

@@ -1,0 +1,420 @@
+// bevconv_h2.cu -- BEV conv / deconv (+BN+ReLU+residual) on the 5th-gen tensor cores with a TWO-TERM FP16 SPLIT of every fp32 operand.
+//
+// Replaces the cuDNN conv blocks of det3d/models/necks/rpn_v1.py:135-210 and the 1x1 head convs of
+// det3d/models/bbox_heads/mg_head_sessd.py:202-230 (fp32 in, fp32 out, fp32 accumulate), like bevconv_tc.cu, but twice as fast:
+//
+//   * numerics: x = 2^-s (x_hi + x_lo) with x_hi = fp16_rn(2^s x), x_lo = fp16_rn(2^s x - x_hi): 22+ significand bits, exactly the
+//     precision of the 3xTF32 split (tf32 and fp16 both carry 11 bits), but kind::f16 MMAs run at twice the tf32 rate and move half the
+//     operand bytes.  fp16's narrow exponent range is handled by exact power-of-two scaling: activations by 2^s with s chosen from the
+//     tensor's running abs-max (device scalar written by the producing kernel's epilogue: max maps into [2^10, 2^11)), weights per output
+//     channel at pack time (folded into the epilogue scale).  Elements more than 2^13 below the maximum lose low bits of x_lo only: the
+//     absolute error stays below 2^-35 of the tensor maximum.  Products a_hi*b_hi + a_hi*b_lo + a_lo*b_hi are accumulated in fp32 (TMEM).
+//   * A operand: ONE halo patch (tile 8x16 pixels + the taps' reach, 64 channels, raw fp32) is TMA-loaded per channel chunk and serves
+//     all taps (9x less L2->SM activation traffic than one box per tap).  Two groups of four warps read the tap-shifted pixel rows from
+//     the (swizzled) patch, scale, split into fp16 hi/lo and store them to TENSOR MEMORY ([hi 16 cols | lo 16 cols] per 32 channels,
+//     two fp16 per 32-bit column); all MMAs take A from TMEM (TS form) -- no shared-memory bandwidth for A at all.
+//   * B operand: fp16 weight planes, K-major SWIZZLE_128B rows of 64 channels; per (chunk, tap) one [b_hi ; b_lo] 2n-row tile
+//     ([b_lo ; b_hi] on odd steps) so that one N=2n MMA produces the main product and the a_hi*b_lo cross term in adjacent accumulators
+//     (TMEM: main0 | cross | main1, alternating, because tcgen05 accumulation truncates -- see bevconv_tc.cu).
+//   * warps: 0 patch TMA, 1 MMA issue (descriptors precomputed, ring unrolled), 2-5 / 6-9 split groups (2-5 also epilogue), 10 weight TMA.
+#include <cuda_fp16.h>
+
+#include <type_traits>
+
+#include "../../include/sessd_b200.h"
+#include "tc_common.cuh"
+
+namespace sessd {
+
+constexpr int kH2BM = 128, kH2TileH = 8, kH2TileW = 16;
+constexpr int kH2Chunk = 64;                                   // channels per weight stage / per patch (two 32-channel fp32 boxes)
+constexpr int kH2BStages = 4;
+constexpr int kH2BStageBytes = 2 * 128 * 128;                  // [X ; Y] planes, up to 128 rows of 128 B each
+constexpr int kH2PatchMaxPix = (kH2TileH + 2) * (kH2TileW + 2);
+constexpr int kH2BoxBytes = ((kH2PatchMaxPix * 128 + 1023) / 1024) * 1024;
+constexpr int kH2PatchBytes = 2 * kH2BoxBytes;
+constexpr int kH2SmemBytes = kH2BStages * kH2BStageBytes + 2 * kH2PatchBytes + 1024 + 256;
+constexpr int kH2Threads = 352;
+constexpr uint32_t kH2ACol = 384;                              // TMEM: 3 accumulators (<= 384 columns) + 4 A slots x 32 columns
+
+struct H2Params {
+    int batch, in_h, in_w, cin;
+    int out_h, out_w, cout;
+    int grid_h, grid_w;
+    int out_stride;
+    int nclass;
+    int cls_ntaps[4], cls_off_y[4], cls_off_x[4];
+    int tap_dy[4][9], tap_dx[4][9], tap_w[4][9];
+    int relu;
+    int n_tile;
+    int tiles_x, tiles_y;
+    int patch_w, patch_h, org_dy, org_dx;     // patch rows = input rows oy0 + org_dy ... (patch_h of them), same for columns
+    const float *amax_in;                     // nullable: abs-max of the input tensor (device scalar)
+    float *amax_out;                          // nullable: running abs-max of the output tensor (atomicMax on the float bits)
+};
+
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) /*C=F32*/ | (0u << 7) /*A=F16*/ | (0u << 10) /*B=F16*/ | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[tmem] * B[smem desc], kind::f16 (K = 16 per instruction; A: two fp16 per 32-bit TMEM column)
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                   const __grid_constant__ CUtensorMap map_b,
+                                                                   const float *__restrict__ scale, const float *__restrict__ shift,
+                                                                   const float *__restrict__ resid, float *__restrict__ out, H2Params p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *tiles = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char *patches = tiles + kH2BStages * kH2BStageBytes;
+    uint64_t *bars = (uint64_t *)(patches + 2 * kH2PatchBytes);
+    uint64_t *patch_full = bars, *patch_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 8, *a_full = bars + 12, *a_free = bars + 16;
+    uint64_t *acc_full = bars + 20;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 21);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int t = blockIdx.x;
+    const int tx = t % p.tiles_x; t /= p.tiles_x;
+    const int ty = t % p.tiles_y;
+    const int b = t / p.tiles_y;
+    const int oy0 = ty * kH2TileH, ox0 = tx * kH2TileW;
+    const int n0 = blockIdx.y * p.n_tile;
+    const int cls = blockIdx.z;
+    const int nchunks = p.cin / kH2Chunk;
+    const int ntaps = p.cls_ntaps[cls];
+    const int nbj = nchunks * ntaps;                           // weight stages = (chunk, tap); each feeds two 32-channel A steps
+    const uint32_t b_plane_bytes = (uint32_t)p.n_tile * 128u;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) { mbar_init(&patch_full[s], 1); mbar_init(&patch_empty[s], 256); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); mbar_init(&a_full[s], 128); mbar_init(&a_free[s], 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== activation patches: one halo patch per 64-channel chunk =====================
+        if (lane == 0) {
+            const uint32_t box_bytes = (uint32_t)(p.patch_w * p.patch_h) * 128u;
+            for (int cc = 0; cc < nchunks; ++cc) {
+                const int pb = cc & 1;
+                mbar_wait(&patch_empty[pb], ((cc >> 1) & 1) ^ 1);
+                mbar_expect_tx(&patch_full[pb], 2 * box_bytes);
+                unsigned char *dst = patches + pb * kH2PatchBytes;
+                tma_load_4d(dst, &map_a, &patch_full[pb], cc * kH2Chunk, ox0 + p.org_dx, oy0 + p.org_dy, b);
+                tma_load_4d(dst + kH2BoxBytes, &map_a, &patch_full[pb], cc * kH2Chunk + 32, ox0 + p.org_dx, oy0 + p.org_dy, b);
+            }
+        }
+    } else if (warp == 10) {
+        // ===================== weight tiles =====================
+        if (lane == 0) {
+            int cc = 0, tap = 0;
+            for (int bj = 0; bj < nbj; ++bj) {
+                const int s = bj & 3;
+                mbar_wait(&b_empty[s], ((bj >> 2) & 1) ^ 1);
+                mbar_expect_tx(&b_full[s], 2 * b_plane_bytes);
+                unsigned char *st = tiles + s * kH2BStageBytes;
+                const int wtap = p.tap_w[cls][tap];
+                const uint32_t hi_off = (bj & 1) ? b_plane_bytes : 0u, lo_off = (bj & 1) ? 0u : b_plane_bytes;
+                tma_load_4d(st + hi_off, &map_b, &b_full[s], cc * kH2Chunk, n0, wtap, 0);
+                tma_load_4d(st + lo_off, &map_b, &b_full[s], cc * kH2Chunk, n0, wtap, 1);
+                if (++tap == ntaps) { tap = 0; ++cc; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issue (one thread; keep its scalar work per tcgen05.mma minimal) =====================
+        const uint32_t idesc1 = make_idesc_f16(kH2BM, p.n_tile), idesc2 = make_idesc_f16(kH2BM, 2 * p.n_tile);
+        const uint32_t acc_main0 = tmem_base, acc_cross = tmem_base + (uint32_t)p.n_tile, acc_main1 = tmem_base + 2 * (uint32_t)p.n_tile;
+        const uint64_t desc_hi = ((uint64_t)(((1024u >> 4)) | (1u << 14) | (2u << 29))) << 32;          // SBO | version | SWIZZLE_128B
+        const uint32_t tiles_lo = ((smem_u32(tiles) >> 4) & 0x3FFFu) | (1u << 16);
+        uint64_t dCat[kH2BStages], dBhi[kH2BStages];
+#pragma unroll
+        for (int sgi = 0; sgi < kH2BStages; ++sgi) {
+            dCat[sgi] = desc_hi | (tiles_lo + (uint32_t)sgi * (kH2BStageBytes >> 4));
+            dBhi[sgi] = dCat[sgi] + ((sgi & 1) ? (b_plane_bytes >> 4) : 0u);
+        }
+        auto issue = [&](auto stage_c, int bj) {
+            constexpr int S = decltype(stage_c)::value;
+            mbar_wait(&b_full[S], (bj >> 2) & 1);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                constexpr int kSlotBase = 2 * (S & 1);
+                const int slot = kSlotBase + h;
+                mbar_wait(&a_full[slot], (bj >> 1) & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_hi = tmem_base + kH2ACol + (uint32_t)slot * 32u, a_lo = a_hi + 16u;
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const uint32_t koff = (uint32_t)(h * 4 + kk * 2);            // 32-channel half: +64 B, K=16 sub-step: +32 B (>>4)
+                        if ((S & 1) == 0) {
+                            tc_mma_f16_ts(acc_main0, a_hi + kk * 8, dCat[S] + koff, idesc2, (bj | h | kk) != 0);   // [main0|cross] (+)= a_hi x [b_hi;b_lo]
+                        } else if (bj == 1 && h == 0 && kk == 0) {
+                            tc_mma_f16_ts(acc_cross, a_hi, dCat[S] + koff, idesc1, 1);                              // cross += a_hi x b_lo
+                            tc_mma_f16_ts(acc_main1, a_hi, dBhi[S] + koff, idesc1, 0);                              // main1  = a_hi x b_hi
+                        } else {
+                            tc_mma_f16_ts(acc_cross, a_hi + kk * 8, dCat[S] + koff, idesc2, 1);                     // [cross|main1] += a_hi x [b_lo;b_hi]
+                        }
+                        tc_mma_f16_ts(acc_cross, a_lo + kk * 8, dBhi[S] + koff, idesc1, 1);                         // cross += a_lo x b_hi
+                    }
+                    tc_commit(&a_free[slot]);
+                }
+                __syncwarp();
+            }
+            if (lane == 0) {
+                tc_commit(&b_empty[S]);
+                if (bj == nbj - 1) tc_commit(acc_full);
+            }
+            __syncwarp();
+        };
+        for (int bj = 0; bj < nbj; bj += kH2BStages) {
+            issue(std::integral_constant<int, 0>{}, bj);
+            if (bj + 1 < nbj) issue(std::integral_constant<int, 1>{}, bj + 1);
+            if (bj + 2 < nbj) issue(std::integral_constant<int, 2>{}, bj + 2);
+            if (bj + 3 < nbj) issue(std::integral_constant<int, 3>{}, bj + 3);
+        }
+    } else {
+        // ===================== split warps: patch (smem, fp32) -> scaled fp16 hi/lo -> tensor memory =====================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;                 // tile pixel = TMEM lane
+        const int grp = (warp - 2) >> 2;             // group g converts channel half g of every (chunk, tap)
+        const int ly = r / kH2TileW, lx = r % kH2TileW;
+        // exact power-of-two scaling of the activations: abs-max -> [2^10, 2^11)
+        float sa = 1.f, inv_sa = 1.f;
+        if (p.amax_in) {
+            const uint32_t e = (__float_as_uint(__ldg(p.amax_in)) >> 23) & 0xFFu;
+            if (e > 0 && e < 255) {
+                int bits = 264 - (int)e;             // biased exponent of 2^(10 - (e - 127))
+                bits = bits < 2 ? 2 : (bits > 252 ? 252 : bits);
+                sa = __uint_as_float((uint32_t)bits << 23);
+                inv_sa = __uint_as_float((uint32_t)(254 - bits) << 23);
+            }
+        }
+        int cc = 0, tap = 0;
+        for (int bj = 0; bj < nbj; ++bj) {
+            const int j = 2 * bj + grp, slot = j & 3;
+            if (tap == 0) mbar_wait(&patch_full[cc & 1], (cc >> 1) & 1);
+            const int prow = (ly + p.tap_dy[cls][tap] - p.org_dy) * p.patch_w + lx + p.tap_dx[cls][tap] - p.org_dx;
+            const unsigned char *a = patches + (cc & 1) * kH2PatchBytes + grp * kH2BoxBytes + prow * 128;
+            uint32_t regs[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {            // SWIZZLE_128B box: logical 16-byte chunk c of patch row prow sits at chunk c ^ (prow & 7)
+                const float4 v = *reinterpret_cast<const float4 *>(a + ((c ^ (prow & 7)) << 4));
+                const float x0 = v.x * sa, x1 = v.y * sa, x2 = v.z * sa, x3 = v.w * sa;
+                const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+                regs[2 * c] = *reinterpret_cast<const uint32_t *>(&h01);
+                regs[2 * c + 1] = *reinterpret_cast<const uint32_t *>(&h23);
+                regs[16 + 2 * c] = *reinterpret_cast<const uint32_t *>(&l01);
+                regs[16 + 2 * c + 1] = *reinterpret_cast<const uint32_t *>(&l23);
+            }
+            if (j >= 4) mbar_wait(&a_free[slot], ((j >> 2) - 1) & 1);      // slot last read by the MMAs of A step j-4
+            tc_fence_after();
+            tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + kH2ACol + (uint32_t)slot * 32u, regs);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&a_full[slot]);
+            if (++tap == ntaps) {
+                mbar_arrive(&patch_empty[cc & 1]);   // this thread is done reading the chunk's patch
+                tap = 0; ++cc;
+            }
+        }
+        if (grp == 0) {
+            // ===================== epilogue =====================
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
+            const int gy = oy0 + ly, gx = ox0 + lx;
+            const bool pix_ok = b < p.batch && gy < p.grid_h && gx < p.grid_w;
+            const size_t opix = (((size_t)b * p.out_h + (size_t)gy * p.out_stride + p.cls_off_y[cls]) * p.out_w + (size_t)gx * p.out_stride + p.cls_off_x[cls]);
+            float vmax = 0.f;
+            for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+                uint32_t v[32], u[32];
+                const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                tmem_ld_32x32b_x32(lane_base, v);                                  // main0
+                tmem_ld_32x32b_x32(lane_base + (uint32_t)p.n_tile, u);             // cross terms
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
+                if (nbj > 1) {
+                    tmem_ld_32x32b_x32(lane_base + 2 * (uint32_t)p.n_tile, u);     // main1
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
+                }
+                if (!pix_ok) continue;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const int n = n0 + c0 + i;
+                    if (n >= p.cout) break;
+                    const float4 sc = *reinterpret_cast<const float4 *>(scale + n);
+                    float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (shift) sh = *reinterpret_cast<const float4 *>(shift + n);
+                    float4 o;
+                    o.x = fmaf(__uint_as_float(v[i + 0]) * inv_sa, sc.x, sh.x); o.y = fmaf(__uint_as_float(v[i + 1]) * inv_sa, sc.y, sh.y);
+                    o.z = fmaf(__uint_as_float(v[i + 2]) * inv_sa, sc.z, sh.z); o.w = fmaf(__uint_as_float(v[i + 3]) * inv_sa, sc.w, sh.w);
+                    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    const size_t off = opix * p.cout + n;
+                    if (resid) {
+                        const float4 rr = *reinterpret_cast<const float4 *>(resid + off);
+                        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                    }
+                    vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+                    *reinterpret_cast<float4 *>(out + off) = o;
+                }
+            }
+            if (p.amax_out) {
+                const unsigned m = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(vmax));     // non-negative floats order like their bits
+                if (lane == 0 && m != 0u) atomicMax(reinterpret_cast<unsigned *>(p.amax_out), m);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+// running abs-max of a tensor (feeds the activation scaling of bev_conv_h2 for tensors produced by other kernels)
+__global__ void absmax_kernel(const float4 *__restrict__ x, long long n4, const float *__restrict__ tail, int ntail, float *__restrict__ amax) {
+    float m = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(x + i);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < ntail) m = fmaxf(m, fabsf(tail[threadIdx.x]));
+    const unsigned w = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(m));
+    __shared__ unsigned s_m[32];
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = w;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const unsigned v = threadIdx.x < (blockDim.x >> 5) ? s_m[threadIdx.x] : 0u;
+        const unsigned r = __reduce_max_sync(0xFFFFFFFFu, v);
+        if (threadIdx.x == 0 && r != 0u) atomicMax(reinterpret_cast<unsigned *>(amax), r);
+    }
+}
+
+}  // namespace sessd
+
+using namespace sessd;
+
+static int launch_h2(const float *d_in, const void *d_w, int w_taps, int cout_pad, const float *d_scale, const float *d_shift,
+                     const float *d_residual, float *d_out, H2Params &p, void *stream) {
+    const int n_tile = p.cout <= 32 ? 32 : 128;
+    if (cout_pad % n_tile || cout_pad < p.cout || !d_scale) return SESSD_EINVAL;
+    int dy0 = 1 << 30, dy1 = -(1 << 30), dx0 = 1 << 30, dx1 = -(1 << 30);
+    for (int c = 0; c < p.nclass; ++c)
+        for (int t = 0; t < p.cls_ntaps[c]; ++t) {
+            dy0 = min(dy0, p.tap_dy[c][t]); dy1 = max(dy1, p.tap_dy[c][t]);
+            dx0 = min(dx0, p.tap_dx[c][t]); dx1 = max(dx1, p.tap_dx[c][t]);
+        }
+    p.org_dy = dy0; p.org_dx = dx0;
+    p.patch_h = kH2TileH + dy1 - dy0; p.patch_w = kH2TileW + dx1 - dx0;
+    if (p.patch_h * p.patch_w > kH2PatchMaxPix) return SESSD_EINVAL;
+    CUtensorMap map_a, map_b;
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)p.cin, (cuuint64_t)p.in_w, (cuuint64_t)p.in_h, (cuuint64_t)p.batch};
+        const cuuint32_t box[4] = {32, (cuuint32_t)p.patch_w, (cuuint32_t)p.patch_h, 1};
+        int rc = encode_map_4d(&map_a, d_in, dims, box);
+        if (rc) return rc;
+    }
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)p.cin, (cuuint64_t)cout_pad, (cuuint64_t)w_taps, 2};
+        const cuuint32_t box[4] = {kH2Chunk, (cuuint32_t)n_tile, 1, 1};
+        int rc = encode_map_4d(&map_b, d_w, dims, box, nullptr, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2);
+        if (rc) return rc;
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        SESSD_CUDA_TRY(cudaFuncSetAttribute(bev_conv_h2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kH2SmemBytes));
+        attr_done = true;
+    }
+    p.n_tile = n_tile;
+    p.tiles_x = div_up(p.grid_w, kH2TileW);
+    p.tiles_y = div_up(p.grid_h, kH2TileH);
+    const int tiles = p.tiles_x * p.tiles_y * p.batch;
+    bev_conv_h2_kernel<<<dim3(tiles, cout_pad / n_tile, p.nclass), kH2Threads, kH2SmemBytes, (cudaStream_t)stream>>>(map_a, map_b, d_scale, d_shift,
+                                                                                                                 d_residual, d_out, p);
+    ++g_launches;
+    return last_error();
+}
+
+// fp16-split tensor-core variant of sessd_bev_conv (stride-1 tap lists whose reach fits a 10x18 halo patch; cin a multiple of 64).
+// d_weight_h2: __half [2 (hi|lo)][ntaps][cout_pad][cin] of the per-output-channel scaled weights 2^e[n] * w (pack: ops.pack_weight_h2);
+// d_scale must carry the matching 2^-e[n] (times the folded BN scale).
+extern "C" int sessd_bev_conv_h2(const float *d_in, const void *d_weight_h2, int cout_pad, const float *d_scale, const float *d_shift,
+                                 const float *d_residual, float *d_out, const sessd_conv_desc *desc, const float *d_amax_in, float *d_amax_out,
+                                 void *stream) {
+    if (!d_in || !d_weight_h2 || !d_out || !desc || !d_scale) return SESSD_EINVAL;
+    const sessd_conv_desc &d = *desc;
+    if (d.batch < 1 || d.cin < kH2Chunk || d.cin % kH2Chunk || d.cout < 4 || d.cout % 4 || d.ntaps < 1 || d.ntaps > 9 || d.in_stride != 1 ||
+        d.out_stride < 1 || d.grid_h < 1 || d.grid_w < 1)
+        return SESSD_EINVAL;
+    if ((d.grid_h - 1) * d.out_stride + d.out_off_y >= d.out_h || (d.grid_w - 1) * d.out_stride + d.out_off_x >= d.out_w) return SESSD_EINVAL;
+    H2Params p = {};
+    p.batch = d.batch; p.in_h = d.in_h; p.in_w = d.in_w; p.cin = d.cin;
+    p.out_h = d.out_h; p.out_w = d.out_w; p.cout = d.cout;
+    p.grid_h = d.grid_h; p.grid_w = d.grid_w;
+    p.out_stride = d.out_stride;
+    p.relu = d.relu;
+    p.nclass = 1;
+    p.cls_ntaps[0] = d.ntaps; p.cls_off_y[0] = d.out_off_y; p.cls_off_x[0] = d.out_off_x;
+    for (int t = 0; t < d.ntaps; ++t) { p.tap_dy[0][t] = d.tap_dy[t]; p.tap_dx[0][t] = d.tap_dx[t]; p.tap_w[0][t] = t; }
+    p.amax_in = d_amax_in; p.amax_out = d_amax_out;
+    return launch_h2(d_in, d_weight_h2, d.ntaps, cout_pad, d_scale, d_shift, d_residual, d_out, p, stream);
+}
+
+// ConvTranspose2d(k3, s2, p1, op1) + BN + ReLU (+ residual), four output-parity classes in one launch (see sessd_bev_deconv_tc).
+extern "C" int sessd_bev_deconv_h2(const float *d_in, const void *d_weight_h2, int cout_pad, const float *d_scale, const float *d_shift,
+                                   const float *d_residual, float *d_out, int batch, int in_h, int in_w, int cin, int cout, int relu,
+                                   const float *d_amax_in, float *d_amax_out, void *stream) {
+    if (!d_in || !d_weight_h2 || !d_out || !d_scale || batch < 1 || in_h < 1 || in_w < 1 || cin < kH2Chunk || cin % kH2Chunk || cout < 4 || cout % 4)
+        return SESSD_EINVAL;
+    H2Params p = {};
+    p.batch = batch; p.in_h = in_h; p.in_w = in_w; p.cin = cin;
+    p.out_h = 2 * in_h; p.out_w = 2 * in_w; p.cout = cout;
+    p.grid_h = in_h; p.grid_w = in_w;
+    p.out_stride = 2;
+    p.relu = relu;
+    p.nclass = 4;
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+            const int c = py * 2 + px;
+            p.cls_off_y[c] = py; p.cls_off_x[c] = px;
+            // out[2y+py] receives in[y+dy] * W[ky] with 2y+py = 2(y+dy) - 1 + ky:  py=0 -> (ky=1,dy=0);  py=1 -> (ky=0,dy=1), (ky=2,dy=0)
+            const int kys[2] = {py == 0 ? 1 : 0, 2}, dys[2] = {py == 0 ? 0 : 1, 0}, ny = py == 0 ? 1 : 2;
+            const int kxs[2] = {px == 0 ? 1 : 0, 2}, dxs[2] = {px == 0 ? 0 : 1, 0}, nx = px == 0 ? 1 : 2;
+            int t = 0;
+            for (int a = 0; a < ny; ++a)
+                for (int bb = 0; bb < nx; ++bb) {
+                    p.tap_dy[c][t] = dys[a]; p.tap_dx[c][t] = dxs[bb]; p.tap_w[c][t] = kys[a] * 3 + kxs[bb];
+                    ++t;
+                }
+            p.cls_ntaps[c] = t;
+        }
+    p.amax_in = d_amax_in; p.amax_out = d_amax_out;
+    return launch_h2(d_in, d_weight_h2, 9, cout_pad, d_scale, d_shift, d_residual, d_out, p, stream);
+}
+
+// *d_amax = max(*d_amax, max |x[i]|); x 16-byte aligned
+extern "C" int sessd_absmax(const float *d_x, long long n, float *d_amax, void *stream) {
+    if (!d_x || !d_amax || n < 0 || ((uintptr_t)d_x & 15)) return SESSD_EINVAL;
+    if (n == 0) return 0;
+    const long long n4 = n / 4;
+    const int blocks = (int)max(1LL, min((long long)148 * 8, (n4 + 255) / 256));
+    absmax_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(d_x), n4, d_x + n4 * 4, (int)(n - n4 * 4), d_amax);
+    ++g_launches;
+    return last_error();
+}

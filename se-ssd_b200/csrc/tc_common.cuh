@@ -167,15 +167,16 @@ static inline EncodeTiledFn get_tensor_map_encoder() {
     return fn;
 }
 
-// fp32 4-D tiled tensor map, SWIZZLE_128B, zero OOB fill; dims / box innermost first
+// 4-D tiled tensor map (fp32 unless told otherwise), SWIZZLE_128B, zero OOB fill; dims / box innermost first
 static inline int encode_map_4d(CUtensorMap *m, const void *base, const cuuint64_t dims[4], const cuuint32_t box[4],
-                                const cuuint32_t *elem_strides = nullptr) {
+                                const cuuint32_t *elem_strides = nullptr, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                                cuuint64_t esize = 4) {
     EncodeTiledFn enc = get_tensor_map_encoder();
     if (!enc) return SESSD_EINVAL;
-    cuuint64_t strides[3] = {dims[0] * 4, dims[0] * dims[1] * 4, dims[0] * dims[1] * dims[2] * 4};
+    cuuint64_t strides[3] = {dims[0] * esize, dims[0] * dims[1] * esize, dims[0] * dims[1] * dims[2] * esize};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     if (elem_strides) for (int i = 0; i < 4; ++i) estr[i] = elem_strides[i];
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(m, dtype, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : 700 + (int)r;
 }

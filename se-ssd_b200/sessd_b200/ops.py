@@ -222,6 +222,43 @@ def bev_deconv_tc(x, weight_split, scale, shift, residual, out, relu=True):
     return out
 
 
+def pack_weight_h2(wp, cout_pad):
+    """[taps, Cin, Cout] (SIMT packing) -> (planes fp16 [2, taps, cout_pad, Cin], exps [cout_pad] fp32 = 2^-e[n]) for sessd_bev_conv_h2:
+    every output channel is scaled by the power of two 2^e[n] that puts its largest |w| into [2^10, 2^11); hi = fp16_rn(2^e w),
+    lo = fp16_rn(2^e w - hi).  The returned 2^-e[n] must be folded into the epilogue scale."""
+    taps, cin, cout = wp.shape
+    wt = torch.zeros((taps, cout_pad, cin), dtype=torch.float32, device=wp.device)
+    wt[:, :cout] = wp.permute(0, 2, 1)
+    amax = wt.abs().amax(dim=(0, 2))
+    _, ex = torch.frexp(amax)                       # amax = m * 2^ex, m in [0.5, 1)
+    e = torch.where(amax > 0, 11 - ex, torch.zeros_like(ex)).clamp(-100, 100).to(torch.float32)
+    ws = wt * torch.exp2(e)[None, :, None]
+    hi = ws.to(torch.float16)
+    lo = (ws - hi.to(torch.float32)).to(torch.float16)
+    return torch.stack([hi, lo], 0).contiguous(), torch.exp2(-e).contiguous()
+
+
+def bev_conv_h2(x, weight_h2, scale, shift, residual, out, desc, amax_in=None, amax_out=None):
+    check(lib.sessd_bev_conv_h2(_p(x), _p(weight_h2), int(weight_h2.shape[2]), _p(scale), _p(shift), _p(residual), _p(out), C.byref(desc),
+                                _p(amax_in), _p(amax_out), _st()), "sessd_bev_conv_h2")
+    return out
+
+
+def bev_deconv_h2(x, weight_h2, scale, shift, residual, out, relu=True, amax_in=None, amax_out=None):
+    """fp16-split twin of bev_deconv_tc; weight_h2 from pack_weight_h2(W.permute(2,3,0,1).reshape(9,Cin,Cout), cout_pad)."""
+    b, h, w, cin = x.shape
+    check(lib.sessd_bev_deconv_h2(_p(x), _p(weight_h2), int(weight_h2.shape[2]), _p(scale), _p(shift), _p(residual), _p(out),
+                                  int(b), int(h), int(w), int(cin), int(out.shape[-1]), int(bool(relu)), _p(amax_in), _p(amax_out), _st()),
+          "sessd_bev_deconv_h2")
+    return out
+
+
+def absmax(x, amax):
+    """amax[0] = max(amax[0], max|x|) on the current stream."""
+    check(lib.sessd_absmax(_p(x), int(x.numel()), _p(amax), _st()), "sessd_absmax")
+    return amax
+
+
 def set_conv_cluster(n):
     """CTAs per cluster sharing weight tiles via TMA multicast in bev_conv_tc (1, 2 or 4)."""
     lib.sessd_set_conv_cluster(int(n))

@@ -207,10 +207,15 @@ class SSFARunner:
 
     TC_STRIDE2 = True     # run the stride-2 conv through the strided-TMA tensor-core path as well
 
-    def __init__(self, batch, hw=(200, 176), device="cuda", use_tc=True):
-        """use_tc: tcgen05 3xTF32 tensor-core convs (default); False = the fp32 SIMT baseline kernels."""
+    def __init__(self, batch, hw=(200, 176), device="cuda", use_tc=True, split="fp16"):
+        """use_tc: tcgen05 tensor-core convs (default); False = the fp32 SIMT baseline kernels.
+        split: "fp16" = two-term fp16 split (kind::f16, bevconv_h2.cu; the stride-2 conv stays on the tf32 kernel),
+               "tf32" = 3xTF32 everywhere (bevconv_tc.cu)."""
         self.batch, self.h, self.w, self.device = batch, int(hw[0]), int(hw[1]), torch.device(device)
         self.use_tc = bool(use_tc)
+        assert split in ("fp16", "tf32")
+        self.use_h2 = self.use_tc and split == "fp16"
+        self.amax = torch.zeros(16, dtype=torch.float32, device=self.device)     # per-tensor abs-max scalars (fp16 split scaling)
         h, w, h2, w2 = self.h, self.w, self.h // 2, self.w // 2
         z = lambda hh, ww, c: torch.zeros((batch, hh, ww, c), dtype=torch.float32, device=self.device)  # noqa: E731
         self.buf = dict(b0a=z(h, w, 128), b0b=z(h, w, 128), x0=z(h, w, 128), b1a=z(h2, w2, 256), b1b=z(h2, w2, 256),
@@ -233,33 +238,60 @@ class SSFARunner:
                           ("trans_0.0", 0), ("trans_1.0", 0), ("conv_0.0", 1), ("conv_1.0", 1)):
             wp, taps = _pack_conv(g(name + ".weight"))
             P[name] = (wp, [(dy - pad, dx - pad) for dy, dx in taps]) + bn(name)
-            if self.use_tc and (self.TC_STRIDE2 or name != "bottom_up_block_1.0"):
+            if self.use_h2 and name != "bottom_up_block_1.0":
+                planes, inv = ops.pack_weight_h2(wp, -(-wp.shape[2] // 128) * 128)
+                sc_, sh_ = bn(name)
+                P[name + ":h2"] = (planes, (sc_ * inv[:sc_.numel()]).contiguous(), sh_)
+            elif self.use_tc and (self.TC_STRIDE2 or name != "bottom_up_block_1.0"):
                 P[name + ":tc"] = ops.pack_weight_tc(wp, -(-wp.shape[2] // 128) * 128)
         for name in ("deconv_block_0.0", "deconv_block_1.0"):
             classes = _deconv_classes(g(name + ".weight"))
             P[name] = (classes,) + bn(name)
             if self.use_tc:     # one launch for the four parity classes: plain 9-tap packing of W[cin][cout][ky][kx]
                 wd = g(name + ".weight")
-                P[name + ":tc"] = ops.pack_weight_tc(wd.permute(2, 3, 0, 1).reshape(9, wd.shape[0], wd.shape[1]).contiguous(), 128)
+                w9 = wd.permute(2, 3, 0, 1).reshape(9, wd.shape[0], wd.shape[1]).contiguous()
+                if self.use_h2:
+                    planes, inv = ops.pack_weight_h2(w9, 128)
+                    sc_, sh_ = bn(name)
+                    P[name + ":h2"] = (planes, (sc_ * inv[:sc_.numel()]).contiguous(), sh_)
+                else:
+                    P[name + ":tc"] = ops.pack_weight_tc(w9, 128)
         for name in ("w_0.0", "w_1.0"):
             sc, sh = bn(name)
             P[name] = (g(name + ".weight").reshape(-1).contiguous(), float(sc[0]), float(sh[0]))
         if head_sd is not None:
             hw, hb = pack_head(head_sd, head_prefix, dev, self.HEAD_STRIDE)
             P["head"] = (hw, hb)
-            if self.use_tc:
+            if self.use_h2:
+                planes, inv = ops.pack_weight_h2(hw, 32)
+                P["head:h2"] = (planes, inv.contiguous())
+            elif self.use_tc:
                 P["head:tc"] = ops.pack_weight_tc(hw, 32)
         self.params = P
 
-    def _conv(self, name, x, out, in_hw, out_hw, cin, cout, stride=1, relu=True):
+    def _am(self, i):
+        return None if i is None else self.amax[i:i + 1]
+
+    def _conv(self, name, x, out, in_hw, out_hw, cin, cout, stride=1, relu=True, ai=None, ao=None):
+        """ai / ao: slots of self.amax holding the abs-max of the input / receiving the abs-max of the output (fp16-split scaling)."""
         wp, taps, sc, sh = self.params[name]
         d = ops.conv_desc(self.batch, in_hw, cin, out_hw, cout, out_hw, taps, in_stride=stride, relu=relu)
+        if (name + ":h2") in self.params:
+            planes, sc2, sh2 = self.params[name + ":h2"]
+            return ops.bev_conv_h2(x, planes, sc2, sh2, None, out, d, self._am(ai), self._am(ao))
         if (name + ":tc") in self.params:
-            return ops.bev_conv_tc(x, self.params[name + ":tc"], sc, sh, None, out, d)
-        return ops.bev_conv(x, wp, sc, sh, None, out, d)
+            ops.bev_conv_tc(x, self.params[name + ":tc"], sc, sh, None, out, d)
+        else:
+            ops.bev_conv(x, wp, sc, sh, None, out, d)
+        if self.use_h2 and ao is not None:
+            ops.absmax(out, self._am(ao))
+        return out
 
-    def _deconv(self, name, x, out, in_hw, out_hw, cin, cout, residual=None):
+    def _deconv(self, name, x, out, in_hw, out_hw, cin, cout, residual=None, ai=None, ao=None):
         classes, sc, sh = self.params[name]
+        if (name + ":h2") in self.params:
+            planes, sc2, sh2 = self.params[name + ":h2"]
+            return ops.bev_deconv_h2(x, planes, sc2, sh2, residual, out, True, self._am(ai), self._am(ao))
         tc = self.params.get(name + ":tc")
         if tc is not None:
             return ops.bev_deconv_tc(x, tc, sc, sh, residual, out, relu=True)
@@ -273,21 +305,26 @@ class SSFARunner:
         assert self.params is not None, "load_state first"
         b = self.buf
         H, H2 = (self.h, self.w), (self.h // 2, self.w // 2)
-        self._conv("bottom_up_block_0.1", x, b["b0a"], H, H, 128, 128)
-        self._conv("bottom_up_block_0.4", b["b0a"], b["b0b"], H, H, 128, 128)
-        self._conv("bottom_up_block_0.7", b["b0b"], b["x0"], H, H, 128, 128)
-        self._conv("bottom_up_block_1.0", b["x0"], b["b1a"], H, H2, 128, 256, stride=2)
-        self._conv("bottom_up_block_1.3", b["b1a"], b["b1b"], H2, H2, 256, 256)
-        self._conv("bottom_up_block_1.6", b["b1b"], b["x1"], H2, H2, 256, 256)
-        self._conv("trans_0.0", b["x0"], b["t0"], H, H, 128, 128)
-        self._conv("trans_1.0", b["x1"], b["t1"], H2, H2, 256, 256)
-        self._deconv("deconv_block_0.0", b["t1"], b["m0"], H2, H, 256, 128, residual=b["t0"])
-        self._deconv("deconv_block_1.0", b["t1"], b["m1"], H2, H, 256, 128)
-        self._conv("conv_0.0", b["m0"], b["o0"], H, H, 128, 128)
-        self._conv("conv_1.0", b["m1"], b["o1"], H, H, 128, 128)
+        if self.use_h2:      # abs-max scalars: 0 x, 1 b0a, 2 b0b, 3 x0, 4 b1a, 5 b1b, 6 x1, 7 t1, 8 m0, 9 m1, 10 out
+            self.amax.zero_()
+            ops.absmax(x, self._am(0))
+        self._conv("bottom_up_block_0.1", x, b["b0a"], H, H, 128, 128, ai=0, ao=1)
+        self._conv("bottom_up_block_0.4", b["b0a"], b["b0b"], H, H, 128, 128, ai=1, ao=2)
+        self._conv("bottom_up_block_0.7", b["b0b"], b["x0"], H, H, 128, 128, ai=2, ao=3)
+        self._conv("bottom_up_block_1.0", b["x0"], b["b1a"], H, H2, 128, 256, stride=2, ai=3, ao=4)
+        self._conv("bottom_up_block_1.3", b["b1a"], b["b1b"], H2, H2, 256, 256, ai=4, ao=5)
+        self._conv("bottom_up_block_1.6", b["b1b"], b["x1"], H2, H2, 256, 256, ai=5, ao=6)
+        self._conv("trans_0.0", b["x0"], b["t0"], H, H, 128, 128, ai=3)
+        self._conv("trans_1.0", b["x1"], b["t1"], H2, H2, 256, 256, ai=6, ao=7)
+        self._deconv("deconv_block_0.0", b["t1"], b["m0"], H2, H, 256, 128, residual=b["t0"], ai=7, ao=8)
+        self._deconv("deconv_block_1.0", b["t1"], b["m1"], H2, H, 256, 128, ai=7, ao=9)
+        self._conv("conv_0.0", b["m0"], b["o0"], H, H, 128, 128, ai=8)
+        self._conv("conv_1.0", b["m1"], b["o1"], H, H, 128, 128, ai=9)
         w0, s0, t0 = self.params["w_0.0"]
         w1, s1, t1 = self.params["w_1.0"]
         ops.ssfa_fuse(b["o0"], b["o1"], w0, w1, s0, t0, s1, t1, b["out"])
+        if self.use_h2 and "head" in self.params:
+            ops.absmax(b["out"], self._am(10))
         if "head" not in self.params:
             return b["out"], None
         self.head(b["out"])
@@ -297,6 +334,9 @@ class SSFARunner:
         hw, hb = self.params["head"]
         H = (self.h, self.w)
         d = ops.conv_desc(self.batch, H, 128, H, self.HEAD_STRIDE, H, [(0, 0)], relu=False)
+        if "head:h2" in self.params:
+            planes, inv = self.params["head:h2"]
+            return ops.bev_conv_h2(x, planes, inv, hb, None, self.buf["head"], d, self._am(10), None)
         if "head:tc" in self.params:
             return ops.bev_conv_tc(x, self.params["head:tc"], None, hb, None, self.buf["head"], d)
         return ops.bev_conv(x, hw, None, hb, None, self.buf["head"], d)

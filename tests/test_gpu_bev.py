@@ -14,8 +14,16 @@ def _rel(a, b):
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
 
 
-@pytest.mark.parametrize("use_tc", [False, True], ids=["simt", "tcgen05"])
-def test_ssfa_and_head_match_reference_golden(golden_dir, use_tc):
+MODES = ["simt", "tf32x3", "fp16x2"]     # fp32 SIMT baseline | tcgen05 3xTF32 | tcgen05 two-term fp16 split (default)
+
+
+def _runner(batch, hw, mode):
+    from sessd_b200.runners import SSFARunner
+    return SSFARunner(batch, hw, "cuda", use_tc=mode != "simt", split="tf32" if mode == "tf32x3" else "fp16")
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_ssfa_and_head_match_reference_golden(golden_dir, mode):
     from oracle import bev_ref
     from sessd_b200.runners import SSFARunner
     g = np.load(os.path.join(golden_dir, "ssfa_head_case.npz"))
@@ -23,7 +31,7 @@ def test_ssfa_and_head_match_reference_golden(golden_dir, use_tc):
     hsd = bev_ref.head_random_state(9, prefix="tasks.0.")
     gen = torch.Generator().manual_seed(8)
     x = torch.relu(torch.randn(1, 128, 24, 16, generator=gen))
-    r = SSFARunner(1, (24, 16), "cuda", use_tc=use_tc)
+    r = _runner(1, (24, 16), mode)
     r.load_state(sd, hsd)
     out, head = r.forward(x.permute(0, 2, 3, 1).contiguous().cuda())
     torch.cuda.synchronize()
@@ -40,8 +48,8 @@ def test_ssfa_and_head_match_reference_golden(golden_dir, use_tc):
     assert _rel(h[..., 20:22], g["iou_preds"]) < TOL
 
 
-@pytest.mark.parametrize("use_tc", [False, True], ids=["simt", "tcgen05"])
-def test_ssfa_intermediates_match_oracle_fp64_batch2(use_tc):
+@pytest.mark.parametrize("mode", MODES)
+def test_ssfa_intermediates_match_oracle_fp64_batch2(mode):
     from oracle import bev_ref
     from sessd_b200.runners import SSFARunner
     sd = bev_ref.ssfa_random_state(17)
@@ -50,7 +58,7 @@ def test_ssfa_intermediates_match_oracle_fp64_batch2(use_tc):
     x = torch.relu(torch.randn(2, 128, 40, 48, generator=gen))
     trace = {}
     ref = bev_ref.ssfa_forward(x.double(), {k: v.double() if v.is_floating_point() else v for k, v in sd.items()}, trace)
-    r = SSFARunner(2, (40, 48), "cuda", use_tc=use_tc)
+    r = _runner(2, (40, 48), mode)
     r.load_state(sd, hsd)
     out, _ = r.forward(x.permute(0, 2, 3, 1).contiguous().cuda())
     torch.cuda.synchronize()
@@ -60,10 +68,10 @@ def test_ssfa_intermediates_match_oracle_fp64_batch2(use_tc):
     assert _rel(out.permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) < 2e-5
 
 
-@pytest.mark.parametrize("use_tc", [False, True], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("cin,cout,k,hw", [(128, 128, 3, (21, 37)), (256, 256, 3, (9, 50)), (128, 128, 1, (8, 16)), (256, 256, 1, (13, 17)),
                                            (128, 24, 1, (20, 33))])
-def test_single_conv_vs_fp64(use_tc, cin, cout, k, hw):
+def test_single_conv_vs_fp64(mode, cin, cout, k, hw):
     """One tap-list conv incl. partial 8x16 tiles, BN scale/shift, ReLU and residual, against an fp64 torch conv."""
     import torch.nn.functional as F
     from sessd_b200 import ops
@@ -82,8 +90,16 @@ def test_single_conv_vs_fp64(use_tc, cin, cout, k, hw):
     rd = res.permute(0, 2, 3, 1).contiguous().cuda()
     out = torch.zeros((b, hw[0], hw[1], cout), device="cuda")
     d = ops.conv_desc(b, hw, cin, hw, cout, hw, taps, relu=True)
-    if use_tc:
-        ops.bev_conv_tc(xd, ops.pack_weight_tc(wp.cuda(), 32 if cout <= 32 else -(-cout // 128) * 128), sc.cuda(), sh.cuda(), rd, out, d)
+    cout_pad = 32 if cout <= 32 else -(-cout // 128) * 128
+    if mode == "tf32x3":
+        ops.bev_conv_tc(xd, ops.pack_weight_tc(wp.cuda(), cout_pad), sc.cuda(), sh.cuda(), rd, out, d)
+    elif mode == "fp16x2":
+        planes, inv = ops.pack_weight_h2(wp.cuda(), cout_pad)
+        amax = torch.zeros(2, device="cuda")
+        ops.absmax(xd, amax[0:1])
+        ops.bev_conv_h2(xd, planes, sc.cuda() * inv[:cout], sh.cuda(), rd, out, d, amax[0:1], amax[1:2])
+        torch.cuda.synchronize()
+        assert float(amax[0]) == float(xd.abs().max()) and float(amax[1]) == float(out.abs().max())
     else:
         ops.bev_conv(xd, wp.cuda(), sc.cuda(), sh.cuda(), rd, out, d)
     torch.cuda.synchronize()
@@ -100,8 +116,35 @@ def test_tf32_split_is_exact():
     assert int((hi.view(torch.int32) & 8191).abs().max()) == 0
 
 
+def test_fp16_split_range_and_precision():
+    """Activations far outside fp16's range (1e7, 1e-7 scales) go through the exact power-of-two scaling: same relative accuracy."""
+    import torch.nn.functional as F
+    from sessd_b200 import ops
+    from sessd_b200.runners import _pack_conv
+    g = torch.Generator().manual_seed(5)
+    cin, cout, hw = 128, 128, (16, 32)
+    w = torch.randn(cout, cin, 3, 3, generator=g) * 0.03
+    wp, taps = _pack_conv(w)
+    taps = [(dy - 1, dx - 1) for dy, dx in taps]
+    planes, inv = ops.pack_weight_h2(wp.cuda(), 128)
+    d = ops.conv_desc(1, hw, cin, hw, cout, hw, taps, relu=False)
+    for scale in (1.0, 1e7, 1e-7, 3e-30):
+        x = torch.randn(1, cin, hw[0], hw[1], generator=g) * scale
+        ref = F.conv2d(x.double(), w.double(), None, 1, 1)
+        xd = x.permute(0, 2, 3, 1).contiguous().cuda()
+        out = torch.zeros((1, hw[0], hw[1], cout), device="cuda")
+        amax = torch.zeros(1, device="cuda")
+        ops.absmax(xd, amax)
+        ops.bev_conv_h2(xd, planes, inv[:cout].contiguous(), None, None, out, d, amax, None)
+        torch.cuda.synchronize()
+        got = out.permute(0, 3, 1, 2).cpu().double()
+        err = float((got - ref).abs().max() / ref.abs().max())
+        assert err < 5e-6, (scale, err)
+
+
+@pytest.mark.parametrize("split", ["tf32", "fp16"])
 @pytest.mark.parametrize("hw", [(13, 17), (100, 88)])
-def test_deconv_single_launch_vs_fp64(hw):
+def test_deconv_single_launch_vs_fp64(hw, split):
     """ConvTranspose2d(k3,s2,p1,op1)+BN+ReLU+residual as one 4-class tensor-core launch."""
     import torch.nn.functional as F
     from sessd_b200 import ops
@@ -114,9 +157,16 @@ def test_deconv_single_launch_vs_fp64(hw):
     res = torch.randn(b, cout, 2 * hw[0], 2 * hw[1], generator=g)
     ref = F.relu(F.conv_transpose2d(x.double(), w.double(), None, 2, 1, output_padding=1) * sc.double().view(1, -1, 1, 1)
                  + sh.double().view(1, -1, 1, 1)) + res.double()
-    wt = ops.pack_weight_tc(w.permute(2, 3, 0, 1).reshape(9, cin, cout).contiguous().cuda(), 128)
+    w9 = w.permute(2, 3, 0, 1).reshape(9, cin, cout).contiguous().cuda()
     out = torch.zeros((b, 2 * hw[0], 2 * hw[1], cout), device="cuda")
-    ops.bev_deconv_tc(x.permute(0, 2, 3, 1).contiguous().cuda(), wt, sc.cuda(), sh.cuda(), res.permute(0, 2, 3, 1).contiguous().cuda(), out)
+    xd, rd = x.permute(0, 2, 3, 1).contiguous().cuda(), res.permute(0, 2, 3, 1).contiguous().cuda()
+    if split == "tf32":
+        ops.bev_deconv_tc(xd, ops.pack_weight_tc(w9, 128), sc.cuda(), sh.cuda(), rd, out)
+    else:
+        planes, inv = ops.pack_weight_h2(w9, 128)
+        amax = torch.zeros(1, device="cuda")
+        ops.absmax(xd, amax)
+        ops.bev_deconv_h2(xd, planes, sc.cuda() * inv[:cout], sh.cuda(), rd, out, True, amax, None)
     torch.cuda.synchronize()
     got = out.permute(0, 3, 1, 2).cpu().double()
     assert float((got - ref).abs().max() / ref.abs().max()) < 5e-6
