@@ -182,6 +182,9 @@ int sessd_bev_conv_h2(const float *d_in, const void *d_weight_h2, int cout_pad, 
 int sessd_bev_deconv_h2(const float *d_in, const void *d_weight_h2, int cout_pad, const float *d_scale,
                         const float *d_shift, const float *d_residual, float *d_out, int batch, int in_h, int in_w,
                         int cin, int cout, int relu, const float *d_amax_in, float *d_amax_out, void *stream);
+/* profiling experiments only: ablation mask (1 no split work, 2 no MMAs, 4 no weight reloads, 8 no stores; results are garbage when
+ * non-zero) and optional [ctas][8] int64 globaltimer stamps (start, split done, accumulators ready, end) */
+void sessd_set_h2_debug(int ablate_mask, void *d_stamps);
 /* *d_amax = max(*d_amax, max_i |d_x[i]|)  (for tensors produced by kernels without an abs-max epilogue) */
 int sessd_absmax(const float *d_x, long long n, float *d_amax, void *stream);
 

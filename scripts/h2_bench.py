@@ -87,3 +87,36 @@ if accuracy():
     bench("conv1x1 256->256 @100x88", 256, 256, (100, 88), (100, 88), [(0, 0)])
     bench("deconv 256->128 100x88->200x176", 256, 128, (100, 88), (200, 176), None, deconv=True)
     bench("head 128->24 @200x176", 128, 24, (200, 176), (200, 176), [(0, 0)])
+
+import ctypes
+from sessd_b200._lib import lib
+print("--- ablations on conv3x3 128->128 @200x176: 1=no split work, 2=no MMAs, 4=no weight reloads, 8=no stores")
+x = torch.randn(1, 200, 176, 128, device="cuda"); wp = torch.randn(9, 128, 128, device="cuda") * 0.05
+planes, inv = ops.pack_weight_h2(wp, 128); out = torch.zeros(1, 200, 176, 128, device="cuda")
+t3 = [(dy - 1, dx - 1) for dy in range(3) for dx in range(3)]
+d = ops.conv_desc(1, (200, 176), 128, (200, 176), 128, (200, 176), t3, relu=True)
+amax = torch.zeros(1, device="cuda"); ops.absmax(x, amax)
+flush = torch.empty(64 * 1024 * 1024, device="cuda")
+sc = inv[:128].contiguous()
+for mode in (0, 1, 2, 3, 4, 8, 7, 15):
+    lib.sessd_set_h2_debug(mode, ctypes.c_void_p(0))
+    ts = []
+    for i in range(8):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); ops.bev_conv_h2(x, planes, sc, None, None, out, d, amax, None); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    print("ablate=%2d  %.1f us" % (mode, float(np.median(ts[2:])) * 1000))
+dbg = torch.zeros((1024, 8), dtype=torch.int64, device="cuda")
+lib.sessd_set_h2_debug(0, ctypes.c_void_p(dbg.data_ptr()))
+ops.bev_conv_h2(x, planes, sc, None, None, out, d, amax, None)
+torch.cuda.synchronize()
+lib.sessd_set_h2_debug(0, ctypes.c_void_p(0))
+t = dbg[:275].cpu().numpy().astype(np.float64)
+t0 = t[:, 0].min()
+print("kernel span %.1f us" % ((t[:, 3].max() - t0) / 1000))
+for lbl, a, b in (("start->split done", 0, 1), ("split done->acc ready", 1, 2), ("epilogue", 2, 3), ("CTA total", 0, 3)):
+    dt = (t[:, b] - t[:, a]) / 1000
+    print("   %-22s median %.2f us  (min %.2f max %.2f)" % (lbl, np.median(dt), dt.min(), dt.max()))
+st = (t[:, 0] - t0) / 1000
+print("   CTA start times: first wave <1us: %d, later: median %.1f us" % (int((st < 1).sum()), float(np.median(st[st >= 1])) if (st >= 1).any() else 0))

@@ -51,6 +51,8 @@ struct H2Params {
     int patch_w, patch_h, org_dy, org_dx;     // patch rows = input rows oy0 + org_dy ... (patch_h of them), same for columns
     const float *amax_in;                     // nullable: abs-max of the input tensor (device scalar)
     float *amax_out;                          // nullable: running abs-max of the output tensor (atomicMax on the float bits)
+    int ablate;                               // timing experiments only (results become garbage): 1 no split work, 2 no MMAs, 4 no weight reloads, 8 no stores
+    long long *dbg;                           // optional [ctas][8] globaltimer stamps
 };
 
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
@@ -92,6 +94,10 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
     const int nbj = nchunks * ntaps;                           // weight stages = (chunk, tap); each feeds two 32-channel A steps
     const uint32_t b_plane_bytes = (uint32_t)p.n_tile * 128u;
 
+    if (p.dbg && threadIdx.x == 0) {
+        long long ts; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
+        p.dbg[(size_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 8 + 0] = ts;
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) { mbar_init(&patch_full[s], 1); mbar_init(&patch_empty[s], 256); }
         for (int s = 0; s < 4; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); mbar_init(&a_full[s], 128); mbar_init(&a_free[s], 1); }
@@ -127,6 +133,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
             for (int bj = 0; bj < nbj; ++bj) {
                 const int s = bj & 3;
                 mbar_wait(&b_empty[s], ((bj >> 2) & 1) ^ 1);
+                if ((p.ablate & 4) && bj >= kH2BStages) { mbar_arrive(&b_full[s]); if (++tap == ntaps) { tap = 0; ++cc; } continue; }
                 mbar_expect_tx(&b_full[s], 2 * b_plane_bytes);
                 unsigned char *st = tiles + s * kH2BStageBytes;
                 const int wtap = p.tap_w[cls][tap];
@@ -161,6 +168,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                     const uint32_t a_hi = tmem_base + kH2ACol + (uint32_t)slot * 32u, a_lo = a_hi + 16u;
 #pragma unroll
                     for (int kk = 0; kk < 2; ++kk) {
+                        if (p.ablate & 2) break;
                         const uint32_t koff = (uint32_t)(h * 4 + kk * 2);            // 32-channel half: +64 B, K=16 sub-step: +32 B (>>4)
                         if ((S & 1) == 0) {
                             tc_mma_f16_ts(acc_main0, a_hi + kk * 8, dCat[S] + koff, idesc2, (bj | h | kk) != 0);   // [main0|cross] (+)= a_hi x [b_hi;b_lo]
@@ -212,6 +220,12 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
             const int prow = (ly + p.tap_dy[cls][tap] - p.org_dy) * p.patch_w + lx + p.tap_dx[cls][tap] - p.org_dx;
             const unsigned char *a = patches + (cc & 1) * kH2PatchBytes + grp * kH2BoxBytes + prow * 128;
             uint32_t regs[32];
+            if (p.ablate & 1) {
+                if (j >= 4) mbar_wait(&a_free[slot], ((j >> 2) - 1) & 1);
+                mbar_arrive(&a_full[slot]);
+                if (++tap == ntaps) { mbar_arrive(&patch_empty[cc & 1]); tap = 0; ++cc; }
+                continue;
+            }
 #pragma unroll
             for (int c = 0; c < 8; ++c) {            // SWIZZLE_128B box: logical 16-byte chunk c of patch row prow sits at chunk c ^ (prow & 7)
                 const float4 v = *reinterpret_cast<const float4 *>(a + ((c ^ (prow & 7)) << 4));
@@ -235,10 +249,12 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                 tap = 0; ++cc;
             }
         }
+        if (p.dbg && threadIdx.x == 64) { long long ts; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts)); p.dbg[(size_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 8 + 1] = ts; }
         if (grp == 0) {
             // ===================== epilogue =====================
             mbar_wait(acc_full, 0);
             tc_fence_after();
+            if (p.dbg && threadIdx.x == 64) { long long ts; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts)); p.dbg[(size_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 8 + 2] = ts; }
             const int gy = oy0 + ly, gx = ox0 + lx;
             const bool pix_ok = b < p.batch && gy < p.grid_h && gx < p.grid_w;
             const size_t opix = (((size_t)b * p.out_h + (size_t)gy * p.out_stride + p.cls_off_y[cls]) * p.out_w + (size_t)gx * p.out_stride + p.cls_off_x[cls]);
@@ -273,7 +289,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                         o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
                     }
                     vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
-                    *reinterpret_cast<float4 *>(out + off) = o;
+                    if (!(p.ablate & 8)) *reinterpret_cast<float4 *>(out + off) = o;
                 }
             }
             if (p.amax_out) {
@@ -285,6 +301,10 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
     tc_fence_before();
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
+    if (p.dbg && threadIdx.x == 0) {
+        long long ts; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
+        p.dbg[(size_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 8 + 3] = ts;
+    }
 }
 
 // running abs-max of a tensor (feeds the activation scaling of bev_conv_h2 for tensors produced by other kernels)
@@ -306,9 +326,16 @@ __global__ void absmax_kernel(const float4 *__restrict__ x, long long n4, const 
     }
 }
 
+static int g_h2_ablate = 0;
+static long long *g_h2_dbg = nullptr;
+
 }  // namespace sessd
 
 using namespace sessd;
+
+// profiling experiments only (see H2Params::ablate / dbg)
+extern "C" void sessd_set_h2_debug(int ablate_mask, void *d_stamps) { sessd::g_h2_ablate = ablate_mask; sessd::g_h2_dbg = (long long *)d_stamps; }
+
 
 static int launch_h2(const float *d_in, const void *d_w, int w_taps, int cout_pad, const float *d_scale, const float *d_shift,
                      const float *d_residual, float *d_out, H2Params &p, void *stream) {
@@ -342,6 +369,8 @@ static int launch_h2(const float *d_in, const void *d_w, int w_taps, int cout_pa
         attr_done = true;
     }
     p.n_tile = n_tile;
+    p.ablate = g_h2_ablate;
+    p.dbg = g_h2_dbg;
     p.tiles_x = div_up(p.grid_w, kH2TileW);
     p.tiles_y = div_up(p.grid_h, kH2TileH);
     const int tiles = p.tiles_x * p.tiles_y * p.batch;
