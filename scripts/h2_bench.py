@@ -112,11 +112,8 @@ lib.sessd_set_h2_debug(0, ctypes.c_void_p(dbg.data_ptr()))
 ops.bev_conv_h2(x, planes, sc, None, None, out, d, amax, None)
 torch.cuda.synchronize()
 lib.sessd_set_h2_debug(0, ctypes.c_void_p(0))
-t = dbg[:275].cpu().numpy().astype(np.float64)
+t = dbg[:148].cpu().numpy().astype(np.float64)
 t0 = t[:, 0].min()
 print("kernel span %.1f us" % ((t[:, 3].max() - t0) / 1000))
-for lbl, a, b in (("start->split done", 0, 1), ("split done->acc ready", 1, 2), ("epilogue", 2, 3), ("CTA total", 0, 3)):
-    dt = (t[:, b] - t[:, a]) / 1000
-    print("   %-22s median %.2f us  (min %.2f max %.2f)" % (lbl, np.median(dt), dt.min(), dt.max()))
-st = (t[:, 0] - t0) / 1000
-print("   CTA start times: first wave <1us: %d, later: median %.1f us" % (int((st < 1).sum()), float(np.median(st[st >= 1])) if (st >= 1).any() else 0))
+dt = (t[:, 3] - t[:, 0]) / 1000
+print("   CTA total median %.2f us  (min %.2f max %.2f)" % (np.median(dt), dt.min(), dt.max()))

@@ -34,7 +34,7 @@ constexpr int kH2PatchMaxPix = (kH2TileH + 2) * (kH2TileW + 2);
 constexpr int kH2BoxBytes = ((kH2PatchMaxPix * 128 + 1023) / 1024) * 1024;
 constexpr int kH2PatchBytes = 2 * kH2BoxBytes;
 constexpr int kH2SmemBytes = kH2BStages * kH2BStageBytes + 2 * kH2PatchBytes + 1024 + 256;
-constexpr int kH2Threads = 352;
+constexpr int kH2Threads = 608;     // w0 patch TMA, w1 MMA, w2-9 split, w10 weight TMA, w11-18 epilogue
 constexpr uint32_t kH2ACol = 384;                              // TMEM: 3 accumulators (<= 384 columns) + 4 A slots x 32 columns
 
 struct H2Params {
@@ -48,6 +48,8 @@ struct H2Params {
     int relu;
     int n_tile;
     int tiles_x, tiles_y;
+    int tiles, nblocks, total;                // pixel tiles, N blocks, work items = nclass * nblocks * tiles
+    int cls_order[4];                         // classes by descending tap count (heavy items first in the static round-robin schedule)
     int patch_w, patch_h, org_dy, org_dx;     // patch rows = input rows oy0 + org_dy ... (patch_h of them), same for columns
     const float *amax_in;                     // nullable: abs-max of the input tensor (device scalar)
     float *amax_out;                          // nullable: running abs-max of the output tensor (atomicMax on the float bits)
@@ -69,6 +71,45 @@ __device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, 
         : "memory");
 }
 
+// exact power-of-two activation scale 2^s that maps abs-max into [2^10, 2^11) (1 when abs-max is 0 / not finite)
+__device__ __forceinline__ float h2_act_scale(float amax) {
+    const uint32_t e = (__float_as_uint(amax) >> 23) & 0xFFu;
+    if (e == 0 || e == 255) return 1.f;
+    int bits = 264 - (int)e;                      // biased exponent of 2^(10 - (e - 127))
+    bits = bits < 2 ? 2 : (bits > 252 ? 252 : bits);
+    return __uint_as_float((uint32_t)bits << 23);
+}
+
+// work item w (persistent CTAs take w = blockIdx.x, + gridDim.x, ...): class-major (heaviest class first), then N block, then pixel tile
+struct H2Item { int cls, n0, b, oy0, ox0, ntaps; };
+__device__ __forceinline__ H2Item h2_decode(const H2Params &p, int w) {
+    H2Item it;
+    const int per_cls = p.nblocks * p.tiles;
+    const int cr = w / per_cls;
+    int rem = w - cr * per_cls;
+    const int nb = rem / p.tiles;
+    int t = rem - nb * p.tiles;
+    it.cls = p.cls_order[cr];
+    it.n0 = nb * p.n_tile;
+    const int tx = t % p.tiles_x; t /= p.tiles_x;
+    const int ty = t % p.tiles_y;
+    it.b = t / p.tiles_y;
+    it.oy0 = ty * kH2TileH; it.ox0 = tx * kH2TileW;
+    it.ntaps = p.cls_ntaps[it.cls];
+    return it;
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x16_nowait(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
 __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                    const __grid_constant__ CUtensorMap map_b,
                                                                    const float *__restrict__ scale, const float *__restrict__ shift,
@@ -78,30 +119,22 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
     unsigned char *patches = tiles + kH2BStages * kH2BStageBytes;
     uint64_t *bars = (uint64_t *)(patches + 2 * kH2PatchBytes);
     uint64_t *patch_full = bars, *patch_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 8, *a_full = bars + 12, *a_free = bars + 16;
-    uint64_t *acc_full = bars + 20;
-    uint32_t *tmem_slot = (uint32_t *)(bars + 21);
+    uint64_t *acc_full = bars + 20, *acc_free = bars + 21;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 22);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int t = blockIdx.x;
-    const int tx = t % p.tiles_x; t /= p.tiles_x;
-    const int ty = t % p.tiles_y;
-    const int b = t / p.tiles_y;
-    const int oy0 = ty * kH2TileH, ox0 = tx * kH2TileW;
-    const int n0 = blockIdx.y * p.n_tile;
-    const int cls = blockIdx.z;
     const int nchunks = p.cin / kH2Chunk;
-    const int ntaps = p.cls_ntaps[cls];
-    const int nbj = nchunks * ntaps;                           // weight stages = (chunk, tap); each feeds two 32-channel A steps
     const uint32_t b_plane_bytes = (uint32_t)p.n_tile * 128u;
 
     if (p.dbg && threadIdx.x == 0) {
         long long ts; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
-        p.dbg[(size_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 8 + 0] = ts;
+        p.dbg[(size_t)blockIdx.x * 8 + 0] = ts;
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) { mbar_init(&patch_full[s], 1); mbar_init(&patch_empty[s], 256); }
         for (int s = 0; s < 4; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); mbar_init(&a_full[s], 128); mbar_init(&a_free[s], 1); }
         mbar_init(acc_full, 1);
+        mbar_init(acc_free, 256);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 1) {
@@ -114,33 +147,41 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== activation patches: one halo patch per 64-channel chunk =====================
+        // ===================== activation patches: one halo patch per (item, 64-channel chunk) =====================
         if (lane == 0) {
             const uint32_t box_bytes = (uint32_t)(p.patch_w * p.patch_h) * 128u;
-            for (int cc = 0; cc < nchunks; ++cc) {
-                const int pb = cc & 1;
-                mbar_wait(&patch_empty[pb], ((cc >> 1) & 1) ^ 1);
-                mbar_expect_tx(&patch_full[pb], 2 * box_bytes);
-                unsigned char *dst = patches + pb * kH2PatchBytes;
-                tma_load_4d(dst, &map_a, &patch_full[pb], cc * kH2Chunk, ox0 + p.org_dx, oy0 + p.org_dy, b);
-                tma_load_4d(dst + kH2BoxBytes, &map_a, &patch_full[pb], cc * kH2Chunk + 32, ox0 + p.org_dx, oy0 + p.org_dy, b);
+            int gcc = 0;
+            for (int w = blockIdx.x; w < p.total; w += gridDim.x) {
+                const H2Item it = h2_decode(p, w);
+                for (int cc = 0; cc < nchunks; ++cc, ++gcc) {
+                    const int pb = gcc & 1;
+                    mbar_wait(&patch_empty[pb], ((gcc >> 1) & 1) ^ 1);
+                    mbar_expect_tx(&patch_full[pb], 2 * box_bytes);
+                    unsigned char *dst = patches + pb * kH2PatchBytes;
+                    tma_load_4d(dst, &map_a, &patch_full[pb], cc * kH2Chunk, it.ox0 + p.org_dx, it.oy0 + p.org_dy, it.b);
+                    tma_load_4d(dst + kH2BoxBytes, &map_a, &patch_full[pb], cc * kH2Chunk + 32, it.ox0 + p.org_dx, it.oy0 + p.org_dy, it.b);
+                }
             }
         }
     } else if (warp == 10) {
-        // ===================== weight tiles =====================
+        // ===================== weight tiles: one [X ; Y] stage per (item, chunk, tap) =====================
         if (lane == 0) {
-            int cc = 0, tap = 0;
-            for (int bj = 0; bj < nbj; ++bj) {
-                const int s = bj & 3;
-                mbar_wait(&b_empty[s], ((bj >> 2) & 1) ^ 1);
-                if ((p.ablate & 4) && bj >= kH2BStages) { mbar_arrive(&b_full[s]); if (++tap == ntaps) { tap = 0; ++cc; } continue; }
-                mbar_expect_tx(&b_full[s], 2 * b_plane_bytes);
-                unsigned char *st = tiles + s * kH2BStageBytes;
-                const int wtap = p.tap_w[cls][tap];
-                const uint32_t hi_off = (bj & 1) ? b_plane_bytes : 0u, lo_off = (bj & 1) ? 0u : b_plane_bytes;
-                tma_load_4d(st + hi_off, &map_b, &b_full[s], cc * kH2Chunk, n0, wtap, 0);
-                tma_load_4d(st + lo_off, &map_b, &b_full[s], cc * kH2Chunk, n0, wtap, 1);
-                if (++tap == ntaps) { tap = 0; ++cc; }
+            int gbj = 0;
+            for (int w = blockIdx.x; w < p.total; w += gridDim.x) {
+                const H2Item it = h2_decode(p, w);
+                for (int cc = 0; cc < nchunks; ++cc)
+                    for (int tap = 0; tap < it.ntaps; ++tap, ++gbj) {
+                        const int s = gbj & 3;
+                        mbar_wait(&b_empty[s], ((gbj >> 2) & 1) ^ 1);
+                        if ((p.ablate & 4) && gbj >= kH2BStages) { mbar_arrive(&b_full[s]); continue; }
+                        mbar_expect_tx(&b_full[s], 2 * b_plane_bytes);
+                        unsigned char *st = tiles + s * kH2BStageBytes;
+                        const int wtap = p.tap_w[it.cls][tap];
+                        // every item has an even number of stages, so the running parity is also the item-local one
+                        const uint32_t hi_off = (gbj & 1) ? b_plane_bytes : 0u, lo_off = (gbj & 1) ? 0u : b_plane_bytes;
+                        tma_load_4d(st + hi_off, &map_b, &b_full[s], cc * kH2Chunk, it.n0, wtap, 0);
+                        tma_load_4d(st + lo_off, &map_b, &b_full[s], cc * kH2Chunk, it.n0, wtap, 1);
+                    }
             }
         }
     } else if (warp == 1) {
@@ -155,14 +196,15 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
             dCat[sgi] = desc_hi | (tiles_lo + (uint32_t)sgi * (kH2BStageBytes >> 4));
             dBhi[sgi] = dCat[sgi] + ((sgi & 1) ? (b_plane_bytes >> 4) : 0u);
         }
-        auto issue = [&](auto stage_c, int bj) {
+        // gbj: running stage counter (ring position / barrier parities); lbj: stage index inside the current item (accumulator roles)
+        auto issue = [&](auto stage_c, int gbj, int lbj, bool last) {
             constexpr int S = decltype(stage_c)::value;
-            mbar_wait(&b_full[S], (bj >> 2) & 1);
+            mbar_wait(&b_full[S], (gbj >> 2) & 1);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 constexpr int kSlotBase = 2 * (S & 1);
                 const int slot = kSlotBase + h;
-                mbar_wait(&a_full[slot], (bj >> 1) & 1);
+                mbar_wait(&a_full[slot], (gbj >> 1) & 1);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t a_hi = tmem_base + kH2ACol + (uint32_t)slot * 32u, a_lo = a_hi + 16u;
@@ -171,8 +213,8 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                         if (p.ablate & 2) break;
                         const uint32_t koff = (uint32_t)(h * 4 + kk * 2);            // 32-channel half: +64 B, K=16 sub-step: +32 B (>>4)
                         if ((S & 1) == 0) {
-                            tc_mma_f16_ts(acc_main0, a_hi + kk * 8, dCat[S] + koff, idesc2, (bj | h | kk) != 0);   // [main0|cross] (+)= a_hi x [b_hi;b_lo]
-                        } else if (bj == 1 && h == 0 && kk == 0) {
+                            tc_mma_f16_ts(acc_main0, a_hi + kk * 8, dCat[S] + koff, idesc2, (lbj | h | kk) != 0);  // [main0|cross] (+)= a_hi x [b_hi;b_lo]
+                        } else if (lbj == 1 && h == 0 && kk == 0) {
                             tc_mma_f16_ts(acc_cross, a_hi, dCat[S] + koff, idesc1, 1);                              // cross += a_hi x b_lo
                             tc_mma_f16_ts(acc_main1, a_hi, dBhi[S] + koff, idesc1, 0);                              // main1  = a_hi x b_hi
                         } else {
@@ -186,116 +228,132 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
             }
             if (lane == 0) {
                 tc_commit(&b_empty[S]);
-                if (bj == nbj - 1) tc_commit(acc_full);
+                if (last) tc_commit(acc_full);
             }
             __syncwarp();
         };
-        for (int bj = 0; bj < nbj; bj += kH2BStages) {
-            issue(std::integral_constant<int, 0>{}, bj);
-            if (bj + 1 < nbj) issue(std::integral_constant<int, 1>{}, bj + 1);
-            if (bj + 2 < nbj) issue(std::integral_constant<int, 2>{}, bj + 2);
-            if (bj + 3 < nbj) issue(std::integral_constant<int, 3>{}, bj + 3);
+        int gbj = 0, iter = 0;
+        for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++iter) {
+            const int nbj = nchunks * p.cls_ntaps[p.cls_order[w / (p.nblocks * p.tiles)]];
+            if (iter > 0) {                          // the epilogue warps must have drained the previous item's accumulators
+                mbar_wait(acc_free, (iter - 1) & 1);
+                tc_fence_after();
+            }
+            for (int lbj = 0; lbj < nbj; ++lbj, ++gbj) {
+                const bool last = lbj == nbj - 1;
+                switch (gbj & 3) {
+                    case 0: issue(std::integral_constant<int, 0>{}, gbj, lbj, last); break;
+                    case 1: issue(std::integral_constant<int, 1>{}, gbj, lbj, last); break;
+                    case 2: issue(std::integral_constant<int, 2>{}, gbj, lbj, last); break;
+                    default: issue(std::integral_constant<int, 3>{}, gbj, lbj, last); break;
+                }
+            }
         }
-    } else {
+    } else if (warp < 10) {
         // ===================== split warps: patch (smem, fp32) -> scaled fp16 hi/lo -> tensor memory =====================
         const int q = warp & 3;
         const int r = q * 32 + lane;                 // tile pixel = TMEM lane
         const int grp = (warp - 2) >> 2;             // group g converts channel half g of every (chunk, tap)
         const int ly = r / kH2TileW, lx = r % kH2TileW;
-        // exact power-of-two scaling of the activations: abs-max -> [2^10, 2^11)
-        float sa = 1.f, inv_sa = 1.f;
-        if (p.amax_in) {
-            const uint32_t e = (__float_as_uint(__ldg(p.amax_in)) >> 23) & 0xFFu;
-            if (e > 0 && e < 255) {
-                int bits = 264 - (int)e;             // biased exponent of 2^(10 - (e - 127))
-                bits = bits < 2 ? 2 : (bits > 252 ? 252 : bits);
-                sa = __uint_as_float((uint32_t)bits << 23);
-                inv_sa = __uint_as_float((uint32_t)(254 - bits) << 23);
-            }
-        }
-        int cc = 0, tap = 0;
-        for (int bj = 0; bj < nbj; ++bj) {
-            const int j = 2 * bj + grp, slot = j & 3;
-            if (tap == 0) mbar_wait(&patch_full[cc & 1], (cc >> 1) & 1);
-            const int prow = (ly + p.tap_dy[cls][tap] - p.org_dy) * p.patch_w + lx + p.tap_dx[cls][tap] - p.org_dx;
-            const unsigned char *a = patches + (cc & 1) * kH2PatchBytes + grp * kH2BoxBytes + prow * 128;
-            uint32_t regs[32];
-            if (p.ablate & 1) {
-                if (j >= 4) mbar_wait(&a_free[slot], ((j >> 2) - 1) & 1);
-                mbar_arrive(&a_full[slot]);
-                if (++tap == ntaps) { mbar_arrive(&patch_empty[cc & 1]); tap = 0; ++cc; }
-                continue;
-            }
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {            // SWIZZLE_128B box: logical 16-byte chunk c of patch row prow sits at chunk c ^ (prow & 7)
-                const float4 v = *reinterpret_cast<const float4 *>(a + ((c ^ (prow & 7)) << 4));
-                const float x0 = v.x * sa, x1 = v.y * sa, x2 = v.z * sa, x3 = v.w * sa;
-                const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
-                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
-                regs[2 * c] = *reinterpret_cast<const uint32_t *>(&h01);
-                regs[2 * c + 1] = *reinterpret_cast<const uint32_t *>(&h23);
-                regs[16 + 2 * c] = *reinterpret_cast<const uint32_t *>(&l01);
-                regs[16 + 2 * c + 1] = *reinterpret_cast<const uint32_t *>(&l23);
-            }
-            if (j >= 4) mbar_wait(&a_free[slot], ((j >> 2) - 1) & 1);      // slot last read by the MMAs of A step j-4
-            tc_fence_after();
-            tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + kH2ACol + (uint32_t)slot * 32u, regs);
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&a_full[slot]);
-            if (++tap == ntaps) {
-                mbar_arrive(&patch_empty[cc & 1]);   // this thread is done reading the chunk's patch
-                tap = 0; ++cc;
-            }
-        }
-        if (p.dbg && threadIdx.x == 64) { long long ts; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts)); p.dbg[(size_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 8 + 1] = ts; }
-        if (grp == 0) {
-            // ===================== epilogue =====================
-            mbar_wait(acc_full, 0);
-            tc_fence_after();
-            if (p.dbg && threadIdx.x == 64) { long long ts; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts)); p.dbg[(size_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 8 + 2] = ts; }
-            const int gy = oy0 + ly, gx = ox0 + lx;
-            const bool pix_ok = b < p.batch && gy < p.grid_h && gx < p.grid_w;
-            const size_t opix = (((size_t)b * p.out_h + (size_t)gy * p.out_stride + p.cls_off_y[cls]) * p.out_w + (size_t)gx * p.out_stride + p.cls_off_x[cls]);
-            float vmax = 0.f;
-            for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
-                uint32_t v[32], u[32];
-                const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-                tmem_ld_32x32b_x32(lane_base, v);                                  // main0
-                tmem_ld_32x32b_x32(lane_base + (uint32_t)p.n_tile, u);             // cross terms
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
-                if (nbj > 1) {
-                    tmem_ld_32x32b_x32(lane_base + 2 * (uint32_t)p.n_tile, u);     // main1
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
-                }
-                if (!pix_ok) continue;
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const int n = n0 + c0 + i;
-                    if (n >= p.cout) break;
-                    const float4 sc = *reinterpret_cast<const float4 *>(scale + n);
-                    float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (shift) sh = *reinterpret_cast<const float4 *>(shift + n);
-                    float4 o;
-                    o.x = fmaf(__uint_as_float(v[i + 0]) * inv_sa, sc.x, sh.x); o.y = fmaf(__uint_as_float(v[i + 1]) * inv_sa, sc.y, sh.y);
-                    o.z = fmaf(__uint_as_float(v[i + 2]) * inv_sa, sc.z, sh.z); o.w = fmaf(__uint_as_float(v[i + 3]) * inv_sa, sc.w, sh.w);
-                    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                    const size_t off = opix * p.cout + n;
-                    if (resid) {
-                        const float4 rr = *reinterpret_cast<const float4 *>(resid + off);
-                        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+        const float sa = p.amax_in ? h2_act_scale(__ldg(p.amax_in)) : 1.f;
+        int gbj = 0, gcc = 0;
+        for (int w = blockIdx.x; w < p.total; w += gridDim.x) {
+            const int cls = p.cls_order[w / (p.nblocks * p.tiles)];
+            const int ntaps = p.cls_ntaps[cls];
+            for (int cc = 0; cc < nchunks; ++cc, ++gcc) {
+                mbar_wait(&patch_full[gcc & 1], (gcc >> 1) & 1);
+                const unsigned char *box = patches + (gcc & 1) * kH2PatchBytes + grp * kH2BoxBytes;
+                for (int tap = 0; tap < ntaps; ++tap, ++gbj) {
+                    const int j = 2 * gbj + grp, slot = j & 3;
+                    if (p.ablate & 1) {
+                        if (j >= 4) mbar_wait(&a_free[slot], ((j >> 2) - 1) & 1);
+                        mbar_arrive(&a_full[slot]);
+                        continue;
                     }
-                    vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
-                    if (!(p.ablate & 8)) *reinterpret_cast<float4 *>(out + off) = o;
+                    const int prow = (ly + p.tap_dy[cls][tap] - p.org_dy) * p.patch_w + lx + p.tap_dx[cls][tap] - p.org_dx;
+                    const unsigned char *a = box + prow * 128;
+                    uint32_t regs[32];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {    // SWIZZLE_128B box: logical 16-byte chunk c of patch row prow sits at chunk c ^ (prow & 7)
+                        const float4 v = *reinterpret_cast<const float4 *>(a + ((c ^ (prow & 7)) << 4));
+                        const float x0 = v.x * sa, x1 = v.y * sa, x2 = v.z * sa, x3 = v.w * sa;
+                        const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+                        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                        const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+                        regs[2 * c] = *reinterpret_cast<const uint32_t *>(&h01);
+                        regs[2 * c + 1] = *reinterpret_cast<const uint32_t *>(&h23);
+                        regs[16 + 2 * c] = *reinterpret_cast<const uint32_t *>(&l01);
+                        regs[16 + 2 * c + 1] = *reinterpret_cast<const uint32_t *>(&l23);
+                    }
+                    if (j >= 4) mbar_wait(&a_free[slot], ((j >> 2) - 1) & 1);      // slot last read by the MMAs of A step j-4
+                    tc_fence_after();
+                    tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + kH2ACol + (uint32_t)slot * 32u, regs);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&a_full[slot]);
+                }
+                mbar_arrive(&patch_empty[gcc & 1]);  // this thread is done reading the chunk's patch
+            }
+        }
+    } else {
+        // ===================== epilogue warps (11-18): drain TMEM to registers, release the accumulators, then BN/ReLU/residual/store
+        const int q = warp & 3;
+        const int half = (warp - 11) >> 2;           // warps 11-14: first half of the N tile's columns, 15-18: second half
+        const int r = q * 32 + lane;
+        const int ly = r / kH2TileW, lx = r % kH2TileW;
+        const int ncol = p.n_tile >> 1;              // 64 (n_tile 128) or 16 (n_tile 32)
+        const float inv_sa = p.amax_in ? 1.f / h2_act_scale(__ldg(p.amax_in)) : 1.f;   // exact: power of two
+        float vmax = 0.f;
+        int iter = 0;
+        for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++iter) {
+            const H2Item it = h2_decode(p, w);
+            float v[64];
+            mbar_wait(acc_full, iter & 1);
+            tc_fence_after();
+            const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * ncol);
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+                if (c0 < ncol) {
+                    uint32_t m0[16], cr[16], m1[16];
+                    tmem_ld_32x32b_x16_nowait(lane_base + c0, m0);
+                    tmem_ld_32x32b_x16_nowait(lane_base + (uint32_t)p.n_tile + c0, cr);
+                    tmem_ld_32x32b_x16_nowait(lane_base + 2 * (uint32_t)p.n_tile + c0, m1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[c0 + i] = (__uint_as_float(m0[i]) + __uint_as_float(cr[i])) + __uint_as_float(m1[i]);
                 }
             }
-            if (p.amax_out) {
-                const unsigned m = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(vmax));     // non-negative floats order like their bits
-                if (lane == 0 && m != 0u) atomicMax(reinterpret_cast<unsigned *>(p.amax_out), m);
+            tc_fence_before();
+            mbar_arrive(acc_free);                   // the next item's MMAs may overwrite the accumulators now
+            const int gy = it.oy0 + ly, gx = it.ox0 + lx;
+            if (gy < p.grid_h && gx < p.grid_w) {
+                const size_t opix = (((size_t)it.b * p.out_h + (size_t)gy * p.out_stride + p.cls_off_y[it.cls]) * p.out_w + (size_t)gx * p.out_stride +
+                                     p.cls_off_x[it.cls]);
+#pragma unroll
+                for (int i = 0; i < 64; i += 4) {
+                    const int n = it.n0 + half * ncol + i;
+                    if (i < ncol && n < p.cout) {
+                        const float4 sc = *reinterpret_cast<const float4 *>(scale + n);
+                        float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (shift) sh = *reinterpret_cast<const float4 *>(shift + n);
+                        float4 o;
+                        o.x = fmaf(v[i + 0] * inv_sa, sc.x, sh.x); o.y = fmaf(v[i + 1] * inv_sa, sc.y, sh.y);
+                        o.z = fmaf(v[i + 2] * inv_sa, sc.z, sh.z); o.w = fmaf(v[i + 3] * inv_sa, sc.w, sh.w);
+                        if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        const size_t off = opix * p.cout + n;
+                        if (resid) {
+                            const float4 rr = *reinterpret_cast<const float4 *>(resid + off);
+                            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                        }
+                        vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+                        if (!(p.ablate & 8)) *reinterpret_cast<float4 *>(out + off) = o;
+                    }
+                }
             }
+        }
+        if (p.amax_out) {
+            const unsigned m = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(vmax));     // non-negative floats order like their bits
+            if (lane == 0 && m != 0u) atomicMax(reinterpret_cast<unsigned *>(p.amax_out), m);
         }
     }
     tc_fence_before();
@@ -303,7 +361,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
     if (p.dbg && threadIdx.x == 0) {
         long long ts; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
-        p.dbg[(size_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 8 + 3] = ts;
+        p.dbg[(size_t)blockIdx.x * 8 + 3] = ts;
     }
 }
 
@@ -373,9 +431,24 @@ static int launch_h2(const float *d_in, const void *d_w, int w_taps, int cout_pa
     p.dbg = g_h2_dbg;
     p.tiles_x = div_up(p.grid_w, kH2TileW);
     p.tiles_y = div_up(p.grid_h, kH2TileH);
-    const int tiles = p.tiles_x * p.tiles_y * p.batch;
-    bev_conv_h2_kernel<<<dim3(tiles, cout_pad / n_tile, p.nclass), kH2Threads, kH2SmemBytes, (cudaStream_t)stream>>>(map_a, map_b, d_scale, d_shift,
-                                                                                                                 d_residual, d_out, p);
+    p.tiles = p.tiles_x * p.tiles_y * p.batch;
+    p.nblocks = cout_pad / n_tile;
+    p.total = p.nclass * p.nblocks * p.tiles;
+    for (int c = 0; c < p.nclass; ++c) p.cls_order[c] = c;
+    for (int i = 1; i < p.nclass; ++i)            // insertion sort by descending tap count
+        for (int k = i; k > 0 && p.cls_ntaps[p.cls_order[k]] > p.cls_ntaps[p.cls_order[k - 1]]; --k) {
+            const int tmp = p.cls_order[k]; p.cls_order[k] = p.cls_order[k - 1]; p.cls_order[k - 1] = tmp;
+        }
+    for (int c = 0; c < p.nclass; ++c)
+        if ((p.cls_ntaps[c] * (p.cin / kH2Chunk)) & 1) return SESSD_EINVAL;     // the [main0|cross|main1] alternation needs an even stage count
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        SESSD_CUDA_TRY(cudaGetDevice(&dev));
+        SESSD_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int grid = p.total < num_sms ? p.total : num_sms;
+    bev_conv_h2_kernel<<<grid, kH2Threads, kH2SmemBytes, (cudaStream_t)stream>>>(map_a, map_b, d_scale, d_shift, d_residual, d_out, p);
     ++g_launches;
     return last_error();
 }
