@@ -110,6 +110,16 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16_nowait(uint32_t taddr, uint32
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
+// profiling aid: CTA 0 writes globaltimer stamps into dbg[4096 + idx]
+#define H2_STAMP(idx)                                                                      \
+    do {                                                                                   \
+        if (p.dbg && blockIdx.x == 0) {                                                    \
+            long long ts_;                                                                 \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts_));                        \
+            p.dbg[4096 + (idx)] = ts_;                                                     \
+        }                                                                                  \
+    } while (0)
+
 __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                    const __grid_constant__ CUtensorMap map_b,
                                                                    const float *__restrict__ scale, const float *__restrict__ shift,
@@ -200,6 +210,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
         auto issue = [&](auto stage_c, int gbj, int lbj, bool last) {
             constexpr int S = decltype(stage_c)::value;
             mbar_wait(&b_full[S], (gbj >> 2) & 1);
+            if (lane == 0 && gbj < 40) H2_STAMP(64 + 2 * gbj);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 constexpr int kSlotBase = 2 * (S & 1);
@@ -229,6 +240,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
             if (lane == 0) {
                 tc_commit(&b_empty[S]);
                 if (last) tc_commit(acc_full);
+                if (gbj < 40) H2_STAMP(64 + 2 * gbj + 1);
             }
             __syncwarp();
         };
@@ -262,6 +274,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
             const int ntaps = p.cls_ntaps[cls];
             for (int cc = 0; cc < nchunks; ++cc, ++gcc) {
                 mbar_wait(&patch_full[gcc & 1], (gcc >> 1) & 1);
+                if (threadIdx.x == 64 && gcc < 16) H2_STAMP(2 * gcc);
                 const unsigned char *box = patches + (gcc & 1) * kH2PatchBytes + grp * kH2BoxBytes;
                 for (int tap = 0; tap < ntaps; ++tap, ++gbj) {
                     const int j = 2 * gbj + grp, slot = j & 3;
@@ -292,6 +305,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                     tc_fence_before();
                     mbar_arrive(&a_full[slot]);
                 }
+                if (threadIdx.x == 64 && gcc < 16) H2_STAMP(2 * gcc + 1);
                 mbar_arrive(&patch_empty[gcc & 1]);  // this thread is done reading the chunk's patch
             }
         }
@@ -310,6 +324,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
             float v[64];
             mbar_wait(acc_full, iter & 1);
             tc_fence_after();
+            if (threadIdx.x == 352 && iter < 4) H2_STAMP(160 + 3 * iter);
             const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * ncol);
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 16) {
@@ -325,6 +340,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
             }
             tc_fence_before();
             mbar_arrive(acc_free);                   // the next item's MMAs may overwrite the accumulators now
+            if (threadIdx.x == 352 && iter < 4) H2_STAMP(160 + 3 * iter + 1);
             const int gy = it.oy0 + ly, gx = it.ox0 + lx;
             if (gy < p.grid_h && gx < p.grid_w) {
                 const size_t opix = (((size_t)it.b * p.out_h + (size_t)gy * p.out_stride + p.cls_off_y[it.cls]) * p.out_w + (size_t)gx * p.out_stride +
@@ -351,6 +367,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                 }
             }
         }
+        if (threadIdx.x == 352) H2_STAMP(160 + 3 * (iter - 1) + 2);
         if (p.amax_out) {
             const unsigned m = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(vmax));     // non-negative floats order like their bits
             if (lane == 0 && m != 0u) atomicMax(reinterpret_cast<unsigned *>(p.amax_out), m);
