@@ -141,10 +141,10 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
         p.dbg[(size_t)blockIdx.x * 8 + 0] = ts;
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(&patch_full[s], 1); mbar_init(&patch_empty[s], 256); }
-        for (int s = 0; s < 4; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); mbar_init(&a_full[s], 128); mbar_init(&a_free[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&patch_full[s], 1); mbar_init(&patch_empty[s], 8); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); mbar_init(&a_full[s], 4); mbar_init(&a_free[s], 1); }
         mbar_init(acc_full, 1);
-        mbar_init(acc_free, 256);
+        mbar_init(acc_free, 8);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 1) {
@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                     const int j = 2 * gbj + grp, slot = j & 3;
                     if (p.ablate & 1) {
                         if (j >= 4) mbar_wait(&a_free[slot], ((j >> 2) - 1) & 1);
-                        mbar_arrive(&a_full[slot]);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&a_full[slot]);
                         continue;
                     }
                     const int prow = (ly + p.tap_dy[cls][tap] - p.org_dy) * p.patch_w + lx + p.tap_dx[cls][tap] - p.org_dx;
@@ -303,10 +304,12 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                     tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + kH2ACol + (uint32_t)slot * 32u, regs);
                     tmem_st_wait();
                     tc_fence_before();
-                    mbar_arrive(&a_full[slot]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_full[slot]);     // one arrival per warp: 128 per-thread arrivals serialise on the barrier
                 }
                 if (threadIdx.x == 64 && gcc < 16) H2_STAMP(2 * gcc + 1);
-                mbar_arrive(&patch_empty[gcc & 1]);  // this thread is done reading the chunk's patch
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&patch_empty[gcc & 1]);  // this warp is done reading the chunk's patch
             }
         }
     } else {
@@ -339,7 +342,8 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                 }
             }
             tc_fence_before();
-            mbar_arrive(acc_free);                   // the next item's MMAs may overwrite the accumulators now
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_free);    // the next item's MMAs may overwrite the accumulators now
             if (threadIdx.x == 352 && iter < 4) H2_STAMP(160 + 3 * iter + 1);
             const int gy = it.oy0 + ly, gx = it.ox0 + lx;
             if (gy < p.grid_h && gx < p.grid_w) {

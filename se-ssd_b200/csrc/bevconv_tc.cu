@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) bev_conv_tc3_kernel(const __gri
     const uint32_t b_tile_bytes = (uint32_t)p.n_tile * kTcBK * 4;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kV3Stages; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 128); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kV3Stages; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 4); mbar_init(&empty[s], 1); }
         for (int q4 = 0; q4 < 4; ++q4) mbar_init(&a_free[q4], 1);
         mbar_init(acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -591,7 +591,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) bev_conv_tc3_kernel(const __gri
             tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + kV3ACol + (uint32_t)(it & 3) * 32u, lo);
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&split[s]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&split[s]);       // one arrival per warp (128 per-thread arrivals serialise on the barrier)
         }
         if (grp == 0) {
         mbar_wait(acc_full, 0);

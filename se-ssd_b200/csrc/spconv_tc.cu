@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kStThreads, 1) spconv_tc_kernel(const float *_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_a[s], 128); mbar_init(&full_b[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_a[s], 4); mbar_init(&full_b[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1);
         *s_kmask = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -140,7 +140,8 @@ __global__ void __launch_bounds__(kStThreads, 1) spconv_tc_kernel(const float *_
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            mbar_arrive(&full_a[s]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_a[s]);      // one arrival per warp (per-thread arrivals serialise on the barrier)
         }
         // ===================== epilogue (warps 0-3) =====================
         if (warp < 4) {
