@@ -198,6 +198,10 @@ void sessd_set_conv_ablate(int mask);
 /* profiling aid: sustained tcgen05.mma kind::tf32 rate (M=128, N=n) of one CTA per SM; mode bit0 = A from TMEM, bit1 = two rotating
  * accumulators; d_out[0..2] = issue cycles, cycles to retire, ns */
 int sessd_mma_probe(int n, int iters, int mode, long long *d_out, void *stream);
+/* profiling aid: handshake latencies in cycles (one CTA): d_out[0] tcgen05.commit->mbarrier, [1] two-warp mbarrier round trip,
+ * [2] tcgen05.st x32 + wait, [3] / [4] one / four f16 MMAs (M128 N256 K16) + commit -> mbarrier, [5] tcgen05.ld x32 + wait,
+ * [6] commit -> other warp -> arrive back round trip */
+int sessd_latency_probe(int iters, long long *d_out, void *stream);
 /* profiling experiments only: device buffer [ctas][8] int64 receiving per-CTA globaltimer stamps of bev_conv_tc (NULL = off) */
 void sessd_set_conv_debug_buffer(void *d_buf);
 

@@ -59,3 +59,118 @@ extern "C" int sessd_mma_probe(int n, int iters, int mode, long long *d_out, voi
     SESSD_LAUNCH(mma_probe_kernel, kNumSMs, 128, 64 * 1024, stream, n, iters, mode, d_out);
     return last_error();
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Latency probe for the producer/consumer handshakes of the tensor-core kernels (one CTA, clock64 cycles averaged over `iters`):
+//   out[0] tcgen05.commit (nothing outstanding) -> mbarrier phase observed by the committing thread
+//   out[1] mbarrier ping-pong between two warps (arrive -> other warp's try_wait returns -> arrive back): cycles per round trip
+//   out[2] tcgen05.st 32x32b.x32 + tcgen05.wait::st
+//   out[3] one kind::f16 TS MMA (M128 N256 K16) + commit -> phase observed
+//   out[4] four such MMAs + commit -> phase observed
+//   out[5] tcgen05.ld 32x32b.x32 + wait::ld
+//   out[6] commit -> phase observed by ANOTHER warp that then arrives back (commit-based ping-pong round trip)
+namespace sessd {
+__global__ void __launch_bounds__(128, 1) latency_probe_kernel(int iters, long long *out) {
+    __shared__ __align__(1024) unsigned char btile[32 * 1024];
+    __shared__ uint64_t bars[4];
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 32 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(btile)[i] = 0u;
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const uint64_t bdesc = make_sw128_desc(smem_u32(btile));
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // kind::f16, fp16 x fp16 -> fp32, M128 N256
+    uint32_t regs[32];
+    for (int i = 0; i < 32; ++i) regs[i] = 0u;
+    if (warp == 0) {
+        tmem_st_32x32b_x32(tmem_base + 384, regs);
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t ph = 0;
+    // [0] commit -> own wait
+    if (threadIdx.x == 0) {
+        long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) { tc_commit(&bars[0]); mbar_wait(&bars[0], ph); ph ^= 1; }
+        out[0] = (clock64() - t0) / iters;
+    }
+    __syncthreads();
+    // [1] mbarrier ping-pong warp0 <-> warp1
+    if (lane == 0 && warp < 2) {
+        long long t0 = clock64();
+        uint32_t p1 = 0;
+        for (int i = 0; i < iters; ++i) {
+            if (warp == 0) { mbar_arrive(&bars[1]); mbar_wait(&bars[2], p1); }
+            else { mbar_wait(&bars[1], p1); mbar_arrive(&bars[2]); }
+            p1 ^= 1;
+        }
+        if (warp == 0) out[1] = (clock64() - t0) / iters;
+    }
+    __syncthreads();
+    // [2] tcgen05.st + wait, [5] tcgen05.ld + wait
+    if (warp == 0) {
+        long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) { tmem_st_32x32b_x32(tmem_base + 384, regs); tmem_st_wait(); }
+        long long t1 = clock64();
+        for (int i = 0; i < iters; ++i) tmem_ld_32x32b_x32(tmem_base, regs);
+        long long t2 = clock64();
+        if (lane == 0) { out[2] = (t1 - t0) / iters; out[5] = (t2 - t1) / iters + (regs[0] & 0); }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // [3] / [4] MMA(s) + commit -> wait
+    if (threadIdx.x == 0) {
+        for (int nm = 1; nm <= 4; nm += 3) {
+            long long t0 = clock64();
+            for (int i = 0; i < iters; ++i) {
+                for (int k = 0; k < nm; ++k)
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_base),
+                        "r"(tmem_base + 384), "l"(bdesc), "r"(idesc), "r"(1)
+                        : "memory");
+                tc_commit(&bars[0]);
+                mbar_wait(&bars[0], ph);
+                ph ^= 1;
+            }
+            out[nm == 1 ? 3 : 4] = (clock64() - t0) / iters;
+        }
+    }
+    __syncthreads();
+    // [6] commit by warp 0 -> observed by warp 1 -> plain arrive back -> observed by warp 0
+    if (lane == 0 && warp < 2) {
+        long long t0 = clock64();
+        uint32_t p1 = 0;     // bars[3] (commit target) and bars[2] start fresh parities: bars[2] has completed `iters` phases
+        uint32_t p2 = iters & 1;
+        for (int i = 0; i < iters; ++i) {
+            if (warp == 0) { tc_commit(&bars[3]); mbar_wait(&bars[2], p2); }
+            else { mbar_wait(&bars[3], p1); mbar_arrive(&bars[2]); }
+            p1 ^= 1; p2 ^= 1;
+        }
+        if (warp == 0) out[6] = (clock64() - t0) / iters;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
+}
+}  // namespace sessd
+
+extern "C" int sessd_latency_probe(int iters, long long *d_out, void *stream) {
+    using namespace sessd;
+    SESSD_LAUNCH(latency_probe_kernel, 1, 128, 0, stream, iters, d_out);
+    return last_error();
+}

@@ -69,6 +69,7 @@ SIGNATURES = {
     "sessd_set_conv_cluster": (None, [_i]),
     "sessd_get_conv_cluster": (_i, []),
     "sessd_mma_probe": (_i, [_i, _i, _i, _vp, _vp]),
+    "sessd_latency_probe": (_i, [_i, _vp, _vp]),
     "sessd_set_conv_ablate": (None, [_i]),
     "sessd_set_conv_variant": (None, [_i]),
     "sessd_set_conv_debug_buffer": (None, [_vp]),
