@@ -209,13 +209,13 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
         // gbj: running stage counter (ring position / barrier parities); lbj: stage index inside the current item (accumulator roles)
         auto issue = [&](auto stage_c, int gbj, int lbj, bool last) {
             constexpr int S = decltype(stage_c)::value;
-            mbar_wait(&b_full[S], (gbj >> 2) & 1);
+            mbar_wait_warp(&b_full[S], (gbj >> 2) & 1);
             if (lane == 0 && gbj < 40) H2_STAMP(64 + 2 * gbj);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 constexpr int kSlotBase = 2 * (S & 1);
                 const int slot = kSlotBase + h;
-                mbar_wait(&a_full[slot], (gbj >> 1) & 1);
+                mbar_wait_warp(&a_full[slot], (gbj >> 1) & 1);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t a_hi = tmem_base + kH2ACol + (uint32_t)slot * 32u, a_lo = a_hi + 16u;
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
         for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++iter) {
             const int nbj = nchunks * p.cls_ntaps[p.cls_order[w / (p.nblocks * p.tiles)]];
             if (iter > 0) {                          // the epilogue warps must have drained the previous item's accumulators
-                mbar_wait(acc_free, (iter - 1) & 1);
+                mbar_wait_warp(acc_free, (iter - 1) & 1);
                 tc_fence_after();
             }
             for (int lbj = 0; lbj < nbj; ++lbj, ++gbj) {
@@ -273,13 +273,13 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
             const int cls = p.cls_order[w / (p.nblocks * p.tiles)];
             const int ntaps = p.cls_ntaps[cls];
             for (int cc = 0; cc < nchunks; ++cc, ++gcc) {
-                mbar_wait(&patch_full[gcc & 1], (gcc >> 1) & 1);
+                mbar_wait_warp(&patch_full[gcc & 1], (gcc >> 1) & 1);
                 if (threadIdx.x == 64 && gcc < 16) H2_STAMP(2 * gcc);
                 const unsigned char *box = patches + (gcc & 1) * kH2PatchBytes + grp * kH2BoxBytes;
                 for (int tap = 0; tap < ntaps; ++tap, ++gbj) {
                     const int j = 2 * gbj + grp, slot = j & 3;
                     if (p.ablate & 1) {
-                        if (j >= 4) mbar_wait(&a_free[slot], ((j >> 2) - 1) & 1);
+                        if (j >= 4) mbar_wait_warp(&a_free[slot], ((j >> 2) - 1) & 1);
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&a_full[slot]);
                         continue;
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                         regs[16 + 2 * c] = *reinterpret_cast<const uint32_t *>(&l01);
                         regs[16 + 2 * c + 1] = *reinterpret_cast<const uint32_t *>(&l23);
                     }
-                    if (j >= 4) mbar_wait(&a_free[slot], ((j >> 2) - 1) & 1);      // slot last read by the MMAs of A step j-4
+                    if (j >= 4) mbar_wait_warp(&a_free[slot], ((j >> 2) - 1) & 1); // slot last read by the MMAs of A step j-4
                     tc_fence_after();
                     tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + kH2ACol + (uint32_t)slot * 32u, regs);
                     tmem_st_wait();
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
         for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++iter) {
             const H2Item it = h2_decode(p, w);
             float v[64];
-            mbar_wait(acc_full, iter & 1);
+            mbar_wait_warp(acc_full, iter & 1);
             tc_fence_after();
             if (threadIdx.x == 352 && iter < 4) H2_STAMP(160 + 3 * iter);
             const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * ncol);
