@@ -47,6 +47,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     mbar_wait_slow(bar, parity);
 }
+// wait with an optional nanosleep back-off between polls (long waits: keeps the polling warp out of the issue slots of the busy ones)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, unsigned ns) {
+    if (mbar_try_wait(bar, parity)) return;
+    if (ns == 0) { mbar_wait_slow(bar, parity); return; }
+    for (int i = 0; i < (1 << 22); ++i) {
+        __nanosleep(ns);
+        if (mbar_try_wait(bar, parity)) return;
+    }
+    __trap();
+}
 // whole-warp wait (all 32 lanes converged): lane 0 polls, the others join through __syncwarp and then observe the completed phase
 // themselves with one (immediately successful) try_wait -- 32x less polling traffic on the barrier
 __device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity) {
