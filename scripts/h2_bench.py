@@ -98,7 +98,7 @@ d = ops.conv_desc(1, (200, 176), 128, (200, 176), 128, (200, 176), t3, relu=True
 amax = torch.zeros(1, device="cuda"); ops.absmax(x, amax)
 flush = torch.empty(64 * 1024 * 1024, device="cuda")
 sc = inv[:128].contiguous()
-def timeit(mode):
+for mode in (0, 2, 15):
     lib.sessd_set_h2_debug(mode, ctypes.c_void_p(0))
     ts = []
     for i in range(8):
@@ -106,21 +106,7 @@ def timeit(mode):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); ops.bev_conv_h2(x, planes, sc, None, None, out, d, amax, None); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
-    lib.sessd_set_h2_debug(0, ctypes.c_void_p(0))
-    return float(np.median(ts[2:])) * 1000
-
-
-for mode in (0, 2, 15):
-    print("ablate=%2d  %.1f us" % (mode, timeit(mode)))
-print("--- wait knobs: one_lane(bit4) | epi<<8 | split<<12 | mma<<16 | prod<<20 ; table idx 0..7 = 0,20,50,100,200,500,1000,2000 ns")
-for one in (0, 1):
-    for epi in (0, 3, 5, 6):
-        for split in (0, 1, 3):
-            for mma in (0, 1):
-                for prod in (0, 3, 5):
-                    k = (one << 4) | (epi << 8) | (split << 12) | (mma << 16) | (prod << 20)
-                    print("one_lane=%d epi=%d split=%d mma=%d prod=%d : full %.1f us   protocol-only %.1f us" % (one, epi, split, mma, prod, timeit(k), timeit(k | 15)))
-
+    print("ablate=%2d  %.1f us" % (mode, float(np.median(ts[2:])) * 1000))
 def trace(mode):
     dbg = torch.zeros((1024, 8), dtype=torch.int64, device="cuda")
     flush.zero_()
@@ -140,6 +126,8 @@ def trace(mode):
     return dbg
 
 
+trace(15)
+trace(2)
 dbg = trace(0)
 lib.sessd_set_h2_debug(0, ctypes.c_void_p(0))
 t = dbg[:148].cpu().numpy().astype(np.float64)

@@ -134,20 +134,6 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunks = p.cin / kH2Chunk;
-    // experiment knobs (p.ablate bits 8..): poll back-off in ns for the epilogue / split / MMA / producer waits, bit 4: one polling lane
-    const unsigned kSleepTab[8] = {0, 20, 50, 100, 200, 500, 1000, 2000};
-    const unsigned ns_epi = kSleepTab[(p.ablate >> 8) & 7], ns_split = kSleepTab[(p.ablate >> 12) & 7], ns_mma = kSleepTab[(p.ablate >> 16) & 7],
-                   ns_prod = kSleepTab[(p.ablate >> 20) & 7];
-    const bool one_lane = (p.ablate >> 4) & 1;
-    auto wait_w = [&](uint64_t *bar, uint32_t parity, unsigned ns) {
-        if (one_lane) {
-            if (lane == 0) mbar_wait_sleep(bar, parity, ns);
-            __syncwarp();
-            while (!mbar_try_wait(bar, parity)) {}
-        } else {
-            mbar_wait_sleep(bar, parity, ns);
-        }
-    };
     const uint32_t b_plane_bytes = (uint32_t)p.n_tile * 128u;
 
     if (p.dbg && threadIdx.x == 0) {
@@ -179,7 +165,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                 const H2Item it = h2_decode(p, w);
                 for (int cc = 0; cc < nchunks; ++cc, ++gcc) {
                     const int pb = gcc & 1;
-                    mbar_wait_sleep(&patch_empty[pb], ((gcc >> 1) & 1) ^ 1, ns_prod);
+                    mbar_wait(&patch_empty[pb], ((gcc >> 1) & 1) ^ 1);
                     mbar_expect_tx(&patch_full[pb], 2 * box_bytes);
                     unsigned char *dst = patches + pb * kH2PatchBytes;
                     tma_load_4d(dst, &map_a, &patch_full[pb], cc * kH2Chunk, it.ox0 + p.org_dx, it.oy0 + p.org_dy, it.b);
@@ -196,7 +182,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                 for (int cc = 0; cc < nchunks; ++cc)
                     for (int tap = 0; tap < it.ntaps; ++tap, ++gbj) {
                         const int s = gbj & 3;
-                        mbar_wait_sleep(&b_empty[s], ((gbj >> 2) & 1) ^ 1, ns_prod);
+                        mbar_wait(&b_empty[s], ((gbj >> 2) & 1) ^ 1);
                         if ((p.ablate & 4) && gbj >= kH2BStages) { mbar_arrive(&b_full[s]); continue; }
                         mbar_expect_tx(&b_full[s], 2 * b_plane_bytes);
                         unsigned char *st = tiles + s * kH2BStageBytes;
@@ -223,13 +209,13 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
         // gbj: running stage counter (ring position / barrier parities); lbj: stage index inside the current item (accumulator roles)
         auto issue = [&](auto stage_c, int gbj, int lbj, bool last) {
             constexpr int S = decltype(stage_c)::value;
-            wait_w(&b_full[S], (gbj >> 2) & 1, ns_mma);
+            mbar_wait(&b_full[S], (gbj >> 2) & 1);
             if (lane == 0 && gbj < 40) H2_STAMP(64 + 2 * gbj);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 constexpr int kSlotBase = 2 * (S & 1);
                 const int slot = kSlotBase + h;
-                wait_w(&a_full[slot], (gbj >> 1) & 1, ns_mma);
+                mbar_wait(&a_full[slot], (gbj >> 1) & 1);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t a_hi = tmem_base + kH2ACol + (uint32_t)slot * 32u, a_lo = a_hi + 16u;
@@ -262,7 +248,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
         for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++iter) {
             const int nbj = nchunks * p.cls_ntaps[p.cls_order[w / (p.nblocks * p.tiles)]];
             if (iter > 0) {                          // the epilogue warps must have drained the previous item's accumulators
-                wait_w(acc_free, (iter - 1) & 1, ns_mma);
+                mbar_wait(acc_free, (iter - 1) & 1);
                 tc_fence_after();
             }
             for (int lbj = 0; lbj < nbj; ++lbj, ++gbj) {
@@ -287,23 +273,23 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
             const int cls = p.cls_order[w / (p.nblocks * p.tiles)];
             const int ntaps = p.cls_ntaps[cls];
             for (int cc = 0; cc < nchunks; ++cc, ++gcc) {
-                wait_w(&patch_full[gcc & 1], (gcc >> 1) & 1, ns_split);
+                mbar_wait(&patch_full[gcc & 1], (gcc >> 1) & 1);
                 if (threadIdx.x == 64 && gcc < 16) H2_STAMP(2 * gcc);
-                const unsigned char *box = patches + (gcc & 1) * kH2PatchBytes + grp * kH2BoxBytes;
+                const uint32_t box = smem_u32(patches) + (uint32_t)((gcc & 1) * kH2PatchBytes + grp * kH2BoxBytes);
                 for (int tap = 0; tap < ntaps; ++tap, ++gbj) {
                     const int j = 2 * gbj + grp, slot = j & 3;
                     if (p.ablate & 1) {
-                        if (j >= 4) wait_w(&a_free[slot], ((j >> 2) - 1) & 1, ns_split);
+                        if (j >= 4) mbar_wait(&a_free[slot], ((j >> 2) - 1) & 1);
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&a_full[slot]);
                         continue;
                     }
                     const int prow = (ly + p.tap_dy[cls][tap] - p.org_dy) * p.patch_w + lx + p.tap_dx[cls][tap] - p.org_dx;
-                    const unsigned char *a = box + prow * 128;
+                    const uint32_t a = box + (uint32_t)prow * 128u;
                     uint32_t regs[32];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {    // SWIZZLE_128B box: logical 16-byte chunk c of patch row prow sits at chunk c ^ (prow & 7)
-                        const float4 v = *reinterpret_cast<const float4 *>(a + ((c ^ (prow & 7)) << 4));
+                        const float4 v = lds128(a + (uint32_t)((c ^ (prow & 7)) << 4));
                         const float x0 = v.x * sa, x1 = v.y * sa, x2 = v.z * sa, x3 = v.w * sa;
                         const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
                         const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
@@ -313,7 +299,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                         regs[16 + 2 * c] = *reinterpret_cast<const uint32_t *>(&l01);
                         regs[16 + 2 * c + 1] = *reinterpret_cast<const uint32_t *>(&l23);
                     }
-                    if (j >= 4) wait_w(&a_free[slot], ((j >> 2) - 1) & 1, ns_split); // slot last read by the MMAs of A step j-4
+                    if (j >= 4) mbar_wait(&a_free[slot], ((j >> 2) - 1) & 1);      // slot last read by the MMAs of A step j-4
                     tc_fence_after();
                     tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + kH2ACol + (uint32_t)slot * 32u, regs);
                     tmem_st_wait();
@@ -339,7 +325,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
         for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++iter) {
             const H2Item it = h2_decode(p, w);
             float v[64];
-            wait_w(acc_full, iter & 1, ns_epi);
+            mbar_wait(acc_full, iter & 1);
             tc_fence_after();
             if (threadIdx.x == 352 && iter < 4) H2_STAMP(160 + 3 * iter);
             const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * ncol);

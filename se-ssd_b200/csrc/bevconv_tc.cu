@@ -576,11 +576,11 @@ __global__ void __launch_bounds__(kV3Threads, 1) bev_conv_tc3_kernel(const __gri
             const int s = it % kV3Stages;
             const uint32_t ph = (it / kV3Stages) & 1;
             mbar_wait(&full[s], ph);
-            const unsigned char *a = tiles + s * kV3StageBytes + r * 128;
+            const uint32_t a = smem_u32(tiles) + (uint32_t)(s * kV3StageBytes + r * 128);
             uint32_t lo[32];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {            // row r of the SWIZZLE_128B tile: logical chunk c sits at chunk c ^ (r & 7)
-                const float4 v = *reinterpret_cast<const float4 *>(a + ((c ^ (r & 7)) << 4));
+                const float4 v = lds128(a + (uint32_t)((c ^ (r & 7)) << 4));
                 const float x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) lo[c * 4 + e] = __float_as_uint(x[e] - __uint_as_float(__float_as_uint(x[e]) & 0xFFFFE000u));

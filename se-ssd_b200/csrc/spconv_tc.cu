@@ -108,14 +108,15 @@ __global__ void __launch_bounds__(kStThreads, 1) spconv_tc_kernel(const float *_
             const uint32_t ph = (j / C::kStages) & 1;
             const int k = s_klist[j];
             mbar_wait(&empty[s], ph ^ 1);
-            unsigned char *a_hi = tiles + s * C::kStage;
-            unsigned char *a_lo = a_hi + C::kATile;
+            const uint32_t a_hi = smem_u32(tiles) + (uint32_t)(s * C::kStage);     // explicit shared-space addresses (see lds128)
+            const uint32_t a_lo = a_hi + (uint32_t)C::kATile;
             // 16 rows per pass of the group (8 lanes per row), 8 row passes, kPasses K blocks
             float4 v[8][kPasses];
 #pragma unroll
             for (int rp = 0; rp < 8; ++rp) {
                 const int r = rp * 16 + (gt >> 3);
-                const int src = s_nbr[r * kStMaxK + k];
+                int src;
+                asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(src) : "r"(smem_u32(s_nbr) + (uint32_t)((r * kStMaxK + k) * 4)));
 #pragma unroll
                 for (int kb = 0; kb < kPasses; ++kb) {
                     if (src >= 0) v[rp][kb] = __ldg(reinterpret_cast<const float4 *>(in_feat + (size_t)src * CIN + kb * 32 + sub * 4));
@@ -135,8 +136,8 @@ __global__ void __launch_bounds__(kStThreads, 1) spconv_tc_kernel(const float *_
                     h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
                     // canonical K-major SWIZZLE_128B: [K block][row][128 B], 16-byte chunk index XOR (row & 7)
                     const int off = kb * (kStBM * 128) + r * 128 + ((sub ^ (r & 7)) << 4);
-                    *reinterpret_cast<float4 *>(a_hi + off) = h;
-                    *reinterpret_cast<float4 *>(a_lo + off) = l;
+                    sts128(a_hi + (uint32_t)off, h);
+                    sts128(a_lo + (uint32_t)off, l);
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");

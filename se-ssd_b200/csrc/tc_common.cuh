@@ -9,6 +9,17 @@ namespace sessd {
 // ---------------------------------------------------------------------------------------------------------------- PTX
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// explicit shared-space 16-byte load: pointers derived from the 1024-byte-aligned dynamic smem base are GENERIC to the compiler (LD.E
+// instead of LDS: slower, and it hides the shared address space from the scheduler)
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -29,40 +40,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// bounded wait: spins on try_wait (each call may block for a hardware time slice); only after many failures it starts watching the wall
-// clock and traps after 2 s (the host sees a launch failure instead of a hung GPU).  %globaltimer reads are slow, keep them off the hot path.
-static __device__ __noinline__ void mbar_wait_slow(uint64_t *bar, uint32_t parity) {
-    for (int i = 0; i < 2048; ++i)
-        if (mbar_try_wait(bar, parity)) return;
+// bounded wait: 2 s of wall clock, then trap (the host sees a launch failure instead of a hung GPU)
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while (true) {
-        for (int i = 0; i < 256; ++i)
+        for (int i = 0; i < 64; ++i)
             if (mbar_try_wait(bar, parity)) return;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         if (t1 - t0 > 2000000000ull) __trap();
     }
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    mbar_wait_slow(bar, parity);
-}
-// wait with an optional nanosleep back-off between polls (long waits: keeps the polling warp out of the issue slots of the busy ones)
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, unsigned ns) {
-    if (mbar_try_wait(bar, parity)) return;
-    if (ns == 0) { mbar_wait_slow(bar, parity); return; }
-    for (int i = 0; i < (1 << 22); ++i) {
-        __nanosleep(ns);
-        if (mbar_try_wait(bar, parity)) return;
-    }
-    __trap();
-}
-// whole-warp wait (all 32 lanes converged): lane 0 polls, the others join through __syncwarp and then observe the completed phase
-// themselves with one (immediately successful) try_wait -- 32x less polling traffic on the barrier
-__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity) {
-    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
-    __syncwarp();
-    while (!mbar_try_wait(bar, parity)) {}
 }
 
 __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
