@@ -98,7 +98,7 @@ d = ops.conv_desc(1, (200, 176), 128, (200, 176), 128, (200, 176), t3, relu=True
 amax = torch.zeros(1, device="cuda"); ops.absmax(x, amax)
 flush = torch.empty(64 * 1024 * 1024, device="cuda")
 sc = inv[:128].contiguous()
-for mode in (0, 2, 15):
+for mode in (0, 1, 2, 3, 4, 8, 15):
     lib.sessd_set_h2_debug(mode, ctypes.c_void_p(0))
     ts = []
     for i in range(8):
@@ -107,28 +107,11 @@ for mode in (0, 2, 15):
         a.record(); ops.bev_conv_h2(x, planes, sc, None, None, out, d, amax, None); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
     print("ablate=%2d  %.1f us" % (mode, float(np.median(ts[2:])) * 1000))
-def trace(mode):
-    dbg = torch.zeros((1024, 8), dtype=torch.int64, device="cuda")
-    flush.zero_()
-    lib.sessd_set_h2_debug(mode, ctypes.c_void_p(dbg.data_ptr()))
-    ops.bev_conv_h2(x, planes, sc, None, None, out, d, amax, None)
-    torch.cuda.synchronize()
-    lib.sessd_set_h2_debug(0, ctypes.c_void_p(0))
-    st = dbg.view(-1)[4096:4096 + 256].cpu().numpy().astype(np.float64)
-    t0 = float(dbg[0, 0])
-    f = lambda v: (v - t0) / 1000 if v > 0 else float("nan")
-    print("=== CTA0 trace (us since CTA start), ablate=%d" % mode)
-    print("  split: (patch ready, chunk done):", " ".join("(%.2f %.2f)" % (f(st[2 * g]), f(st[2 * g + 1])) for g in range(4)))
-    print("  mma (b_full seen, issued) per stage:")
-    for g in range(0, 36, 6):
-        print("     ", " ".join("%2d:(%.2f %.2f)" % (k, f(st[64 + 2 * k]), f(st[64 + 2 * k + 1])) for k in range(g, g + 6)))
-    print("  epilogue (acc_full seen, drained, stored):", " ".join("(%.2f %.2f %.2f)" % (f(st[160 + 3 * i]), f(st[161 + 3 * i]), f(st[162 + 3 * i])) for i in range(2)))
-    return dbg
-
-
-trace(15)
-trace(2)
-dbg = trace(0)
+dbg = torch.zeros((1024, 8), dtype=torch.int64, device="cuda")
+flush.zero_()
+lib.sessd_set_h2_debug(0, ctypes.c_void_p(dbg.data_ptr()))
+ops.bev_conv_h2(x, planes, sc, None, None, out, d, amax, None)
+torch.cuda.synchronize()
 lib.sessd_set_h2_debug(0, ctypes.c_void_p(0))
 t = dbg[:148].cpu().numpy().astype(np.float64)
 t0 = t[:, 0].min()

@@ -200,50 +200,9 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
         const uint32_t acc_main0 = tmem_base, acc_cross = tmem_base + (uint32_t)p.n_tile, acc_main1 = tmem_base + 2 * (uint32_t)p.n_tile;
         const uint64_t desc_hi = ((uint64_t)(((1024u >> 4)) | (1u << 14) | (2u << 29))) << 32;          // SBO | version | SWIZZLE_128B
         const uint32_t tiles_lo = ((smem_u32(tiles) >> 4) & 0x3FFFu) | (1u << 16);
-        uint64_t dCat[kH2BStages], dBhi[kH2BStages];
-#pragma unroll
-        for (int sgi = 0; sgi < kH2BStages; ++sgi) {
-            dCat[sgi] = desc_hi | (tiles_lo + (uint32_t)sgi * (kH2BStageBytes >> 4));
-            dBhi[sgi] = dCat[sgi] + ((sgi & 1) ? (b_plane_bytes >> 4) : 0u);
-        }
-        // gbj: running stage counter (ring position / barrier parities); lbj: stage index inside the current item (accumulator roles)
-        auto issue = [&](auto stage_c, int gbj, int lbj, bool last) {
-            constexpr int S = decltype(stage_c)::value;
-            mbar_wait(&b_full[S], (gbj >> 2) & 1);
-            if (lane == 0 && gbj < 40) H2_STAMP(64 + 2 * gbj);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                constexpr int kSlotBase = 2 * (S & 1);
-                const int slot = kSlotBase + h;
-                mbar_wait(&a_full[slot], (gbj >> 1) & 1);
-                tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t a_hi = tmem_base + kH2ACol + (uint32_t)slot * 32u, a_lo = a_hi + 16u;
-#pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
-                        if (p.ablate & 2) break;
-                        const uint32_t koff = (uint32_t)(h * 4 + kk * 2);            // 32-channel half: +64 B, K=16 sub-step: +32 B (>>4)
-                        if ((S & 1) == 0) {
-                            tc_mma_f16_ts(acc_main0, a_hi + kk * 8, dCat[S] + koff, idesc2, (lbj | h | kk) != 0);  // [main0|cross] (+)= a_hi x [b_hi;b_lo]
-                        } else if (lbj == 1 && h == 0 && kk == 0) {
-                            tc_mma_f16_ts(acc_cross, a_hi, dCat[S] + koff, idesc1, 1);                              // cross += a_hi x b_lo
-                            tc_mma_f16_ts(acc_main1, a_hi, dBhi[S] + koff, idesc1, 0);                              // main1  = a_hi x b_hi
-                        } else {
-                            tc_mma_f16_ts(acc_cross, a_hi + kk * 8, dCat[S] + koff, idesc2, 1);                     // [cross|main1] += a_hi x [b_lo;b_hi]
-                        }
-                        tc_mma_f16_ts(acc_cross, a_lo + kk * 8, dBhi[S] + koff, idesc1, 1);                         // cross += a_lo x b_hi
-                    }
-                    tc_commit(&a_free[slot]);
-                }
-                __syncwarp();
-            }
-            if (lane == 0) {
-                tc_commit(&b_empty[S]);
-                if (last) tc_commit(acc_full);
-                if (gbj < 40) H2_STAMP(64 + 2 * gbj + 1);
-            }
-            __syncwarp();
-        };
+        const uint64_t dcat0 = desc_hi | tiles_lo;
+        const uint32_t plane_lo = b_plane_bytes >> 4;
+        // compact run-time loop on purpose (no per-stage unrolling): this warp's instruction footprint must stay in the instruction cache
         int gbj = 0, iter = 0;
         for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++iter) {
             const int nbj = nchunks * p.cls_ntaps[p.cls_order[w / (p.nblocks * p.tiles)]];
@@ -251,14 +210,41 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                 mbar_wait(acc_free, (iter - 1) & 1);
                 tc_fence_after();
             }
+#pragma unroll 1
             for (int lbj = 0; lbj < nbj; ++lbj, ++gbj) {
-                const bool last = lbj == nbj - 1;
-                switch (gbj & 3) {
-                    case 0: issue(std::integral_constant<int, 0>{}, gbj, lbj, last); break;
-                    case 1: issue(std::integral_constant<int, 1>{}, gbj, lbj, last); break;
-                    case 2: issue(std::integral_constant<int, 2>{}, gbj, lbj, last); break;
-                    default: issue(std::integral_constant<int, 3>{}, gbj, lbj, last); break;
+                // gbj: running stage counter (ring position / barrier parities); lbj: stage index inside the item (accumulator roles);
+                // every item has an even stage count, so both have the same parity
+                const int S = gbj & 3, par = gbj & 1;
+                const uint64_t dcat = dcat0 + (uint32_t)(S * (kH2BStageBytes >> 4));
+                const uint64_t dbhi = dcat + (par ? plane_lo : 0u);
+                const uint32_t d2 = par ? acc_cross : acc_main0;        // even stages: [main0|cross], odd stages: [cross|main1]
+                mbar_wait(&b_full[S], (gbj >> 2) & 1);
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    const int slot = 2 * par + h;
+                    mbar_wait(&a_full[slot], (gbj >> 1) & 1);
+                    tc_fence_after();
+                    if (lane == 0 && !(p.ablate & 2)) {
+                        const uint32_t a_hi = tmem_base + kH2ACol + (uint32_t)slot * 32u, a_lo = a_hi + 16u;
+                        const uint32_t k0 = (uint32_t)(h * 4);                      // 32-channel half: +64 B (>>4); K=16 sub-step: +32 B
+                        if (lbj == 1 && h == 0) {
+                            tc_mma_f16_ts(acc_cross, a_hi, dcat + k0, idesc1, 1);               // cross += a_hi x b_lo
+                            tc_mma_f16_ts(acc_main1, a_hi, dbhi + k0, idesc1, 0);               // main1  = a_hi x b_hi (first write)
+                        } else {
+                            tc_mma_f16_ts(d2, a_hi, dcat + k0, idesc2, (lbj | h) != 0);          // [main|cross] (+)= a_hi x [b_hi;b_lo]
+                        }
+                        tc_mma_f16_ts(acc_cross, a_lo, dbhi + k0, idesc1, 1);                   // cross += a_lo x b_hi
+                        tc_mma_f16_ts(d2, a_hi + 8, dcat + k0 + 2, idesc2, 1);
+                        tc_mma_f16_ts(acc_cross, a_lo + 8, dbhi + k0 + 2, idesc1, 1);
+                    }
+                    if (lane == 0) tc_commit(&a_free[slot]);
+                    __syncwarp();
                 }
+                if (lane == 0) {
+                    tc_commit(&b_empty[S]);
+                    if (lbj == nbj - 1) tc_commit(acc_full);
+                }
+                __syncwarp();
             }
         }
     } else if (warp < 10) {
@@ -274,7 +260,6 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
             const int ntaps = p.cls_ntaps[cls];
             for (int cc = 0; cc < nchunks; ++cc, ++gcc) {
                 mbar_wait(&patch_full[gcc & 1], (gcc >> 1) & 1);
-                if (threadIdx.x == 64 && gcc < 16) H2_STAMP(2 * gcc);
                 const uint32_t box = smem_u32(patches) + (uint32_t)((gcc & 1) * kH2PatchBytes + grp * kH2BoxBytes);
                 for (int tap = 0; tap < ntaps; ++tap, ++gbj) {
                     const int j = 2 * gbj + grp, slot = j & 3;
@@ -307,7 +292,6 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&a_full[slot]);     // one arrival per warp: 128 per-thread arrivals serialise on the barrier
                 }
-                if (threadIdx.x == 64 && gcc < 16) H2_STAMP(2 * gcc + 1);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&patch_empty[gcc & 1]);  // this warp is done reading the chunk's patch
             }
@@ -327,7 +311,6 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
             float v[64];
             mbar_wait(acc_full, iter & 1);
             tc_fence_after();
-            if (threadIdx.x == 352 && iter < 4) H2_STAMP(160 + 3 * iter);
             const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * ncol);
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 16) {
@@ -344,7 +327,6 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_free);    // the next item's MMAs may overwrite the accumulators now
-            if (threadIdx.x == 352 && iter < 4) H2_STAMP(160 + 3 * iter + 1);
             const int gy = it.oy0 + ly, gx = it.ox0 + lx;
             if (gy < p.grid_h && gx < p.grid_w) {
                 const size_t opix = (((size_t)it.b * p.out_h + (size_t)gy * p.out_stride + p.cls_off_y[it.cls]) * p.out_w + (size_t)gx * p.out_stride +
@@ -371,7 +353,6 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                 }
             }
         }
-        if (threadIdx.x == 352) H2_STAMP(160 + 3 * (iter - 1) + 2);
         if (p.amax_out) {
             const unsigned m = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(vmax));     // non-negative floats order like their bits
             if (lane == 0 && m != 0u) atomicMax(reinterpret_cast<unsigned *>(p.amax_out), m);

@@ -40,17 +40,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// bounded wait: 2 s of wall clock, then trap (the host sees a launch failure instead of a hung GPU)
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
+// bounded wait: 2 s of wall clock, then trap (the host sees a launch failure instead of a hung GPU).  The retry loop lives in ONE
+// out-of-line function: inlined at every call site it bloated the warp-specialised kernels by ~100 instructions per wait, and the
+// single-thread MMA-issue warp then lost half of its cycles to instruction-cache misses (ncu: stall_no_inst).
+static __device__ __noinline__ void mbar_wait_slow(uint64_t *bar, uint32_t parity) {
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while (true) {
+#pragma unroll 1
         for (int i = 0; i < 64; ++i)
             if (mbar_try_wait(bar, parity)) return;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         if (t1 - t0 > 2000000000ull) __trap();
     }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    mbar_wait_slow(bar, parity);
 }
 
 __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
