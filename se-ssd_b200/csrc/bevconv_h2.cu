@@ -128,7 +128,9 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
     unsigned char *tiles = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char *patches = tiles + kH2BStages * kH2BStageBytes;
     uint64_t *bars = (uint64_t *)(patches + 2 * kH2PatchBytes);
-    uint64_t *patch_full = bars, *patch_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 8, *a_full = bars + 12, *a_free = bars + 16;
+    // stage_done[S]: ONE tcgen05.commit per weight stage releases the stage's B tile (to the weight producer) and its two A slots (to the
+    // split warps); commits are serialised in the tensor pipe at a few hundred cycles each (scripts/latency_probe.py), so fewer is faster
+    uint64_t *patch_full = bars, *patch_empty = bars + 2, *b_full = bars + 4, *stage_done = bars + 8, *a_full = bars + 12;
     uint64_t *acc_full = bars + 20, *acc_free = bars + 21;
     uint32_t *tmem_slot = (uint32_t *)(bars + 22);
 
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) { mbar_init(&patch_full[s], 1); mbar_init(&patch_empty[s], 8); }
-        for (int s = 0; s < 4; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); mbar_init(&a_full[s], 4); mbar_init(&a_free[s], 1); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&b_full[s], 1); mbar_init(&stage_done[s], 1); mbar_init(&a_full[s], 4); }
         mbar_init(acc_full, 1);
         mbar_init(acc_free, 8);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                 for (int cc = 0; cc < nchunks; ++cc)
                     for (int tap = 0; tap < it.ntaps; ++tap, ++gbj) {
                         const int s = gbj & 3;
-                        mbar_wait(&b_empty[s], ((gbj >> 2) & 1) ^ 1);
+                        mbar_wait(&stage_done[s], ((gbj >> 2) & 1) ^ 1);
                         if ((p.ablate & 4) && gbj >= kH2BStages) { mbar_arrive(&b_full[s]); continue; }
                         mbar_expect_tx(&b_full[s], 2 * b_plane_bytes);
                         unsigned char *st = tiles + s * kH2BStageBytes;
@@ -237,11 +239,10 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                         tc_mma_f16_ts(d2, a_hi + 8, dcat + k0 + 2, idesc2, 1);
                         tc_mma_f16_ts(acc_cross, a_lo + 8, dbhi + k0 + 2, idesc1, 1);
                     }
-                    if (lane == 0) tc_commit(&a_free[slot]);
                     __syncwarp();
                 }
                 if (lane == 0) {
-                    tc_commit(&b_empty[S]);
+                    tc_commit(&stage_done[S]);
                     if (lbj == nbj - 1) tc_commit(acc_full);
                 }
                 __syncwarp();
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                 for (int tap = 0; tap < ntaps; ++tap, ++gbj) {
                     const int j = 2 * gbj + grp, slot = j & 3;
                     if (p.ablate & 1) {
-                        if (j >= 4) mbar_wait(&a_free[slot], ((j >> 2) - 1) & 1);
+                        if (gbj >= 2) mbar_wait(&stage_done[(gbj - 2) & 3], ((gbj - 2) >> 2) & 1);
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&a_full[slot]);
                         continue;
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                         regs[16 + 2 * c] = *reinterpret_cast<const uint32_t *>(&l01);
                         regs[16 + 2 * c + 1] = *reinterpret_cast<const uint32_t *>(&l23);
                     }
-                    if (j >= 4) mbar_wait(&a_free[slot], ((j >> 2) - 1) & 1);      // slot last read by the MMAs of A step j-4
+                    if (gbj >= 2) mbar_wait(&stage_done[(gbj - 2) & 3], ((gbj - 2) >> 2) & 1);   // slot last read by the MMAs of stage gbj-2
                     tc_fence_after();
                     tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + kH2ACol + (uint32_t)slot * 32u, regs);
                     tmem_st_wait();

@@ -163,6 +163,20 @@ __global__ void __launch_bounds__(128, 1) latency_probe_kernel(int iters, long l
         }
         if (warp == 0) out[6] = (clock64() - t0) / iters;
     }
+    __syncthreads();
+    // [7] eight back-to-back commits on one barrier (count 8) -> phase observed: are commits serialised in the tensor pipe?
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 8);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        uint32_t p8 = 0;
+        long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            for (int k = 0; k < 8; ++k) tc_commit(&bars[0]);
+            mbar_wait(&bars[0], p8);
+            p8 ^= 1;
+        }
+        out[7] = (clock64() - t0) / iters;
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
