@@ -164,6 +164,28 @@ __global__ void __launch_bounds__(128, 1) latency_probe_kernel(int iters, long l
         if (warp == 0) out[6] = (clock64() - t0) / iters;
     }
     __syncthreads();
+    // [8] tcgen05.st x32 + wait::st by warp 1 WHILE warp 0 streams MMAs (does the store wait for the tensor pipe?)  [9] same for tcgen05.ld
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < iters * 4; ++i)
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_base),
+                "r"(tmem_base + 384), "l"(bdesc), "r"(idesc), "r"(1)
+                : "memory");
+        tc_commit(&bars[0]);
+        mbar_wait(&bars[0], ph);
+        ph ^= 1;
+    } else if (warp == 1) {
+        long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) { tmem_st_32x32b_x32(tmem_base + ((uint32_t)32 << 16) + 448, regs); tmem_st_wait(); }
+        long long t1 = clock64();
+        for (int i = 0; i < iters; ++i) tmem_ld_32x32b_x32(tmem_base + ((uint32_t)32 << 16) + 448, regs);
+        long long t2 = clock64();
+        if (lane == 0) { out[8] = (t1 - t0) / iters; out[9] = (t2 - t1) / iters + (regs[0] & 0); }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
     // [7] eight back-to-back commits on one barrier (count 8) -> phase observed: are commits serialised in the tensor pipe?
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 8);
