@@ -53,7 +53,7 @@ struct H2Params {
     int patch_w, patch_h, org_dy, org_dx;     // patch rows = input rows oy0 + org_dy ... (patch_h of them), same for columns
     const float *amax_in;                     // nullable: abs-max of the input tensor (device scalar)
     float *amax_out;                          // nullable: running abs-max of the output tensor (atomicMax on the float bits)
-    int ablate;                               // timing experiments only (results become garbage): 1 no split work, 2 no MMAs, 4 no weight reloads, 8 no stores
+    int ablate;                               // timing experiments only (garbage results): 1 no split work, 2 no MMAs, 4 no weight reloads, 8 no stores, 32 / 64 drop the A / B handshakes
     long long *dbg;                           // optional [ctas][8] globaltimer stamps
 };
 
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                 for (int cc = 0; cc < nchunks; ++cc)
                     for (int tap = 0; tap < it.ntaps; ++tap, ++gbj) {
                         const int s = gbj & 3;
-                        mbar_wait(&stage_done[s], ((gbj >> 2) & 1) ^ 1);
+                        if (!(p.ablate & 64)) mbar_wait(&stage_done[s], ((gbj >> 2) & 1) ^ 1);
                         if ((p.ablate & 4) && gbj >= kH2BStages) { mbar_arrive(&b_full[s]); continue; }
                         mbar_expect_tx(&b_full[s], 2 * b_plane_bytes);
                         unsigned char *st = tiles + s * kH2BStageBytes;
@@ -220,11 +220,11 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                 const uint64_t dcat = dcat0 + (uint32_t)(S * (kH2BStageBytes >> 4));
                 const uint64_t dbhi = dcat + (par ? plane_lo : 0u);
                 const uint32_t d2 = par ? acc_cross : acc_main0;        // even stages: [main0|cross], odd stages: [cross|main1]
-                mbar_wait(&b_full[S], (gbj >> 2) & 1);
+                if (!(p.ablate & 64)) mbar_wait(&b_full[S], (gbj >> 2) & 1);
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
                     const int slot = 2 * par + h;
-                    mbar_wait(&a_full[slot], (gbj >> 1) & 1);
+                    if (!(p.ablate & 32)) mbar_wait(&a_full[slot], (gbj >> 1) & 1);
                     tc_fence_after();
                     if (lane == 0 && !(p.ablate & 2)) {
                         const uint32_t a_hi = tmem_base + kH2ACol + (uint32_t)slot * 32u, a_lo = a_hi + 16u;
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
                         regs[16 + 2 * c] = *reinterpret_cast<const uint32_t *>(&l01);
                         regs[16 + 2 * c + 1] = *reinterpret_cast<const uint32_t *>(&l23);
                     }
-                    if (gbj >= 2) mbar_wait(&stage_done[(gbj - 2) & 3], ((gbj - 2) >> 2) & 1);   // slot last read by the MMAs of stage gbj-2
+                    if (gbj >= 2 && !(p.ablate & 32)) mbar_wait(&stage_done[(gbj - 2) & 3], ((gbj - 2) >> 2) & 1);   // slot last read by the MMAs of stage gbj-2
                     tc_fence_after();
                     tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + kH2ACol + (uint32_t)slot * 32u, regs);
                     tmem_st_wait();
