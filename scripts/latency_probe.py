@@ -10,7 +10,7 @@ for _ in range(2):
     torch.cuda.synchronize()
 o = out.cpu().tolist()
 names = ["commit(empty)->own wait", "mbarrier 2-warp round trip", "tcgen05.st x32 + wait::st", "1 MMA(N256 f16 TS)+commit->wait",
-         "4 MMAs+commit->wait", "tcgen05.ld x32 + wait::ld", "commit->other warp->arrive back", "8 commits back-to-back -> wait", "tcgen05.st x32+wait under MMA load", "tcgen05.ld x32+wait under MMA load"]
+         "4 MMAs+commit->wait", "tcgen05.ld x32 + wait::ld", "commit->other warp->arrive back", "8 commits back-to-back -> wait", "tcgen05.st x32+wait under MMA load", "tcgen05.ld x32+wait under MMA load", "pair N256->[0,256) + N128->[128,256) (overlap)", "pair N256 + N128->[256,384) (disjoint)", "single N256 MMA"]
 print("rc", rc)
 for n, v in zip(names, o):
     print("%-36s %6d clk" % (n, v))

@@ -186,6 +186,34 @@ __global__ void __launch_bounds__(128, 1) latency_probe_kernel(int iters, long l
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // [10]/[11]/[12]: 64 (N256 -> cols [0,256), N128 -> X) MMA pairs + commit -> wait, per pair: X = [128,256) overlapping the N256
+    // destination (the conv kernels' [main|cross] + cross pattern), X = [256,384) disjoint, and [12] = 128 N256-only MMAs per 2
+    if (threadIdx.x == 0) {
+        const uint32_t idesc128 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        for (int variant = 0; variant < 3; ++variant) {
+            long long t0 = clock64();
+            for (int i = 0; i < 16; ++i) {
+                for (int k = 0; k < 64; ++k) {
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_base),
+                        "r"(tmem_base + 384), "l"(bdesc), "r"(idesc), "r"(1)
+                        : "memory");
+                    if (variant < 2)
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_base + (variant == 0 ? 128u : 256u)),
+                            "r"(tmem_base + 400), "l"(bdesc), "r"(idesc128), "r"(1)
+                            : "memory");
+                }
+                tc_commit(&bars[0]);
+                mbar_wait(&bars[0], ph);
+                ph ^= 1;
+            }
+            out[10 + variant] = (clock64() - t0) / (16 * 64);
+        }
+    }
+    __syncthreads();
     // [7] eight back-to-back commits on one barrier (count 8) -> phase observed: are commits serialised in the tensor pipe?
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 8);
