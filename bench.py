@@ -327,24 +327,25 @@ def run_ours(args):
 
 
 def dominant_kernel_roofline(e, reps=20):
-    """The conv3x3 128->128 @200x176 layer (largest share of the step), timed alone with CUDA events on the engine stream.
-    tcgen05 path: bev_conv_tc_kernel runs THREE tf32 products per algorithmic MAC (3xTF32 for fp32-level parity) and tf32
-    issues at half the bf16 rate, so the ceiling of `frac` against the bf16 peak is 1/6."""
-    from sessd_b200 import ops
+    """The conv3x3 128->128 @200x176 layer (largest share of the step; 8 of the 18 neck launches have this shape), timed alone
+    with CUDA events on the engine stream, through the same runner call the frame graph uses.
+    fp16-split path (bev_conv_h2_kernel): THREE kind::f16 products per algorithmic MAC (two-term split of both operands for
+    fp32-level parity) => ceiling of `frac` against the bf16 peak is 1/3.  3xTF32 path (bev_conv_tc*): tf32 issues at half the
+    bf16 rate => ceiling 1/6."""
     neck = e.neck
-    x = neck.buf["x0"]
+    x = neck.buf["x0"]                # abs-max slot 3 (valid after any forward)
     name = "bottom_up_block_0.4"
-    wp, taps, sc, sh = neck.params[name]
-    tcw = neck.params.get(name + ":tc")
     H = (neck.h, neck.w)
-    d = ops.conv_desc(1, H, 128, H, 128, H, taps, relu=True)
     flush = torch.empty((64 * 1024 * 1024,), dtype=torch.float32, device=x.device)   # 256 MB > L2
+    if (name + ":h2") in neck.params:
+        kern, factor = "bev_conv_h2_kernel (tcgen05 kind::f16, two-term fp16 split)", 3
+    elif (name + ":tc") in neck.params:
+        kern, factor = "bev_conv_tc3_kernel (tcgen05 3xTF32)", 6
+    else:
+        kern, factor = "bev_conv_kernel (fp32 SIMT)", None
 
     def launch():
-        if tcw is not None:
-            ops.bev_conv_tc(x, tcw, sc, sh, None, neck.buf["b0b"], d)
-        else:
-            ops.bev_conv(x, wp, sc, sh, None, neck.buf["b0b"], d)
+        neck._conv(name, x, neck.buf["b0b"], H, H, 128, 128, ai=3, ao=2)
 
     ms = []
     with torch.cuda.stream(e.stream):
@@ -360,10 +361,9 @@ def dominant_kernel_roofline(e, reps=20):
             ms.append(a.elapsed_time(b))
     t = float(np.mean(ms)) / 1000.0
     flops = 2.0 * neck.h * neck.w * 128 * 128 * 9
-    kern = "bev_conv_tc_kernel (tcgen05 3xTF32)" if tcw is not None else "bev_conv_kernel (fp32 SIMT)"
     return {"kernel": kern + ", conv3x3 128->128 @200x176", "bound": "tensor", "achieved": flops / t / 1e12,
             "unit": "TFLOP/s", "avg_launch_ms": t * 1000.0, "algorithmic_flops": flops, "traffic": None,
-            "tensor_work_factor": 6 if tcw is not None else None,
+            "tensor_work_factor": factor,
             "timing": "CUDA events on the launch stream, L2 flushed (256 MB memset) before every launch, mean of %d" % reps}
 
 

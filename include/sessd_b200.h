@@ -267,6 +267,26 @@ size_t sessd_nms_workspace_bytes(int n);
 int sessd_nms_sorted(const float *d_boxes, int n, float thresh, int mode, long long *d_keep, int *d_num_keep,
                      void *workspace, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * T1: IoU target assignment of the SSD head, batched over frames on the device.
+ * Replaces the DataLoader-worker path det3d/core/anchor/target_assigner.py:68-136 (TargetAssigner.assign_v2 with
+ * enable_similar_type=True: every GT is class 1) -> det3d/core/anchor/target_ops_v2.py:11-126 (create_target_np) with
+ * NearestIouSimilarity (det3d/core/bbox/region_similarity.py:85-98; box_np_ops.py:354-366, :1007-1046 iou_jit eps=0)
+ * and second_box_encode (det3d/core/bbox/box_np_ops.py:52-113), called from AssignTarget
+ * (det3d/datasets/pipelines/preprocess.py:286-358).
+ *   d_anchors [A,7] (x,y,z,w,l,h,r), shared by all frames; d_gt_boxes [batch,max_gt,7] padded, d_num_gt [batch].
+ *   d_labels [batch,A] (1 positive / 0 negative / -1 ignore), d_bbox_targets [batch,A,7] (zeros off the positives),
+ *   d_bbox_outside_weights [batch,A] (1 on positives), d_pos_anchor / d_pos_gt_id [batch,A]: the first d_num_pos[b]
+ *   entries of row b are the positive anchors in ascending order and their GT index (`positive_gt_id`).
+ * labels / positive sets are bit-exact against the reference (its mixed fp32/fp64 IoU rounding is reproduced).
+ * max_gt <= 1024.  Workspace: sessd_assign_workspace_bytes().
+ * ------------------------------------------------------------------------------------------------ */
+size_t sessd_assign_workspace_bytes(int num_anchors, int batch, int max_gt);
+int sessd_assign_targets(const float *d_anchors, int num_anchors, const float *d_gt_boxes, const int *d_num_gt, int batch,
+                         int max_gt, float matched_thr, float unmatched_thr, int *d_labels, float *d_bbox_targets,
+                         float *d_bbox_outside_weights, int *d_pos_anchor, int *d_pos_gt_id, int *d_num_pos,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -343,3 +343,31 @@ def nms_sorted(boxes, thresh, mode):
     ws = torch.empty((lib.sessd_nms_workspace_bytes(n),), dtype=torch.uint8, device=dev)
     check(lib.sessd_nms_sorted(_p(boxes), n, float(thresh), int(mode), _p(keep), _p(num), _p(ws), ws.numel(), _st()), "sessd_nms_sorted")
     return keep, num
+
+
+# ------------------------------------------------------------------------------------------------ target assignment (T1)
+class AssignBuffers:
+    """Device outputs + workspace of sessd_assign_targets for `batch` frames of `num_anchors` anchors, up to `max_gt` GT boxes."""
+
+    def __init__(self, num_anchors, batch, max_gt, device):
+        self.num_anchors, self.batch, self.max_gt = int(num_anchors), int(batch), int(max_gt)
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)   # noqa: E731
+        self.labels = z((batch, num_anchors), torch.int32)
+        self.bbox_targets = z((batch, num_anchors, 7), torch.float32)
+        self.bbox_outside_weights = z((batch, num_anchors), torch.float32)
+        self.pos_anchor = z((batch, num_anchors), torch.int32)
+        self.pos_gt_id = z((batch, num_anchors), torch.int32)
+        self.num_pos = z((batch,), torch.int32)
+        self.ws = torch.empty((lib.sessd_assign_workspace_bytes(self.num_anchors, self.batch, self.max_gt),), dtype=torch.uint8,
+                              device=device)
+
+
+def assign_targets(anchors, gt_boxes, num_gt, buf, matched_thr=0.6, unmatched_thr=0.45):
+    """anchors [A,7] f32, gt_boxes [B,max_gt,7] f32 (padded), num_gt [B] i32 -- all on the device; fills `buf` on the current stream."""
+    _cuda(anchors, torch.float32, "anchors"); _cuda(gt_boxes, torch.float32, "gt_boxes"); _cuda(num_gt, torch.int32, "num_gt")
+    assert anchors.shape == (buf.num_anchors, 7) and tuple(gt_boxes.shape) == (buf.batch, buf.max_gt, 7) and num_gt.numel() == buf.batch
+    check(lib.sessd_assign_targets(_p(anchors), buf.num_anchors, _p(gt_boxes), _p(num_gt), buf.batch, buf.max_gt, float(matched_thr),
+                                   float(unmatched_thr), _p(buf.labels), _p(buf.bbox_targets), _p(buf.bbox_outside_weights),
+                                   _p(buf.pos_anchor), _p(buf.pos_gt_id), _p(buf.num_pos), _p(buf.ws), buf.ws.numel(), _st()),
+          "sessd_assign_targets")
+    return buf

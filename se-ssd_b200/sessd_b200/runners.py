@@ -111,14 +111,17 @@ class SpMiddleRunner:
             tc = ops.pack_weight_tc(wp, p["cout"]) if (self.use_tc and p["cin"] >= 32) else None
             self.weights.append((wp, sc, sh, tc))
 
-    def forward(self, feat0, coors0, n0):
-        """feat0 [cap0, Cin] f32, coors0 [cap0,4] i32 (b,z,y,x), n0 [1] i32 (device).  Returns dense NHWC."""
+    def forward(self, feat0, coors0, n0, mark=None):
+        """feat0 [cap0, Cin] f32, coors0 [cap0,4] i32 (b,z,y,x), n0 [1] i32 (device).  Returns dense NHWC.
+        mark: optional callable(label) invoked after every launch group (profiling scripts record a CUDA event there)."""
+        mark = mark or (lambda label: None)
         assert self.weights is not None, "load_weights first"
         L0 = self.levels[0]
         assert coors0.shape[0] <= L0["cap"] or True
         cap0 = min(coors0.shape[0], L0["cap"])
         L0["coors"], L0["n_ext"] = coors0, n0
         ops.hash_build(coors0, n0, cap0, L0["grid"], L0["index"])
+        mark("hash_build")
         x = feat0
         for li, p in enumerate(self.plan):
             lin, lout = self.levels[p["lin"]], self.levels[p["lout"]]
@@ -127,19 +130,24 @@ class SpMiddleRunner:
             if p["kind"] == "subm":
                 if p["first"]:
                     ops.subm_rulebook(lin["coors"], n_in, cap_in, lin["grid"], p["ks"], lin["index_kind"], lin["index"], p["nbr"])
+                    mark("rulebook:%s" % p["key"])
                 n_out, cap_out = n_in, cap_in
             else:
                 ops.strided_rulebook(lin["coors"], n_in, cap_in, lin["grid"], lin["index_kind"], lin["index"], p["ks"], p["st"],
                                      p["pd"], lout["grid"], lout["index"], lout["scratch"], lout["coors"], lout["n"], lout["cap"],
                                      p["nbr"], self.status)
                 n_out, cap_out = lout["n"], lout["cap"]
+                mark("rulebook:sp%d" % p["lout"])
             w, sc, sh, tc = self.weights[li]
             if tc is not None:
                 x = ops.spconv_forward_tc(x, p["nbr"], n_out, cap_out, tc, sc, sh, True, self.feats[li])
             else:
                 x = ops.spconv_forward(x, p["nbr"], n_out, cap_out, w, sc, sh, True, self.feats[li])
+            mark("conv:%d" % li)
         last = self.levels[-1]
-        return ops.sparse_to_dense(x, last["coors"], last["n"], last["cap"], last["grid"], self.dense)
+        out = ops.sparse_to_dense(x, last["coors"], last["n"], last["cap"], last["grid"], self.dense)
+        mark("dense")
+        return out
 
 
 # ---------------------------------------------------------------------------------------------------------------

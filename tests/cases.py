@@ -41,3 +41,26 @@ def iou_inputs():
     b1[20, 3] = 0.0
     b1[21:25, 6] = np.float32([0.0, np.pi / 2, -np.pi / 2, np.pi])
     return b1, b2
+
+
+def assign_cases():
+    """(name, gt_boxes [M,7]) inputs of the IoU target assigner (anchors: the 70 400 KITTI car anchors)."""
+    out = []
+    g12, _ = synth.random_boxes(21, 12)
+    g12[:, 2] = -1.0
+    out.append(("m12", g12))
+    out.append(("m0", np.zeros((0, 7), np.float32)))
+    out.append(("m1", synth.random_boxes(22, 1)[0]))
+    out.append(("m40", synth.random_boxes(23, 40)[0]))
+    e, _ = synth.random_boxes(24, 10)
+    e[0, 0] = -20.0                       # no overlap with any anchor => its column max is 0 => never forces a positive
+    e[1, 0] = 95.0
+    e[2, 3:5] = np.float32([0.5, 0.6])    # pedestrian-sized: max IoU < 0.45, positives only through the forced rule
+    e[3, 3:5] = np.float32([0.6, 1.7])
+    e[4] = e[5]                           # duplicate GT: argmax ties resolve to the first
+    e[6, :2] = np.float32([10.2, 0.2]); e[6, 3:7] = np.float32([1.6, 3.9, 1.56, 0.0])      # exactly an anchor (IoU 1)
+    e[7, :2] = np.float32([10.4, 4.4]); e[7, 3:7] = np.float32([1.6, 3.9, 1.56, 0.0])      # half-way between 2 anchors: tie
+    e[8, 6] = np.float32(np.pi / 4)       # on the near-bbox swap boundary
+    e[9, 6] = np.float32(-3 * np.pi / 4)
+    out.append(("edge", e))
+    return out

@@ -32,7 +32,7 @@ from sessd_b200 import synth  # noqa: E402
 from oracle import bev_ref, build as obuild, cpu as ocpu  # noqa: E402
 
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from cases import iou_inputs, sha, voxel_cases  # noqa: E402  (seeded inputs shared with the tests)
+from cases import assign_cases, iou_inputs, sha, voxel_cases  # noqa: E402  (seeded inputs shared with the tests)
 
 
 def _pkg(name):
@@ -176,6 +176,23 @@ def gen_anchors_assign():
                         labels=res["labels"].astype(np.int8), pos_idx=pos.astype(np.int32),
                         pos_targets=res["bbox_targets"][pos], weights_sum=np.float64(res["bbox_outside_weights"].sum()))
     print("anchors", anchors.shape, "pos", len(pos), "neg", int((res["labels"] == 0).sum()))
+    # more assigner cases (empty / single / many GT, GT without any overlap, forced-only positives, ties)
+    cases = {}
+    for name, g in assign_cases():
+        m = len(g)
+        r = ta.assign_v2(ad, g, None, gt_classes=np.ones(m, np.int32), gt_names=np.array(["Car"] * m), enable_similar_type=True)
+        o = oa.assign_targets(anchors.reshape(-1, 7), g)
+        assert (o["labels"] == r["labels"]).all(), name
+        assert np.array_equal(o["bbox_targets"], r["bbox_targets"]), name
+        assert np.array_equal(o["bbox_outside_weights"], r["bbox_outside_weights"]), name
+        assert np.array_equal(o["positive_gt_id"], r["positive_gt_id"][0]), name
+        p_ = np.nonzero(r["labels"] > 0)[0]
+        cases[name + "_labels"] = r["labels"].astype(np.int8)
+        cases[name + "_pos_idx"] = p_.astype(np.int32)
+        cases[name + "_pos_targets"] = r["bbox_targets"][p_]
+        cases[name + "_positive_gt_id"] = np.asarray(r["positive_gt_id"][0], np.int32)
+        print("assign", name, "gt", m, "pos", len(p_), "neg", int((r["labels"] == 0).sum()), "ignore", int((r["labels"] < 0).sum()))
+    np.savez_compressed(os.path.join(HERE, "assign_cases.npz"), **cases)
     # decode fixture from the reference torch op
     g = torch.Generator().manual_seed(5)
     enc = torch.randn(2048, 7, generator=g) * 0.3
@@ -228,8 +245,13 @@ def gen_models():
 
 
 if __name__ == "__main__":
-    gen_voxel()
-    gen_iou()
+    only = sys.argv[1:]           # e.g. `make_golden.py assign` regenerates only the anchor / assigner fixtures
+    if not only or "voxel" in only:
+        gen_voxel()
+    if not only or "iou" in only:
+        gen_iou()
     install_det3d_shims()
-    gen_anchors_assign()
-    gen_models()
+    if not only or "assign" in only:
+        gen_anchors_assign()
+    if not only or "models" in only:
+        gen_models()

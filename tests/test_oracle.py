@@ -61,6 +61,21 @@ def test_oracle_anchors_and_assigner_equal_reference_golden(golden_dir):
     assert float(res["bbox_outside_weights"].sum()) == float(g["weights_sum"])
 
 
+def test_oracle_assigner_equals_reference_on_all_golden_cases(golden_dir):
+    """Empty / single / 40 GT, GT without any overlap, forced-only positives, duplicate GT, ties, near-bbox swap boundary."""
+    from cases import assign_cases
+    from oracle import anchors as oa
+    g = np.load(os.path.join(golden_dir, "assign_cases.npz"))
+    anc = oa.create_anchors_3d_range().reshape(-1, 7)
+    for name, gt in assign_cases():
+        res = oa.assign_targets(anc, gt)
+        assert np.array_equal(res["labels"].astype(np.int8), g[name + "_labels"]), name
+        pos = np.nonzero(res["labels"] > 0)[0]
+        assert np.array_equal(pos, g[name + "_pos_idx"]), name
+        assert np.array_equal(res["bbox_targets"][pos], g[name + "_pos_targets"]), name
+        assert np.array_equal(res["positive_gt_id"], g[name + "_positive_gt_id"]), name
+
+
 def test_oracle_decode_ssfa_head_vfe_equal_reference_golden(golden_dir):
     from oracle import anchors as oa, bev_ref, cpu as ocpu
     from sessd_b200 import synth
