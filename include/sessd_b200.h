@@ -131,6 +131,23 @@ int sessd_spconv_forward_tc(const float *d_in_feat, int cin, const int *d_nbr, i
 int sessd_sparse_to_dense(const float *d_feat, const int *d_coors, const int *d_n, int max_rows, int channels,
                           sessd_grid grid, float *d_out, void *stream);
 
+/* S4 (fp16-split tensor-core path with TMA gather; csrc/spconv_h2.cu).  Same contract as sessd_spconv_forward (spconv 1.x
+ * gather -> GEMM -> scatter-add at det3d/models/backbones/scn.py:106-149, + folded BN + ReLU), but the input features are
+ * read as fp16 (hi, lo) planes [plane_rows][2][cp] -- x = 2^-s (hi + lo), s chosen from *d_amax_in exactly like
+ * sessd_bev_conv_h2 -- produced by sessd_split_h2 from the producing layer's fp32 rows; row `zero_row` of the planes must be
+ * all zero (missing neighbours read it).  d_weight_h2: cp = 64: [kvol][2 (hi|lo)][cout][64] fp16, cp = 32:
+ * [kvol][cout][hi 32 | lo 32] fp16 (Cin 16 zero-padded), every output channel scaled by a power of two 2^e[c];
+ * d_scale[c] must be bn_scale[c] * 2^-e[c].  d_amax_out (nullable) receives the running abs-max of the output.
+ * Supported (cp, cout): (32,16) (32,32) (32,64) (64,64). */
+/* pipeline depth of sessd_spconv_forward_h2: 0 = auto (deep when max_out <= 262144), 1 = 2 CTAs/SM x 2-4 stages, 2 = 1 CTA/SM x 4-8 stages */
+void sessd_set_sp_h2_depth(int mode);
+int sessd_split_h2(const float *d_feat, const int *d_n, int max_rows, int channels, const float *d_amax, void *d_planes, int cp,
+                   void *stream);
+int sessd_absmax_rows(const float *d_feat, const int *d_n, int max_rows, int channels, float *d_amax, void *stream);
+int sessd_spconv_forward_h2(const void *d_in_planes, int cp, int plane_rows, int zero_row, const float *d_amax_in, const int *d_nbr,
+                            int kvol, const int *d_n_out, int max_out, const void *d_weight_h2, int cout, const float *d_scale,
+                            const float *d_shift, int relu, float *d_out_feat, float *d_amax_out, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * N1/H1: BEV neck (SSFA) + head.  Replaces the cuDNN conv/deconv + BatchNorm2d + ReLU blocks of
  * det3d/models/necks/rpn_v1.py:135-235 and the four 1x1 convs of

@@ -19,7 +19,11 @@ timeout 900 python scripts/kernel_rooflines.py --shape stress > $OUT/roofline_st
 fi
 if [ -z "$SKIP_NCU" ]; then
 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches.csv python scripts/profile_frame.py --frames 2 --cloud ${CLOUD:-ring} > $OUT/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
-for K in ${NCU_KERNELS:-bev_conv_h2_kernel spconv_tc_kernel}; do
+for K in ${NCU_KERNELS:-bev_conv_h2_kernel spconv_h2_kernel}; do
 timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:$K -s ${NCU_SKIP:-2} -c ${NCU_COUNT:-2} -f -o $OUT/prof_$K python scripts/profile_frame.py --frames 1 --cloud ${CLOUD:-ring} > $OUT/ncu_$K.log 2>&1; echo "ncu $K rc=$?"
 done
+fi
+if [ -n "$NCU_STRESS" ]; then
+# stress-shape capture of the sparse conv kernel: launches 2..5 of the first pass = layers 3, 4 (32->32), 5 (32->64), 6 (64->64)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:spconv_h2_kernel -s 2 -c 4 -f -o $OUT/prof_stress_spconv_h2 python scripts/kernel_rooflines.py --shape stress --iters 1 > $OUT/ncu_stress.log 2>&1; echo "ncu stress rc=$?"
 fi

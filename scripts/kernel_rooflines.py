@@ -24,15 +24,16 @@ ap.add_argument("--shape", default="stress", choices=["stress", "frame"])
 ap.add_argument("--batch", type=int, default=None)
 ap.add_argument("--points", type=int, default=None)
 ap.add_argument("--iters", type=int, default=5)
+ap.add_argument("--sparse-split", default=None, choices=["fp16", "tf32"])
 a = ap.parse_args()
 if a.shape == "stress":
     B, N = a.batch or 16, a.points or 200000
     clouds = [synth.uniform_cloud(1000 + f, N) for f in range(B)]
-    eng = FrameEngine(batch=B, max_points_per_frame=N, max_voxels=200000, growth=(1.0, 8.0, 8.0, 8.0, 8.0))
+    eng = FrameEngine(batch=B, max_points_per_frame=N, max_voxels=200000, growth=(1.0, 8.0, 8.0, 8.0, 8.0), sparse_split=a.sparse_split)
 else:
     B, N = a.batch or 1, a.points or 20000
     clouds = [synth.ring_cloud(f, N) for f in range(B)]
-    eng = FrameEngine(batch=B, max_points_per_frame=max(c.shape[0] for c in clouds))
+    eng = FrameEngine(batch=B, max_points_per_frame=max(c.shape[0] for c in clouds), sparse_split=a.sparse_split)
 layers, ssfa, head = weights.split_detector_state(weights.random_detector_state(0, cls_bias=-3.0))
 eng.load_weights(layers, ssfa, head, weights.kitti_car_anchors())
 eng.calibrate_cls_bias(clouds, 400)
@@ -101,6 +102,9 @@ for li, p in enumerate(mid.plan):
     work["conv:%d" % li] = ("tensor", 2.0 * pairs * p["cin"] * p["cout"],
                             4.0 * n_in * p["cin"] + 4.0 * n_out * p["cout"] + 4.0 * kvol * n_out + 4.0 * kvol * p["cin"] * p["cout"],
                             dict(kind=p["kind"], cin=p["cin"], cout=p["cout"], n_out=n_out, pairs=pairs))
+for li, p in enumerate(mid.plan):
+    if mid.planes[li] is not None:
+        work["split:%d" % li] = ("hbm", 8.0 * n_lvl[p["lout"]] * p["cout"])
 work["dense"] = ("hbm", 4.0 * mid.dense.numel() + 4.0 * n_lvl[-1] * 64)
 h, w = eng.neck.h, eng.neck.w
 NECK = {"bottom_up_block_0.1": (h, w, 128, 128, 9), "bottom_up_block_0.4": (h, w, 128, 128, 9), "bottom_up_block_0.7": (h, w, 128, 128, 9),
@@ -127,7 +131,7 @@ for lab, t in zip(labels, ms):
             if wk[3]:
                 row.update(wk[3])
     rows.append(row)
-out = {"shape": a.shape, "batch": B, "points_per_frame": N, "voxels": M, "active_sites": n_lvl, "capacity_status": int(mid.status.item()),
+out = {"shape": a.shape, "sparse_split": mid.split if mid.use_tc else "simt", "batch": B, "points_per_frame": N, "voxels": M, "active_sites": n_lvl, "capacity_status": int(mid.status.item()),
        "peaks": {"hbm_GBps": HBM, "bf16_TFLOPs_sustained": TF, "source": "MEASURED_PEAKS.json" if peaks else "fallback"},
        "total_ms": round(float(ms.sum()), 3), "frames_per_sec_eager": round(B / (ms.sum() / 1e3), 1),
        "mem_GB": round(torch.cuda.memory_allocated() / 2 ** 30, 1), "groups": rows,

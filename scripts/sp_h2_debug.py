@@ -1,0 +1,110 @@
+"""Single-layer check of the TMA-gather fp16-split sparse conv (spconv_h2.cu) against an fp64 gather-GEMM reference computed with torch
+on the GPU, for every supported (Cin, Cout); prints max errors relative to the output abs-max (no asserts: one run, all the evidence)."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "se-ssd_b200"))
+import torch
+from sessd_b200 import ops
+
+torch.manual_seed(0)
+dev = "cuda"
+
+
+def run(cin, cout, kvol, n_in, n_out, density, relu=True, reps=0):
+    cap_in, cap_out = n_in + 37, n_out + 91
+    feat = torch.zeros((cap_in, cin), device=dev)
+    feat[:n_in] = torch.relu(torch.randn((n_in, cin), device=dev)) * 3.0
+    feat[n_in:] = 1e6                                        # stale rows must never be read
+    nbr = torch.full((cap_out, kvol), -1, dtype=torch.int32, device=dev)
+    pick = torch.rand((n_out, kvol), device=dev) < density
+    idx = torch.randint(0, n_in, (n_out, kvol), device=dev, dtype=torch.int32)
+    nbr[:n_out] = torch.where(pick, idx, torch.full_like(idx, -1))
+    if n_out > 300:
+        nbr[128:256] = -1                                    # a tile without any neighbour
+        nbr[256:384, 1:] = -1                                # a tile with a single active offset
+        nbr[384:512, 2:] = -1                                # two active offsets
+    w = torch.randn((kvol, cin, cout), device=dev) * 0.1
+    sc = torch.rand((cout,), device=dev) + 0.5
+    sh = torch.randn((cout,), device=dev) * 0.1
+    d_nin = torch.tensor([n_in], dtype=torch.int32, device=dev)
+    d_nout = torch.tensor([n_out], dtype=torch.int32, device=dev)
+    # reference (fp64)
+    f64 = torch.cat([feat[:n_in].double(), torch.zeros((1, cin), dtype=torch.float64, device=dev)], 0)
+    ref = torch.zeros((n_out, cout), dtype=torch.float64, device=dev)
+    nb = nbr[:n_out].long()
+    nb = torch.where(nb < 0, torch.full_like(nb, n_in), nb)
+    for k in range(kvol):
+        ref += f64[nb[:, k]] @ w[k].double()
+    ref = ref * sc.double() + sh.double()
+    if relu:
+        ref = torch.relu(ref)
+    # h2 path
+    cp = 64 if cin > 32 else 32
+    planes = ops.alloc_planes(cap_in, cp, dev)
+    amax = torch.zeros((2,), device=dev)
+    ops.absmax_rows(feat, d_nin, cap_in, amax[0:1])
+    ops.split_h2(feat, d_nin, cap_in, amax[0:1], planes)
+    tiles, inv = ops.pack_weight_sp_h2(w, cp)
+    out = torch.full((cap_out, cout), -7.0, device=dev)
+    ops.spconv_forward_h2(planes, amax[0:1], nbr, d_nout, cap_out, tiles, (sc * inv).contiguous(), sh, relu, out, amax[1:2])
+    torch.cuda.synchronize()
+    got = out[:n_out].double()
+    scale = ref.abs().max().item() + 1e-30
+    err = (got - ref).abs().max().item() / scale
+    untouched = bool((out[n_out:] == -7.0).all().item())
+    amax_ok = abs(amax[1].item() - out[:n_out].abs().max().item()) == 0.0
+    amax_in_ok = abs(amax[0].item() - feat[:n_in].abs().max().item()) == 0.0
+    msg = "cin %2d cout %2d kvol %2d n_out %7d density %.2f : max err / max|ref| = %.3e  rows-beyond-n untouched %s  amax_in %s amax_out %s" % (
+        cin, cout, kvol, n_out, density, err, untouched, amax_in_ok, amax_ok)
+    if reps:
+        outs = torch.empty_like(out)
+        # 3xTF32 SIMT-gather kernel for comparison (cin >= 32 only)
+        t_tc = None
+        if cin >= 32:
+            wtc = ops.pack_weight_tc(w, cout)
+            for _ in range(2):
+                ops.spconv_forward_tc(feat, nbr, d_nout, cap_out, wtc, sc, sh, relu, outs)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                ops.spconv_forward_tc(feat, nbr, d_nout, cap_out, wtc, sc, sh, relu, outs)
+            e1.record(); torch.cuda.synchronize()
+            t_tc = e0.elapsed_time(e1) / reps
+        scl = (sc * inv).contiguous()
+        for _ in range(2):
+            ops.spconv_forward_h2(planes, amax[0:1], nbr, d_nout, cap_out, tiles, scl, sh, relu, out, amax[1:2])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            ops.spconv_forward_h2(planes, amax[0:1], nbr, d_nout, cap_out, tiles, scl, sh, relu, out, amax[1:2])
+        e1.record(); torch.cuda.synchronize()
+        t_h2 = e0.elapsed_time(e1) / reps
+        e0.record()
+        for _ in range(reps):
+            ops.split_h2(feat, d_nin, cap_in, amax[0:1], planes)
+        e1.record(); torch.cuda.synchronize()
+        t_sp = e0.elapsed_time(e1) / reps
+        pairs = int((nbr[:n_out] >= 0).sum().item())
+        msg += "\n      time h2 %.4f ms (%.1f TFLOP/s alg), split %.4f ms, 3xTF32 kernel %s ms" % (
+            t_h2, 2.0 * pairs * cin * cout / t_h2 / 1e9, t_sp, ("%.4f" % t_tc) if t_tc else "n/a")
+    print(msg, flush=True)
+
+
+modes = [int(x) for x in sys.argv[1:]] or [0]
+for mode in modes:
+  ops.SP_H2_ZERO_MODE = mode
+  print("=== missing-neighbour mode", mode, flush=True)
+  for cin, cout in ((64, 64), (32, 32), (32, 64), (16, 16), (16, 32)):
+    run(cin, cout, 27, 5000, 4000, 0.5)
+  for cin, cout in ((64, 64), (32, 32)):
+    run(cin, cout, 27, 300000, 300000, 0.5, reps=5)
+    run(cin, cout, 27, 300000, 300000, 1.0, reps=5)
+sys.exit(0)
+run(64, 64, 3, 5000, 4000, 0.7)
+run(64, 64, 27, 100, 77, 0.3)
+run(32, 32, 27, 300, 129, 1.0)
+run(64, 64, 27, 4000, 4000, 0.0)
+run(64, 64, 27, 5000, 4000, 0.5, relu=False)
+# timing at a size that fills the machine: 300k outputs (2344 tiles), 50 % of the 27 offsets present, random (cache-hostile) neighbours
+for cin, cout in ((64, 64), (32, 32), (16, 32)):
+    run(cin, cout, 27, 300000, 300000, 0.5, reps=5)

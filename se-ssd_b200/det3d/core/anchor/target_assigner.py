@@ -60,3 +60,36 @@ class TargetAssigner:
         out["labels"] = np.concatenate([t["labels"].reshape(*fmap, -1) for t in results], axis=-1).reshape(-1)
         out["bbox_outside_weights"] = np.concatenate([t["bbox_outside_weights"].reshape(*fmap, -1) for t in results], axis=-1).reshape(-1)
         return out
+
+    def assign_batch_gpu(self, anchors_dict, gt_boxes_list, device="cuda", max_gt=None, buffers=None):
+        """Device twin of ``assign_v2`` for a whole batch of frames: single anchor class,
+        ``enable_similar_type=True`` semantics (every GT box is class 1), thresholds taken from the anchor generator.
+        ``gt_boxes_list``: one [M_i, 7] array per frame (already filtered / yaw-normalised like AssignTarget._assign).
+        Returns device tensors ``labels [B,A] i32, bbox_targets [B,A,7], bbox_outside_weights [B,A]`` plus the compacted
+        positives ``pos_anchor / positive_gt_id [B,A]`` with their per-frame count ``num_pos [B]`` (no host sync)."""
+        import torch
+        from sessd_b200 import ops
+        if len(anchors_dict) != 1:
+            raise NotImplementedError("assign_batch_gpu supports the single-class SE-SSD KITTI config")
+        (ad,) = anchors_dict.values()
+        gen = self._anchor_generators[0]
+        anchors = np.ascontiguousarray(ad["anchors"].reshape(-1, self._box_coder.code_size), np.float32)
+        B = len(gt_boxes_list)
+        max_gt = int(max_gt or max([1] + [len(g) for g in gt_boxes_list]))
+        gt = np.zeros((B, max_gt, 7), np.float32)
+        num = np.zeros((B,), np.int32)
+        for b, g in enumerate(gt_boxes_list):
+            if len(g) > max_gt:
+                raise ValueError("frame %d has %d GT boxes > max_gt=%d" % (b, len(g), max_gt))
+            gt[b, :len(g)] = g
+            num[b] = len(g)
+        key = (str(device), anchors.shape[0])
+        cache = self.__dict__.setdefault("_gpu_anchor_cache", {})
+        if key not in cache:
+            cache[key] = torch.from_numpy(anchors).to(device)
+        if buffers is None or (buffers.batch, buffers.max_gt, buffers.num_anchors) != (B, max_gt, anchors.shape[0]):
+            buffers = ops.AssignBuffers(anchors.shape[0], B, max_gt, device)
+        ops.assign_targets(cache[key], torch.from_numpy(gt).to(device), torch.from_numpy(num).to(device), buffers,
+                           float(gen.match_threshold), float(gen.unmatch_threshold))
+        return dict(labels=buffers.labels, bbox_targets=buffers.bbox_targets, bbox_outside_weights=buffers.bbox_outside_weights,
+                    pos_anchor=buffers.pos_anchor, positive_gt_id=buffers.pos_gt_id, num_pos=buffers.num_pos, buffers=buffers)

@@ -43,13 +43,16 @@ def rbbox2d_to_near_bbox(rbboxes):
 
 
 def iou_jit(boxes, query_boxes, eps=1.0):
-    """Axis-aligned IoU matrix [N,K] (reference :1007-1046), vectorised; zero where the boxes do not overlap."""
+    """Axis-aligned IoU matrix [N,K] (reference :1007-1046), vectorised; zero where the boxes do not overlap.
+    Rounding follows the reference under numba: differences in the input dtype, then `+ eps` (a Python float = float64)
+    promotes the remaining arithmetic to fp64 and the quotient is rounded once into the output dtype."""
     b = boxes[:, None, :]
     q = query_boxes[None, :, :]
-    area_q = (q[..., 2] - q[..., 0] + eps) * (q[..., 3] - q[..., 1] + eps)
-    iw = np.minimum(b[..., 2], q[..., 2]) - np.maximum(b[..., 0], q[..., 0]) + eps
-    ih = np.minimum(b[..., 3], q[..., 3]) - np.maximum(b[..., 1], q[..., 1]) + eps
-    ua = (b[..., 2] - b[..., 0] + eps) * (b[..., 3] - b[..., 1] + eps) + area_q - iw * ih
+    f8 = np.float64
+    area_q = ((q[..., 2] - q[..., 0]).astype(f8) + eps) * ((q[..., 3] - q[..., 1]).astype(f8) + eps)
+    iw = (np.minimum(b[..., 2], q[..., 2]) - np.maximum(b[..., 0], q[..., 0])).astype(f8) + eps
+    ih = (np.minimum(b[..., 3], q[..., 3]) - np.maximum(b[..., 1], q[..., 1])).astype(f8) + eps
+    ua = ((b[..., 2] - b[..., 0]).astype(f8) + eps) * ((b[..., 3] - b[..., 1]).astype(f8) + eps) + area_q - iw * ih
     with np.errstate(divide="ignore", invalid="ignore"):
         ov = iw * ih / ua
     return np.where((iw > 0) & (ih > 0), ov, 0).astype(boxes.dtype)

@@ -164,6 +164,61 @@ def spconv_forward_tc(in_feat, nbr, n_out, max_out, weight_split, scale, shift, 
     return out
 
 
+def pack_weight_sp_h2(wp, cp):
+    """[kvol, Cin, Cout] (spconv layout, flattened offsets) -> (fp16 weight tiles for sessd_spconv_forward_h2, 2^-e[Cout]).
+    Every output channel is scaled by the power of two that puts its largest |w| into [2^10, 2^11); hi = fp16_rn(2^e w),
+    lo = fp16_rn(2^e w - hi).  cp = 64: [kvol, 2, Cout, 64]; cp = 32: [kvol, Cout, 64] with hi in columns [0, Cin), lo in [32, 32+Cin)."""
+    kvol, cin, cout = wp.shape
+    assert cp in (32, 64) and cin <= cp and (cp == 32 or cin == 64)
+    wt = wp.permute(0, 2, 1).contiguous().to(torch.float32)                      # [kvol, Cout, Cin]
+    amax = wt.abs().amax(dim=(0, 2))
+    _, ex = torch.frexp(amax)
+    e = torch.where(amax > 0, 11 - ex, torch.zeros_like(ex)).clamp(-100, 100).to(torch.float32)
+    ws = wt * torch.exp2(e)[None, :, None]
+    hi = ws.to(torch.float16)
+    lo = (ws - hi.to(torch.float32)).to(torch.float16)
+    if cp == 64:
+        tiles = torch.stack([hi, lo], 1).contiguous()                            # [kvol, 2, Cout, 64]
+    else:
+        tiles = torch.zeros((kvol, cout, 64), dtype=torch.float16, device=wp.device)
+        tiles[:, :, :cin] = hi
+        tiles[:, :, 32:32 + cin] = lo
+    return tiles, torch.exp2(-e).contiguous()
+
+
+def alloc_planes(max_rows, cp, device):
+    """fp16 (hi, lo) planes of a sparse feature tensor: [max_rows + 1, 2 * cp]; the extra last row stays zero (missing neighbours)."""
+    return torch.zeros((max_rows + 1, 2 * cp), dtype=torch.float16, device=device)
+
+
+def absmax_rows(feat, n, max_rows, amax):
+    check(lib.sessd_absmax_rows(_p(feat), _p(n), int(max_rows), int(feat.shape[1]), _p(amax), _st()), "sessd_absmax_rows")
+    return amax
+
+
+def split_h2(feat, n, max_rows, amax, planes):
+    cp = planes.shape[1] // 2
+    assert planes.shape[0] >= max_rows + 1 and planes.dtype == torch.float16
+    check(lib.sessd_split_h2(_p(feat), _p(n), int(max_rows), int(feat.shape[1]), _p(amax), _p(planes), int(cp), _st()), "sessd_split_h2")
+    return planes
+
+
+SP_H2_ZERO_MODE = 1      # missing neighbours: 0 = read the all-zero last row, 1 = row index -1 (TMA OOB fill), 2 = row index rows (OOB)
+
+
+def spconv_forward_h2(in_planes, amax_in, nbr, n_out, max_out, weight_h2, scale, shift, relu, out, amax_out=None):
+    """in_planes from split_h2 (its last row is the zero row); weight_h2 / scale from pack_weight_sp_h2 (scale = bn_scale * 2^-e)."""
+    cp = in_planes.shape[1] // 2
+    kvol = weight_h2.shape[0]
+    cout = weight_h2.shape[2] if cp == 64 else weight_h2.shape[1]
+    rows = in_planes.shape[0]
+    zero_row = (rows - 1, -1, rows)[SP_H2_ZERO_MODE]
+    check(lib.sessd_spconv_forward_h2(_p(in_planes), int(cp), int(rows), int(zero_row), _p(amax_in), _p(nbr), int(kvol), _p(n_out), int(max_out),
+                                      _p(weight_h2), int(cout), _p(scale), _p(shift), int(bool(relu)), _p(out), _p(amax_out), _st()),
+          "sessd_spconv_forward_h2")
+    return out
+
+
 def sparse_to_dense(feat, coors, n, max_rows, grid, out=None):
     c = feat.shape[1]
     d, h, w = grid.shape[0], grid.shape[1], grid.shape[2]

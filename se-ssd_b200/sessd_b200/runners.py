@@ -46,12 +46,18 @@ class SpMiddleRunner:
 
     # active-site growth bounds per level relative to the level-0 capacity (uniform 20k cloud: 3.4 / 5.2 / 4.3 / 2.6)
     GROWTH = (1.0, 4.0, 6.0, 5.0, 3.0)
+    SPLIT = "fp16"
 
     def __init__(self, batch, max_voxels_total, input_shape_xyz=(1408, 1600, 40), num_input_features=4, device="cuda",
-                 growth=None, use_tc=True):
-        """use_tc: run the Cin >= 32 layers on the tcgen05 tensor cores (3xTF32); False = fp32 SIMT baseline for all layers."""
+                 growth=None, use_tc=True, split=None):
+        """use_tc: run the layers on the tcgen05 tensor cores; False = fp32 SIMT baseline for all layers.
+        split: "fp16" = TMA-gather two-term fp16 split kernel (spconv_h2.cu) for every layer with Cin >= 16 (13 of 14 layers);
+               "tf32" = 3xTF32 kernel with SIMT gather warps (spconv_tc.cu) for the Cin >= 32 layers.  Default: SPLIT."""
         self.batch, self.device = batch, torch.device(device)
         self.use_tc = bool(use_tc)
+        self.split = split or self.SPLIT
+        assert self.split in ("fp16", "tf32")
+        self.use_h2 = self.use_tc and self.split == "fp16"
         self.cin0 = num_input_features
         shape = (int(input_shape_xyz[2]) + 1, int(input_shape_xyz[1]), int(input_shape_xyz[0]))   # scn.py:179
         growth = growth or self.GROWTH
@@ -85,6 +91,14 @@ class SpMiddleRunner:
                                  device=self.device)
         self.status = torch.zeros((1,), dtype=torch.int32, device=self.device)
         self.weights = None
+        # fp16-split path: (hi, lo) planes of every layer output that feeds a tensor-core layer + one abs-max scalar per tensor
+        self.planes = [None] * len(self.plan)
+        self.amax = torch.zeros((len(self.plan) + 1,), dtype=torch.float32, device=self.device)
+        if self.use_h2:
+            for li, p in enumerate(self.plan[:-1]):
+                if self.plan[li + 1]["cin"] >= 16:
+                    cp = 64 if p["cout"] > 32 else 32
+                    self.planes[li] = ops.alloc_planes(self.levels[p["lout"]]["cap"], cp, self.device)
 
     def _add_level(self, shape, cap, hash_index):
         grid = ops.make_grid(self.batch, shape)
@@ -108,7 +122,12 @@ class SpMiddleRunner:
             assert tuple(w.shape) == (*p["ks"], p["cin"], p["cout"]), (w.shape, p)
             sc, sh = fold_bn(*[torch.as_tensor(l[k], device=self.device) for k in ("gamma", "beta", "mean", "var")])
             wp = w.reshape(-1, p["cin"], p["cout"]).contiguous()
-            tc = ops.pack_weight_tc(wp, p["cout"]) if (self.use_tc and p["cin"] >= 32) else None
+            tc = None
+            if self.use_h2 and p["cin"] >= 16:
+                tiles, inv = ops.pack_weight_sp_h2(wp, 64 if p["cin"] > 32 else 32)
+                tc = ("h2", tiles, (sc * inv).contiguous())
+            elif self.use_tc and p["cin"] >= 32:
+                tc = ops.pack_weight_tc(wp, p["cout"])
             self.weights.append((wp, sc, sh, tc))
 
     def forward(self, feat0, coors0, n0, mark=None):
@@ -122,6 +141,8 @@ class SpMiddleRunner:
         L0["coors"], L0["n_ext"] = coors0, n0
         ops.hash_build(coors0, n0, cap0, L0["grid"], L0["index"])
         mark("hash_build")
+        if self.use_h2:
+            self.amax.zero_()
         x = feat0
         for li, p in enumerate(self.plan):
             lin, lout = self.levels[p["lin"]], self.levels[p["lout"]]
@@ -139,11 +160,20 @@ class SpMiddleRunner:
                 n_out, cap_out = lout["n"], lout["cap"]
                 mark("rulebook:sp%d" % p["lout"])
             w, sc, sh, tc = self.weights[li]
-            if tc is not None:
+            if isinstance(tc, tuple):
+                # fp16-split tensor-core layer: reads the (hi, lo) planes of its input, writes fp32 rows + the output's abs-max
+                x = ops.spconv_forward_h2(self.planes[li - 1], self.amax[li - 1:li], p["nbr"], n_out, cap_out, tc[1], tc[2], sh, True,
+                                          self.feats[li], self.amax[li:li + 1])
+            elif tc is not None:
                 x = ops.spconv_forward_tc(x, p["nbr"], n_out, cap_out, tc, sc, sh, True, self.feats[li])
             else:
                 x = ops.spconv_forward(x, p["nbr"], n_out, cap_out, w, sc, sh, True, self.feats[li])
+                if self.planes[li] is not None:
+                    ops.absmax_rows(x, n_out, cap_out, self.amax[li:li + 1])
             mark("conv:%d" % li)
+            if self.planes[li] is not None:
+                ops.split_h2(x, n_out, cap_out, self.amax[li:li + 1], self.planes[li])
+                mark("split:%d" % li)
         last = self.levels[-1]
         out = ops.sparse_to_dense(x, last["coors"], last["n"], last["cap"], last["grid"], self.dense)
         mark("dense")

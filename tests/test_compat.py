@@ -73,6 +73,23 @@ def test_anchor_assigner_pipeline_matches_reference_golden(golden_dir):
     assert np.array_equal(pos, g["pos_idx"]) and np.array_equal(t["reg_targets"][0][pos], g["pos_targets"])
 
 
+def test_host_assigner_mirror_matches_reference_on_all_golden_cases(golden_dir):
+    """Host TargetAssigner.assign_v2 (numpy) == the reference on empty / single / many GT, GT without overlap, forced-only positives, ties."""
+    from cases import assign_cases
+    from det3d.datasets.pipelines import AssignTarget
+    from det3d.torchie import Config
+    at = AssignTarget(cfg=Config.fromfile(OUR_CFG).train_cfg.assigner)
+    ta, ad = at.target_assigners[0], at.anchor_dicts_by_task[0]
+    g = np.load(os.path.join(golden_dir, "assign_cases.npz"))
+    for name, gt in assign_cases():
+        m = len(gt)
+        r = ta.assign_v2(ad, gt, None, gt_classes=np.ones(m, np.int32), gt_names=np.array(["Car"] * m), enable_similar_type=True)
+        assert np.array_equal(r["labels"].astype(np.int8), g[name + "_labels"]), name
+        pos = np.nonzero(r["labels"] > 0)[0]
+        assert np.array_equal(pos, g[name + "_pos_idx"]) and np.array_equal(r["bbox_targets"][pos], g[name + "_pos_targets"]), name
+        assert np.array_equal(np.asarray(r["positive_gt_id"][0], np.int32), g[name + "_positive_gt_id"]), name
+
+
 def _example_from_clouds(cfg, clouds):
     from det3d.datasets.pipelines import AssignTarget, Reformat, Voxelization
     from det3d.torchie.parallel import collate_kitti

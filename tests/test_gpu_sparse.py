@@ -91,8 +91,8 @@ def _weights(seed=3):
     return weights.split_detector_state(sd)
 
 
-@pytest.mark.parametrize("use_tc", [False, True], ids=["simt", "tcgen05"])
-def test_spmiddle_features_match_fp64_oracle(use_tc):
+@pytest.mark.parametrize("use_tc,split", [(False, None), (True, "tf32"), (True, "fp16")], ids=["simt", "tcgen05", "tma-gather-fp16x2"])
+def test_spmiddle_features_match_fp64_oracle(use_tc, split):
     from oracle import spconv_ref as S
     from sessd_b200 import synth
     from sessd_b200.runners import SpMiddleRunner
@@ -104,7 +104,7 @@ def test_spmiddle_features_match_fp64_oracle(use_tc):
                    var=l["var"].numpy()) for l in layers]
     trace = []
     ref = S.spmiddle_forward(feat, coors, 1, (1408, 1600, 40), params, np.float64, trace)   # [1,128,200,176]
-    r = SpMiddleRunner(1, n, device="cuda", use_tc=use_tc)
+    r = SpMiddleRunner(1, n, device="cuda", use_tc=use_tc, split=split)
     r.load_weights(layers)
     dense = r.forward(torch.from_numpy(feat).cuda(), torch.from_numpy(coors).cuda(), torch.tensor([n], dtype=torch.int32, device="cuda"))
     torch.cuda.synchronize()
