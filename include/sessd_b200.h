@@ -130,6 +130,10 @@ int sessd_spconv_forward_tc(const float *d_in_feat, int cin, const int *d_nbr, i
 /* dense(): out NHWC [batch, H, W, C*D] with channel index c*D + d (zero-filled by the call) */
 int sessd_sparse_to_dense(const float *d_feat, const int *d_coors, const int *d_n, int max_rows, int channels,
                           sessd_grid grid, float *d_out, void *stream);
+/* same result in one gather pass (no memset + scatter): the rows of every BEV cell are looked up in the level's bitmap index
+ * (the `d_out_bitmap` that sessd_strided_rulebook filled for this level); writes each output byte exactly once. */
+int sessd_sparse_to_dense_indexed(const float *d_feat, int max_rows, const void *d_bitmap_index, int channels, sessd_grid grid,
+                                  float *d_out, void *stream);
 
 /* S4 (fp16-split tensor-core path with TMA gather; csrc/spconv_h2.cu).  Same contract as sessd_spconv_forward (spconv 1.x
  * gather -> GEMM -> scatter-add at det3d/models/backbones/scn.py:106-149, + folded BN + ReLU), but the input features are
@@ -139,6 +143,12 @@ int sessd_sparse_to_dense(const float *d_feat, const int *d_coors, const int *d_
  * [kvol][cout][hi 32 | lo 32] fp16 (Cin 16 zero-padded), every output channel scaled by a power of two 2^e[c];
  * d_scale[c] must be bn_scale[c] * 2^-e[c].  d_amax_out (nullable) receives the running abs-max of the output.
  * Supported (cp, cout): (32,16) (32,32) (32,64) (64,64). */
+/* S4, narrow layers (Cin <= 32; csrc/spconv_rows.cu): same contract and arguments as sessd_spconv_forward, fp32 SIMT, but the work is
+ * proportional to the number of rulebook PAIRS instead of N_out x kvol row slots (a warp owns 8 output rows and visits only their valid
+ * neighbours).  d_amax_out (nullable) receives the running abs-max of the output.  (Cin, Cout): (4,16) (16,16) (16,32) (32,32) (32,64). */
+int sessd_spconv_forward_rows(const float *d_in_feat, int cin, const int *d_nbr, int kvol, const int *d_n_out, int max_out,
+                              const float *d_weight, int cout, const float *d_scale, const float *d_shift, int relu,
+                              float *d_out_feat, float *d_amax_out, void *stream);
 /* pipeline depth of sessd_spconv_forward_h2: 0 = auto (deep when max_out <= 262144), 1 = 2 CTAs/SM x 2-4 stages, 2 = 1 CTA/SM x 4-8 stages */
 void sessd_set_sp_h2_depth(int mode);
 int sessd_split_h2(const float *d_feat, const int *d_n, int max_rows, int channels, const float *d_amax, void *d_planes, int cp,

@@ -25,15 +25,16 @@ ap.add_argument("--batch", type=int, default=None)
 ap.add_argument("--points", type=int, default=None)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--sparse-split", default=None, choices=["fp16", "tf32"])
+ap.add_argument("--rows-max-cin", type=int, default=None)
 a = ap.parse_args()
 if a.shape == "stress":
     B, N = a.batch or 16, a.points or 200000
     clouds = [synth.uniform_cloud(1000 + f, N) for f in range(B)]
-    eng = FrameEngine(batch=B, max_points_per_frame=N, max_voxels=200000, growth=(1.0, 8.0, 8.0, 8.0, 8.0), sparse_split=a.sparse_split)
+    eng = FrameEngine(batch=B, max_points_per_frame=N, max_voxels=200000, growth=(1.0, 8.0, 8.0, 8.0, 8.0), sparse_split=a.sparse_split, rows_max_cin=a.rows_max_cin)
 else:
     B, N = a.batch or 1, a.points or 20000
     clouds = [synth.ring_cloud(f, N) for f in range(B)]
-    eng = FrameEngine(batch=B, max_points_per_frame=max(c.shape[0] for c in clouds), sparse_split=a.sparse_split)
+    eng = FrameEngine(batch=B, max_points_per_frame=max(c.shape[0] for c in clouds), sparse_split=a.sparse_split, rows_max_cin=a.rows_max_cin)
 layers, ssfa, head = weights.split_detector_state(weights.random_detector_state(0, cls_bias=-3.0))
 eng.load_weights(layers, ssfa, head, weights.kitti_car_anchors())
 eng.calibrate_cls_bias(clouds, 400)
@@ -101,7 +102,7 @@ for li, p in enumerate(mid.plan):
         work[key] = ("hbm", 16.0 * n_in + 4.0 * kvol * n_out + 16.0 * n_out)
     work["conv:%d" % li] = ("tensor", 2.0 * pairs * p["cin"] * p["cout"],
                             4.0 * n_in * p["cin"] + 4.0 * n_out * p["cout"] + 4.0 * kvol * n_out + 4.0 * kvol * p["cin"] * p["cout"],
-                            dict(kind=p["kind"], cin=p["cin"], cout=p["cout"], n_out=n_out, pairs=pairs))
+                            dict(kind=p["kind"], impl=p.get("impl"), cin=p["cin"], cout=p["cout"], n_out=n_out, pairs=pairs))
 for li, p in enumerate(mid.plan):
     if mid.planes[li] is not None:
         work["split:%d" % li] = ("hbm", 8.0 * n_lvl[p["lout"]] * p["cout"])

@@ -31,6 +31,13 @@ struct HashIndex {
     const unsigned long long *tbl;
     int mask;
     __device__ __forceinline__ int find(unsigned long long lin) const { return hash_lookup(tbl, mask, lin); }
+    // rows of the cells (row_base + x0 + c), c = 0..n-1, of one x-line; -1 outside [0, W) or where no voxel lives
+    __device__ __forceinline__ void find_line(unsigned long long row_base, int x0, int n, int W, int *dst) const {
+        for (int c = 0; c < n; ++c) {
+            const int x = x0 + c;
+            dst[c] = (x >= 0 && x < W) ? find(row_base + x) : -1;
+        }
+    }
 };
 
 struct BitmapIndex {
@@ -40,6 +47,21 @@ struct BitmapIndex {
         const unsigned int bit = (unsigned int)lin & 31u;
         if (!((e.x >> bit) & 1u)) return -1;
         return (int)e.y + __popc(e.x & ((1u << bit) - 1u));
+    }
+    __device__ __forceinline__ void find_line(unsigned long long row_base, int x0, int n, int W, int *dst) const {
+        unsigned long long cached = ~0ull;
+        uint2 e = make_uint2(0u, 0u);
+        for (int c = 0; c < n; ++c) {
+            const int x = x0 + c;
+            int res = -1;
+            if (x >= 0 && x < W) {
+                const unsigned long long lin = row_base + x;
+                if ((lin >> 5) != cached) { cached = lin >> 5; e = __ldg(&words[cached]); }
+                const unsigned int bit = (unsigned int)lin & 31u;
+                if ((e.x >> bit) & 1u) res = (int)e.y + __popc(e.x & ((1u << bit) - 1u));
+            }
+            dst[c] = res;
+        }
     }
 };
 
@@ -52,46 +74,96 @@ __global__ void __launch_bounds__(256) hash_build_kernel(const int4 *__restrict_
     }
 }
 
-// nbr table: one thread per (output row, kernel offset), k fastest (coalesced 4-byte stores)
-template <class Index>
+// nbr table: one thread per (output row, kernel z, kernel y) = one x-line of the kernel window.  The kw cells of the line are
+// consecutive in the input grid, so a bitmap-indexed level answers them from one (rarely two) 8-byte words; index arithmetic and the
+// coordinate load are shared by the line, and the thread writes kw consecutive ints (warp: one contiguous segment of the table).
+// KD..SW > 0: kernel shape / stride known at compile time (the SpMiddleFHD shapes) -- the per-thread divisions and modulos become
+// multiplies and shifts (ncu: the runtime-divisor version was ALU-bound, sm 67 %, at 16 % of the DRAM write peak); KD = 0: runtime values.
+// IdxT = unsigned int when the work-item count fits 31 bits (host check), long long otherwise.
+template <class Index, class IdxT, int KD, int KH, int KW, int SD, int SH, int SW>
 __global__ void __launch_bounds__(256) nbr_kernel(const int4 *__restrict__ out_coors, const int *__restrict__ d_n_out, int max_out,
-                                                  GridDims gin, Index index, int kd, int kh, int kw, int sd, int sh, int sw,
+                                                  GridDims gin, Index index, int kd_, int kh_, int kw_, int sd_, int sh_, int sw_,
                                                   int pd, int ph, int pw, int *__restrict__ nbr) {
-    const int kvol = kd * kh * kw;
-    const long long total = (long long)min(*d_n_out, max_out) * kvol;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int o = (int)(t / kvol);
-        const int k = (int)(t - (long long)o * kvol);
-        const int a = k / (kh * kw), r = k - a * (kh * kw), bb = r / kw, c = r - bb * kw;
+    const int kd = KD ? KD : kd_, kh = KD ? KH : kh_, kw = KD ? KW : kw_;
+    const int sd = KD ? SD : sd_, sh = KD ? SH : sh_, sw = KD ? SW : sw_;
+    const int lines = kd * kh;
+    const IdxT total = (IdxT)min(*d_n_out, max_out) * (IdxT)lines;
+    for (IdxT t = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (IdxT)gridDim.x * blockDim.x) {
+        const int o = (int)(t / (IdxT)lines);
+        const int l = (int)(t - (IdxT)o * (IdxT)lines);
+        const int a = l / kh, bb = l - a * kh;
         const int4 oc = __ldg(&out_coors[o]);
-        const int z = oc.y * sd - pd + a, y = oc.z * sh - ph + bb, x = oc.w * sw - pw + c;
-        int res = -1;
-        if (z >= 0 && z < gin.D && y >= 0 && y < gin.H && x >= 0 && x < gin.W) res = index.find(lin_index(gin, oc.x, z, y, x));
-        nbr[t] = res;
+        const int z = oc.y * sd - pd + a, y = oc.z * sh - ph + bb, x0 = oc.w * sw - pw;
+        int *dst = nbr + (size_t)t * kw;           // == nbr[o * kvol + (a * kh + bb) * kw]
+        if (z < 0 || z >= gin.D || y < 0 || y >= gin.H) {
+            for (int c = 0; c < kw; ++c) dst[c] = -1;
+            continue;
+        }
+        index.find_line(lin_index(gin, oc.x, z, y, 0), x0, kw, gin.W, dst);
     }
 }
 
-// strided conv, step 1: mark every reachable output cell
+// strided conv, step 1: mark every reachable output cell.  One thread per (input voxel, kernel z, kernel y): along each axis only the
+// taps with (i + pad - k) divisible by the stride reach an output (1 or 2 of 3 for k3 s2); the thread walks the kw taps of its x-line.
+template <class IdxT, int KD, int KH, int KW, int SD, int SH, int SW>
 __global__ void __launch_bounds__(256) mark_outputs_kernel(const int4 *__restrict__ in_coors, const int *__restrict__ d_n_in, int max_in,
-                                                           GridDims gout, int kd, int kh, int kw, int sd, int sh, int sw,
+                                                           GridDims gout, int kd_, int kh_, int kw_, int sd_, int sh_, int sw_,
                                                            int pd, int ph, int pw, uint2 *bitmap) {
-    const int kvol = kd * kh * kw;
-    const long long total = (long long)min(*d_n_in, max_in) * kvol;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(t / kvol);
-        const int k = (int)(t - (long long)i * kvol);
-        const int a = k / (kh * kw), r = k - a * (kh * kw), bb = r / kw, c = r - bb * kw;
+    const int kd = KD ? KD : kd_, kh = KD ? KH : kh_, kw = KD ? KW : kw_;
+    const int sd = KD ? SD : sd_, sh = KD ? SH : sh_, sw = KD ? SW : sw_;
+    const int lines = kd * kh;
+    const IdxT total = (IdxT)min(*d_n_in, max_in) * (IdxT)lines;
+    for (IdxT t = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (IdxT)gridDim.x * blockDim.x) {
+        const int i = (int)(t / (IdxT)lines);
+        const int l = (int)(t - (IdxT)i * (IdxT)lines);
+        const int a = l / kh, bb = l - a * kh;
         const int4 ic = __ldg(&in_coors[i]);
-        const int nz = ic.y + pd - a, ny = ic.z + ph - bb, nx = ic.w + pw - c;
-        if (nz < 0 || ny < 0 || nx < 0) continue;
-        if (nz % sd || ny % sh || nx % sw) continue;
-        const int z = nz / sd, y = ny / sh, x = nx / sw;
-        if (z >= gout.D || y >= gout.H || x >= gout.W) continue;
-        const unsigned long long lin = lin_index(gout, ic.x, z, y, x);
-        unsigned int *w = &bitmap[lin >> 5].x;
-        const unsigned int bit = 1u << ((unsigned int)lin & 31u);
-        if (!(*(volatile unsigned int *)w & bit)) atomicOr(w, bit);
+        const int nz = ic.y + pd - a, ny = ic.z + ph - bb;
+        if (nz < 0 || ny < 0 || nz % sd || ny % sh) continue;
+        const int z = nz / sd, y = ny / sh;
+        if (z >= gout.D || y >= gout.H) continue;
+        const unsigned long long row = lin_index(gout, ic.x, z, y, 0);
+        for (int c = 0; c < kw; ++c) {
+            const int nx = ic.w + pw - c;
+            if (nx < 0 || nx % sw) continue;
+            const int x = nx / sw;
+            if (x >= gout.W) continue;
+            const unsigned long long lin = row + x;
+            unsigned int *w = &bitmap[lin >> 5].x;
+            const unsigned int bit = 1u << ((unsigned int)lin & 31u);
+            if (!(*(volatile unsigned int *)w & bit)) atomicOr(w, bit);
+        }
     }
+}
+
+// host dispatch over the compile-time shapes of SpMiddleFHD (scn.py:106-149): 3x3x3 s1 (SubM), 3x3x3 s2, (3,1,1) s(2,1,1); else generic
+template <class Index>
+static void launch_nbr(int grid_sz, cudaStream_t st, const int4 *coors, const int *d_n, int max_out, GridDims g, Index idx, const int k[3],
+                       const int s[3], const int p[3], int *nbr) {
+    const bool small = (long long)max_out * k[0] * k[1] < (1ll << 31);
+#define SESSD_NBR(IT, KD, KH, KW, SD, SH, SW)                                                                                             \
+    SESSD_LAUNCH((nbr_kernel<Index, IT, KD, KH, KW, SD, SH, SW>), grid_sz, 256, 0, st, coors, d_n, max_out, g, idx, k[0], k[1], k[2], s[0], \
+                 s[1], s[2], p[0], p[1], p[2], nbr)
+    if (!small) SESSD_NBR(long long, 0, 0, 0, 0, 0, 0);
+    else if (k[0] == 3 && k[1] == 3 && k[2] == 3 && s[0] == 1 && s[1] == 1 && s[2] == 1) SESSD_NBR(unsigned int, 3, 3, 3, 1, 1, 1);
+    else if (k[0] == 3 && k[1] == 3 && k[2] == 3 && s[0] == 2 && s[1] == 2 && s[2] == 2) SESSD_NBR(unsigned int, 3, 3, 3, 2, 2, 2);
+    else if (k[0] == 3 && k[1] == 1 && k[2] == 1 && s[0] == 2 && s[1] == 1 && s[2] == 1) SESSD_NBR(unsigned int, 3, 1, 1, 2, 1, 1);
+    else SESSD_NBR(unsigned int, 0, 0, 0, 0, 0, 0);
+#undef SESSD_NBR
+}
+
+static void launch_mark(cudaStream_t st, const int4 *coors, const int *d_n, int max_in, GridDims g, const int k[3], const int s[3],
+                        const int p[3], uint2 *bm) {
+    const int grid_sz = persistent_grid((long long)max_in * k[0] * k[1], 256);
+    const bool small = (long long)max_in * k[0] * k[1] < (1ll << 31);
+#define SESSD_MARK(IT, KD, KH, KW, SD, SH, SW)                                                                                           \
+    SESSD_LAUNCH((mark_outputs_kernel<IT, KD, KH, KW, SD, SH, SW>), grid_sz, 256, 0, st, coors, d_n, max_in, g, k[0], k[1], k[2], s[0], s[1], \
+                 s[2], p[0], p[1], p[2], bm)
+    if (!small) SESSD_MARK(long long, 0, 0, 0, 0, 0, 0);
+    else if (k[0] == 3 && k[1] == 3 && k[2] == 3 && s[0] == 2 && s[1] == 2 && s[2] == 2) SESSD_MARK(unsigned int, 3, 3, 3, 2, 2, 2);
+    else if (k[0] == 3 && k[1] == 1 && k[2] == 1 && s[0] == 2 && s[1] == 1 && s[2] == 1) SESSD_MARK(unsigned int, 3, 1, 1, 2, 1, 1);
+    else SESSD_MARK(unsigned int, 0, 0, 0, 0, 0, 0);
+#undef SESSD_MARK
 }
 
 struct PopcLoad {
@@ -236,15 +308,14 @@ extern "C" int sessd_subm_rulebook(const int *d_coors, const int *d_n, int max_r
     const int kd = ksize[0], kh = ksize[1], kw = ksize[2];
     if (kd < 1 || kh < 1 || kw < 1 || !(kd & 1) || !(kh & 1) || !(kw & 1)) return SESSD_EINVAL;
     const GridDims g = to_dims(grid);
-    const int grid_sz = persistent_grid((long long)max_rows * kd * kh * kw, 256);
+    const int grid_sz = persistent_grid((long long)max_rows * kd * kh, 256);
+    const int one[3] = {1, 1, 1}, pad[3] = {kd / 2, kh / 2, kw / 2};
     if (index_kind == 0) {
         HashIndex idx{(const unsigned long long *)d_index, hash_capacity - 1};
-        SESSD_LAUNCH((nbr_kernel<HashIndex>), grid_sz, 256, 0, stream, (const int4 *)d_coors, d_n, max_rows, g, idx, kd, kh, kw, 1, 1, 1,
-                     kd / 2, kh / 2, kw / 2, d_nbr);
+        launch_nbr(grid_sz, (cudaStream_t)stream, (const int4 *)d_coors, d_n, max_rows, g, idx, ksize, one, pad, d_nbr);
     } else if (index_kind == 1) {
         BitmapIndex idx{(const uint2 *)d_index};
-        SESSD_LAUNCH((nbr_kernel<BitmapIndex>), grid_sz, 256, 0, stream, (const int4 *)d_coors, d_n, max_rows, g, idx, kd, kh, kw, 1, 1, 1,
-                     kd / 2, kh / 2, kw / 2, d_nbr);
+        launch_nbr(grid_sz, (cudaStream_t)stream, (const int4 *)d_coors, d_n, max_rows, g, idx, ksize, one, pad, d_nbr);
     } else {
         return SESSD_EINVAL;
     }
@@ -268,10 +339,8 @@ extern "C" int sessd_strided_rulebook(const int *d_in_coors, const int *d_n_in, 
     const size_t words = sessd_bitmap_words(out_grid);
     if (words >= (1ull << 31)) return SESSD_ECAPACITY;
     uint2 *bm = (uint2 *)d_out_bitmap;
-    const int kvol = ksize[0] * ksize[1] * ksize[2];
     SESSD_CUDA_TRY(cudaMemsetAsync(bm, 0, sizeof(uint2) * words, st));
-    SESSD_LAUNCH(mark_outputs_kernel, persistent_grid((long long)max_in * kvol, 256), 256, 0, st, (const int4 *)d_in_coors, d_n_in,
-                 max_in, go, ksize[0], ksize[1], ksize[2], stride[0], stride[1], stride[2], padding[0], padding[1], padding[2], bm);
+    launch_mark(st, (const int4 *)d_in_coors, d_n_in, max_in, go, ksize, stride, padding, bm);
     int *scratch = (int *)d_scan_scratch;
     int *d_total = scratch;                    // first int: total; tile sums follow (256-byte offset)
     PopcLoad ld{bm};
@@ -279,18 +348,54 @@ extern "C" int sessd_strided_rulebook(const int *d_in_coors, const int *d_n_in, 
     device_scan(ld, stf, nullptr, (long long)words, (long long)words, scratch + 64, d_total, st);
     SESSD_LAUNCH(enumerate_kernel, persistent_grid((long long)words, 256), 256, 0, st, bm, (long long)words, go, d_total, max_out,
                  (int4 *)d_out_coors, d_n_out, d_status);
-    const int grid_sz = persistent_grid((long long)max_out * kvol, 256);
+    const int grid_sz = persistent_grid((long long)max_out * ksize[0] * ksize[1], 256);
     if (in_index_kind == 0) {
         HashIndex idx{(const unsigned long long *)d_in_index, in_hash_capacity - 1};
-        SESSD_LAUNCH((nbr_kernel<HashIndex>), grid_sz, 256, 0, st, (const int4 *)d_out_coors, d_n_out, max_out, gi, idx, ksize[0], ksize[1],
-                     ksize[2], stride[0], stride[1], stride[2], padding[0], padding[1], padding[2], d_nbr);
+        launch_nbr(grid_sz, st, (const int4 *)d_out_coors, d_n_out, max_out, gi, idx, ksize, stride, padding, d_nbr);
     } else if (in_index_kind == 1) {
         BitmapIndex idx{(const uint2 *)d_in_index};
-        SESSD_LAUNCH((nbr_kernel<BitmapIndex>), grid_sz, 256, 0, st, (const int4 *)d_out_coors, d_n_out, max_out, gi, idx, ksize[0], ksize[1],
-                     ksize[2], stride[0], stride[1], stride[2], padding[0], padding[1], padding[2], d_nbr);
+        launch_nbr(grid_sz, st, (const int4 *)d_out_coors, d_n_out, max_out, gi, idx, ksize, stride, padding, d_nbr);
     } else {
         return SESSD_EINVAL;
     }
+    return last_error();
+}
+
+// dense() as ONE gather pass over the output (no memset + scatter): thread = 4 consecutive output channels of one BEV cell; the rows of
+// the D z-slices of the cell come from the level's bitmap index (bit test + popcount rank).  NHWC [B, H, W, C*D], channel = c*D + d
+// (== NCDHW .view(N, C*D, H, W) of det3d/models/backbones/scn.py:184-187, channels-last).  Writes every output byte exactly once with
+// 16-byte stores; reads each feature row once.
+__global__ void __launch_bounds__(256) dense_gather_kernel(const float *__restrict__ feat, BitmapIndex index, GridDims g, int C,
+                                                           int max_rows, float4 *__restrict__ out) {
+    const unsigned int cd4 = (unsigned int)(C * g.D) >> 2;
+    const unsigned int total = (unsigned int)g.B * g.H * g.W * cd4;          // < 2^31 (checked by the host)
+    for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const unsigned int cell = t / cd4;
+        const int j = (int)(t - cell * cd4) * 4;
+        const unsigned int r = cell / (unsigned int)g.W;
+        const int x = (int)(cell - r * g.W);
+        const int b = (int)(r / (unsigned int)g.H), y = (int)(r - (r / (unsigned int)g.H) * g.H);
+        float v[4];
+        int last_d = -1, row = -1;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int ch = j + e;
+            const int c = ch / g.D, d = ch - c * g.D;
+            if (d != last_d) { row = index.find(lin_index(g, b, d, y, x)); last_d = d; }
+            v[e] = (row >= 0 && row < max_rows) ? __ldg(&feat[(size_t)row * C + c]) : 0.f;    // rows past the capacity were dropped (status flag)
+        }
+        out[t] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+extern "C" int sessd_sparse_to_dense_indexed(const float *d_feat, int max_rows, const void *d_bitmap_index, int channels, sessd_grid grid,
+                                             float *d_out, void *stream) {
+    if (!d_feat || !d_bitmap_index || !d_out || channels < 1 || max_rows < 1 || ((channels * grid.shape[0]) & 3)) return SESSD_EINVAL;
+    const GridDims g = to_dims(grid);
+    BitmapIndex idx{(const uint2 *)d_bitmap_index};
+    const long long total = (long long)g.B * g.H * g.W * ((channels * g.D) >> 2);
+    if (total >= (1ll << 31)) return SESSD_ECAPACITY;
+    SESSD_LAUNCH(dense_gather_kernel, persistent_grid(total, 256), 256, 0, stream, d_feat, idx, g, channels, max_rows, (float4 *)d_out);
     return last_error();
 }
 

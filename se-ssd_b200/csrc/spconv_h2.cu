@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kG4Threads, DEEP ? 1 : 2) spconv_h2_kernel(con
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], C::kWide ? 1 : 4); mbar_init(&empty[s], 1); }   // narrow: one arrival per producer warp
         mbar_init(acc_full, 1);
         *s_kmask = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -209,19 +209,43 @@ __global__ void __launch_bounds__(kG4Threads, DEEP ? 1 : 2) spconv_h2_kernel(con
         const int first_row = warp * 32 + g * 4;
         const uint32_t dst_off = (uint32_t)first_row * 128u + ((C::kWide && lane >= 8) ? (uint32_t)(kG4BM * 128) : 0u);
         const int col = (C::kWide && lane >= 8) ? 64 : 0;
+        // A gather4 whose four rows are all missing only has to leave zeros behind: it is SKIPPED when the four shared-memory lines of
+        // that stage are known to be zero already (each lane tracks its own lines: bit s of `dirty` = stage s holds real data or has
+        // never been written), otherwise issued once with out-of-bounds indices (zero fill) to clean them.  Narrow layers only (fill
+        // 5-25 %): removes a third of the TMA row requests, the resource that bounds this kernel (stress shape: 12.3 -> 9.8 ms).
+        uint32_t dirty = (1u << C::kStages) - 1u;
         for (int j = 0; j < nact; ++j) {
             const int s = j % C::kStages;
             const uint32_t ph = (j / C::kStages) & 1;
             const int k = s_klist[j];
-            if (lane == 0) {
-                mbar_wait(&empty[s], ph ^ 1);
-                if (warp == 0) mbar_expect_tx(&full[s], C::kATile + C::kBTile);
-            }
-            __syncwarp();
+            int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+            bool issue = false;
             if (lane < kIssuers) {
                 const int *nb = s_nbr + first_row * kvol + k;
-                tma_gather4(tiles_u32 + (uint32_t)(s * C::kStage) + dst_off, &map_a, &full[s], col, nb[0], nb[kvol], nb[2 * kvol], nb[3 * kvol]);
+                i0 = nb[0]; i1 = nb[kvol]; i2 = nb[2 * kvol]; i3 = nb[3 * kvol];
+                issue = true;
+                if constexpr (!C::kWide) {
+                    const bool all_missing = (i0 == zero_row) & (i1 == zero_row) & (i2 == zero_row) & (i3 == zero_row);
+                    if (!all_missing) dirty |= 1u << s;
+                    else if ((dirty >> s) & 1u) dirty &= ~(1u << s);
+                    else issue = false;
+                }
             }
+            if constexpr (C::kWide) {
+                // 64-channel layers (fill 35-90 %): skipping rarely triggers and its bookkeeping costs ~4 % -- every gather is issued
+                if (lane == 0) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    if (warp == 0) mbar_expect_tx(&full[s], C::kATile + C::kBTile);
+                }
+            } else {
+                const uint32_t nissue = __popc(__ballot_sync(0xffffffffu, issue));
+                if (lane == 0) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], nissue * 512u + (warp == 0 ? (uint32_t)C::kBTile : 0u));      // arrive + this warp's bytes
+                }
+            }
+            __syncwarp();
+            if (issue) tma_gather4(tiles_u32 + (uint32_t)(s * C::kStage) + dst_off, &map_a, &full[s], col, i0, i1, i2, i3);
             if (warp == 0 && lane == 0) {
                 unsigned char *b_tile = tiles + s * C::kStage + C::kATile;
                 if constexpr (C::kWide) {

@@ -1,0 +1,175 @@
+// spconv_rows.cu -- sparse 3-D convolution for the NARROW layers (Cin <= 32) of SpMiddleFHD with work proportional to the number of
+// rulebook PAIRS (fp32 SIMT), + folded BN + ReLU.
+//
+// Why a second formulation: the output-stationary tensor-core kernels (spconv_tc.cu, spconv_h2.cu) move and multiply a full 128-row
+// operand tile for every kernel offset, i.e. N_out x 27 row slots per layer whatever the neighbour fill.  On the first two levels of
+// det3d/models/backbones/scn.py:106-131 the fill is low (SubM level 0: ~1 of 27 slots, the stride-2 SparseConv3d layers: 1-3 of 27,
+// SubM level 1: ~6 of 27 on KITTI-like and on the dense synthetic clouds alike) and the channels are few (4..32), so > 75 % of that work
+// is zeros and the layers are bound by operand movement, not by math.  Here a warp owns 4 output rows and touches ONLY their valid
+// (row, offset) pairs:
+//   * persistent CTAs of 32 warps; ALL kvol weight slices of the layer (7 .. 110 KB fp32) are loaded into shared memory once per CTA
+//     and stay there: no per-offset staging, no block-wide synchronisation in the main loop;
+//   * per tile of 128 output rows the neighbour table is staged in shared memory; lane k of a warp holds nbr[row][k], a ballot gives
+//     the row's valid offsets, and the warp walks them in ascending k: the input row is one coalesced 16-128 byte segment (lane c
+//     holds channel c; the rows of up to 6 pairs are in flight together), acc[cout] += in[c] * W[k][c][cout] with the input value broadcast
+//     by warp shuffle and the weights read as consecutive lanes = consecutive output channels (conflict-free);
+//   * epilogue per row: folded BatchNorm1d scale / shift + ReLU, coalesced row store, running abs-max of the output (feeds the fp16
+//     split of the next tensor-core layer).
+// Same contract and results as sessd_spconv_forward (fp32 FMA accumulation; only the summation order over offsets is the same too:
+// ascending k).  Algorithmic work: 2 P Cin Cout flops, 4 (P Cin + N_out Cout) + 4 kvol N_out bytes.
+#include "common.cuh"
+
+namespace sessd {
+
+constexpr int kRwRows = 128;
+constexpr int kRwWarps = 32;
+constexpr int kRwThreads = kRwWarps * 32;
+constexpr int kRwRpw = kRwRows / kRwWarps;          // rows per warp
+constexpr int kRwMaxK = 27;
+constexpr int kRwBatch = 6;                         // input rows in flight per warp
+
+template <int CIN, int COUT>
+struct RwCfg {
+    static constexpr int kJ = (COUT + 31) / 32;                  // output channels per lane
+    static constexpr int kWFloats = CIN * COUT;                  // per kernel offset
+    static constexpr size_t smem(int kvol) { return (size_t)kvol * kWFloats * 4 + (size_t)kRwRows * kRwMaxK * 4 + 64; }
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(kRwThreads, 1) spconv_rows_kernel(const float *__restrict__ in_feat, const int *__restrict__ nbr, int kvol,
+                                                                    const int *__restrict__ d_n_out, int max_out,
+                                                                    const float *__restrict__ weight, const float *__restrict__ scale,
+                                                                    const float *__restrict__ shift, int relu, float *__restrict__ out_feat,
+                                                                    float *__restrict__ amax_out) {
+    using C = RwCfg<CIN, COUT>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *s_w = reinterpret_cast<float *>(smem_raw);                              // [kvol][CIN][COUT], resident for the CTA's lifetime
+    int *s_nbr = reinterpret_cast<int *>(s_w + (size_t)kvol * C::kWFloats);        // [128][kvol]
+
+    const int n_out = min(*d_n_out, max_out);
+    const int tiles = (n_out + kRwRows - 1) / kRwRows;
+    if ((int)blockIdx.x >= tiles) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // all weight slices of the layer (7 .. 110 KB): loaded once, every (row, offset) pair of every tile of this CTA reads them from here
+    {
+        const float4 *gw = reinterpret_cast<const float4 *>(weight);
+        float4 *sw4 = reinterpret_cast<float4 *>(s_w);
+        const int n4 = kvol * C::kWFloats / 4;
+        for (int e = tid; e < n4; e += kRwThreads) sw4[e] = __ldg(gw + e);
+    }
+    float sc[C::kJ], sh[C::kJ];
+#pragma unroll
+    for (int j = 0; j < C::kJ; ++j) {
+        const int co = lane + 32 * j;
+        sc[j] = (scale && co < COUT) ? scale[co] : 1.f;
+        sh[j] = (shift && co < COUT) ? shift[co] : 0.f;
+    }
+    float wmax = 0.f;
+
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int row0 = tile * kRwRows;
+        const int rows = min(kRwRows, n_out - row0);
+        __syncthreads();                      // previous tile's s_nbr fully consumed (and s_w written, first iteration)
+        const int nent = rows * kvol;         // the tile's neighbour table is contiguous in global memory
+        for (int e = tid; e < nent; e += kRwThreads) s_nbr[e] = __ldg(&nbr[(size_t)row0 * kvol + e]);
+        __syncthreads();
+        // each warp walks the valid (row, offset) pairs of its rows; no block-wide synchronisation inside
+#pragma unroll 1
+        for (int r = 0; r < kRwRpw; ++r) {
+            const int row = warp * kRwRpw + r;
+            if (row >= rows) break;                                              // warp-uniform
+            const int mine = (lane < kvol) ? s_nbr[row * kvol + lane] : -1;      // lane k holds nbr[row][k]
+            unsigned int m = __ballot_sync(0xffffffffu, mine >= 0);
+            float acc[C::kJ];
+#pragma unroll
+            for (int j = 0; j < C::kJ; ++j) acc[j] = 0.f;
+            // up to kRwBatch pairs at a time: all their input rows are requested back to back (independent loads), then multiplied
+            while (m) {
+                int ks[kRwBatch];
+                float vs[kRwBatch];
+#pragma unroll
+                for (int i = 0; i < kRwBatch; ++i) {
+                    ks[i] = -1;
+                    vs[i] = 0.f;
+                    if (m) {                                                     // warp-uniform
+                        const int k = __ffs(m) - 1;
+                        m &= m - 1;
+                        ks[i] = k;
+                        const int src = __shfl_sync(0xffffffffu, mine, k);
+                        if (lane < CIN) vs[i] = __ldg(&in_feat[(size_t)src * CIN + lane]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < kRwBatch; ++i) {
+                    if (ks[i] < 0) break;
+                    const float *sw = s_w + (size_t)ks[i] * C::kWFloats;
+#pragma unroll
+                    for (int c = 0; c < CIN; ++c) {
+                        const float a = __shfl_sync(0xffffffffu, vs[i], c);
+#pragma unroll
+                        for (int j = 0; j < C::kJ; ++j) {
+                            const int co = lane + 32 * j;
+                            const float wv = sw[c * COUT + (COUT >= 32 ? co : (co & (COUT - 1)))];
+                            acc[j] = fmaf(a, wv, acc[j]);
+                        }
+                    }
+                }
+            }
+            // epilogue: folded BatchNorm1d (eval) + ReLU, one coalesced segment per row
+#pragma unroll
+            for (int j = 0; j < C::kJ; ++j) {
+                const int co = lane + 32 * j;
+                if (co < COUT) {
+                    float o = fmaf(acc[j], sc[j], sh[j]);
+                    if (relu) o = fmaxf(o, 0.f);
+                    wmax = fmaxf(wmax, fabsf(o));
+                    out_feat[(size_t)(row0 + row) * COUT + co] = o;
+                }
+            }
+        }
+    }
+    if (amax_out) {
+        const unsigned mm = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(wmax));
+        if (lane == 0 && mm != 0u) atomicMax(reinterpret_cast<unsigned *>(amax_out), mm);
+    }
+}
+
+template <int CIN, int COUT>
+static int launch_rows(const float *in, const int *nbr, int kvol, const int *d_n, int max_out, const float *w, const float *sc, const float *sh,
+                       int relu, float *out, float *amax_out, cudaStream_t st) {
+    using C = RwCfg<CIN, COUT>;
+    const size_t smem = C::smem(kvol);
+    if (smem > 227 * 1024) return SESSD_ECAPACITY;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(spconv_rows_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_smem = smem;
+    }
+    const int tiles = div_up(max_out, kRwRows);
+    const int per_sm = smem <= 100 * 1024 ? 2 : 1;                         // 1024 threads per CTA: at most two resident CTAs
+    const int grid = tiles < per_sm * kNumSMs ? tiles : per_sm * kNumSMs;  // persistent
+    SESSD_LAUNCH((spconv_rows_kernel<CIN, COUT>), grid, kRwThreads, smem, st, in, nbr, kvol, d_n, max_out, w, sc, sh, relu, out, amax_out);
+    return last_error();
+}
+
+}  // namespace sessd
+
+using namespace sessd;
+
+// Same arguments as sessd_spconv_forward plus d_amax_out (nullable): running abs-max of the output.  Supported (Cin, Cout): (4,16),
+// (16,16), (16,32), (32,32) -- the whole weight tensor must fit in shared memory.
+extern "C" int sessd_spconv_forward_rows(const float *d_in_feat, int cin, const int *d_nbr, int kvol, const int *d_n_out, int max_out,
+                                         const float *d_weight, int cout, const float *d_scale, const float *d_shift, int relu,
+                                         float *d_out_feat, float *d_amax_out, void *stream) {
+    if (!d_in_feat || !d_nbr || !d_n_out || !d_weight || !d_out_feat || max_out < 1 || kvol < 1 || kvol > kRwMaxK) return SESSD_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+#define RW_CASE(CI, CO) \
+    if (cin == CI && cout == CO) return launch_rows<CI, CO>(d_in_feat, d_nbr, kvol, d_n_out, max_out, d_weight, d_scale, d_shift, relu, d_out_feat, d_amax_out, st)
+    RW_CASE(4, 16);
+    RW_CASE(16, 16);
+    RW_CASE(16, 32);
+    RW_CASE(32, 32);
+#undef RW_CASE
+    return SESSD_EINVAL;
+}

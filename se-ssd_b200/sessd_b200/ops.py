@@ -156,6 +156,14 @@ def spconv_forward(in_feat, nbr, n_out, max_out, weight, scale, shift, relu, out
     return out
 
 
+def spconv_forward_rows(in_feat, nbr, n_out, max_out, weight, scale, shift, relu, out, amax_out=None):
+    """Pair-proportional fp32 kernel for the narrow layers (Cin <= 32); same arguments as spconv_forward (+ optional abs-max output)."""
+    kvol, cin, cout = weight.shape
+    check(lib.sessd_spconv_forward_rows(_p(in_feat), int(cin), _p(nbr), int(kvol), _p(n_out), int(max_out), _p(weight), int(cout),
+                                        _p(scale), _p(shift), int(bool(relu)), _p(out), _p(amax_out), _st()), "sessd_spconv_forward_rows")
+    return out
+
+
 def spconv_forward_tc(in_feat, nbr, n_out, max_out, weight_split, scale, shift, relu, out):
     """weight_split [2, kvol, Cout, Cin] from pack_weight_tc(weight [kvol,Cin,Cout], Cout)."""
     _two, kvol, cout, cin = weight_split.shape
@@ -225,6 +233,13 @@ def sparse_to_dense(feat, coors, n, max_rows, grid, out=None):
     if out is None:
         out = torch.empty((grid.batch, h, w, c * d), dtype=torch.float32, device=feat.device)
     check(lib.sessd_sparse_to_dense(_p(feat), _p(coors), _p(n), int(max_rows), int(c), grid, _p(out), _st()), "sessd_sparse_to_dense")
+    return out
+
+
+def sparse_to_dense_indexed(feat, bitmap_index, grid, out):
+    """dense() in one gather pass through the level's bitmap index (see sessd_sparse_to_dense_indexed)."""
+    check(lib.sessd_sparse_to_dense_indexed(_p(feat), int(feat.shape[0]), _p(bitmap_index), int(feat.shape[1]), grid, _p(out), _st()),
+          "sessd_sparse_to_dense_indexed")
     return out
 
 

@@ -47,9 +47,12 @@ class SpMiddleRunner:
     # active-site growth bounds per level relative to the level-0 capacity (uniform 20k cloud: 3.4 / 5.2 / 4.3 / 2.6)
     GROWTH = (1.0, 4.0, 6.0, 5.0, 3.0)
     SPLIT = "fp16"
+    ROWS_SHAPES = ((4, 16), (16, 16), (16, 32), (32, 32))     # (Cin, Cout) whose whole weight tensor fits in shared memory
+    ROWS_MAX_CIN = 16         # layers with Cin <= this run on the pair-proportional SIMT kernel (0: tensor-core kernels wherever possible)
+    DENSE_GATHER = True       # dense() as one gather pass through the last level's bitmap index (False: memset + scatter)
 
     def __init__(self, batch, max_voxels_total, input_shape_xyz=(1408, 1600, 40), num_input_features=4, device="cuda",
-                 growth=None, use_tc=True, split=None):
+                 growth=None, use_tc=True, split=None, rows_max_cin=None):
         """use_tc: run the layers on the tcgen05 tensor cores; False = fp32 SIMT baseline for all layers.
         split: "fp16" = TMA-gather two-term fp16 split kernel (spconv_h2.cu) for every layer with Cin >= 16 (13 of 14 layers);
                "tf32" = 3xTF32 kernel with SIMT gather warps (spconv_tc.cu) for the Cin >= 32 layers.  Default: SPLIT."""
@@ -58,6 +61,9 @@ class SpMiddleRunner:
         self.split = split or self.SPLIT
         assert self.split in ("fp16", "tf32")
         self.use_h2 = self.use_tc and self.split == "fp16"
+        # per-layer kernel: "rows" = pair-proportional fp32 SIMT (narrow layers), "h2" = TMA-gather fp16-split tcgen05, "tc" = 3xTF32
+        # tcgen05 with SIMT gather warps, "simt" = the dense output-stationary fp32 baseline
+        self.rows_max_cin = (self.ROWS_MAX_CIN if rows_max_cin is None else int(rows_max_cin)) if self.use_tc else 0
         self.cin0 = num_input_features
         shape = (int(input_shape_xyz[2]) + 1, int(input_shape_xyz[1]), int(input_shape_xyz[0]))   # scn.py:179
         growth = growth or self.GROWTH
@@ -94,11 +100,19 @@ class SpMiddleRunner:
         # fp16-split path: (hi, lo) planes of every layer output that feeds a tensor-core layer + one abs-max scalar per tensor
         self.planes = [None] * len(self.plan)
         self.amax = torch.zeros((len(self.plan) + 1,), dtype=torch.float32, device=self.device)
-        if self.use_h2:
-            for li, p in enumerate(self.plan[:-1]):
-                if self.plan[li + 1]["cin"] >= 16:
-                    cp = 64 if p["cout"] > 32 else 32
-                    self.planes[li] = ops.alloc_planes(self.levels[p["lout"]]["cap"], cp, self.device)
+        for p in self.plan:
+            if self.use_tc and p["cin"] <= self.rows_max_cin and (p["cin"], p["cout"]) in self.ROWS_SHAPES:
+                p["impl"] = "rows"
+            elif self.use_h2 and p["cin"] >= 16:
+                p["impl"] = "h2"
+            elif self.use_tc and p["cin"] >= 32:
+                p["impl"] = "tc"
+            else:
+                p["impl"] = "simt"
+        for li, p in enumerate(self.plan[:-1]):
+            if self.plan[li + 1]["impl"] == "h2":
+                cp = 64 if p["cout"] > 32 else 32
+                self.planes[li] = ops.alloc_planes(self.levels[p["lout"]]["cap"], cp, self.device)
 
     def _add_level(self, shape, cap, hash_index):
         grid = ops.make_grid(self.batch, shape)
@@ -123,10 +137,10 @@ class SpMiddleRunner:
             sc, sh = fold_bn(*[torch.as_tensor(l[k], device=self.device) for k in ("gamma", "beta", "mean", "var")])
             wp = w.reshape(-1, p["cin"], p["cout"]).contiguous()
             tc = None
-            if self.use_h2 and p["cin"] >= 16:
+            if p["impl"] == "h2":
                 tiles, inv = ops.pack_weight_sp_h2(wp, 64 if p["cin"] > 32 else 32)
                 tc = ("h2", tiles, (sc * inv).contiguous())
-            elif self.use_tc and p["cin"] >= 32:
+            elif p["impl"] == "tc":
                 tc = ops.pack_weight_tc(wp, p["cout"])
             self.weights.append((wp, sc, sh, tc))
 
@@ -160,7 +174,10 @@ class SpMiddleRunner:
                 n_out, cap_out = lout["n"], lout["cap"]
                 mark("rulebook:sp%d" % p["lout"])
             w, sc, sh, tc = self.weights[li]
-            if isinstance(tc, tuple):
+            if p["impl"] == "rows":
+                x = ops.spconv_forward_rows(x, p["nbr"], n_out, cap_out, w, sc, sh, True, self.feats[li],
+                                            self.amax[li:li + 1] if self.planes[li] is not None else None)
+            elif isinstance(tc, tuple):
                 # fp16-split tensor-core layer: reads the (hi, lo) planes of its input, writes fp32 rows + the output's abs-max
                 x = ops.spconv_forward_h2(self.planes[li - 1], self.amax[li - 1:li], p["nbr"], n_out, cap_out, tc[1], tc[2], sh, True,
                                           self.feats[li], self.amax[li:li + 1])
@@ -175,7 +192,10 @@ class SpMiddleRunner:
                 ops.split_h2(x, n_out, cap_out, self.amax[li:li + 1], self.planes[li])
                 mark("split:%d" % li)
         last = self.levels[-1]
-        out = ops.sparse_to_dense(x, last["coors"], last["n"], last["cap"], last["grid"], self.dense)
+        if last["index_kind"] == 1 and self.DENSE_GATHER:
+            out = ops.sparse_to_dense_indexed(x, last["index"], last["grid"], self.dense)
+        else:
+            out = ops.sparse_to_dense(x, last["coors"], last["n"], last["cap"], last["grid"], self.dense)
         mark("dense")
         return out
 

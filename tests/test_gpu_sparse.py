@@ -91,8 +91,9 @@ def _weights(seed=3):
     return weights.split_detector_state(sd)
 
 
-@pytest.mark.parametrize("use_tc,split", [(False, None), (True, "tf32"), (True, "fp16")], ids=["simt", "tcgen05", "tma-gather-fp16x2"])
-def test_spmiddle_features_match_fp64_oracle(use_tc, split):
+@pytest.mark.parametrize("use_tc,split,rows", [(False, None, 0), (True, "tf32", 0), (True, "fp16", 0), (True, "fp16", 32), (True, "fp16", 16)],
+                         ids=["simt", "tcgen05-3xtf32", "tma-gather-fp16x2", "rows32+tma-gather", "rows16+tma-gather(default)"])
+def test_spmiddle_features_match_fp64_oracle(use_tc, split, rows):
     from oracle import spconv_ref as S
     from sessd_b200 import synth
     from sessd_b200.runners import SpMiddleRunner
@@ -104,7 +105,8 @@ def test_spmiddle_features_match_fp64_oracle(use_tc, split):
                    var=l["var"].numpy()) for l in layers]
     trace = []
     ref = S.spmiddle_forward(feat, coors, 1, (1408, 1600, 40), params, np.float64, trace)   # [1,128,200,176]
-    r = SpMiddleRunner(1, n, device="cuda", use_tc=use_tc, split=split)
+    r = SpMiddleRunner(1, n, device="cuda", use_tc=use_tc, split=split, rows_max_cin=rows)
+    assert [p["impl"] for p in r.plan].count("rows") == {0: 0, 16: 3, 32: 5}[rows]
     r.load_weights(layers)
     dense = r.forward(torch.from_numpy(feat).cuda(), torch.from_numpy(coors).cuda(), torch.tensor([n], dtype=torch.int32, device="cuda"))
     torch.cuda.synchronize()
