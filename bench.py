@@ -290,6 +290,18 @@ def run_ours(args):
     ms_e2e = timed(step_host, args.steps)
     e2e = world * F * args.steps / (ms_e2e / 1000.0)
 
+    # ---- single-frame latency through the public API (one engine, one frame in flight): host numpy in -> detections out ----------
+    lat = []
+    e = engines[0]
+    for i in range(30):
+        t0 = time.perf_counter()
+        e.stage([clouds[i % args.pool]])
+        e.launch()
+        e.results()
+        lat.append((time.perf_counter() - t0) * 1000.0)
+    latency = {"median_ms": float(np.median(lat[5:])), "p90_ms": float(np.percentile(lat[5:], 90)),
+               "what": "stage() + graph replay (H2D, 85 kernels, D2H) + results() of ONE frame, nothing else in flight; host wall clock"}
+
     # ---- roofline of the dominant kernel, timed live with CUDA events on its launch stream -----------------------
     e = engines[0]
     roof = dominant_kernel_roofline(e)
@@ -317,7 +329,7 @@ def run_ours(args):
                         "h2d_bytes_per_step": h2d[0] // args.steps, "d2h_bytes_per_step": d2h[0] // args.steps},
                 "gpu_launches": int(launches_full) * F * args.steps,
                 "launches_per_frame": int(launches_full),
-                "clocks": clocks, "roofline": roof, "stages_ms": stages}
+                "clocks": clocks, "roofline": roof, "stages_ms": stages, "latency_single_frame": latency}
         if world == 1:
             line["cpu_baseline"] = cpu_baseline_sample(args, layers, ssfa, head, anchors, clouds)
         print(json.dumps(line))
@@ -361,8 +373,13 @@ def dominant_kernel_roofline(e, reps=20):
             ms.append(a.elapsed_time(b))
     t = float(np.mean(ms)) / 1000.0
     flops = 2.0 * neck.h * neck.w * 128 * 128 * 9
+    # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed `ncu --set full` capture (bytes per launch);
+    # the algorithmic bytes are 18.0 MB activations read + 0.6 MB weights (the 18 MB output stays in L2 until evicted)
+    traffic = {"bev_conv_h2_kernel": (18673920 + 12544, "profiles/r1d_bev_conv_h2_ncu.txt"),
+               "bev_conv_tc3_kernel": (None, None), "bev_conv_kernel": (None, None)}[kern.split(" ")[0]]
     return {"kernel": kern + ", conv3x3 128->128 @200x176", "bound": "tensor", "achieved": flops / t / 1e12,
-            "unit": "TFLOP/s", "avg_launch_ms": t * 1000.0, "algorithmic_flops": flops, "traffic": None,
+            "unit": "TFLOP/s", "avg_launch_ms": t * 1000.0, "algorithmic_flops": flops, "traffic": traffic[0],
+            "traffic_unit": "bytes/launch (ncu dram read + write)", "traffic_source": traffic[1],
             "tensor_work_factor": factor,
             "timing": "CUDA events on the launch stream, L2 flushed (256 MB memset) before every launch, mean of %d" % reps}
 

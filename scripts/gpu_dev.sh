@@ -3,7 +3,6 @@
 TAG=${1:-dev}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-timeout 300 python scripts/sp_rows_debug.py > $OUT/sp_rows_debug.log 2>&1; echo "sp_rows_debug rc=$?"; tail -40 $OUT/sp_rows_debug.log
 if [ -n "$2" ]; then
 timeout 600 python -m pytest tests -m gpu -q -x --timeout 300 -k "$2" > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 $OUT/pytest_gpu.log
 fi

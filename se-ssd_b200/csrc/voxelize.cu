@@ -170,7 +170,40 @@ __global__ void __launch_bounds__(256) vox_collect_kernel(const int *__restrict_
 }
 
 // 5. gather --------------------------------------------------------------------------------------------
-// one thread per (voxel, slot-in-voxel); float4 path for the 4-feature KITTI layout.
+// 4-feature KITTI layout (MP = max_points known at compile time, 5 in the config): one thread per voxel loads its <= MP points as
+// float4 (independent loads), writes the zero-padded [MP][4] block and num_points, and forms the VoxelFeatureExtractorV3 mean from the
+// registers in the reference's order (voxel_encoder.py:209: sum over the point axis k = 0..MP-1, then divide by the count) -- no
+// 64-bit divisions, no second gather for the mean (ncu at the stress shape: the per-(voxel, slot) version was ALU-bound, sm 70 %).
+template <int MP>
+__global__ void __launch_bounds__(256) vox_gather4_kernel(const float4 *__restrict__ pts, const int *__restrict__ num_voxels, int batch,
+                                                          const int *__restrict__ lists, const int *__restrict__ counts,
+                                                          float4 *__restrict__ voxels, int *__restrict__ num_points,
+                                                          float4 *__restrict__ mean) {
+    const int total = num_voxels[batch];
+    for (int vid = blockIdx.x * blockDim.x + threadIdx.x; vid < total; vid += gridDim.x * blockDim.x) {
+        int cnt = counts[vid];
+        cnt = cnt < MP ? cnt : MP;
+        float4 v[MP];
+#pragma unroll
+        for (int k = 0; k < MP; ++k) {
+            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < cnt) v[k] = __ldg(&pts[lists[(size_t)vid * MP + k]]);
+        }
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < MP; ++k) {
+            voxels[(size_t)vid * MP + k] = v[k];
+            if (k < cnt) { s.x = __fadd_rn(s.x, v[k].x); s.y = __fadd_rn(s.y, v[k].y); s.z = __fadd_rn(s.z, v[k].z); s.w = __fadd_rn(s.w, v[k].w); }
+        }
+        num_points[vid] = cnt;
+        if (mean) {
+            const float c = (float)cnt;
+            mean[vid] = make_float4(__fdiv_rn(s.x, c), __fdiv_rn(s.y, c), __fdiv_rn(s.z, c), __fdiv_rn(s.w, c));
+        }
+    }
+}
+
+// generic layout: one thread per (voxel, slot-in-voxel)
 __global__ void __launch_bounds__(256) vox_gather_kernel(const float *__restrict__ pts, VoxParams p,
                                                          const int *__restrict__ num_voxels, const int *__restrict__ lists,
                                                          const int *__restrict__ counts, float *__restrict__ voxels,
@@ -185,11 +218,9 @@ __global__ void __launch_bounds__(256) vox_gather_kernel(const float *__restrict
         float *dst = voxels + ((size_t)vid * p.max_points + k) * p.nfeat;
         if (k < cnt) {
             const float *src = pts + (size_t)lists[(size_t)vid * p.max_points + k] * p.nfeat;
-            if (p.nfeat == 4) *reinterpret_cast<float4 *>(dst) = *reinterpret_cast<const float4 *>(src);
-            else for (int j = 0; j < p.nfeat; ++j) dst[j] = src[j];
+            for (int j = 0; j < p.nfeat; ++j) dst[j] = src[j];
         } else {
-            if (p.nfeat == 4) *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-            else for (int j = 0; j < p.nfeat; ++j) dst[j] = 0.f;
+            for (int j = 0; j < p.nfeat; ++j) dst[j] = 0.f;
         }
         if (k == 0) {
             num_points[vid] = cnt;
@@ -281,9 +312,14 @@ extern "C" int sessd_voxelize(const float *d_points, const int *d_frame_off, int
     SESSD_LAUNCH(vox_assign_kernel, grid, 256, sm, st, d_points, d_frame_off, p, w.slot_of, w.rank, w.frame_first,
                  w.vbase, w.slot_vid, d_coors, w.cut);
     SESSD_LAUNCH(vox_collect_kernel, grid, 256, sm, st, d_frame_off, p, w.slot_of, w.slot_vid, w.cut, w.lists, w.counts);
-    const int ggrid = persistent_grid((long long)nv * cfg->max_points, 256);
-    SESSD_LAUNCH(vox_gather_kernel, ggrid, 256, 0, st, d_points, p, d_num_voxels, w.lists, w.counts, d_voxels,
-                 d_num_points, d_mean);
+    if (cfg->num_feat == 4 && cfg->max_points == 5) {
+        SESSD_LAUNCH((vox_gather4_kernel<5>), persistent_grid((long long)nv, 256), 256, 0, st, (const float4 *)d_points, d_num_voxels, batch,
+                     w.lists, w.counts, (float4 *)d_voxels, d_num_points, (float4 *)d_mean);
+    } else {
+        const int ggrid = persistent_grid((long long)nv * cfg->max_points, 256);
+        SESSD_LAUNCH(vox_gather_kernel, ggrid, 256, 0, st, d_points, p, d_num_voxels, w.lists, w.counts, d_voxels,
+                     d_num_points, d_mean);
+    }
     return last_error();
 }
 
