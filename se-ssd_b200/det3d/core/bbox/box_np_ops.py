@@ -82,3 +82,78 @@ def create_anchors_3d_range(feature_size, anchor_range, sizes=(1.6, 3.9, 1.56), 
     flat = kitti_car_anchors(tuple(feature_size), tuple(anchor_range), tuple(np.ravel(sizes)), tuple(rotations), dtype)
     ns = int(np.array(sizes).reshape(-1, 3).shape[0])
     return flat.reshape(feature_size[0], feature_size[1], feature_size[2], ns, len(rotations), 7)
+
+
+# ------------------------------------------------------------------------------------------------ KITTI wire format
+def camera_to_lidar(points, r_rect, velo2cam):
+    """Camera-rect coordinates -> velodyne coordinates (reference :937-942)."""
+    shape = list(points.shape[:-1])
+    if points.shape[-1] == 3:
+        points = np.concatenate([points, np.ones(shape + [1])], axis=-1)
+    return (points @ np.linalg.inv((r_rect @ velo2cam).T))[..., :3]
+
+
+def lidar_to_camera(points, r_rect, velo2cam):
+    shape = list(points.shape[:-1])
+    if points.shape[-1] == 3:
+        points = np.concatenate([points, np.ones(shape + [1])], axis=-1)
+    return (points @ (r_rect @ velo2cam).T)[..., :3]
+
+
+def box_camera_to_lidar(data, r_rect, velo2cam):
+    """(x, y, z)cam, l, h, w, ry -> (x, y, z)velo, w, l, h, ry (reference :965-970)."""
+    xyz_lidar = camera_to_lidar(data[:, 0:3], r_rect, velo2cam)
+    l, h, w, r = data[:, 3:4], data[:, 4:5], data[:, 5:6], data[:, 6:7]
+    return np.concatenate([xyz_lidar, w, l, h, r], axis=1)
+
+
+def box_lidar_to_camera(data, r_rect, velo2cam):
+    xyz = lidar_to_camera(data[:, 0:3], r_rect, velo2cam)
+    w, l, h, r = data[:, 3:4], data[:, 4:5], data[:, 5:6], data[:, 6:7]
+    return np.concatenate([xyz, l, h, w, r], axis=1)
+
+
+def change_box3d_center_(box3d, src, dst):
+    """In place: move the box origin from the relative position `src` to `dst` (reference :1406-1409)."""
+    dst = np.array(dst, dtype=box3d.dtype)
+    src = np.array(src, dtype=box3d.dtype)
+    box3d[..., :3] += box3d[..., 3:6] * (dst - src)
+
+
+def projection_matrix_to_CRT_kitti(proj):
+    """P = C @ [R|T] with C upper triangular (reference :623-634)."""
+    cr, ct = proj[0:3, 0:3], proj[0:3, 3]
+    rinv, cinv = np.linalg.qr(np.linalg.inv(cr))
+    return np.linalg.inv(cinv), np.linalg.inv(rinv), cinv @ ct
+
+
+def get_frustum(bbox_image, C, near_clip=0.001, far_clip=100):
+    """8 corners (camera coordinates) of the viewing frustum behind an image box (reference :637-654)."""
+    fku, fkv = C[0, 0], -C[1, 1]
+    u0v0 = C[0:2, 2]
+    z = np.array([near_clip] * 4 + [far_clip] * 4, dtype=C.dtype)[:, np.newaxis]
+    b = bbox_image
+    corners = np.array([[b[0], b[1]], [b[0], b[3]], [b[2], b[3]], [b[2], b[1]]], dtype=C.dtype)
+    near = (corners - u0v0) / np.array([fku / near_clip, -fkv / near_clip], dtype=C.dtype)
+    far = (corners - u0v0) / np.array([fku / far_clip, -fkv / far_clip], dtype=C.dtype)
+    return np.concatenate([np.concatenate([near, far], axis=0), z], axis=1)
+
+
+def corner_to_surfaces_3d(corners):
+    """[N, 8, 3] box corners -> [N, 6, 4, 3] surfaces with inward normals (reference :1193-1212)."""
+    idx = np.array([0, 1, 2, 3, 7, 6, 5, 4, 0, 3, 7, 4, 1, 5, 6, 2, 0, 4, 5, 1, 3, 2, 6, 7]).reshape(6, 4)
+    return corners[:, idx]
+
+
+corner_to_surfaces_3d_jit = corner_to_surfaces_3d
+
+
+def get_valid_frustum(rect, Trv2c, P2, image_shape):
+    """Image frustum in velodyne coordinates as 6 surfaces [1, 6, 4, 3] (reference :995-1003): `calib["frustum"]` of the detector's
+    post-processing filter (mg_head_sessd.py:1024-1030)."""
+    C, R, T = projection_matrix_to_CRT_kitti(P2)
+    frustum = get_frustum([0, 0, image_shape[1], image_shape[0]], C)
+    frustum -= T
+    frustum = np.linalg.inv(R) @ frustum.T
+    frustum = camera_to_lidar(frustum.T, rect, Trv2c)
+    return corner_to_surfaces_3d(frustum[np.newaxis, ...])

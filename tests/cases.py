@@ -64,3 +64,24 @@ def assign_cases():
     e[9, 6] = np.float32(-3 * np.pi / 4)
     out.append(("edge", e))
     return out
+
+
+def kitti_wire_case():
+    """A KITTI-style calibration (typical values of the training split), image shape and a 5-object annotation dict (1 DontCare)."""
+    P2 = np.array([[7.215377e+02, 0.0, 6.095593e+02, 4.485728e+01], [0.0, 7.215377e+02, 1.728540e+02, 2.163791e-01],
+                   [0.0, 0.0, 1.0, 2.745884e-03], [0.0, 0.0, 0.0, 1.0]], np.float32)
+    R0 = np.eye(4, dtype=np.float32)
+    R0[:3, :3] = np.array([[0.9999239, 0.00983776, -0.00744505], [-0.0098698, 0.9999421, -0.00427846],
+                           [0.00740253, 0.00435161, 0.9999631]], np.float32)
+    Tr = np.eye(4, dtype=np.float32)
+    Tr[:3, :4] = np.array([[7.533745e-03, -9.999714e-01, -6.166020e-04, -4.069766e-03], [1.480249e-02, 7.280733e-04, -9.998902e-01, -7.631618e-02],
+                           [9.998621e-01, 7.523790e-03, 1.480755e-02, -2.717806e-01]], np.float32)
+    rng = np.random.default_rng(77)
+    n = 5
+    annos = dict(name=np.array(["Car", "DontCare", "Pedestrian", "Car", "Cyclist"]),
+                 location=np.stack([rng.uniform(-10, 10, n), rng.uniform(1.2, 1.9, n), rng.uniform(5, 60, n)], 1),
+                 dimensions=np.stack([rng.normal(3.9, 0.3, n), rng.normal(1.56, 0.1, n), rng.normal(1.6, 0.1, n)], 1),
+                 rotation_y=rng.uniform(-np.pi, np.pi, n), bbox=rng.uniform(0, 300, (n, 4)), difficulty=np.arange(n, dtype=np.int32))
+    info = dict(calib={"P2": P2, "R0_rect": R0, "Tr_velo_to_cam": Tr}, image={"image_shape": np.array([375, 1242], np.int32)}, annos=annos,
+                point_cloud={"velodyne_path": "training/velodyne/000007.bin"})
+    return info

@@ -32,7 +32,7 @@ from sessd_b200 import synth  # noqa: E402
 from oracle import bev_ref, build as obuild, cpu as ocpu  # noqa: E402
 
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from cases import assign_cases, iou_inputs, sha, voxel_cases  # noqa: E402  (seeded inputs shared with the tests)
+from cases import assign_cases, iou_inputs, kitti_wire_case, sha, voxel_cases  # noqa: E402  (seeded inputs shared with the tests)
 
 
 def _pkg(name):
@@ -203,6 +203,21 @@ def gen_anchors_assign():
     print("decode", dec.shape)
 
 
+def gen_wire():
+    """KITTI wire format: reference box_np_ops.get_valid_frustum / box_camera_to_lidar / change_box3d_center_ on a synthetic calibration."""
+    bn = sys.modules.get("det3d.core.bbox.box_np_ops") or _load("det3d.core.bbox.box_np_ops", "det3d/core/bbox/box_np_ops.py")
+    info = kitti_wire_case()
+    c = info["calib"]
+    fr = bn.get_valid_frustum(c["R0_rect"], c["Tr_velo_to_cam"], c["P2"], info["image"]["image_shape"])
+    a = info["annos"]
+    keep = [i for i, x in enumerate(a["name"]) if x != "DontCare"]
+    gt = np.concatenate([a["location"][keep], a["dimensions"][keep], a["rotation_y"][keep][..., np.newaxis]], axis=1).astype(np.float32)
+    gt = bn.box_camera_to_lidar(gt, c["R0_rect"], c["Tr_velo_to_cam"])
+    bn.change_box3d_center_(gt, [0.5, 0.5, 0], [0.5, 0.5, 0.5])
+    np.savez_compressed(os.path.join(HERE, "kitti_wire.npz"), frustum=fr, gt_boxes=gt)
+    print("wire: frustum", fr.shape, fr.dtype, "gt", gt.shape, gt.dtype)
+
+
 def gen_models():
     import logging
 
@@ -253,5 +268,7 @@ if __name__ == "__main__":
     install_det3d_shims()
     if not only or "assign" in only:
         gen_anchors_assign()
+    if not only or "wire" in only:
+        gen_wire()
     if not only or "models" in only:
         gen_models()

@@ -207,3 +207,57 @@ def test_voxel_generator_and_rotate_nms_api(golden_dir):
     assert sel.dtype == torch.int64 and np.array_equal(sel.cpu().numpy(), ref)
     lst = rotate_nms_cc(np.concatenate([b5, scores[:, None]], 1), 0.01)
     assert isinstance(lst, list) and lst[:100] == list(ref)
+
+
+def test_kitti_wire_format_loaders_match_reference_golden(golden_dir, tmp_path):
+    """LoadPointCloudFromFile / LoadPointCloudAnnotations: .bin points, calib frustum and camera->lidar GT boxes equal the reference's
+    box_np_ops outputs (tests/golden/kitti_wire.npz); the frustum feeds the detector's post-processing filter."""
+    from cases import kitti_wire_case
+    from det3d.core.bbox.geometry import frustum_planes
+    from det3d.datasets.pipelines import LoadPointCloudAnnotations, LoadPointCloudFromFile
+    from sessd_b200 import synth
+    g = np.load(os.path.join(golden_dir, "kitti_wire.npz"))
+    info = kitti_wire_case()
+    pts = synth.ring_cloud(3, 5000)
+    (tmp_path / "training" / "velodyne").mkdir(parents=True)
+    pts.tofile(str(tmp_path / "training" / "velodyne" / "000007.bin"))
+    res = dict(metadata=dict(image_prefix=str(tmp_path), num_point_features=4), lidar={}, mode="val")
+    res, _ = LoadPointCloudFromFile(dataset="KittiDataset")(res, info)
+    assert np.array_equal(res["lidar"]["points"], pts)
+    (tmp_path / "training" / "velodyne_reduced").mkdir()
+    pts[:100].tofile(str(tmp_path / "training" / "velodyne_reduced" / "000007.bin"))      # the reduced file wins when it exists
+    res, _ = LoadPointCloudFromFile(dataset="KittiDataset")(res, info)
+    assert res["lidar"]["points"].shape == (100, 4)
+    res, _ = LoadPointCloudAnnotations(with_bbox=True)(res, info)
+    assert res["calib"]["frustum"].shape == (1, 6, 4, 3) and np.array_equal(res["calib"]["frustum"], g["frustum"])
+    ann = res["lidar"]["annotations"]
+    assert list(ann["names"]) == ["Car", "Pedestrian", "Car", "Cyclist"]
+    assert ann["boxes"].dtype == g["gt_boxes"].dtype and np.array_equal(ann["boxes"], g["gt_boxes"])
+    planes = frustum_planes(res["calib"]["frustum"])            # what MultiGroupHead.predict hands to sessd_postprocess
+    assert planes.shape[-2:] == (6, 4) and np.isfinite(planes).all()
+
+
+def test_checkpoint_wire_format_roundtrip(tmp_path):
+    """{"meta", "state_dict"} files, bare state dicts and DataParallel `module.` prefixes load into the config-built detector."""
+    from collections import OrderedDict
+    from det3d.torchie.trainer import load_checkpoint, save_checkpoint
+    from sessd_b200 import weights
+    cfg, model = _build(OUR_CFG)
+    sd = weights.random_detector_state(11)
+    model.load_state_dict(sd, strict=True)
+    f1 = str(tmp_path / "epoch_1.pth")
+    save_checkpoint(model, f1, meta=dict(epoch=1))
+    ck = torch.load(f1, weights_only=False)
+    assert set(ck.keys()) == {"meta", "state_dict"} and set(ck["state_dict"].keys()) == set(sd.keys())
+    assert tuple(ck["state_dict"]["backbone.middle_conv.0.weight"].shape) == (3, 3, 3, 4, 16)      # spconv layout kz,ky,kx,Cin,Cout
+    cfg2, fresh = _build(OUR_CFG)
+    load_checkpoint(fresh, f1, map_location="cpu", strict=True)
+    for k, v in fresh.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    f2 = str(tmp_path / "dp.pth")
+    torch.save({"state_dict": OrderedDict(("module." + k, v) for k, v in sd.items())}, f2)
+    cfg3, fresh2 = _build(OUR_CFG)
+    load_checkpoint(fresh2, f2, map_location="cpu", strict=True)
+    assert torch.equal(fresh2.state_dict()["neck.conv_0.0.weight"], sd["neck.conv_0.0.weight"])
+    with pytest.raises(IOError):
+        load_checkpoint(fresh2, str(tmp_path / "missing.pth"))
