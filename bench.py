@@ -331,7 +331,7 @@ def run_ours(args):
                 "launches_per_frame": int(launches_full),
                 "clocks": clocks, "roofline": roof, "stages_ms": stages, "latency_single_frame": latency}
         if world == 1:
-            line["cpu_baseline"] = cpu_baseline_sample(args, layers, ssfa, head, anchors, clouds)
+            line["cpu_baseline"], line["parity_vs_oracle"] = cpu_baseline_sample(args, layers, ssfa, head, anchors, clouds, engine=engines[0])
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -408,21 +408,46 @@ def stage_breakdown(e, cloud):
     return out
 
 
-def cpu_baseline_sample(args, layers, ssfa, head, anchors, clouds):
+def cpu_baseline_sample(args, layers, ssfa, head, anchors, clouds, engine=None):
+    """CPU oracle port timed on a bounded sample (3 frames) of the same workload; when `engine` is given its detections on the same
+    frames are compared with the oracle's: the "IoU vs ref" half of BASELINE.json's metric."""
     cores = os.cpu_count() or 1
     layers_np = [{k: l[k].numpy() for k in ("weight", "gamma", "beta", "mean", "var")} for l in layers]
     n = 3
     cpu_frame_oracle(clouds[0], layers_np, ssfa, head, anchors, cores)     # warm-up (page-in, thread pools)
     t0 = time.perf_counter()
     stage = {}
+    outs = []
     for i in range(n):
-        _, t = cpu_frame_oracle(clouds[i % len(clouds)], layers_np, ssfa, head, anchors, cores)
+        out, t = cpu_frame_oracle(clouds[i % len(clouds)], layers_np, ssfa, head, anchors, cores)
+        outs.append(out)
         for k, v in t.items():
             stage[k] = stage.get(k, 0.0) + v / n
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": "%d frames of the same workload after 1 warm-up; per-frame stage seconds %s (sparse encoder has no CPU "
-                      "implementation in the reference: numpy restatement, labelled non-reference)" % (n, {k: round(v, 3) for k, v in stage.items()})}
+    res = {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+           "sample": "%d frames of the same workload after 1 warm-up; per-frame stage seconds %s (sparse encoder has no CPU "
+                     "implementation in the reference: numpy restatement, labelled non-reference)" % (n, {k: round(v, 3) for k, v in stage.items()})}
+    parity = None
+    if engine is not None:
+        from oracle import cpu as ocpu
+        same_count, max_box, max_score, ious, ndet = True, 0.0, 0.0, [], 0
+        for i in range(n):
+            got = engine.infer([clouds[i % len(clouds)]])[0]
+            ob, osc = outs[i][0].numpy(), outs[i][1].numpy()
+            if got["box3d_lidar"].shape[0] != ob.shape[0]:
+                same_count = False
+                continue
+            ndet += ob.shape[0]
+            if ob.shape[0]:
+                max_box = max(max_box, float(np.abs(got["box3d_lidar"] - ob).max()))
+                max_score = max(max_score, float(np.abs(got["scores"] - osc).max()))
+                iou = ocpu.boxes_iou_bev(ocpu.boxes3d_to_bev(got["box3d_lidar"]), ocpu.boxes3d_to_bev(ob))
+                ious.extend(np.diag(iou).tolist())
+        parity = {"frames": n, "detections": ndet, "same_detection_sets": same_count, "max_abs_box_diff": max_box,
+                  "max_abs_score_diff": max_score, "mean_bev_iou_vs_oracle": float(np.mean(ious)) if ious else None,
+                  "min_bev_iou_vs_oracle": float(np.min(ious)) if ious else None,
+                  "what": "FrameEngine detections vs the CPU oracle of the reference path on the same frames (kept boxes in NMS order)"}
+    return res, parity
 
 
 if __name__ == "__main__":

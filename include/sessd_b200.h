@@ -314,6 +314,24 @@ int sessd_assign_targets(const float *d_anchors, int num_anchors, const float *d
                          float *d_bbox_outside_weights, int *d_pos_anchor, int *d_pos_gt_id, int *d_num_pos,
                          void *workspace, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * SURVEY.md 8(f) row 1, first slice of the training step: the supervised SSD-head loss terms, value AND gradient in one pass.
+ * Replaces (for the terms without the teacher model) det3d/models/bbox_heads/mg_head_sessd.py:706-760:
+ * prepare_loss_weights/NormByNumPositives (:525-572), SigmoidFocalLoss (det3d/models/losses/losses.py:345-420, gamma = 2),
+ * add_sin_difference + WeightedSmoothL1Loss (mg_head_sessd.py:39-44, losses.py:147-204), get_direction_target +
+ * WeightedSoftmaxClassificationLoss (mg_head_sessd.py:62-76, losses.py:489-531) and their autograd backward.
+ *   d_head [batch, A/2, head_stride]: the fused head tensor (box 2x7 | cls 2 | dir 2x2 | iou 2 | pad), as sessd_postprocess reads it;
+ *   d_labels [batch, A] (1 / 0 / -1) and d_reg_targets [batch, A, 7]: outputs of sessd_assign_targets; d_anchors [A, 7].
+ *   d_losses [batch, 8] = per-frame SUMS {cls, loc, dir, cls on positives, cls on negatives, 0, num_pos, num_neg} (the reference
+ *   reports loss_weight * batch total / batch); d_grad_head (nullable) [batch, A/2, head_stride] = d/d_head of
+ *   (w_cls * sum cls + w_loc * sum loc + w_dir * sum dir) / batch.  Sums are reduced in a fixed order (deterministic).
+ * ------------------------------------------------------------------------------------------------ */
+size_t sessd_head_loss_workspace_bytes(int batch);
+int sessd_head_loss(const float *d_head, const float *d_anchors, const int *d_labels, const float *d_reg_targets, int batch,
+                    int num_anchors, int anchors_per_loc, int head_stride, float alpha, float sigma, float dir_offset,
+                    float pos_cls_weight, float neg_cls_weight, float w_cls, float w_loc, float w_dir, float *d_losses,
+                    float *d_grad_head, void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,6 +90,8 @@ SIGNATURES = {
     "sessd_boxes_iou3d": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "sessd_nms_workspace_bytes": (_sz, [_i]),
     "sessd_nms_sorted": (_i, [_vp, _i, _f, _i, _vp, _vp, _vp, _sz, _vp]),
+    "sessd_head_loss_workspace_bytes": (_sz, [_i]),
+    "sessd_head_loss": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp, _sz, _vp]),
     "sessd_assign_workspace_bytes": (_sz, [_i, _i, _i]),
     "sessd_assign_targets": (_i, [_vp, _i, _vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }

@@ -441,3 +441,21 @@ def assign_targets(anchors, gt_boxes, num_gt, buf, matched_thr=0.6, unmatched_th
                                    _p(buf.pos_anchor), _p(buf.pos_gt_id), _p(buf.num_pos), _p(buf.ws), buf.ws.numel(), _st()),
           "sessd_assign_targets")
     return buf
+
+
+# ------------------------------------------------------------------------------------------------ supervised head loss (training, first slice)
+def head_loss(head, anchors, labels, reg_targets, alpha=0.25, sigma=3.0, dir_offset=0.0, pos_cls_weight=1.0, neg_cls_weight=1.0,
+              w_cls=1.0, w_loc=2.0, w_dir=0.2, with_grad=True):
+    """head [B, A/2, stride] f32 (fused head tensor), anchors [A,7], labels [B,A] i32, reg_targets [B,A,7] -- device tensors.
+    Returns (losses [B,8] = per-frame sums {cls, loc, dir, cls_pos, cls_neg, 0, num_pos, num_neg}, grad_head or None)."""
+    _cuda(head, torch.float32, "head"); _cuda(anchors, torch.float32, "anchors"); _cuda(labels, torch.int32, "labels")
+    _cuda(reg_targets, torch.float32, "reg_targets")
+    B, A = labels.shape
+    assert head.shape[0] == B and head.shape[1] * 2 == A and anchors.shape == (A, 7) and tuple(reg_targets.shape) == (B, A, 7)
+    losses = torch.empty((B, 8), dtype=torch.float32, device=head.device)
+    grad = torch.empty_like(head) if with_grad else None
+    ws = torch.empty((lib.sessd_head_loss_workspace_bytes(int(B)),), dtype=torch.uint8, device=head.device)
+    check(lib.sessd_head_loss(_p(head), _p(anchors), _p(labels), _p(reg_targets), int(B), int(A), 2, int(head.shape[2]), float(alpha), float(sigma),
+                              float(dir_offset), float(pos_cls_weight), float(neg_cls_weight), float(w_cls), float(w_loc), float(w_dir),
+                              _p(losses), _p(grad), _p(ws), ws.numel(), _st()), "sessd_head_loss")
+    return losses, grad

@@ -85,3 +85,20 @@ def kitti_wire_case():
     info = dict(calib={"P2": P2, "R0_rect": R0, "Tr_velo_to_cam": Tr}, image={"image_shape": np.array([375, 1242], np.int32)}, annos=annos,
                 point_cloud={"velodyne_path": "training/velodyne/000007.bin"})
     return info
+
+
+def head_loss_case():
+    """Inputs of the supervised head loss: fused head tensor [2, 35200, 24] (seeded), labels / regression targets of two assigner cases."""
+    import torch
+    from oracle import anchors as oa
+    anc = oa.create_anchors_3d_range().reshape(-1, 7)
+    cases = dict(assign_cases())
+    labels, targets = [], []
+    for name in ("m12", "m40"):
+        r = oa.assign_targets(anc, cases[name])
+        labels.append(r["labels"])
+        targets.append(r["bbox_targets"])
+    g = torch.Generator().manual_seed(41)
+    head = torch.randn(2, 35200, 24, generator=g) * 0.5
+    head[..., 14:16] -= 2.0                       # mostly-negative classification logits, like an early training step
+    return head.numpy(), anc, np.stack(labels, 0).astype(np.int32), np.stack(targets, 0).astype(np.float32)

@@ -32,7 +32,7 @@ from sessd_b200 import synth  # noqa: E402
 from oracle import bev_ref, build as obuild, cpu as ocpu  # noqa: E402
 
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from cases import assign_cases, iou_inputs, kitti_wire_case, sha, voxel_cases  # noqa: E402  (seeded inputs shared with the tests)
+from cases import assign_cases, head_loss_case, iou_inputs, kitti_wire_case, sha, voxel_cases  # noqa: E402  (seeded inputs shared with the tests)
 
 
 def _pkg(name):
@@ -218,6 +218,46 @@ def gen_wire():
     print("wire: frustum", fr.shape, fr.dtype, "gt", gt.shape, gt.dtype)
 
 
+def gen_loss():
+    """Supervised head loss terms from the REFERENCE's own loss classes (losses.py) and head helpers (mg_head_sessd.py)."""
+    from oracle import loss_ref
+    _stub("det3d.models.losses.utils", weight_reduce_loss=None)
+    losses = _load("det3d.models.losses.losses", "det3d/models/losses/losses.py")
+    mg = sys.modules.get("det3d.models.bbox_heads.mg_head_sessd") or _load("det3d.models.bbox_heads.mg_head_sessd",
+                                                                           "det3d/models/bbox_heads/mg_head_sessd.py")
+    head_np, anc_np, labels_np, targets_np = head_loss_case()
+    head = torch.from_numpy(head_np).clone().requires_grad_(True)
+    anchors, labels, reg_targets = torch.from_numpy(anc_np), torch.from_numpy(labels_np).long(), torch.from_numpy(targets_np)
+    box, cls, dr = loss_ref.split_head(head)
+    B = 2
+    loss_norm = dict(type="NormByNumPositives", pos_cls_weight=1.0, neg_cls_weight=1.0)
+    cls_w, reg_w, cared = mg.MultiGroupHead.prepare_loss_weights(None, labels, loss_norm=loss_norm, dtype=torch.float32)
+    cls_targets = (labels * cared.type_as(labels)).unsqueeze(-1)
+    enc_p, enc_t = mg.add_sin_difference(box, reg_targets)
+    loc = losses.WeightedSmoothL1Loss(sigma=3.0, code_weights=[1.0] * 7, codewise=True, loss_weight=2.0)(enc_p, enc_t, weights=reg_w)
+    cl = losses.SigmoidFocalLoss(alpha=0.25, gamma=2.0, loss_weight=1.0)(cls.unsqueeze(-1), cls_targets, weights=cls_w)
+    dir_t = mg.get_direction_target(anchors.unsqueeze(0).expand(B, -1, -1).contiguous(), reg_targets, dir_offset=0.0)
+    w = (labels > 0).type_as(dr)
+    w = w / torch.clamp(w.sum(-1, keepdim=True), min=1.0)
+    dl = losses.WeightedSoftmaxClassificationLoss(name="direction_classifier", loss_weight=0.2)(dr, dir_t, weights=w)
+    cls_pos, cls_neg = mg._get_pos_neg_loss(cl, labels)
+    total = 1.0 * cl.sum() / B + 2.0 * loc.sum() / B + 0.2 * dl.sum() / B
+    total.backward()
+    grad = head.grad.numpy()
+    # oracle == reference
+    o = loss_ref.head_supervised_loss(*loss_ref.split_head(torch.from_numpy(head_np)), anchors, labels, reg_targets)
+    for k, ref in (("cls", cl.sum((1, 2))), ("loc", loc.sum((1, 2))), ("dir", dl.sum(1))):
+        assert torch.allclose(o[k], ref.detach(), rtol=1e-6, atol=1e-7), (k, o[k], ref)
+    pos = np.nonzero(labels_np.reshape(-1) > 0)[0]
+    sample = np.arange(0, labels_np.size, 97)
+    np.savez_compressed(os.path.join(HERE, "head_loss_case.npz"), cls=cl.sum((1, 2)).detach().numpy(), loc=loc.sum((1, 2)).detach().numpy(),
+                        dir=dl.sum(1).detach().numpy(), cls_pos=np.float32(cls_pos.item()), cls_neg=np.float32(cls_neg.item()),
+                        total=np.float32(total.item()), grad_sha=sha(grad), grad_abs_sum=np.float64(np.abs(grad).sum()),
+                        grad_pix_idx=np.unique(np.concatenate([pos // 2, sample // 2])).astype(np.int32),
+                        grad_pix=grad.reshape(-1, 24)[np.unique(np.concatenate([pos // 2, sample // 2]))])
+    print("loss: cls", cl.sum((1, 2)).tolist(), "loc", loc.sum((1, 2)).tolist(), "dir", dl.sum(1).tolist(), "total", float(total))
+
+
 def gen_models():
     import logging
 
@@ -268,6 +308,8 @@ if __name__ == "__main__":
     install_det3d_shims()
     if not only or "assign" in only:
         gen_anchors_assign()
+    if not only or "loss" in only:
+        gen_loss()
     if not only or "wire" in only:
         gen_wire()
     if not only or "models" in only:

@@ -118,3 +118,115 @@ def test_spmiddle_features_match_fp64_oracle(use_tc, split, rows):
     assert got.shape == ref.shape
     assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-5
     assert ((got != 0) == (ref != 0)).all()
+
+
+def _full_size_runner(n_frames=4, pts=200000, **kw):
+    """BASELINE config #5-style clouds (uniform 200 k points per frame) through the voxeliser + SpMiddleRunner on the device."""
+    from sessd_b200 import ops, synth
+    from sessd_b200.runners import SpMiddleRunner
+    clouds = [synth.uniform_cloud(500 + f, pts) for f in range(n_frames)]
+    cfg = ops.make_voxel_cfg(synth.VOXEL_SIZE, synth.PC_RANGE, 5, 200000)
+    total = sum(c.shape[0] for c in clouds)
+    vox = ops.VoxelBuffers(cfg, n_frames, total, "cuda", with_mean=True)
+    off = np.zeros(n_frames + 1, np.int32)
+    off[1:] = np.cumsum([c.shape[0] for c in clouds])
+    ops.voxelize(torch.from_numpy(np.concatenate(clouds, 0)).cuda(), torch.from_numpy(off).cuda(), vox)
+    r = SpMiddleRunner(n_frames, n_frames * 200000, device="cuda", growth=(1.0, 8.0, 8.0, 8.0, 8.0), **kw)
+    layers, _, _ = _weights()
+    r.load_weights(layers)
+    return r, vox, n_frames
+
+
+def test_full_size_rulebook_symmetry_and_conv_properties():
+    """Size-independent properties at the stress shape (4 frames x 200 k points, ~0.8 M voxels, up to 3 M active sites):
+    * SubM rulebook symmetry: nbr[o][k] = i  <=>  nbr[i][26-k] = o, centre offset = identity, rows in range;
+    * strided levels: output coordinates strictly ascending in linear index (canonical order), every output has >= 1 input;
+    * the three sparse-conv implementations agree layer by layer (<= 1e-5 of the layer maximum) and are run-to-run deterministic (bitwise);
+    * dense(): the one-pass gather equals memset + scatter bitwise."""
+    from sessd_b200 import ops
+    from sessd_b200.runners import SpMiddleRunner
+    r, vox, B = _full_size_runner()
+    n0 = vox.num_voxels[B:B + 1]
+    d1 = r.forward(vox.mean, vox.coors, n0).clone()
+    torch.cuda.synchronize()
+    assert int(r.status.item()) == 0
+    feats1 = [f.clone() for f in r.feats]
+    # --- rulebooks
+    seen = set()
+    for p in r.plan:
+        n = int((n0 if p["lout"] == 0 else r.levels[p["lout"]]["n"]).item())
+        nbr = p["nbr"][:n].long()
+        if p["kind"] == "subm":
+            if p["key"] in seen:
+                continue
+            seen.add(p["key"])
+            ar = torch.arange(n, device="cuda")
+            assert torch.equal(nbr[:, 13], ar)
+            assert int(nbr.max()) < n and int(nbr.min()) >= -1
+            for k in (0, 5, 12):
+                o = torch.nonzero(nbr[:, k] >= 0).squeeze(1)
+                i = nbr[o, k]
+                assert torch.equal(nbr[i, 26 - k], o), (p["key"], k)
+        else:
+            lv = r.levels[p["lout"]]
+            c = lv["coors"][:n].long()
+            d, h, w = lv["shape"]
+            lin = ((c[:, 0] * d + c[:, 1]) * h + c[:, 2]) * w + c[:, 3]
+            assert bool((lin[1:] > lin[:-1]).all())
+            assert bool((nbr >= 0).any(dim=1).all())
+    # --- determinism + agreement between implementations
+    d2 = r.forward(vox.mean, vox.coors, n0)
+    torch.cuda.synchronize()
+    assert torch.equal(d1, d2)
+    for a, b in zip(feats1, r.feats):
+        assert torch.equal(a, b)
+    counts = [int((n0 if p["lout"] == 0 else r.levels[p["lout"]]["n"]).item()) for p in r.plan]
+    for kw in (dict(split="tf32", rows_max_cin=0), dict(use_tc=False)):
+        q = SpMiddleRunner(B, B * 200000, device="cuda", growth=(1.0, 8.0, 8.0, 8.0, 8.0), **kw)
+        q.load_weights(_weights()[0])
+        dq = q.forward(vox.mean, vox.coors, n0)
+        torch.cuda.synchronize()
+        for li, (a, b) in enumerate(zip(feats1, q.feats)):
+            n = counts[li]
+            scale = float(a[:n].abs().max()) + 1e-30
+            assert float((a[:n] - b[:n]).abs().max()) / scale < 1e-5, (kw, li)
+        assert float((dq - d1).abs().max()) / float(d1.abs().max()) < 1e-5
+        assert torch.equal(dq != 0, d1 != 0)
+        del q
+    # --- dense(): gather == memset + scatter
+    last = r.levels[-1]
+    ref = ops.sparse_to_dense(r.feats[-1], last["coors"], last["n"], last["cap"], last["grid"], torch.empty_like(d1))
+    torch.cuda.synchronize()
+    assert torch.equal(ref, d1)
+
+
+def test_h2_sparse_conv_power_of_two_scaling_is_exact():
+    """Linearity property of the fp16-split tensor-core layer: the activation scale is an exact power of two taken from the tensor's
+    abs-max, so conv(4 x) == 4 conv(x) BITWISE (shift = 0, ReLU on), at 300 k rows with a real SubM rulebook."""
+    from sessd_b200 import ops
+    r, vox, B = _full_size_runner(n_frames=2, pts=150000)
+    n0 = vox.num_voxels[B:B + 1]
+    r.forward(vox.mean, vox.coors, n0)
+    torch.cuda.synchronize()
+    p = r.plan[7]                                   # a 64 -> 64 SubM layer on level 2
+    lv = r.levels[p["lout"]]
+    n, cap = lv["n"], lv["cap"]
+    x = r.feats[6].clone()
+    w = torch.randn((27, 64, 64), device="cuda") * 0.05
+    tiles, inv = ops.pack_weight_sp_h2(w, 64)
+    sc = (torch.rand(64, device="cuda") + 0.5) * inv
+    outs = []
+    for mul in (1.0, 4.0):
+        xx = (x * mul).contiguous()
+        planes = ops.alloc_planes(cap, 64, "cuda")
+        amax = torch.zeros(2, device="cuda")
+        ops.absmax_rows(xx, n, cap, amax[0:1])
+        ops.split_h2(xx, n, cap, amax[0:1], planes)
+        out = torch.zeros((cap, 64), device="cuda")
+        ops.spconv_forward_h2(planes, amax[0:1], p["nbr"], n, cap, tiles, sc.contiguous(), None, True, out, amax[1:2])
+        torch.cuda.synchronize()
+        outs.append((out, float(amax[1])))
+    nn = int(n.item())
+    assert nn > 100000
+    assert torch.equal(outs[0][0][:nn] * 4.0, outs[1][0][:nn])
+    assert outs[0][1] * 4.0 == outs[1][1]

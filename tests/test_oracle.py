@@ -179,3 +179,24 @@ def test_rotate_nms_second_opinion_exact_polygon_clip():
     ref = order[ocpu.rotate_nms_cc(dets, 0.01, ge=True)]
     if not near:
         assert np.array_equal(np.array(keep), ref)
+
+
+def test_oracle_head_loss_equals_reference_golden(golden_dir):
+    """Supervised head loss (focal + sin-difference smooth-L1 + direction CE) and its autograd gradient vs the reference's loss classes."""
+    import torch
+    from cases import head_loss_case, sha
+    from oracle import loss_ref
+    g = np.load(os.path.join(golden_dir, "head_loss_case.npz"))
+    head_np, anc, labels, targets = head_loss_case()
+    head = torch.from_numpy(head_np).clone().requires_grad_(True)
+    o = loss_ref.head_supervised_loss(*loss_ref.split_head(head), torch.from_numpy(anc), torch.from_numpy(labels).long(), torch.from_numpy(targets))
+    for k in ("cls", "loc", "dir"):
+        np.testing.assert_allclose(o[k].detach().numpy(), g[k], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(float(o["cls_pos"].detach().sum() / 2), float(g["cls_pos"]), rtol=1e-6)
+    np.testing.assert_allclose(float(o["cls_neg"].detach().sum() / 2), float(g["cls_neg"]), rtol=1e-6)
+    total = (o["cls"].sum() + 2.0 * o["loc"].sum() + 0.2 * o["dir"].sum()) / 2
+    np.testing.assert_allclose(float(total.detach()), float(g["total"]), rtol=1e-6)
+    total.backward()
+    grad = head.grad.numpy().reshape(-1, 24)
+    np.testing.assert_allclose(grad[g["grad_pix_idx"]], g["grad_pix"], rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(np.abs(grad).sum(), float(g["grad_abs_sum"]), rtol=1e-5)
