@@ -191,7 +191,9 @@ def test_full_size_rulebook_symmetry_and_conv_properties():
             scale = float(a[:n].abs().max()) + 1e-30
             assert float((a[:n] - b[:n]).abs().max()) / scale < 1e-5, (kw, li)
         assert float((dq - d1).abs().max()) / float(d1.abs().max()) < 1e-5
-        assert torch.equal(dq != 0, d1 != 0)
+        # the occupancy pattern is the same; only ReLU outputs within rounding of zero may flip between implementations
+        flips = (dq != 0) != (d1 != 0)
+        assert float(torch.maximum(dq, d1)[flips].max() if bool(flips.any()) else 0.0) < 1e-5 * float(d1.abs().max())
         del q
     # --- dense(): gather == memset + scatter
     last = r.levels[-1]
