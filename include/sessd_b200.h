@@ -327,6 +327,14 @@ int sessd_assign_targets(const float *d_anchors, int num_anchors, const float *d
  *   (w_cls * sum cls + w_loc * sum loc + w_dir * sum dir) / batch.  Sums are reduced in a fixed order (deterministic).
  * ------------------------------------------------------------------------------------------------ */
 size_t sessd_head_loss_workspace_bytes(int batch);
+/* IoU-prediction term (mg_head_sessd.py:755-768): smooth-L1 of the head's iou output against 2 * aligned-3D-IoU(decoded prediction,
+ * decoded target) - 1 on the positives (det3d/core/iou3d/iou3d_utils.py:197-252 as the constant target).  Run AFTER sessd_head_loss on the
+ * same stream: reads num_pos from d_losses[b][6], writes the per-frame sum to d_losses[b][5] and d(w_iou * sum / batch) into the iou
+ * channels of d_grad_head. */
+size_t sessd_iou_pred_loss_workspace_bytes(int batch);
+int sessd_iou_pred_loss(const float *d_head, const float *d_anchors, const int *d_labels, const float *d_reg_targets, int batch,
+                        int num_anchors, int anchors_per_loc, int head_stride, float sigma, float w_iou, float *d_losses,
+                        float *d_grad_head, void *workspace, size_t workspace_bytes, void *stream);
 int sessd_head_loss(const float *d_head, const float *d_anchors, const int *d_labels, const float *d_reg_targets, int batch,
                     int num_anchors, int anchors_per_loc, int head_stride, float alpha, float sigma, float dir_offset,
                     float pos_cls_weight, float neg_cls_weight, float w_cls, float w_loc, float w_dir, float *d_losses,

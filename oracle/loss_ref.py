@@ -61,3 +61,33 @@ def split_head(head, apl=2):
     cls = head[..., 7 * apl:8 * apl].reshape(B, P * apl)
     dr = head[..., 8 * apl:10 * apl].reshape(B, P * apl, 2)
     return box, cls, dr
+
+
+def iou_pred_loss(iou_preds, box_preds, anchors, labels, reg_targets, sigma=3.0):
+    """mg_head_sessd.py:755-768: smooth-L1(iou_pred, 2 * aligned_iou3d(decode(pred), decode(target)) - 1) * (1 / num_pos) on the positives,
+    per-frame sums [B].  The aligned IoU follows det3d/core/iou3d/iou3d_utils.py:197-252 with the rotated BEV overlap of the C oracle
+    (oracle/csrc/oracle.c == the reference's iou3d_cpu.cpp arithmetic).  iou_preds [B,A], box_preds [B,A,7]; the target is a constant."""
+    import numpy as np
+    from . import bev_ref, cpu as ocpu
+    B = labels.shape[0]
+    out = []
+    for b in range(B):
+        pos = labels[b] > 0
+        n = int(pos.sum())
+        if n == 0:
+            out.append(iou_preds[b].sum() * 0.0)
+            continue
+        q = bev_ref.box_decode(box_preds[b][pos].detach(), anchors[pos]).numpy().astype(np.float32)
+        g = bev_ref.box_decode(reg_targets[b][pos], anchors[pos]).numpy().astype(np.float32)
+        ov = np.diag(ocpu.boxes_overlap_bev(ocpu.boxes3d_to_bev(q), ocpu.boxes3d_to_bev(g))).astype(np.float32)
+        two = np.float32(2)
+        lo = np.maximum(q[:, 2] - q[:, 5] / two, g[:, 2] - g[:, 5] / two)
+        hi = np.minimum(q[:, 2] + q[:, 5] / two, g[:, 2] + g[:, 5] / two)
+        ov3 = ov * np.maximum(hi - lo, np.float32(0))
+        iou = ov3 / np.maximum(q[:, 3] * q[:, 4] * q[:, 5] + g[:, 3] * g[:, 4] * g[:, 5] - ov3, np.float32(1e-7))
+        target = torch.from_numpy((two * iou - np.float32(1)).astype(np.float32))
+        ad = torch.abs(iou_preds[b][pos] - target)
+        lt = (ad <= 1 / sigma ** 2).type_as(ad)
+        loss = lt * 0.5 * torch.pow(ad * sigma, 2) + (ad - 0.5 / sigma ** 2) * (1.0 - lt)
+        out.append((loss / float(max(n, 1))).sum())
+    return torch.stack(out)

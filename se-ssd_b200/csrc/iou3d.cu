@@ -119,6 +119,77 @@ __global__ void __launch_bounds__(256) nms_reduce_kernel(const unsigned long lon
     if (threadIdx.x == 0) *num_keep = s_nkeep;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// IoU-prediction loss of the SE-SSD head (training; det3d/models/bbox_heads/mg_head_sessd.py:755-768): for every positive anchor decode
+// the predicted and the target box (det3d/core/bbox/box_torch_ops.py:81-147), take their ALIGNED rotated 3-D IoU
+// (det3d/core/iou3d/iou3d_utils.py:197-252: bev overlap x height overlap / clamp(vol_a + vol_b - overlap, 1e-7)) as a constant target
+// 2 IoU - 1 and apply WeightedSmoothL1Loss(sigma = 3) to the head's iou output with weight 1 / num_pos.  One thread per anchor (only the
+// positives work), fixed-order reduction.  Lives in this file because the polygon arithmetic must be compiled without FMA contraction.
+constexpr int kIpThreads = 256;
+constexpr int kIpBlocks = 74;
+
+__global__ void __launch_bounds__(kIpThreads) iou_pred_loss_kernel(const float *__restrict__ head, const float *__restrict__ anchors,
+                                                                   const int *__restrict__ labels, const float *__restrict__ reg_targets,
+                                                                   int batch, int A, int apl, int stride, float sigma, float w_iou,
+                                                                   const float *__restrict__ losses, float *__restrict__ partial,
+                                                                   float *__restrict__ grad_head) {
+    __shared__ float s_red[kIpThreads / 32];
+    const int b = blockIdx.y;
+    const float rw = 1.f / fmaxf(losses[b * 8 + 6], 1.f);            // 1 / num_pos (written by sessd_head_loss)
+    const float inv_s2 = 1.f / (sigma * sigma);
+    float acc = 0.f;
+    for (int a = blockIdx.x * kIpThreads + threadIdx.x; a < A; a += gridDim.x * kIpThreads) {
+        if (labels[(size_t)b * A + a] <= 0) continue;
+        const int pix = a / apl, r = a - pix * apl;
+        const size_t hb = ((size_t)b * (A / apl) + pix) * stride;
+        const float *h = head + hb;
+        const float *an = anchors + (size_t)a * 7;
+        const float *tg = reg_targets + ((size_t)b * A + a) * 7;
+        const float diag = sqrtf(an[4] * an[4] + an[3] * an[3]);
+        float q[7], g[7];
+        {
+            const float *e = h + 7 * r;
+            q[0] = e[0] * diag + an[0]; q[1] = e[1] * diag + an[1]; q[2] = e[2] * an[5] + an[2];
+            q[3] = expf(e[3]) * an[3]; q[4] = expf(e[4]) * an[4]; q[5] = expf(e[5]) * an[5]; q[6] = e[6] + an[6];
+            g[0] = tg[0] * diag + an[0]; g[1] = tg[1] * diag + an[1]; g[2] = tg[2] * an[5] + an[2];
+            g[3] = expf(tg[3]) * an[3]; g[4] = expf(tg[4]) * an[4]; g[5] = expf(tg[5]) * an[5]; g[6] = tg[6] + an[6];
+        }
+        const float ov_bev = rot_overlap(q[0] - q[3] / 2.f, q[1] - q[4] / 2.f, q[0] + q[3] / 2.f, q[1] + q[4] / 2.f, q[6],
+                                         g[0] - g[3] / 2.f, g[1] - g[4] / 2.f, g[0] + g[3] / 2.f, g[1] + g[4] / 2.f, g[6]);
+        const float lo = fmaxf(q[2] - q[5] / 2.f, g[2] - g[5] / 2.f), hi = fminf(q[2] + q[5] / 2.f, g[2] + g[5] / 2.f);
+        const float ov3 = ov_bev * fmaxf(hi - lo, 0.f);
+        const float iou = ov3 / fmaxf(q[3] * q[4] * q[5] + g[3] * g[4] * g[5] - ov3, 1e-7f);
+        const float target = 2.f * iou - 1.f;
+        const int ch = 7 * apl + apl + 2 * apl + r;
+        const float d = h[ch] - target;
+        const float ad = fabsf(d);
+        const bool small = ad <= inv_s2;
+        const float sd = ad * sigma;
+        acc += (small ? 0.5f * sd * sd : ad - 0.5f * inv_s2) * rw;
+        if (grad_head) grad_head[hb + ch] = (small ? sigma * sigma * d : (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f))) * rw * w_iou / (float)batch;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+    if (lane == 0) s_red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float v = 0.f;
+        for (int i = 0; i < kIpThreads / 32; ++i) v += s_red[i];
+        partial[(size_t)b * gridDim.x + blockIdx.x] = v;
+    }
+}
+
+__global__ void iou_pred_finish_kernel(const float *__restrict__ partial, int nblocks, float *__restrict__ losses) {
+    const int b = blockIdx.x;
+    if (threadIdx.x == 0) {
+        float v = 0.f;
+        for (int i = 0; i < nblocks; ++i) v += partial[(size_t)b * nblocks + i];
+        losses[b * 8 + 5] = v;
+    }
+}
+
 }  // namespace sessd
 
 using namespace sessd;
@@ -174,5 +245,24 @@ extern "C" int sessd_nms_sorted(const float *d_boxes, int n, float thresh, int m
     if (sm > 48 * 1024)
         SESSD_CUDA_TRY(cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     SESSD_LAUNCH(nms_reduce_kernel, 1, 256, sm, st, mask, n, n, d_keep, d_num_keep);
+    return last_error();
+}
+
+extern "C" size_t sessd_iou_pred_loss_workspace_bytes(int batch) { return batch < 1 ? 0 : sizeof(float) * (size_t)batch * kIpBlocks; }
+
+// Must run after sessd_head_loss on the same stream: reads num_pos from d_losses[b][6], writes the per-frame sum to d_losses[b][5] and the
+// gradient of  w_iou * sum / batch  into the iou channels of d_grad_head (which sessd_head_loss zeroed).
+extern "C" int sessd_iou_pred_loss(const float *d_head, const float *d_anchors, const int *d_labels, const float *d_reg_targets, int batch,
+                                   int num_anchors, int anchors_per_loc, int head_stride, float sigma, float w_iou, float *d_losses,
+                                   float *d_grad_head, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!d_head || !d_anchors || !d_labels || !d_reg_targets || !d_losses || batch < 1 || num_anchors < 1 || anchors_per_loc != 2 ||
+        head_stride < 22 || !(sigma > 0.f))
+        return SESSD_EINVAL;
+    if (!workspace || workspace_bytes < sessd_iou_pred_loss_workspace_bytes(batch)) return SESSD_EWORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(kIpBlocks, batch);
+    SESSD_LAUNCH(iou_pred_loss_kernel, grid, kIpThreads, 0, st, d_head, d_anchors, d_labels, d_reg_targets, batch, num_anchors, anchors_per_loc,
+                 head_stride, sigma, w_iou, d_losses, (float *)workspace, d_grad_head);
+    SESSD_LAUNCH(iou_pred_finish_kernel, batch, 32, 0, st, (const float *)workspace, kIpBlocks, d_losses);
     return last_error();
 }

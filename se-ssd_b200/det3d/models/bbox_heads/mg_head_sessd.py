@@ -125,11 +125,11 @@ class MultiGroupHead(nn.Module):
                                   "supervised terms (focal cls, sin-difference smooth-L1, direction CE) are available as loss_supervised()")
 
     def loss_supervised(self, example, preds_dicts, with_grad=True):
-        """Supervised terms of ``loss`` (reference mg_head_sessd.py:706-760 without the teacher / ODIoU / IoU-prediction parts) for the
+        """Supervised terms of ``loss`` (reference mg_head_sessd.py:706-768 without the teacher / ODIoU parts) for the
         single-task car head, value and gradient w.r.t. the fused head tensor in one device pass (csrc/headloss.cu).
         ``example``: ``anchors`` [[B,A,7]], ``labels`` [[B,A]], ``reg_targets`` [[B,A,7]] (device tensors, e.g. from
         TargetAssigner.assign_batch_gpu).  Returns the reference's reduced values (loss_weight * batch total / batch_size) and the gradient
-        of ``cls_loss_reduced + dir_loss_reduced`` (the reference's total does not include the smooth-L1 term)."""
+        of ``cls_loss_reduced + dir_loss_reduced + iou_pred_loss`` (the reference's total does not include the smooth-L1 term)."""
         from sessd_b200 import ops
         packed = preds_dicts[0]["_packed"]
         b = packed.shape[0]
@@ -141,11 +141,11 @@ class MultiGroupHead(nn.Module):
         losses, grad = ops.head_loss(head, anchors, labels, reg_targets, alpha=float(self.loss_cls._alpha), sigma=float(self.loss_reg._sigma),
                                      dir_offset=float(self.direction_offset), pos_cls_weight=float(self.loss_norm["pos_cls_weight"]),
                                      neg_cls_weight=float(self.loss_norm["neg_cls_weight"]), w_cls=w_cls, w_loc=0.0, w_dir=w_dir,
-                                     with_grad=with_grad)
+                                     w_iou=1.0, with_grad=with_grad)
         tot = losses.sum(0) / b
         return dict(cls_loss_reduced=w_cls * tot[0], loc_loss_reduced=float(self.loss_reg._loss_weight) * tot[1], dir_loss_reduced=w_dir * tot[2],
                     cls_pos_loss=tot[3] / float(self.loss_norm["pos_cls_weight"]), cls_neg_loss=tot[4] / float(self.loss_norm["neg_cls_weight"]),
-                    num_pos=losses[0, 6], num_neg=losses[0, 7], grad_head=None if grad is None else grad.view_as(packed))
+                    iou_pred_loss=tot[5], num_pos=losses[0, 6], num_neg=losses[0, 7], grad_head=None if grad is None else grad.view_as(packed))
 
     # ------------------------------------------------------------------------------------------------------------------
     def predict(self, example, preds_dicts, test_cfg, **kwargs):

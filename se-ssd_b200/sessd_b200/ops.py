@@ -445,9 +445,10 @@ def assign_targets(anchors, gt_boxes, num_gt, buf, matched_thr=0.6, unmatched_th
 
 # ------------------------------------------------------------------------------------------------ supervised head loss (training, first slice)
 def head_loss(head, anchors, labels, reg_targets, alpha=0.25, sigma=3.0, dir_offset=0.0, pos_cls_weight=1.0, neg_cls_weight=1.0,
-              w_cls=1.0, w_loc=2.0, w_dir=0.2, with_grad=True):
+              w_cls=1.0, w_loc=2.0, w_dir=0.2, w_iou=None, with_grad=True):
     """head [B, A/2, stride] f32 (fused head tensor), anchors [A,7], labels [B,A] i32, reg_targets [B,A,7] -- device tensors.
-    Returns (losses [B,8] = per-frame sums {cls, loc, dir, cls_pos, cls_neg, 0, num_pos, num_neg}, grad_head or None)."""
+    w_iou: None = skip the IoU-prediction term; a float = also run sessd_iou_pred_loss (smooth-L1 of the iou head vs 2*IoU3D-1 on positives).
+    Returns (losses [B,8] = per-frame sums {cls, loc, dir, cls_pos, cls_neg, iou_pred, num_pos, num_neg}, grad_head or None)."""
     _cuda(head, torch.float32, "head"); _cuda(anchors, torch.float32, "anchors"); _cuda(labels, torch.int32, "labels")
     _cuda(reg_targets, torch.float32, "reg_targets")
     B, A = labels.shape
@@ -458,4 +459,8 @@ def head_loss(head, anchors, labels, reg_targets, alpha=0.25, sigma=3.0, dir_off
     check(lib.sessd_head_loss(_p(head), _p(anchors), _p(labels), _p(reg_targets), int(B), int(A), 2, int(head.shape[2]), float(alpha), float(sigma),
                               float(dir_offset), float(pos_cls_weight), float(neg_cls_weight), float(w_cls), float(w_loc), float(w_dir),
                               _p(losses), _p(grad), _p(ws), ws.numel(), _st()), "sessd_head_loss")
+    if w_iou is not None:
+        ws2 = torch.empty((lib.sessd_iou_pred_loss_workspace_bytes(int(B)),), dtype=torch.uint8, device=head.device)
+        check(lib.sessd_iou_pred_loss(_p(head), _p(anchors), _p(labels), _p(reg_targets), int(B), int(A), 2, int(head.shape[2]), float(sigma),
+                                      float(w_iou), _p(losses), _p(grad), _p(ws2), ws2.numel(), _st()), "sessd_iou_pred_loss")
     return losses, grad
