@@ -35,10 +35,12 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=32)
-    ap.add_argument("--streams", type=int, default=8)
+    ap.add_argument("--streams", type=int, default=12)
     ap.add_argument("--cloud", default="ring", choices=["ring", "uniform"])
     ap.add_argument("--pool", type=int, default=16, help="distinct synthetic frames per rank")
     ap.add_argument("--quick", action="store_true", help="skip the e2e / roofline / cpu_baseline legs (tuning runs)")
+    ap.add_argument("--sp-h2-depth", type=int, default=0, choices=[0, 1, 2],
+                    help="pipeline depth of the tensor-core sparse conv: 0 auto, 1 two CTAs/SM, 2 one CTA/SM with twice the stages (tuning)")
     return ap.parse_args()
 
 
@@ -182,6 +184,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    _lib.lib.sessd_set_sp_h2_depth(int(args.sp_h2_depth))
     sd = weights.random_detector_state(0, cls_bias=-3.0)
     layers, ssfa, head = weights.split_detector_state(sd)
     anchors = weights.kitti_car_anchors()

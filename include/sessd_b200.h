@@ -149,7 +149,7 @@ int sessd_sparse_to_dense_indexed(const float *d_feat, int max_rows, const void 
 int sessd_spconv_forward_rows(const float *d_in_feat, int cin, const int *d_nbr, int kvol, const int *d_n_out, int max_out,
                               const float *d_weight, int cout, const float *d_scale, const float *d_shift, int relu,
                               float *d_out_feat, float *d_amax_out, void *stream);
-/* pipeline depth of sessd_spconv_forward_h2: 0 = auto (deep when max_out <= 262144), 1 = 2 CTAs/SM x 2-4 stages, 2 = 1 CTA/SM x 4-8 stages */
+/* pipeline depth of sessd_spconv_forward_h2: 0 / 1 = two CTAs per SM x 2-4 stages (default), 2 = one CTA per SM x 4-8 stages */
 void sessd_set_sp_h2_depth(int mode);
 int sessd_split_h2(const float *d_feat, const int *d_n, int max_rows, int channels, const float *d_amax, void *d_planes, int cp,
                    void *stream);

@@ -28,5 +28,5 @@ if [ -n "$NCU_STRESS" ]; then
 #  (a) the tensor-core sparse conv: launches 0..3 = layers 3, 4 (32->32), 5 (32->64), 6 (64->64)
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:spconv_h2_kernel -s 0 -c 4 -f -o $OUT/prof_stress_spconv_h2 python scripts/kernel_rooflines.py --shape stress --iters 1 > $OUT/ncu_stress.log 2>&1; echo "ncu stress rc=$?"
 #  (b) the bandwidth-bound kernels: voxeliser, rulebook, narrow-layer conv, split, dense(), NMS mask
-timeout 900 ncu --set full --clock-control none -k regex:"vox_|hash_build|nbr_kernel|mark_outputs|enumerate_kernel|spconv_rows|split_h2|dense_gather|post_mask" -c 22 -f -o $OUT/prof_stress_hbm python scripts/kernel_rooflines.py --shape stress --iters 1 > $OUT/ncu_stress_hbm.log 2>&1; echo "ncu stress hbm rc=$?"
+timeout 900 ncu --set full --clock-control none -k regex:"vox_|hash_build|nbr_kernel|mark_outputs|enumerate_kernel|spconv_rows|split_h2|dense_gather|post_mask" -c 14 -f -o $OUT/prof_stress_hbm python scripts/kernel_rooflines.py --shape stress --iters 1 > $OUT/ncu_stress_hbm.log 2>&1; echo "ncu stress hbm rc=$?"
 fi

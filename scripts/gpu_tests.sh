@@ -1,4 +1,3 @@
-mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
-timeout 1500 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -30 gpurun_out/pytest_gpu.log
+mkdir -p gpurun_out/${1:-tests}
+timeout 1500 python -m pytest tests -m gpu -q --timeout 600 --durations=8 > gpurun_out/${1:-tests}/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${1:-tests}/pytest_gpu.log
+tail -40 gpurun_out/${1:-tests}/pytest_gpu.log

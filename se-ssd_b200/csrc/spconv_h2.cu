@@ -360,7 +360,7 @@ static int encode_map_2d_f16(CUtensorMap *m, const void *base, cuuint64_t cols, 
     return r == CUDA_SUCCESS ? 0 : 700 + (int)r;
 }
 
-static int g_sp_h2_depth = 0;      // 0 auto, 1 shallow (2 CTAs / SM), 2 deep (1 CTA / SM)
+static int g_sp_h2_depth = 0;      // 0 / 1: two CTAs per SM (default), 2: one CTA per SM with twice the stages
 
 template <int CP, int COUT, int DEEP>
 static int launch_spconv_h2(const void *planes, int plane_rows, int zero_row, const float *amax_in, const int *nbr, int kvol, const int *d_n,
@@ -424,8 +424,10 @@ extern "C" int sessd_spconv_forward_h2(const void *d_in_planes, int cp, int plan
         plane_rows < 1)
         return SESSD_EINVAL;     // zero_row outside [0, plane_rows) = rely on the TMA's out-of-bounds zero fill (no memory traffic)
     cudaStream_t st = (cudaStream_t)stream;
-    // few tiles (capacity of a one- or two-frame engine): deep pipeline, one CTA per SM; many tiles: two CTAs per SM
-    const bool deep = g_sp_h2_depth == 2 || (g_sp_h2_depth == 0 && max_out <= 262144);
+    // two CTAs per SM by default.  The deep variant (one CTA per SM, twice the stages, 207 KB of shared memory) does not shorten a
+    // single layer (the K loop is bound by the per-SM TMA row rate, not by latency) and its footprint keeps other streams' kernels off
+    // the SM: 1400 vs 1528 frames/s in the 8-stream batch-1 bench (profiles/r1g_tune_streams_depth.log) -- kept as an explicit option.
+    const bool deep = g_sp_h2_depth == 2;
 #define SESSD_G4_CASE(CPV, CO)                                                                                                              \
     if (cp == CPV && cout == CO)                                                                                                            \
         return deep ? launch_spconv_h2<CPV, CO, 1>(d_in_planes, plane_rows, zero_row, d_amax_in, d_nbr, kvol, d_n_out, max_out, d_weight_h2, \
