@@ -1,8 +1,11 @@
-"""VoxelNet detector (reference: det3d/models/detectors/voxelnet_sessd.py:5-43).  ``forward(example, return_loss=False)`` consumes
-the collate_kitti batch dict (voxels, coordinates with batch column, num_points, num_voxels, shape, anchors, calib, metadata) and
-returns the per-frame detection dicts, exactly like the reference; every stage runs on the B200 kernels."""
+"""VoxelNet detector with the reference's call contract (det3d/models/detectors/voxelnet_sessd.py): ``forward(example, is_ema,
+return_loss)`` takes the collate_kitti batch dict (voxels, coordinates with a batch column, num_points, num_voxels, shape, anchors, calib,
+metadata; ``*_raw`` twins for the teacher branch) and returns per-frame detection dicts (``return_loss=False``), the head outputs
+(teacher branch) or the loss; every stage runs on the B200 kernels."""
 from ..registry import DETECTORS
 from .single_stage import SingleStageDetector
+
+_STAGE_INPUTS = (("voxels", "voxels"), ("num_points_per_voxel", "num_points"), ("coors", "coordinates"))
 
 
 @DETECTORS.register_module
@@ -11,20 +14,19 @@ class VoxelNet(SingleStageDetector):
         super().__init__(reader, backbone, neck, bbox_head, train_cfg, test_cfg, pretrained)
 
     def extract_feat(self, data):
-        feats = self.reader(data["voxels"], data["num_points_per_voxel"])
-        x = self.backbone(feats, data["coors"], data["batch_size"], data["input_shape"])
-        if self.with_neck:
-            x = self.neck(x)
-        return x
+        voxel_features = self.reader(data["voxels"], data["num_points_per_voxel"])
+        bev = self.backbone(voxel_features, data["coors"], data["batch_size"], data["input_shape"])
+        return self.neck(bev) if self.with_neck else bev
 
     def forward(self, example, is_ema=[False, None], return_loss=True, **kwargs):
-        tag = "_raw" if is_ema[0] else ""
-        num_voxels = example["num_voxels" + tag]
-        data = dict(voxels=example["voxels" + tag], num_points_per_voxel=example["num_points" + tag],
-                    coors=example["coordinates" + tag], batch_size=len(num_voxels), input_shape=example["shape" + tag][0])
+        teacher, preds_ema = is_ema[0], is_ema[1]
+        suffix = "_raw" if teacher else ""              # the teacher sees the un-augmented copy of the frame
+        data = {name: example[key + suffix] for name, key in _STAGE_INPUTS}
+        data["batch_size"] = len(example["num_voxels" + suffix])
+        data["input_shape"] = example["shape" + suffix][0]
         preds = self.bbox_head(self.extract_feat(data))
-        if is_ema[0]:
+        if teacher:
             return preds
-        if return_loss:
-            return self.bbox_head.loss(example, preds, is_ema[1])
-        return self.bbox_head.predict(example, preds, self.test_cfg)
+        if not return_loss:
+            return self.bbox_head.predict(example, preds, self.test_cfg)
+        return self.bbox_head.loss(example, preds, preds_ema)

@@ -1,11 +1,7 @@
-"""Model registries (reference: det3d/models/registry.py:1-10)."""
+"""Model registries, same names as the reference's det3d/models/registry.py so that ``from det3d.models.registry import HEADS`` keeps working."""
 from det3d.utils import Registry
 
-READERS = Registry("reader")
-BACKBONES = Registry("backbone")
-NECKS = Registry("neck")
-ROI_EXTRACTORS = Registry("roi_extractor")
-SHARED_HEADS = Registry("shared_head")
-HEADS = Registry("head")
-LOSSES = Registry("loss")
-DETECTORS = Registry("detector")
+_KINDS = dict(READERS="reader", BACKBONES="backbone", NECKS="neck", ROI_EXTRACTORS="roi_extractor", SHARED_HEADS="shared_head",
+              HEADS="head", LOSSES="loss", DETECTORS="detector")
+globals().update({var: Registry(kind) for var, kind in _KINDS.items()})
+__all__ = list(_KINDS)

@@ -1,53 +1,51 @@
-"""String -> class registries (reference: det3d/utils/registry.py:6-76)."""
+"""String -> class registries with the reference's surface (det3d/utils/registry.py): ``Registry(name)``, ``.name``, ``.module_dict``,
+``.get(key)``, ``@registry.register_module`` (duplicate names are a KeyError, non-classes a TypeError) and
+``build_from_cfg(cfg, registry, default_args)`` (pops ``type``; unknown type strings are a KeyError; ``default_args`` only fill keys the
+config leaves unset)."""
 import inspect
 
 
 class Registry(object):
     def __init__(self, name):
-        self._name = name
-        self._module_dict = {}
+        self._name, self._module_dict = name, {}
+
+    name = property(lambda self: self._name)
+    module_dict = property(lambda self: self._module_dict)
 
     def __repr__(self):
-        return "%s(name=%s, items=%s)" % (type(self).__name__, self._name, list(self._module_dict))
+        return "{}(name={}, items={})".format(type(self).__name__, self._name, sorted(self._module_dict))
 
-    @property
-    def name(self):
-        return self._name
-
-    @property
-    def module_dict(self):
-        return self._module_dict
+    def __contains__(self, key):
+        return key in self._module_dict
 
     def get(self, key):
-        return self._module_dict.get(key)
+        return self._module_dict.get(key, None)
 
     def register_module(self, cls):
-        """Class decorator; a second class of the same name is an error (KeyError), as in the reference (:36-39)."""
         if not inspect.isclass(cls):
             raise TypeError("module must be a class, but got %s" % type(cls))
-        if cls.__name__ in self._module_dict:
-            raise KeyError("%s is already registered in %s" % (cls.__name__, self._name))
-        self._module_dict[cls.__name__] = cls
+        key = cls.__name__
+        if key in self:
+            raise KeyError("%s is already registered in %s" % (key, self._name))
+        self._module_dict[key] = cls
         return cls
 
 
-def build_from_cfg(cfg, registry, default_args=None):
-    """Pop ``type`` from a config dict, look it up (KeyError when unknown) and call it with the remaining keys
-    plus ``default_args`` for keys the config does not set (reference :47-76)."""
-    if not (isinstance(cfg, dict) and "type" in cfg):
-        raise AssertionError("cfg must be a dict with a 'type' key")
-    if not (default_args is None or isinstance(default_args, dict)):
-        raise AssertionError("default_args must be a dict or None")
-    kwargs = dict(cfg)
-    kind = kwargs.pop("type")
-    if isinstance(kind, str):
-        cls = registry.get(kind)
-        if cls is None:
-            raise KeyError("%s is not in the %s registry" % (kind, registry.name))
-    elif inspect.isclass(kind):
-        cls = kind
-    else:
+def _resolve(kind, registry):
+    if inspect.isclass(kind):
+        return kind
+    if not isinstance(kind, str):
         raise TypeError("type must be a str or valid type, but got %s" % type(kind))
+    found = registry.get(kind)
+    if found is None:
+        raise KeyError("%s is not in the %s registry" % (kind, registry.name))
+    return found
+
+
+def build_from_cfg(cfg, registry, default_args=None):
+    assert isinstance(cfg, dict) and "type" in cfg, "cfg must be a dict with a 'type' key"
+    assert default_args is None or isinstance(default_args, dict), "default_args must be a dict or None"
+    kwargs = {k: v for k, v in cfg.items() if k != "type"}
     for k, v in (default_args or {}).items():
         kwargs.setdefault(k, v)
-    return cls(**kwargs)
+    return _resolve(cfg["type"], registry)(**kwargs)
