@@ -261,3 +261,41 @@ def test_checkpoint_wire_format_roundtrip(tmp_path):
     assert torch.equal(fresh2.state_dict()["neck.conv_0.0.weight"], sd["neck.conv_0.0.weight"])
     with pytest.raises(IOError):
         load_checkpoint(fresh2, str(tmp_path / "missing.pth"))
+
+
+def test_voxelnet_forward_control_flow_with_stub_stages():
+    """VoxelNet.forward wiring (CPU, stub stages): which example keys reach which stage, `_raw` twins for the teacher branch,
+    predict vs loss dispatch -- the call contract of det3d/models/detectors/voxelnet_sessd.py."""
+    from det3d.models.detectors import VoxelNet
+    calls = []
+
+    class Stage:
+        def __init__(self, name):
+            self.name = name
+
+        def __call__(self, *a):
+            calls.append((self.name, a))
+            return (self.name,) + tuple(x if isinstance(x, (str, int)) else type(x).__name__ for x in a)
+
+    class HeadStub(Stage):
+        def predict(self, example, preds, test_cfg):
+            return ("predict", preds, test_cfg)
+
+        def loss(self, example, preds, preds_ema):
+            return ("loss", preds, preds_ema)
+
+    net = object.__new__(VoxelNet)
+    net.reader, net.backbone, net.neck, net.bbox_head = Stage("reader"), Stage("backbone"), Stage("neck"), HeadStub("head")
+    net.test_cfg = "TEST_CFG"
+    ex = dict(voxels="V", num_points="NP", coordinates="C", num_voxels=[1, 2, 3], shape=["SHAPE"],
+              voxels_raw="Vr", num_points_raw="NPr", coordinates_raw="Cr", num_voxels_raw=[1, 2], shape_raw=["SHAPEr"])
+    out = net.forward(ex, return_loss=False)
+    assert out[0] == "predict" and out[2] == "TEST_CFG"
+    assert calls[0] == ("reader", ("V", "NP")) and calls[1][0] == "backbone" and calls[1][1][1:] == ("C", 3, "SHAPE")
+    assert [c[0] for c in calls] == ["reader", "backbone", "neck", "head"]
+    calls.clear()
+    out = net.forward(ex, is_ema=[True, None])                       # teacher branch: raw copy in, head outputs back
+    assert out[0] == "head" and calls[0] == ("reader", ("Vr", "NPr")) and calls[1][1][1:] == ("Cr", 2, "SHAPEr")
+    calls.clear()
+    out = net.forward(ex, is_ema=[False, "EMA_PREDS"], return_loss=True)
+    assert out[0] == "loss" and out[2] == "EMA_PREDS"
