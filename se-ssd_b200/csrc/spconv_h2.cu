@@ -8,13 +8,17 @@
 //     same bytes as the fp32 row.  sessd_split_h2 produces them from the producing layer's fp32 output;
 //   * the 128 input rows of a (tile, kernel offset) are fetched by 32 (CP=32) or 64 (CP=64) TMA gather4 instructions -- four 128-byte rows
 //     each, written by the copy engine straight into the K-major SWIZZLE_128B layout the UMMA descriptors address.  Missing neighbours
-//     (nbr = -1) read the all-zero row kept at index `zero_row`.  No SIMT warp touches the operands: no register staging, no
-//     st.shared, no split arithmetic in the main loop;
+//     are passed as the out-of-bounds row index `zero_row` = -1: the TMA zero-fills them without memory traffic (reading a real
+//     all-zero row instead serialises every SM on two L2 lines: 1.46 ms vs 0.34 ms on 300 k rows at 50 % fill).  No SIMT warp touches
+//     the operands: no register staging, no st.shared, no split arithmetic in the main loop;
 //   * kind::f16 MMAs (twice the tf32 rate, half the operand bytes in shared memory): a_hi*b_hi -> main0 / main1 (alternating per
 //     offset), a_hi*b_lo + a_lo*b_hi -> cross; the three TMEM accumulators are summed in RN fp32 by the epilogue (tcgen05
 //     accumulation truncates, see bevconv_tc.cu);
-//   * 96-111 KB of shared memory and <= 256 TMEM columns per CTA => TWO CTAs per SM: one tile's prologue / epilogue overlaps the
-//     other's main loop without a persistent scheduler.
+//   * 96-114 KB of shared memory and <= 256 TMEM columns per CTA => TWO CTAs per SM: one tile's prologue / epilogue overlaps the
+//     other's main loop without a persistent scheduler, and kernels of other streams can share the SM (the one-CTA-per-SM deep variant
+//     costs 9 % of the multi-stream frame throughput).
+// Bound (measured): the per-SM TMA row rate, ~5-6 clk per gathered 128-byte row whether it is in bounds or not (~25 B/clk/SM, ~7 TB/s
+// over the chip = the L2 -> SM fabric).  At 4 bytes per gathered element and Cout = 64 that caps the tensor pipe near 31 % (ncu: 29-30 %).
 // One CTA = 128 consecutive output rows x all Cout; 160 threads: warps 0-3 issue the gathers of their 32 rows (a TMA instruction is
 // issued by one elected lane at a time, ~40 clk each: four warps issue in parallel), then run the epilogue (TMEM -> registers -> fp32
 // rows + running abs-max of the output for the next layer's split); warp 4 loads the weight tiles and issues the MMAs.

@@ -112,3 +112,27 @@ def test_frame_sharding_two_ranks_gloo(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_sparse_fp16_split_weight_packing_layout_and_precision():
+    """ops.pack_weight_sp_h2: tile layouts the TMA maps of spconv_h2.cu assume, per-channel power-of-two scales, hi + lo == scaled weight
+    to fp16-split precision (22+ significand bits)."""
+    from sessd_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    for cin, cout, cp in ((64, 64, 64), (32, 32, 32), (32, 64, 32), (16, 32, 32)):
+        w = torch.randn(27, cin, cout, generator=g) * torch.logspace(-3, 1, cout)[None, None, :]      # channel scales over 4 decades
+        tiles, inv = ops.pack_weight_sp_h2(w, cp)
+        assert tiles.dtype == torch.float16 and inv.shape == (cout,)
+        ex = torch.log2(inv)
+        assert torch.equal(ex, ex.round())                                   # exact powers of two
+        scaled = w.permute(0, 2, 1) / inv[None, :, None]                     # [kvol, cout, cin] * 2^e
+        assert float(scaled.abs().amax()) < 2048.0 and float(scaled.abs().amax(dim=(0, 2)).min()) >= 1024.0
+        if cp == 64:
+            assert tuple(tiles.shape) == (27, 2, cout, 64)
+            hi, lo = tiles[:, 0].float(), tiles[:, 1].float()
+        else:
+            assert tuple(tiles.shape) == (27, cout, 64)
+            hi, lo = tiles[:, :, :cin].float(), tiles[:, :, 32:32 + cin].float()
+            assert not tiles[:, :, cin:32].any() and not tiles[:, :, 32 + cin:].any()     # zero padding of the 16-channel layers
+        err = (hi + lo - scaled).abs().max() / scaled.abs().max()
+        assert float(err) < 2.0 ** -21
