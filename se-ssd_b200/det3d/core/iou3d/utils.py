@@ -1,6 +1,4 @@
 """Box layout conversions for the iou3d ops (reference: det3d/core/iou3d/utils.py:74-126)."""
-import torch
-
 
 def _wl_index(box_mode, width):
     off = 2 if width == 5 else 3

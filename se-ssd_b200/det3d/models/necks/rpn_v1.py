@@ -5,7 +5,6 @@ Identical module tree (hence identical state-dict keys: ``bottom_up_block_0.1.we
 B200 kernels: 12 conv / deconv layers as NHWC implicit GEMMs on the tcgen05 tensor cores with BatchNorm + ReLU (+ the
 deconv_0 + trans_0 residual) fused into the epilogue, and one fused kernel for the two 1-channel attention convs, their BN, the
 2-way softmax and the weighted sum (:229-233)."""
-import torch
 from torch import nn
 
 from sessd_b200.runners import SSFARunner
