@@ -331,6 +331,19 @@ size_t sessd_head_loss_workspace_bytes(int batch);
  * decoded target) - 1 on the positives (det3d/core/iou3d/iou3d_utils.py:197-252 as the constant target).  Run AFTER sessd_head_loss on the
  * same stream: reads num_pos from d_losses[b][6], writes the per-frame sum to d_losses[b][5] and d(w_iou * sum / batch) into the iou
  * channels of d_grad_head. */
+/* ODIoU box-regression loss (det3d/models/losses/odious.py:845-900 called from mg_head_sessd.py:770-778; the reference evaluates it with
+ * per-box numpy loops on the CPU inside the training step): odiou = 1 - IoU3D + centre distance^2 / (min bounding rectangle diagonal^2 +
+ * inter_h^2) + 1.25 (1 - |cos dr|) between the decoded prediction and the decoded target of every positive anchor, weight 1 / num_pos.
+ * Run AFTER sessd_head_loss on the same stream (reads num_pos from d_losses[b][6]); d_odiou_sum [batch] receives the per-frame sums,
+ * and w_odiou * d(sum over frames) / batch is ADDED to the box channels of d_grad_head (nullable).  The reference's ious_loss is
+ * 2.0 * batch total / batch_size: pass w_odiou = 2.0.  Gradients are exact (forward-mode differentiation of the same arithmetic). */
+size_t sessd_odiou_loss_workspace_bytes(int batch);
+int sessd_odiou_loss(const float *d_head, const float *d_anchors, const int *d_labels, const float *d_reg_targets, int batch,
+                     int num_anchors, int anchors_per_loc, int head_stride, float w_odiou, const float *d_losses, float *d_odiou_sum,
+                     float *d_grad_head, void *workspace, size_t workspace_bytes, void *stream);
+/* HOST evaluation of the identical arithmetic for n (target, prediction) box pairs [n,7]: odiou values [n] and d(odiou)/d(prediction)
+ * [n,7] (nullable).  Used to pin the kernel's math to the reference's odiou_3D on the CPU; not a fallback of the device path. */
+int sessd_odiou_pairs_host(const float *h_gboxes, const float *h_qboxes, int n, float *h_odiou, float *h_grad_q);
 size_t sessd_iou_pred_loss_workspace_bytes(int batch);
 int sessd_iou_pred_loss(const float *d_head, const float *d_anchors, const int *d_labels, const float *d_reg_targets, int batch,
                         int num_anchors, int anchors_per_loc, int head_stride, float sigma, float w_iou, float *d_losses,

@@ -17,7 +17,7 @@ OUT = os.path.join(HERE, "libsessd_b200.so")
 OBJ = os.path.join(HERE, "build")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
-NO_FMA = {"iou3d.cu", "postproc.cu", "assign.cu"}
+NO_FMA = {"iou3d.cu", "postproc.cu", "assign.cu", "odiou.cu"}
 
 
 def sources():

@@ -92,6 +92,9 @@ SIGNATURES = {
     "sessd_nms_sorted": (_i, [_vp, _i, _f, _i, _vp, _vp, _vp, _sz, _vp]),
     "sessd_head_loss_workspace_bytes": (_sz, [_i]),
     "sessd_head_loss": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp, _sz, _vp]),
+    "sessd_odiou_loss_workspace_bytes": (_sz, [_i]),
+    "sessd_odiou_loss": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "sessd_odiou_pairs_host": (_i, [_vp, _vp, _i, _vp, _vp]),
     "sessd_iou_pred_loss_workspace_bytes": (_sz, [_i]),
     "sessd_iou_pred_loss": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _sz, _vp]),
     "sessd_assign_workspace_bytes": (_sz, [_i, _i, _i]),

@@ -464,3 +464,26 @@ def head_loss(head, anchors, labels, reg_targets, alpha=0.25, sigma=3.0, dir_off
         check(lib.sessd_iou_pred_loss(_p(head), _p(anchors), _p(labels), _p(reg_targets), int(B), int(A), 2, int(head.shape[2]), float(sigma),
                                       float(w_iou), _p(losses), _p(grad), _p(ws2), ws2.numel(), _st()), "sessd_iou_pred_loss")
     return losses, grad
+
+
+def odiou_pairs_host(gboxes, qboxes, with_grad=True):
+    """HOST evaluation (numpy in / out) of the ODIoU arithmetic the device kernel uses: (odiou [n], d odiou / d qboxes [n,7])."""
+    g = np.ascontiguousarray(gboxes, np.float32).reshape(-1, 7)
+    q = np.ascontiguousarray(qboxes, np.float32).reshape(-1, 7)
+    assert g.shape == q.shape
+    out = np.zeros((g.shape[0],), np.float32)
+    grad = np.zeros_like(q) if with_grad else None
+    check(lib.sessd_odiou_pairs_host(g.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), int(g.shape[0]), out.ctypes.data_as(C.c_void_p),
+                                     grad.ctypes.data_as(C.c_void_p) if with_grad else C.c_void_p(0)), "sessd_odiou_pairs_host")
+    return out, grad
+
+
+def odiou_loss(head, anchors, labels, reg_targets, losses, grad_head=None, w_odiou=2.0):
+    """ODIoU term on the device; `losses` / `grad_head` are the outputs of head_loss() on the same stream (grad_head is updated in place).
+    Returns the per-frame sums [B] of odiou / num_pos over the positives."""
+    B, A = labels.shape
+    out = torch.empty((B,), dtype=torch.float32, device=head.device)
+    ws = torch.empty((lib.sessd_odiou_loss_workspace_bytes(int(B)),), dtype=torch.uint8, device=head.device)
+    check(lib.sessd_odiou_loss(_p(head), _p(anchors), _p(labels), _p(reg_targets), int(B), int(A), 2, int(head.shape[2]), float(w_odiou),
+                               _p(losses), _p(out), _p(grad_head), _p(ws), ws.numel(), _st()), "sessd_odiou_loss")
+    return out

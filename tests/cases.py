@@ -102,3 +102,23 @@ def head_loss_case():
     head = torch.randn(2, 35200, 24, generator=g) * 0.5
     head[..., 14:16] -= 2.0                       # mostly-negative classification logits, like an early training step
     return head.numpy(), anc, np.stack(labels, 0).astype(np.int32), np.stack(targets, 0).astype(np.float32)
+
+
+def odiou_pairs():
+    """(gboxes, qboxes) [n,7] for the ODIoU loss: predictions = targets + noise at three scales, plus disjoint / contained / identical /
+    perpendicular / zero-height-overlap pairs."""
+    rng = np.random.default_rng(91)
+    g, _ = synth.random_boxes(92, 48)
+    q = g.copy()
+    for k, s in enumerate((0.02, 0.1, 0.4)):
+        sl = slice(16 * k, 16 * (k + 1))
+        q[sl] += rng.normal(0, 1, (16, 7)).astype(np.float32) * np.float32([s, s, 0.3 * s, 0.3 * s, 0.5 * s, 0.3 * s, s])
+    extra_g = np.float32([[10, 0, -1, 1.6, 3.9, 1.5, 0.3]] * 6)
+    extra_q = extra_g.copy()
+    extra_q[0, :2] += np.float32([8.0, 6.0])                      # disjoint
+    extra_q[1, 3:6] *= np.float32(0.5)                            # contained
+    extra_q[2] = extra_g[2]                                       # identical
+    extra_q[3, 6] += np.float32(np.pi / 2)                        # perpendicular
+    extra_q[4, 2] += np.float32(3.0)                              # no height overlap
+    extra_q[5, :2] += np.float32([0.4, -1.1]); extra_q[5, 6] -= np.float32(2.5)
+    return np.concatenate([g, extra_g], 0), np.concatenate([q, extra_q], 0)

@@ -32,7 +32,7 @@ from sessd_b200 import synth  # noqa: E402
 from oracle import bev_ref, build as obuild, cpu as ocpu  # noqa: E402
 
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from cases import assign_cases, head_loss_case, iou_inputs, kitti_wire_case, sha, voxel_cases  # noqa: E402  (seeded inputs shared with the tests)
+from cases import assign_cases, head_loss_case, iou_inputs, kitti_wire_case, odiou_pairs, sha, voxel_cases  # noqa: E402  (seeded inputs shared with the tests)
 
 
 def _pkg(name):
@@ -258,6 +258,23 @@ def gen_loss():
     print("loss: cls", cl.sum((1, 2)).tolist(), "loc", loc.sum((1, 2)).tolist(), "dir", dl.sum(1).tolist(), "total", float(total))
 
 
+def gen_odiou():
+    """ODIoU loss of the REFERENCE (det3d/models/losses/odious.py, imported where it lies; runs on the CPU): per-pair value and the gradient
+    w.r.t. the predicted box through the reference's own custom autograd Functions."""
+    od = _load("odious_ref", "det3d/models/losses/odious.py")
+    g, q = odiou_pairs()
+    vals, grads = [], []
+    for i in range(len(g)):
+        gi = torch.from_numpy(g[i:i + 1].copy())
+        qi = torch.from_numpy(q[i:i + 1].copy()).requires_grad_(True)
+        loss = od.odiou_3D()(gi, qi, torch.ones(1), 2)            # = 2.0 * odiou / 2
+        loss.backward()
+        vals.append(float(loss.detach()))
+        grads.append(qi.grad.numpy()[0].copy())
+    np.savez_compressed(os.path.join(HERE, "odiou_case.npz"), odiou=np.float32(vals), grad_q=np.stack(grads, 0).astype(np.float32))
+    print("odiou:", np.round(np.float32(vals), 4).tolist()[:8], "...", np.round(np.float32(vals)[-6:], 4).tolist())
+
+
 def gen_models():
     import logging
 
@@ -308,6 +325,8 @@ if __name__ == "__main__":
     install_det3d_shims()
     if not only or "assign" in only:
         gen_anchors_assign()
+    if not only or "odiou" in only:
+        gen_odiou()
     if not only or "loss" in only:
         gen_loss()
     if not only or "wire" in only:
