@@ -106,8 +106,8 @@ SESSD_HD T od_inter_area(const Pt<T> clip[4], const Pt<T> subj[4]) {
             const T cs = ex * (s.y - p0.y) - ey * (s.x - p0.x);
             const T ct = ex * (t.y - p0.y) - ey * (t.x - p0.x);
             const bool ins = val(cs) <= 0.f, int_ = val(ct) <= 0.f;
-            if (ins) b[nb++] = s;
-            if (ins != int_) {
+            if (ins && nb < 10) b[nb++] = s;
+            if (ins != int_ && nb < 10) {      // (rect n rect has <= 8 vertices; the bound only matters for non-finite input)
                 const T u = cs / (cs - ct);                   // s + u (t - s) lies on the clip edge
                 Pt<T> m;
                 m.x = s.x + u * (t.x - s.x);

@@ -124,7 +124,7 @@ class MultiGroupHead(nn.Module):
         raise NotImplementedError("MultiGroupHead.loss: the SE-SSD training step (consistency + ODIoU losses) is a 'next' row; the "
                                   "supervised terms (focal cls, sin-difference smooth-L1, direction CE) are available as loss_supervised()")
 
-    def loss_supervised(self, example, preds_dicts, with_grad=True):
+    def loss_supervised(self, example, preds_dicts, with_grad=True, with_odiou=False):
         """Supervised terms of ``loss`` (reference mg_head_sessd.py:706-768 without the teacher / ODIoU parts) for the
         single-task car head, value and gradient w.r.t. the fused head tensor in one device pass (csrc/headloss.cu).
         ``example``: ``anchors`` [[B,A,7]], ``labels`` [[B,A]], ``reg_targets`` [[B,A,7]] (device tensors, e.g. from
@@ -143,9 +143,12 @@ class MultiGroupHead(nn.Module):
                                      neg_cls_weight=float(self.loss_norm["neg_cls_weight"]), w_cls=w_cls, w_loc=0.0, w_dir=w_dir,
                                      w_iou=1.0, with_grad=with_grad)
         tot = losses.sum(0) / b
+        ious_loss = None
+        if with_odiou:          # ODIoU box loss (odious.py:845-900): 2.0 * batch total / batch_size, gradient added to the box channels
+            ious_loss = 2.0 * ops.odiou_loss(head, anchors, labels, reg_targets, losses, grad, w_odiou=2.0).sum() / b
         return dict(cls_loss_reduced=w_cls * tot[0], loc_loss_reduced=float(self.loss_reg._loss_weight) * tot[1], dir_loss_reduced=w_dir * tot[2],
                     cls_pos_loss=tot[3] / float(self.loss_norm["pos_cls_weight"]), cls_neg_loss=tot[4] / float(self.loss_norm["neg_cls_weight"]),
-                    iou_pred_loss=tot[5], num_pos=losses[0, 6], num_neg=losses[0, 7], grad_head=None if grad is None else grad.view_as(packed))
+                    iou_pred_loss=tot[5], ious_loss=ious_loss, num_pos=losses[0, 6], num_neg=losses[0, 7], grad_head=None if grad is None else grad.view_as(packed))
 
     # ------------------------------------------------------------------------------------------------------------------
     def predict(self, example, preds_dicts, test_cfg, **kwargs):
