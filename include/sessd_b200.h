@@ -271,6 +271,16 @@ int sessd_postprocess(const float *d_head, const float *d_anchors, const float *
                       const sessd_post_cfg *cfg, float *d_boxes, float *d_scores, int *d_labels, int *d_count,
                       int *d_aux, int *d_sel_anchor, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Same as sessd_postprocess, plus a packed copy of the results for ONE device->host transfer per batch (the reference moves boxes,
+ * scores and labels to the host separately and syncs twice per frame: box_torch_ops.py:536, mg_head_sessd.py:1026):
+ * d_packed [batch, post_max, 8] = box 7 | score; d_meta [batch, 8 + post_max] i32 = count, candidates, pre-NMS count,
+ * NMS-selected count, d_num_voxels[b] (0 if null), *d_status (0 if null), 0, 0, then the anchor index of every returned
+ * detection (-1 beyond count). */
+int sessd_postprocess_packed(const float *d_head, const float *d_anchors, const float *d_frustum,
+                             const sessd_post_cfg *cfg, float *d_boxes, float *d_scores, int *d_labels, int *d_count,
+                             int *d_aux, int *d_sel_anchor, float *d_packed, int *d_meta, const int *d_num_voxels,
+                             const int *d_status, void *workspace, size_t workspace_bytes, void *stream);
+
 /* stand-alone rotated NMS on [n,5] (x,y,w,l,r) + scores: box_torch_ops.rotate_nms semantics
  * (top-k pre_max by score, greedy, keep <= post_max); d_keep [post_max] i32 indices into the input */
 size_t sessd_rotate_nms_workspace_bytes(int max_boxes, int pre_max);

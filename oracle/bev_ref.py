@@ -164,22 +164,25 @@ def predict_frame(box_enc, cls_logit, dir_logit, iou_pred, anchors, score_thresh
     aux = dict(n_candidates=int(keep.sum()))
     if scores.shape[0] == 0:
         out = (torch.zeros([0, 7]), torch.zeros([0]), torch.zeros([0], dtype=torch.long))
+        aux["final_anchor"] = torch.zeros([0], dtype=torch.long)
         return out + (aux,) if return_aux else out
     b = boxes[keep]
     d = dir_labels[keep]
     sel = rotate_nms(b[:, [0, 1, 3, 4, 6]], scores, nms_pre, nms_post, nms_thr)
     aux["nms_selected_anchor"] = torch.nonzero(keep).view(-1)[sel]
+    fin = aux["nms_selected_anchor"]
     b, d, s = b[sel], d[sel], scores[sel]
     if frustum_surfaces is not None and b.shape[0] > 0:
         ok = points_in_frustum(b[:, :3].numpy(), frustum_surfaces)
         ok = torch.from_numpy(ok)
-        b, d, s = b[ok], d[ok], s[ok]
+        b, d, s, fin = b[ok], d[ok], s[ok], fin[ok]
     if b.shape[0] > 0:
         opp = ((b[:, -1] - direction_offset) > 0) ^ (d.byte() == 1)
         b = b.clone()
         b[:, -1] += torch.where(opp, torch.tensor(np.pi).type_as(b), torch.tensor(0.0).type_as(b))
     pr = torch.tensor(post_range, dtype=b.dtype)
     m = (b[:, :3] >= pr[:3]).all(1) & (b[:, :3] <= pr[3:]).all(1)
+    aux["final_anchor"] = fin[m]        # anchor index of every returned detection (bench.py matches detections by it)
     out = (b[m], s[m], torch.zeros(int(m.sum()), dtype=torch.long))
     return out + (aux,) if return_aux else out
 

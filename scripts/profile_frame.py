@@ -16,9 +16,8 @@ ap.add_argument("--simt", action="store_true")
 a = ap.parse_args()
 mk = synth.ring_cloud if a.cloud == "ring" else synth.uniform_cloud
 eng = FrameEngine(batch=1, max_points_per_frame=20000, use_tc=not a.simt)
-layers, ssfa, head = weights.split_detector_state(weights.random_detector_state(0, cls_bias=-3.0))
+layers, ssfa, head = weights.bench_detector_state(a.cloud, 0)
 eng.load_weights(layers, ssfa, head, weights.kitti_car_anchors())
-eng.calibrate_cls_bias([mk(0, 20000)], 400)
 for i in range(3):
     eng.infer([mk(i, 20000)])
 torch.cuda.synchronize()

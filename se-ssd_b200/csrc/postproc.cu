@@ -314,10 +314,20 @@ __device__ int greedy_scan(const unsigned long long *__restrict__ mask, int m, i
     return s_misc[0];
 }
 
+// optional packed copy of the results for ONE device->host transfer per batch (FrameEngine): packed [B, P, 8] = box 7 | score,
+// meta [B, 8 + P] = count, candidates, pre-NMS count, NMS-selected count, voxels of the frame, capacity status, 0, 0,
+// then the anchor index of every returned detection (-1 beyond count)
+struct PostPack {
+    float *packed;
+    int *meta;
+    const int *num_voxels;     // [B] nullable
+    const int *status;         // [1] nullable
+};
+
 __global__ void __launch_bounds__(256) post_finalize_kernel(PostWs w, sessd_post_cfg cfg, const float *__restrict__ frustum,
                                                             float *__restrict__ out_boxes, float *__restrict__ out_scores,
                                                             int *__restrict__ out_labels, int *__restrict__ out_count,
-                                                            int *__restrict__ out_aux, int *__restrict__ out_sel_anchor) {
+                                                            int *__restrict__ out_aux, int *__restrict__ out_sel_anchor, PostPack pk) {
     extern __shared__ unsigned long long dyn[];
     const int K = cfg.nms_pre_max, P = cfg.nms_post_max;
     const int col_blocks = (K + 63) / 64;
@@ -364,6 +374,13 @@ __global__ void __launch_bounds__(256) post_finalize_kernel(PostWs w, sessd_post
         out_aux[b * 4 + 2] = nk;
         out_aux[b * 4 + 3] = 0;
         s_misc[1] = c;
+        if (pk.meta) {
+            int *mt = pk.meta + (size_t)b * (8 + P);
+            mt[0] = c; mt[1] = n; mt[2] = m; mt[3] = nk;
+            mt[4] = pk.num_voxels ? pk.num_voxels[b] : 0;
+            mt[5] = pk.status ? *pk.status : 0;
+            mt[6] = 0; mt[7] = 0;
+        }
     }
     __syncthreads();
     const int total = s_misc[1];
@@ -380,6 +397,14 @@ __global__ void __launch_bounds__(256) post_finalize_kernel(PostWs w, sessd_post
             ob[6] = r;
             out_scores[(size_t)b * P + dst] = w.sscore[src];
             out_labels[(size_t)b * P + dst] = 0;
+            if (pk.packed) {
+                float *pp = pk.packed + ((size_t)b * P + dst) * 8;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) pp[j] = ob[j];
+                pp[6] = r;
+                pp[7] = w.sscore[src];
+                pk.meta[(size_t)b * (8 + P) + 8 + dst] = key_index(w.sel[src]);
+            }
         }
     }
     for (int t = total + threadIdx.x; t < P; t += blockDim.x) {
@@ -387,6 +412,11 @@ __global__ void __launch_bounds__(256) post_finalize_kernel(PostWs w, sessd_post
         for (int j = 0; j < 7; ++j) ob[j] = 0.f;
         out_scores[(size_t)b * P + t] = 0.f;
         out_labels[(size_t)b * P + t] = -1;
+        if (pk.packed) {
+            float *pp = pk.packed + ((size_t)b * P + t) * 8;
+            for (int j = 0; j < 8; ++j) pp[j] = 0.f;
+            pk.meta[(size_t)b * (8 + P) + 8 + t] = -1;
+        }
     }
 }
 
@@ -418,9 +448,9 @@ static size_t finalize_smem(int K, int P) {
     return sizeof(unsigned long long) * (cb + 64) + sizeof(int) * (2 * (size_t)P + 8);
 }
 
-extern "C" int sessd_postprocess(const float *d_head, const float *d_anchors, const float *d_frustum,
-                                 const sessd_post_cfg *cfg, float *d_boxes, float *d_scores, int *d_labels, int *d_count,
-                                 int *d_aux, int *d_sel_anchor, void *workspace, size_t workspace_bytes, void *stream) {
+static int postprocess_impl(const float *d_head, const float *d_anchors, const float *d_frustum,
+                            const sessd_post_cfg *cfg, float *d_boxes, float *d_scores, int *d_labels, int *d_count,
+                            int *d_aux, int *d_sel_anchor, PostPack pk, void *workspace, size_t workspace_bytes, void *stream) {
     if (!cfg || !d_head || !d_anchors || !d_boxes || !d_scores || !d_labels || !d_count || !d_aux || !d_sel_anchor)
         return SESSD_EINVAL;
     if (cfg->batch < 1 || cfg->num_anchors < 1 || cfg->anchors_per_loc < 1 || cfg->num_anchors % cfg->anchors_per_loc ||
@@ -443,8 +473,26 @@ extern "C" int sessd_postprocess(const float *d_head, const float *d_anchors, co
     SESSD_LAUNCH(post_mask_kernel, g4, kMaskThreads, 0, st, w, K, cfg->nms_iou_thresh, cfg->nms_ge);
     const size_t sm = finalize_smem(K, P);
     if (sm > 48 * 1024) SESSD_CUDA_TRY(cudaFuncSetAttribute(post_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    SESSD_LAUNCH(post_finalize_kernel, B, 256, sm, st, w, *cfg, d_frustum, d_boxes, d_scores, d_labels, d_count, d_aux, d_sel_anchor);
+    SESSD_LAUNCH(post_finalize_kernel, B, 256, sm, st, w, *cfg, d_frustum, d_boxes, d_scores, d_labels, d_count, d_aux, d_sel_anchor, pk);
     return last_error();
+}
+
+extern "C" int sessd_postprocess(const float *d_head, const float *d_anchors, const float *d_frustum,
+                                 const sessd_post_cfg *cfg, float *d_boxes, float *d_scores, int *d_labels, int *d_count,
+                                 int *d_aux, int *d_sel_anchor, void *workspace, size_t workspace_bytes, void *stream) {
+    PostPack pk = {nullptr, nullptr, nullptr, nullptr};
+    return postprocess_impl(d_head, d_anchors, d_frustum, cfg, d_boxes, d_scores, d_labels, d_count, d_aux, d_sel_anchor, pk, workspace,
+                            workspace_bytes, stream);
+}
+
+extern "C" int sessd_postprocess_packed(const float *d_head, const float *d_anchors, const float *d_frustum,
+                                        const sessd_post_cfg *cfg, float *d_boxes, float *d_scores, int *d_labels, int *d_count,
+                                        int *d_aux, int *d_sel_anchor, float *d_packed, int *d_meta, const int *d_num_voxels,
+                                        const int *d_status, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!d_packed || !d_meta) return SESSD_EINVAL;
+    PostPack pk = {d_packed, d_meta, d_num_voxels, d_status};
+    return postprocess_impl(d_head, d_anchors, d_frustum, cfg, d_boxes, d_scores, d_labels, d_count, d_aux, d_sel_anchor, pk, workspace,
+                            workspace_bytes, stream);
 }
 
 extern "C" size_t sessd_rotate_nms_workspace_bytes(int max_boxes, int pre_max) {

@@ -11,6 +11,28 @@ from det3d.core.input.voxel_generator import VoxelGenerator
 from ..registry import PIPELINES
 
 
+def _dict_select(dict_, inds):
+    """reference preprocess.py:22-27"""
+    for k, v in dict_.items():
+        if isinstance(v, dict):
+            _dict_select(v, inds)
+        else:
+            dict_[k] = v[inds]
+
+
+def filter_gt_box_outside_range(gt_boxes, limit_range):
+    """Mask of the GT boxes that have at least one BEV corner STRICTLY inside the rectangle limit_range = [x0, y0, x1, y1]
+    (reference det3d/core/sampler/preprocess.py:138-148: center_to_corner_box2d + points_in_convex_polygon_jit, whose test
+    `cross >= 0 -> outside` makes points on the boundary count as outside)."""
+    gt_boxes = np.asarray(gt_boxes)
+    if gt_boxes.shape[0] == 0:
+        return np.zeros((0,), dtype=np.bool_)
+    corners = box_np_ops.center_to_corner_box2d(gt_boxes[:, [0, 1]], gt_boxes[:, [3, 4]], gt_boxes[:, -1])      # [N, 4, 2]
+    x0, y0, x1, y1 = [float(v) for v in limit_range]
+    inside = (corners[..., 0] > x0) & (corners[..., 0] < x1) & (corners[..., 1] > y0) & (corners[..., 1] < y1)
+    return inside.any(axis=1)
+
+
 @PIPELINES.register_module
 class Voxelization(object):
     def __init__(self, **kwargs):
@@ -27,6 +49,12 @@ class Voxelization(object):
                     num_voxels=np.array([voxels.shape[0]], dtype=np.int64), shape=self.voxel_generator.grid_size)
 
     def __call__(self, res, info):
+        if res.get("mode") == "train" and res.get("labeled", False):
+            # reference :199-205: drop the GT boxes with no BEV corner inside the point-cloud range BEFORE target assignment
+            gt = res["lidar"]["annotations"]
+            pc_range = np.asarray(self.voxel_generator.point_cloud_range)
+            _dict_select(gt, filter_gt_box_outside_range(gt["gt_boxes"], pc_range[[0, 1, 3, 4]]))
+            res["lidar"]["annotations"] = gt
         res["lidar"]["voxels"] = self._pack(res["lidar"]["points"])
         if "points_raw" in res["lidar"]:                      # SE-SSD teacher branch: un-augmented copy (:218-230)
             res["lidar"]["voxels_raw"] = self._pack(res["lidar"]["points_raw"])

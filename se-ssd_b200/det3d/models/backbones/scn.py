@@ -39,15 +39,18 @@ class SpMiddleFHD(nn.Module):
         self._weights_key = None
 
     def init_weights(self, pretrained=None):
-        if pretrained is not None:
-            raise NotImplementedError("load checkpoints with load_state_dict (the torchie checkpoint loader is out of scope)")
+        if isinstance(pretrained, str):       # reference convention (e.g. rpn.py / resnet): a checkpoint path
+            from det3d.torchie.trainer.checkpoint import load_checkpoint
+            load_checkpoint(self, pretrained, strict=False)
+        elif pretrained is not None:
+            raise TypeError("pretrained must be a str or None")
 
     def _layers(self):
         out = []
         for i in range(len(SPMIDDLE_LAYERS)):
             conv, bn = self.middle_conv[3 * i], self.middle_conv[3 * i + 1]
             out.append(dict(weight=conv.weight.detach(), gamma=bn.weight.detach(), beta=bn.bias.detach(),
-                            mean=bn.running_mean, var=bn.running_var))
+                            mean=bn.running_mean, var=bn.running_var, eps=float(bn.eps)))
         return out
 
     def forward(self, voxel_features, coors, batch_size, input_shape):
@@ -70,4 +73,5 @@ class SpMiddleFHD(nn.Module):
         dense = self._runner.forward(feats, coors, n_dev)                 # NHWC [B, 200, 176, 128]
         if int(self._runner.status.item()) != 0:
             raise RuntimeError("SpMiddleFHD: active-site capacity exceeded")
-        return dense.permute(0, 3, 1, 2)                                  # logical NCHW, channels-last memory
+        # logical NCHW, channels-last memory; a fresh tensor per call (the runner's dense buffer is overwritten by the next forward)
+        return dense.permute(0, 3, 1, 2).clone()

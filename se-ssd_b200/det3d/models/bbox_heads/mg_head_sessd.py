@@ -52,7 +52,9 @@ class Head(nn.Module):
         return self._runner.forward(x.detach().float().permute(0, 2, 3, 1).contiguous())
 
     def forward(self, x):
-        packed = self.packed_forward(x)
+        # a fresh tensor per call (like the reference): the runner's output buffer is overwritten by the next forward, and the SE-SSD
+        # teacher / student flow runs two forwards before either result is consumed
+        packed = self.packed_forward(x).clone()
         ret = {"box_preds": packed[..., 0:14].contiguous(), "cls_preds": packed[..., 14:16].contiguous()}
         if self.use_dir:
             ret["dir_cls_preds"] = packed[..., 16:20].contiguous()
@@ -109,8 +111,12 @@ class MultiGroupHead(nn.Module):
         self._post_key = None
 
     def init_weights(self, pretrained=None):
+        if isinstance(pretrained, str):
+            from det3d.torchie.trainer.checkpoint import load_checkpoint
+            load_checkpoint(self, pretrained, strict=False)
+            return
         if pretrained is not None:
-            raise NotImplementedError("load checkpoints with load_state_dict")
+            raise TypeError("pretrained must be a str or None")
         for m in self.modules():
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")

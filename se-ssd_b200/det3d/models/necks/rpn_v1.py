@@ -69,8 +69,10 @@ class SSFA(nn.Module):
             self._runner_key, self._weights_key = key, None
         wkey = tuple((p.data_ptr(), p._version) for p in self.parameters()) + tuple((t.data_ptr(), t._version) for t in self.buffers())
         if wkey != self._weights_key:
-            self._runner.load_state({k: v.detach() for k, v in self.state_dict().items()})
+            eps = {float(m.eps) for m in self.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm)}
+            assert len(eps) == 1, "SSFA: all BatchNorm layers must share one eps"
+            self._runner.load_state({k: v.detach() for k, v in self.state_dict().items()}, bn_eps=eps.pop())
             self._weights_key = wkey
         x_nhwc = x.detach().float().permute(0, 2, 3, 1).contiguous()     # no copy when x is channels-last already
         out, _ = self._runner.forward(x_nhwc)
-        return out.permute(0, 3, 1, 2)
+        return out.permute(0, 3, 1, 2).clone()        # fresh tensor per call: the runner buffer is overwritten by the next forward

@@ -36,12 +36,19 @@ def load_state_dict(module, state_dict, strict=False, logger=None):
     return msgs
 
 
-def load_checkpoint(model, filename, map_location=None, strict=False, logger=None):
+def load_checkpoint(model, filename, map_location=None, strict=False, logger=None, trusted=False):
+    """trusted: the wire format is tensors + plain containers, so the file is read with ``weights_only=True`` (no arbitrary pickle
+    execution from a downloaded checkpoint); pass trusted=True to fall back to the full unpickler for a file you wrote yourself."""
     if "://" in filename:
         raise NotImplementedError("only local checkpoint files are supported (no network on the target boxes)")
     if not osp.isfile(filename):
         raise IOError("{} is not a checkpoint file".format(filename))
-    checkpoint = torch.load(filename, map_location=map_location, weights_only=False)
+    try:
+        checkpoint = torch.load(filename, map_location=map_location, weights_only=True)
+    except Exception:
+        if not trusted:
+            raise
+        checkpoint = torch.load(filename, map_location=map_location, weights_only=False)
     if isinstance(checkpoint, OrderedDict):
         state_dict = checkpoint
     elif isinstance(checkpoint, dict) and "state_dict" in checkpoint:

@@ -37,12 +37,12 @@ class FrameEngine:
         self.pcfg = ops.make_post_cfg(**pk)
         self.post = ops.PostBuffers(self.pcfg, dev)
         P = self.pcfg.nms_post_max
-        # packed result block: per frame [count, n_candidates, status, pad] + boxes + scores
-        self.res_floats = self.batch * (P * 8)
+        # packed result block (written by post_finalize_kernel): [B,P,8] = box 7 | score; meta [B, 8+P] = count, candidates, pre-NMS,
+        # NMS-selected, voxels, capacity status, 0, 0, anchor index of every returned detection
         self.d_result = torch.zeros((self.batch, P, 8), dtype=torch.float32, device=dev)
         self.h_result = torch.zeros((self.batch, P, 8), dtype=torch.float32).pin_memory()
-        self.d_meta = torch.zeros((self.batch, 8), dtype=torch.int32, device=dev)
-        self.h_meta = torch.zeros((self.batch, 8), dtype=torch.int32).pin_memory()
+        self.d_meta = torch.zeros((self.batch, 8 + P), dtype=torch.int32, device=dev)
+        self.h_meta = torch.zeros((self.batch, 8 + P), dtype=torch.int32).pin_memory()
         self.frustum = None
         self.graph = None
         self.graph_dev = None
@@ -56,22 +56,6 @@ class FrameEngine:
         assert self.anchors.shape[0] == self.pcfg.num_anchors
         self.graph = None
 
-    def calibrate_cls_bias(self, clouds, target_candidates=400):
-        """Random-init weights put ~0 % or ~50 % of the anchors over the 0.3 score threshold.  Shift the classification
-        bias so that ~`target_candidates` anchors per frame pass, which is what a trained SE-SSD produces on a KITTI frame
-        (hundreds of candidates, tens of detections).  Returns the shift; deterministic for a given seed / cloud."""
-        import math
-        self.stage(clouds)
-        with torch.cuda.stream(self.stream):
-            self._step_body()
-        self.stream.synchronize()
-        logits = self.neck.buf["head"][..., 14:16].reshape(-1)
-        k = min(int(target_candidates) * self.batch, logits.numel() - 1)
-        kth = torch.topk(logits, k + 1).values[-2:].mean()
-        shift = float(math.log(self.pcfg.score_thresh / (1.0 - self.pcfg.score_thresh)) - kth.item())
-        self.neck.params["head"][1][14:16] += shift
-        return shift
-
     # ---------------------------------------------------------------------------------------------- device pipeline
     def _device_pipeline(self):
         """All launches of one batch of frames on the current stream (capturable)."""
@@ -79,14 +63,8 @@ class FrameEngine:
         n0 = self.vox.num_voxels[self.batch:self.batch + 1]
         dense = self.middle.forward(self.vox.mean, self.vox.coors, n0)
         _, head = self.neck.forward(dense)
-        ops.postprocess(head, self.anchors, self.frustum, self.post)
-        # pack results for a single D2H
-        self.d_result[:, :, :7].copy_(self.post.boxes)
-        self.d_result[:, :, 7].copy_(self.post.scores)
-        self.d_meta[:, 0].copy_(self.post.count)
-        self.d_meta[:, 1:5].copy_(self.post.aux)
-        self.d_meta[:, 5].copy_(self.vox.num_voxels[:self.batch])
-        self.d_meta[:, 6].copy_(self.middle.status.expand(self.batch))
+        ops.postprocess_packed(head, self.anchors, self.frustum, self.post, self.d_result, self.d_meta,
+                               self.vox.num_voxels[:self.batch], self.middle.status)
 
     def _step_body(self):
         self.d_points.copy_(self.h_points, non_blocking=True)
@@ -147,14 +125,15 @@ class FrameEngine:
         """Synchronise and unpack: list of dict(box3d_lidar [K,7], scores [K], label_preds [K])."""
         self.stream.synchronize()
         meta = self.h_meta.numpy()
-        if int(meta[:, 6].max()) != 0:
-            raise RuntimeError("sparse active-site capacity exceeded (status=%d); raise `growth`" % int(meta[:, 6].max()))
+        if int(meta[:, 5].max()) != 0:
+            raise RuntimeError("sparse active-site capacity exceeded (status=%d); raise `growth`" % int(meta[:, 5].max()))
         out = []
         res = self.h_result.numpy()
         for f in range(self.batch):
             k = int(meta[f, 0])
             out.append(dict(box3d_lidar=res[f, :k, :7].copy(), scores=res[f, :k, 7].copy(),
-                            label_preds=np.zeros((k,), np.int64), num_voxels=int(meta[f, 5]), num_candidates=int(meta[f, 1])))
+                            label_preds=np.zeros((k,), np.int64), num_voxels=int(meta[f, 4]), num_candidates=int(meta[f, 1]),
+                            anchor_index=meta[f, 8:8 + k].astype(np.int64)))
         return out
 
     def infer(self, clouds):

@@ -374,6 +374,14 @@ def postprocess(head, anchors, frustum_planes, buf):
     return buf
 
 
+def postprocess_packed(head, anchors, frustum_planes, buf, packed, meta, num_voxels=None, status=None):
+    """postprocess + a packed copy [B,P,8] / meta [B,8+P] of the results (one D2H per batch; see sessd_postprocess_packed)."""
+    check(lib.sessd_postprocess_packed(_p(head), _p(anchors), _p(frustum_planes), C.byref(buf.cfg), _p(buf.boxes), _p(buf.scores),
+                                       _p(buf.labels), _p(buf.count), _p(buf.aux), _p(buf.sel_anchor), _p(packed), _p(meta),
+                                       _p(num_voxels), _p(status), _p(buf.ws), buf.ws.numel(), _st()), "sessd_postprocess_packed")
+    return buf
+
+
 def rotate_nms(boxes5, scores, n, max_boxes, pre_max, post_max, iou_thresh, ge=True):
     dev = boxes5.device
     keep = torch.empty((post_max,), dtype=torch.int32, device=dev)

@@ -7,29 +7,11 @@ Layer tables mirror det3d/models/backbones/scn.py:106-149 (SpMiddleFHD) and det3
 import math
 
 import torch
+from sessd_data.layers import SPMIDDLE_LAYERS  # (kind, cout, ksize, stride, padding, indice_key)   scn.py:106-149
 
 from . import ops
 
 BN_EPS = 1e-3   # norm_cfg eps of both BN1d (scn.py:103) and BN2d (rpn_v1.py:131)
-
-# (kind, cout, ksize, stride, padding, indice_key)   scn.py:106-149
-SPMIDDLE_LAYERS = [
-    ("subm", 16, (3, 3, 3), (1, 1, 1), (1, 1, 1), "subm0"),
-    ("subm", 16, (3, 3, 3), (1, 1, 1), (1, 1, 1), "subm0"),
-    ("spconv", 32, (3, 3, 3), (2, 2, 2), (1, 1, 1), None),
-    ("subm", 32, (3, 3, 3), (1, 1, 1), (1, 1, 1), "subm1"),
-    ("subm", 32, (3, 3, 3), (1, 1, 1), (1, 1, 1), "subm1"),
-    ("spconv", 64, (3, 3, 3), (2, 2, 2), (1, 1, 1), None),
-    ("subm", 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), "subm2"),
-    ("subm", 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), "subm2"),
-    ("subm", 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), "subm2"),
-    ("spconv", 64, (3, 3, 3), (2, 2, 2), (0, 1, 1), None),
-    ("subm", 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), "subm3"),
-    ("subm", 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), "subm3"),
-    ("subm", 64, (3, 3, 3), (1, 1, 1), (1, 1, 1), "subm3"),
-    ("spconv", 64, (3, 1, 1), (2, 1, 1), (0, 0, 0), None),
-]
-
 
 def conv_out_shape(shape, ksize, stride, padding):
     return tuple((int(i) + 2 * p - k) // s + 1 for i, k, s, p in zip(shape, ksize, stride, padding))
@@ -134,7 +116,7 @@ class SpMiddleRunner:
         for p, l in zip(self.plan, layers):
             w = torch.as_tensor(l["weight"], dtype=torch.float32, device=self.device)
             assert tuple(w.shape) == (*p["ks"], p["cin"], p["cout"]), (w.shape, p)
-            sc, sh = fold_bn(*[torch.as_tensor(l[k], device=self.device) for k in ("gamma", "beta", "mean", "var")])
+            sc, sh = fold_bn(*[torch.as_tensor(l[k], device=self.device) for k in ("gamma", "beta", "mean", "var")], eps=float(l.get("eps", BN_EPS)))
             wp = w.reshape(-1, p["cin"], p["cout"]).contiguous()
             tc = None
             if p["impl"] == "h2":
@@ -281,7 +263,8 @@ class SSFARunner:
                         o0=z(h, w, 128), o1=z(h, w, 128), out=z(h, w, 128), head=z(h, w, self.HEAD_STRIDE))
         self.params = None
 
-    def load_state(self, ssfa_sd, head_sd=None, head_prefix="tasks.0."):
+    def load_state(self, ssfa_sd, head_sd=None, head_prefix="tasks.0.", bn_eps=BN_EPS):
+        """bn_eps: eps of the neck's BatchNorm2d layers (rpn_v1.py:131-132 uses 1e-3; pass the module's own value otherwise)."""
         dev = self.device
         g = lambda k: ssfa_sd[k].to(dev, torch.float32)   # noqa: E731
         P = {}
@@ -289,7 +272,7 @@ class SSFARunner:
         def bn(conv_name):
             blk, idx = conv_name.rsplit(".", 1)
             b = "%s.%d" % (blk, int(idx) + 1)
-            return fold_bn(g(b + ".weight"), g(b + ".bias"), g(b + ".running_mean"), g(b + ".running_var"))
+            return fold_bn(g(b + ".weight"), g(b + ".bias"), g(b + ".running_mean"), g(b + ".running_var"), eps=bn_eps)
 
         for name, pad in (("bottom_up_block_0.1", 1), ("bottom_up_block_0.4", 1), ("bottom_up_block_0.7", 1),
                           ("bottom_up_block_1.0", 1), ("bottom_up_block_1.3", 1), ("bottom_up_block_1.6", 1),
@@ -358,35 +341,65 @@ class SSFARunner:
             ops.bev_conv(x, wp, sc, sh, residual, out, d)
         return out
 
-    def forward(self, x):
-        """x NHWC [B,200,176,128] -> (neck out NHWC [B,200,176,128], head NHWC [B,200,176,24])."""
+    def forward(self, x, mark=None):
+        """x NHWC [B,200,176,128] -> (neck out NHWC [B,200,176,128], head NHWC [B,200,176,24]).
+        mark: optional callable(label) invoked after every layer (profiling scripts record a CUDA event there)."""
         assert self.params is not None, "load_state first"
+        mark = mark or (lambda label: None)
         b = self.buf
         H, H2 = (self.h, self.w), (self.h // 2, self.w // 2)
+
+        def conv(name, *a, **kw):
+            self._conv(name, *a, **kw)
+            mark("neck:" + name)
+
+        def deconv(name, *a, **kw):
+            self._deconv(name, *a, **kw)
+            mark("neck:" + name)
+
         if self.use_h2:      # abs-max scalars: 0 x, 1 b0a, 2 b0b, 3 x0, 4 b1a, 5 b1b, 6 x1, 7 t1, 8 m0, 9 m1, 10 out
             self.amax.zero_()
             ops.absmax(x, self._am(0))
-        self._conv("bottom_up_block_0.1", x, b["b0a"], H, H, 128, 128, ai=0, ao=1)
-        self._conv("bottom_up_block_0.4", b["b0a"], b["b0b"], H, H, 128, 128, ai=1, ao=2)
-        self._conv("bottom_up_block_0.7", b["b0b"], b["x0"], H, H, 128, 128, ai=2, ao=3)
-        self._conv("bottom_up_block_1.0", b["x0"], b["b1a"], H, H2, 128, 256, stride=2, ai=3, ao=4)
-        self._conv("bottom_up_block_1.3", b["b1a"], b["b1b"], H2, H2, 256, 256, ai=4, ao=5)
-        self._conv("bottom_up_block_1.6", b["b1b"], b["x1"], H2, H2, 256, 256, ai=5, ao=6)
-        self._conv("trans_0.0", b["x0"], b["t0"], H, H, 128, 128, ai=3)
-        self._conv("trans_1.0", b["x1"], b["t1"], H2, H2, 256, 256, ai=6, ao=7)
-        self._deconv("deconv_block_0.0", b["t1"], b["m0"], H2, H, 256, 128, residual=b["t0"], ai=7, ao=8)
-        self._deconv("deconv_block_1.0", b["t1"], b["m1"], H2, H, 256, 128, ai=7, ao=9)
-        self._conv("conv_0.0", b["m0"], b["o0"], H, H, 128, 128, ai=8)
-        self._conv("conv_1.0", b["m1"], b["o1"], H, H, 128, 128, ai=9)
+        conv("bottom_up_block_0.1", x, b["b0a"], H, H, 128, 128, ai=0, ao=1)
+        conv("bottom_up_block_0.4", b["b0a"], b["b0b"], H, H, 128, 128, ai=1, ao=2)
+        conv("bottom_up_block_0.7", b["b0b"], b["x0"], H, H, 128, 128, ai=2, ao=3)
+        conv("bottom_up_block_1.0", b["x0"], b["b1a"], H, H2, 128, 256, stride=2, ai=3, ao=4)
+        conv("bottom_up_block_1.3", b["b1a"], b["b1b"], H2, H2, 256, 256, ai=4, ao=5)
+        conv("bottom_up_block_1.6", b["b1b"], b["x1"], H2, H2, 256, 256, ai=5, ao=6)
+        conv("trans_0.0", b["x0"], b["t0"], H, H, 128, 128, ai=3)
+        conv("trans_1.0", b["x1"], b["t1"], H2, H2, 256, 256, ai=6, ao=7)
+        deconv("deconv_block_0.0", b["t1"], b["m0"], H2, H, 256, 128, residual=b["t0"], ai=7, ao=8)
+        deconv("deconv_block_1.0", b["t1"], b["m1"], H2, H, 256, 128, ai=7, ao=9)
+        conv("conv_0.0", b["m0"], b["o0"], H, H, 128, 128, ai=8)
+        conv("conv_1.0", b["m1"], b["o1"], H, H, 128, 128, ai=9)
         w0, s0, t0 = self.params["w_0.0"]
         w1, s1, t1 = self.params["w_1.0"]
         ops.ssfa_fuse(b["o0"], b["o1"], w0, w1, s0, t0, s1, t1, b["out"])
         if self.use_h2 and "head" in self.params:
             ops.absmax(b["out"], self._am(10))
         if "head" not in self.params:
+            mark("neck:fuse+head")
             return b["out"], None
         self.head(b["out"])
+        mark("neck:fuse+head")
         return b["out"], b["head"]
+
+    def bench_layer(self, name="bottom_up_block_0.4"):
+        """(launch closure, kernel description) of one 3x3 128->128 layer on the buffers / abs-max slots a frame uses (valid after any
+        forward): what bench.py times alone for the `roofline` object."""
+        H = (self.h, self.w)
+        x, out = self.buf["x0"], self.buf["b0b"]
+
+        def launch():
+            self._conv(name, x, out, H, H, 128, 128, ai=3, ao=2)
+
+        if (name + ":h2") in self.params:
+            kern = "bev_conv_h2_kernel (tcgen05 kind::f16, two-term fp16 split)"
+        elif (name + ":tc") in self.params:
+            kern = "bev_conv_tc3_kernel (tcgen05 3xTF32)"
+        else:
+            kern = "bev_conv_kernel (fp32 SIMT)"
+        return launch, kern
 
     def head(self, x):
         hw, hb = self.params["head"]

@@ -1,88 +1,4 @@
-"""Seeded random-initialised parameters of the SE-SSD car model (no checkpoint is available offline) and the
-conversion of reference-style state dicts into the runner inputs.
-
-State-dict key names follow the reference modules (``backbone.middle_conv.{0,3,..}``, ``neck.bottom_up_block_0.1`` ...,
-``bbox_head.tasks.0.conv_box`` ...) so that a real SE-SSD checkpoint (det3d/torchie/trainer/checkpoint.py:117-171)
-can be fed through ``split_detector_state``.
-"""
-import math
-
-import numpy as np
-import torch
-
-from .runners import SPMIDDLE_LAYERS
-
-SSFA_CONVS = [  # name, kind, cin, cout, k     (rpn_v1.py:135-210)
-    ("bottom_up_block_0.1", "conv", 128, 128, 3), ("bottom_up_block_0.4", "conv", 128, 128, 3),
-    ("bottom_up_block_0.7", "conv", 128, 128, 3), ("bottom_up_block_1.0", "conv", 128, 256, 3),
-    ("bottom_up_block_1.3", "conv", 256, 256, 3), ("bottom_up_block_1.6", "conv", 256, 256, 3),
-    ("trans_0.0", "conv", 128, 128, 1), ("trans_1.0", "conv", 256, 256, 1),
-    ("deconv_block_0.0", "deconv", 256, 128, 3), ("deconv_block_1.0", "deconv", 256, 128, 3),
-    ("conv_0.0", "conv", 128, 128, 3), ("w_0.0", "conv", 128, 1, 1),
-    ("conv_1.0", "conv", 128, 128, 3), ("w_1.0", "conv", 128, 1, 1),
-]
-
-
-def _bn(g, c, prefix, sd):
-    sd[prefix + ".weight"] = 1.0 + 0.1 * torch.randn(c, generator=g)
-    sd[prefix + ".bias"] = 0.1 * torch.randn(c, generator=g)
-    sd[prefix + ".running_mean"] = 0.1 * torch.randn(c, generator=g)
-    sd[prefix + ".running_var"] = 1.0 + 0.2 * torch.rand(c, generator=g)
-    sd[prefix + ".num_batches_tracked"] = torch.tensor(0)
-
-
-def random_detector_state(seed=0, num_input_features=4, cls_bias=None):
-    """Full VoxelNet state dict with kaiming-style conv weights and non-trivial BN statistics.
-    ``cls_bias``: bias of the classification conv (e.g. -2.5 makes ~few % of anchors pass the 0.3 score threshold,
-    resembling a trained detector's candidate counts instead of random init's ~50 %)."""
-    g = torch.Generator().manual_seed(seed)
-    sd = {}
-    cin = num_input_features
-    for i, (_kind, cout, ks, _st, _pd, _key) in enumerate(SPMIDDLE_LAYERS):
-        fan_in = cin * ks[0] * ks[1] * ks[2]
-        sd["backbone.middle_conv.%d.weight" % (3 * i)] = torch.randn((*ks, cin, cout), generator=g) * math.sqrt(2.0 / fan_in)
-        _bn(g, cout, "backbone.middle_conv.%d" % (3 * i + 1), sd)
-        cin = cout
-    for name, kind, ci, co, k in SSFA_CONVS:
-        shape = (co, ci, k, k) if kind == "conv" else (ci, co, k, k)
-        sd["neck." + name + ".weight"] = torch.randn(shape, generator=g) * math.sqrt(2.0 / (ci * k * k))
-        blk, idx = name.rsplit(".", 1)
-        _bn(g, co, "neck.%s.%d" % (blk, int(idx) + 1), sd)
-    for nm, co in (("conv_box", 14), ("conv_cls", 2), ("conv_iou", 2), ("conv_dir", 4)):
-        sd["bbox_head.tasks.0.%s.weight" % nm] = torch.randn((co, 128, 1, 1), generator=g) * math.sqrt(1.0 / 128)
-        sd["bbox_head.tasks.0.%s.bias" % nm] = 0.1 * torch.randn(co, generator=g)
-    if cls_bias is not None:
-        sd["bbox_head.tasks.0.conv_cls.bias"] = torch.full((2,), float(cls_bias))
-    return sd
-
-
-def split_detector_state(sd):
-    """-> (middle_layers for SpMiddleRunner.load_weights, ssfa_state, head_state) from a VoxelNet state dict."""
-    layers = []
-    for i in range(len(SPMIDDLE_LAYERS)):
-        c, b = "backbone.middle_conv.%d" % (3 * i), "backbone.middle_conv.%d" % (3 * i + 1)
-        layers.append(dict(weight=sd[c + ".weight"], gamma=sd[b + ".weight"], beta=sd[b + ".bias"],
-                           mean=sd[b + ".running_mean"], var=sd[b + ".running_var"]))
-    ssfa = {k[len("neck."):]: v for k, v in sd.items() if k.startswith("neck.")}
-    head = {k[len("bbox_head."):]: v for k, v in sd.items() if k.startswith("bbox_head.")}
-    return layers, ssfa, head
-
-
-def kitti_car_anchors(feature_size=(1, 200, 176), anchor_range=(0, -40.0, -1.0, 70.4, 40.0, -1.0), sizes=(1.6, 3.9, 1.56),
-                      rotations=(0, 1.57), dtype=np.float32):
-    """Anchor grid of examples/second/configs/config.py:82-100 == create_anchors_3d_range (box_np_ops.py:780-833):
-    [70400, 7] with anchor index (y*176 + x)*2 + rot."""
-    ar = np.array(anchor_range, dtype)
-    stride = (ar[3] - ar[0]) / feature_size[2]
-    zc = np.linspace(ar[2], ar[5], feature_size[0], dtype=dtype)
-    yc = np.linspace(ar[1], ar[4], feature_size[1], endpoint=False, dtype=dtype) + stride / 2
-    xc = np.linspace(ar[0], ar[3], feature_size[2], endpoint=False, dtype=dtype) + stride / 2
-    rot = np.array(rotations, dtype)
-    sz = np.array(sizes, dtype).reshape(-1, 3)
-    out = np.zeros((len(zc), len(yc), len(xc), sz.shape[0], len(rot), 7), dtype)
-    out[..., 0] = xc[None, None, :, None, None]
-    out[..., 1] = yc[None, :, None, None, None]
-    out[..., 2] = zc[:, None, None, None, None]
-    out[..., 3:6] = sz[None, None, None, :, None, :]
-    out[..., 6] = rot[None, None, None, None, :]
-    return out.reshape(-1, 7)
+"""Seeded model parameters: re-export of sessd_data.weights (the generators live in the library-free package)."""
+from sessd_data.weights import *  # noqa: F401,F403
+from sessd_data.weights import (SSFA_CONVS, bench_detector_state, kitti_car_anchors, random_detector_state,  # noqa: F401
+                                split_detector_state)

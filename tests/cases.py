@@ -3,7 +3,7 @@ import hashlib
 
 import numpy as np
 
-from sessd_b200 import synth
+from sessd_data import synth
 
 
 def sha(a):
@@ -122,3 +122,28 @@ def odiou_pairs():
     extra_q[4, 2] += np.float32(3.0)                              # no height overlap
     extra_q[5, :2] += np.float32([0.4, -1.1]); extra_q[5, 6] -= np.float32(2.5)
     return np.concatenate([g, extra_g], 0), np.concatenate([q, extra_q], 0)
+
+
+def checkpoint_model(seed):
+    """Small module with the parameter kinds of an SE-SSD checkpoint: a spconv-layout weight [kz,ky,kx,Cin,Cout], BatchNorm1d
+    (incl. num_batches_tracked), a Conv2d with bias.  Seeded."""
+    import torch
+    from torch import nn
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.middle_conv = nn.Module()
+            self.middle_conv.weight = nn.Parameter(torch.zeros(3, 3, 3, 4, 16))
+            self.bn = nn.BatchNorm1d(16, eps=1e-3, momentum=0.01)
+            self.conv_box = nn.Conv2d(8, 14, 1)
+
+    g = torch.Generator().manual_seed(seed)
+    m = M()
+    with torch.no_grad():
+        for p in m.parameters():
+            p.copy_(torch.randn(p.shape, generator=g))
+        m.bn.running_mean.copy_(torch.randn(16, generator=g))
+        m.bn.running_var.copy_(torch.rand(16, generator=g) + 0.5)
+        m.bn.num_batches_tracked.fill_(seed)
+    return m

@@ -71,11 +71,16 @@ def test_nms_sorted_keep_matches_oracle(mode, thr, n):
     keep, num = ops.nms_sorted(_dev(bx), thr, mode)
     got = keep[: int(num.item())].cpu().numpy()
     if not np.array_equal(got, ref):
-        # only acceptable cause: a pair whose IoU sits within 1e-4 of the threshold
+        # the ONLY acceptable cause: the box whose fate differs first is decided by a pair whose IoU sits within 1e-4 of the threshold
+        # (CUDA sinf/cosf vs glibc); assert that this is the case -- no skip
         iou = ocpu.boxes_iou_3d(bx, bx) if mode == 1 else ocpu.boxes_iou_bev(bx, bx)
-        assert _borderline(iou, thr).any(), "keep sets differ without a borderline pair"
-        pytest.skip("borderline IoU pair at the threshold")
-    assert np.array_equal(got, ref)
+        m = min(len(got), len(ref))
+        first = next((i for i in range(m) if got[i] != ref[i]), m)
+        cand = [int(x[first]) for x in (got, ref) if first < len(x)]
+        b = min(cand)                              # kept by one side, suppressed by the other
+        kept_before = ref[:first]                  # common prefix of kept boxes
+        assert len(kept_before) and np.any(np.abs(iou[kept_before, b] - thr) < 1e-4), \
+            "keep sets differ at box %d without a borderline pair deciding it" % b
 
 
 def test_nms_empty():

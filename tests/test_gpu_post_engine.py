@@ -74,62 +74,45 @@ def test_postprocess_frustum_and_gt_mode():
     np.testing.assert_allclose(buf.boxes[0, :k].cpu().numpy(), boxes[keep].numpy(), rtol=1e-4, atol=1e-5)
 
 
-def _full_oracle(cloud, sd, anchors):
-    """CPU oracle of the whole frame: voxelise -> VFE -> SpMiddleFHD -> SSFA -> head -> predict."""
-    from oracle import bev_ref, cpu as ocpu, spconv_ref as S
-    from sessd_b200 import synth, weights
-    layers, ssfa, head = weights.split_detector_state(sd)
-    v, c, n = ocpu.points_to_voxel(cloud, synth.VOXEL_SIZE, synth.PC_RANGE, 5, 20000)
-    feat = bev_ref.vfe_mean(torch.from_numpy(v), torch.from_numpy(n)).numpy()
-    coors = np.concatenate([np.zeros((len(c), 1), np.int32), c], 1)
-    params = [{k: l[k].numpy() for k in ("weight", "gamma", "beta", "mean", "var")} for l in layers]
-    dense = S.spmiddle_forward(feat, coors, 1, (1408, 1600, 40), params, np.float32)
-    x = torch.from_numpy(dense.astype(np.float32))
-    neck = bev_ref.ssfa_forward(x, ssfa)
-    hd = bev_ref.head_forward(neck, head)
-    enc = hd["box_preds"].reshape(-1, 7)
-    cls = hd["cls_preds"].reshape(-1)
-    dirs = hd["dir_cls_preds"].reshape(-1, 2)
-    iou = hd["iou_preds"].reshape(-1)
-    out = bev_ref.predict_frame(enc, cls, dirs, iou, torch.from_numpy(anchors), return_aux=True)
-    return hd, out, len(c)
-
-
-def _calibrated_state(seed, cloud, anchors, target=300):
-    """Random init puts no anchor over the 0.3 threshold; shift the cls bias (a pure logit offset) so ~target pass."""
+def _check_engine_vs_oracle(kind, clouds, batch):
+    from oracle import frame as oframe
     from sessd_b200 import weights
-    sd = weights.random_detector_state(seed, cls_bias=-3.0)
-    hd, _out, _n = _full_oracle(cloud, sd, anchors)
-    logits = np.sort(hd["cls_preds"].reshape(-1).numpy())[::-1]
-    shift = np.log(0.3 / 0.7) - 0.5 * (logits[target] + logits[target + 1])
-    sd["bbox_head.tasks.0.conv_cls.bias"] = torch.full((2,), float(-3.0 + shift))
-    return sd
-
-
-def test_engine_end_to_end_matches_cpu_oracle():
-    from sessd_b200 import synth, weights
     from sessd_b200.engine import FrameEngine
     anchors = weights.kitti_car_anchors()
-    clouds = [synth.ring_cloud(21, 20000), synth.ring_cloud(22, 18000)]
-    sd = _calibrated_state(11, clouds[0], anchors)
-    eng = FrameEngine(batch=2, max_points_per_frame=20000)
-    eng.load_weights(*weights.split_detector_state(sd), anchors)
+    layers, ssfa, head = weights.bench_detector_state(kind, 0)
+    lnp = oframe.layers_to_numpy(layers)
+    eng = FrameEngine(batch=batch, max_points_per_frame=max(c.shape[0] for c in clouds))
+    eng.load_weights(layers, ssfa, head, anchors)
     eager = eng.infer(clouds)
     eng.capture()
     graph = eng.infer(clouds)
     graph2 = eng.infer(clouds[::-1])[::-1]
     head_gpu = eng.neck.buf["head"].cpu().numpy()      # holds the reversed batch now
     for f, cloud in enumerate(clouds):
-        hd, (boxes, scores, _labels, aux), nvox = _full_oracle(cloud, sd, anchors)
+        hd = oframe.frame_head(cloud, lnp, ssfa, head)
+        boxes, scores, _labels, aux = oframe.frame_detections(cloud, lnp, ssfa, head, anchors)
         assert aux["n_candidates"] > 100 and boxes.shape[0] > 5, "vacuous test: no detections"
+        sc = np.sort(scores.numpy().astype(np.float64))
+        assert np.min(np.diff(sc) / sc[1:]) > 1e-6, "tie-degenerate workload"
         for res in (eager[f], graph[f], graph2[f]):
-            assert res["num_voxels"] == nvox
             assert res["num_candidates"] == aux["n_candidates"]
-            assert res["box3d_lidar"].shape[0] == boxes.shape[0]
+            assert np.array_equal(res["anchor_index"], aux["final_anchor"].numpy()), "kept detections differ (matched by anchor index)"
             np.testing.assert_allclose(res["box3d_lidar"], boxes.numpy(), rtol=1e-4, atol=1e-4)
             np.testing.assert_allclose(res["scores"], scores.numpy(), rtol=1e-4, atol=1e-6)
         # raw head maps within 1e-4 relative
-        hg = head_gpu[1 - f]
+        hg = head_gpu[batch - 1 - f]
         for sl, key in ((slice(0, 14), "box_preds"), (slice(14, 16), "cls_preds"), (slice(16, 20), "dir_cls_preds"), (slice(20, 22), "iou_preds")):
             ref = hd[key][0].numpy()
             assert np.abs(hg[..., sl] - ref).max() / np.abs(ref).max() < 1e-4, key
+
+
+def test_engine_end_to_end_matches_cpu_oracle():
+    """Whole path (eager, CUDA graph, graph with the batch reversed) on the bench workload's weights: ring clouds, batch 2."""
+    from sessd_b200 import synth
+    _check_engine_vs_oracle("ring", [synth.ring_cloud(21, 20000), synth.ring_cloud(22, 18000)], 2)
+
+
+def test_engine_end_to_end_uniform20k_matches_cpu_oracle():
+    """Same on the uniform-20k input (SURVEY 8(d) primary input), batch 1."""
+    from sessd_b200 import synth
+    _check_engine_vs_oracle("uniform", [synth.uniform_cloud(3, 20000)], 1)

@@ -232,3 +232,83 @@ def test_h2_sparse_conv_power_of_two_scaling_is_exact():
     assert nn > 100000
     assert torch.equal(outs[0][0][:nn] * 4.0, outs[1][0][:nn])
     assert outs[0][1] * 4.0 == outs[1][1]
+
+
+# ---------------------------------------------------------------------------------------------------- BASELINE shapes
+def _frame_through_runner(cloud, max_voxels=20000, growth=None):
+    from oracle import cpu as ocpu
+    from sessd_b200 import synth
+    from sessd_b200.runners import SpMiddleRunner
+    v, c, num = ocpu.points_to_voxel(cloud, synth.VOXEL_SIZE, synth.PC_RANGE, 5, max_voxels)
+    coors = np.concatenate([np.zeros((len(c), 1), np.int32), c], 1).astype(np.int32)
+    n = len(coors)
+    feat = (v.sum(1) / num[:, None]).astype(np.float32)
+    r = SpMiddleRunner(1, n, device="cuda", growth=growth)
+    layers, _, _ = _weights()
+    r.load_weights(layers)
+    dense = r.forward(torch.from_numpy(feat).cuda(), torch.from_numpy(coors).cuda(), torch.tensor([n], dtype=torch.int32, device="cuda"))
+    torch.cuda.synchronize()
+    assert int(r.status.item()) == 0
+    return r, feat, coors, layers, dense
+
+
+def _check_rulebooks(r, coors):
+    """all 8 rulebooks (nbr tables) and the 4 strided coordinate lists of the frame vs the oracle, bit-exact"""
+    from oracle import spconv_ref as S
+    cur, shape, lvl, seen = coors, (41, 1600, 1408), 0, set()
+    sites = [len(coors)]
+    for p in r.plan:
+        if p["kind"] == "subm":
+            if p["key"] in seen:
+                continue
+            seen.add(p["key"])
+            ref = S.neighbor_table(cur, shape, cur, p["ks"], (1, 1, 1), (1, 1, 1))
+            assert np.array_equal(p["nbr"][: len(cur)].cpu().numpy(), ref), p["key"]
+        else:
+            oc, oshape = S.strided_out_coors(cur, shape, p["ks"], p["st"], p["pd"])
+            lv = r.levels[lvl + 1]
+            assert int(lv["n"].item()) == len(oc)
+            assert np.array_equal(lv["coors"][: len(oc)].cpu().numpy(), oc)
+            ref = S.neighbor_table(cur, shape, oc, p["ks"], p["st"], p["pd"])
+            assert np.array_equal(p["nbr"][: len(oc)].cpu().numpy(), ref)
+            cur, shape, lvl = oc, oshape, lvl + 1
+            sites.append(len(oc))
+    assert shape == (2, 200, 176)
+    return sites
+
+
+@pytest.mark.parametrize("kind", ["ring", "uniform"])
+def test_rulebooks_bit_exact_on_full_20k_frames(kind):
+    """BASELINE config #2 inputs, one full frame each: ring-20k and uniform-20k (20 k -> 68 k -> 103 k -> 86 k -> 52 k sites)."""
+    from sessd_b200 import synth
+    cloud = synth.ring_cloud(0, 20000) if kind == "ring" else synth.uniform_cloud(0, 20000)
+    r, _feat, coors, _layers, _dense = _frame_through_runner(cloud)
+    sites = _check_rulebooks(r, coors)
+    if kind == "uniform":
+        assert sites == [19998, 67955, 103374, 85774, 52169]          # SURVEY.md 8(d) [probe] counts of seed 0
+
+
+def test_rulebooks_bit_exact_on_a_200k_point_frame():
+    """BASELINE config #5 input (uniform-200k, max_voxels 200000), one frame: every rulebook and coordinate list vs the oracle."""
+    from sessd_b200 import synth
+    r, _feat, coors, _layers, _dense = _frame_through_runner(synth.uniform_cloud(1000, 200000), 200000, growth=(1.0, 8.0, 8.0, 8.0, 8.0))
+    sites = _check_rulebooks(r, coors)
+    assert sites[0] > 190000 and max(sites) > 600000
+
+
+def test_features_uniform20k_match_fp64_oracle():
+    """Per-layer features of the DEFAULT kernels on the uniform-20k frame (SURVEY 8(d) primary input) vs the fp64 oracle:
+    <= 1e-5 of the layer maximum (north_star bar: 1e-4 relative)."""
+    from oracle import spconv_ref as S
+    from sessd_b200 import synth
+    r, feat, coors, layers, dense = _frame_through_runner(synth.uniform_cloud(0, 20000))
+    params = [dict(weight=l["weight"].numpy(), gamma=l["gamma"].numpy(), beta=l["beta"].numpy(), mean=l["mean"].numpy(),
+                   var=l["var"].numpy()) for l in layers]
+    trace = []
+    ref = S.spmiddle_forward(feat, coors, 1, (1408, 1600, 40), params, np.float64, trace)
+    for li, t in enumerate(trace):
+        got = r.feats[li][: len(t["coors"])].cpu().numpy().astype(np.float64)
+        scale = np.abs(t["feat"]).max() + 1e-30
+        assert np.abs(got - t["feat"]).max() / scale < 1e-5, "layer %d" % li
+    got = dense.permute(0, 3, 1, 2).cpu().numpy().astype(np.float64)
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-5

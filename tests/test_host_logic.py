@@ -136,3 +136,74 @@ def test_sparse_fp16_split_weight_packing_layout_and_precision():
             assert not tiles[:, :, cin:32].any() and not tiles[:, :, 32 + cin:].any()     # zero padding of the 16-channel layers
         err = (hi + lo - scaled).abs().max() / scaled.abs().max()
         assert float(err) < 2.0 ** -21
+
+
+def test_checkpoint_reads_reference_written_file(golden_dir):
+    """Files written by the REFERENCE's own save_checkpoint (tests/golden/make_checkpoint_golden.py, which also verified that the
+    reference's load_checkpoint reads OUR files): {'meta','state_dict','optimizer'} and a bare 'module.'-prefixed OrderedDict."""
+    import os
+    import torch
+    from cases import checkpoint_model
+    from det3d.torchie.trainer.checkpoint import load_checkpoint
+    want = checkpoint_model(seed=7).state_dict()
+    for name in ("ref_checkpoint.pth", "ref_checkpoint_module_prefix.pth"):
+        m = checkpoint_model(seed=1)
+        ck = load_checkpoint(m, os.path.join(golden_dir, name), map_location="cpu", strict=True)
+        for k, v in m.state_dict().items():
+            assert torch.equal(v, want[k]), (name, k)
+    assert ck is not None
+    ck = load_checkpoint(checkpoint_model(seed=1), os.path.join(golden_dir, "ref_checkpoint.pth"), map_location="cpu")
+    assert ck["meta"] == {"epoch": 3, "iter": 1234} and "optimizer" in ck
+
+
+def test_voxelization_train_mode_filters_gt_outside_range():
+    """reference preprocess.py:199-205 + sampler/preprocess.py:138-148: a labeled training frame loses the GT boxes that have NO BEV
+    corner strictly inside [0,-40,70.4,40]; a straddling box (one corner inside) stays."""
+    from det3d.datasets.pipelines.preprocess import filter_gt_box_outside_range
+    rng = [0.0, -40.0, 70.4, 40.0]
+    boxes = np.array([
+        [30.0, 0.0, -1.0, 1.6, 3.9, 1.5, 0.3],      # inside
+        [-5.0, 0.0, -1.0, 1.6, 3.9, 1.5, 0.0],      # fully outside (x < 0)
+        [0.5, 0.0, -1.0, 1.6, 3.9, 1.5, 0.0],       # straddles x = 0: corners at x = -0.3 and 1.3
+        [71.2, 39.0, -1.0, 1.6, 3.9, 1.5, 0.0],     # corners x in [70.4, 72.0]: x = 70.4 is ON the boundary -> outside
+        [35.0, 41.0, -1.0, 1.6, 1.9, 1.5, 0.0],     # y in [40.05, 41.95]: outside
+    ], np.float64)
+    m = filter_gt_box_outside_range(boxes, rng)
+    assert m.tolist() == [True, False, True, False, False]
+    assert filter_gt_box_outside_range(np.zeros((0, 7)), rng).shape == (0,)
+
+
+def test_bench_weights_are_quiet_calibrated_and_library_free():
+    """bench / parity workload parameters: exact silence over empty space, committed calibration, and importable without the
+    CUDA library (the CPU reference arm must not load libsessd_b200.so)."""
+    import subprocess
+    import sys
+    import torch
+    from oracle import frame as oframe
+    from sessd_data import weights
+    layers, ssfa, head = weights.bench_detector_state("ring", 0)
+    assert np.all(oframe.empty_space_logits(ssfa, head) == weights.EMPTY_LOGIT)
+    cal = weights.load_bench_calibration()
+    for kind in ("ring", "uniform"):
+        assert 300 <= cal[kind]["candidates_on_seed0"] <= 500 and cal[kind]["distinct_in_top1000"] == 1000
+    code = ("import sys; sys.path[:0] = %r; import sessd_data.weights as w, sessd_data.synth as s, oracle.frame; "
+            "w.bench_detector_state('ring', 0); s.ring_cloud(0, 100); "
+            "import ctypes; assert not any('sessd_b200' in m for m in sys.modules), 'product package imported'; "
+            "maps = open('/proc/self/maps').read(); assert 'libsessd_b200' not in maps, 'product library loaded'") % (sys.path[:3],)
+    subprocess.check_call([sys.executable, "-c", code])
+    assert isinstance(head["tasks.0.conv_cls.bias"], torch.Tensor)
+
+
+def test_bench_parity_matcher_by_anchor_index():
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    ref_boxes = np.arange(21, dtype=np.float32).reshape(3, 7)
+    ref_scores = np.array([0.9, 0.8, 0.7], np.float32)
+    got = {"anchor_index": np.array([5, 9, 11]), "box3d_lidar": ref_boxes[[0, 1]].tolist() + [[0] * 7], "scores": np.array([0.9, 0.8, 0.31], np.float32)}
+    got["box3d_lidar"] = np.array(got["box3d_lidar"], np.float32)
+    m = b.match_detections(got, ref_boxes, ref_scores, np.array([5, 9, 13]))
+    assert m["n_matched"] == 2 and m["max_abs_box_diff"] == 0.0 and m["same_order"]
+    assert sorted((u["side"], u["anchor"]) for u in m["unmatched"]) == [("gpu", 11), ("oracle", 13)]

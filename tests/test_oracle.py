@@ -3,6 +3,7 @@
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from cases import iou_inputs, sha, voxel_cases
@@ -200,3 +201,53 @@ def test_oracle_head_loss_equals_reference_golden(golden_dir):
     grad = head.grad.numpy().reshape(-1, 24)
     np.testing.assert_allclose(grad[g["grad_pix_idx"]], g["grad_pix"], rtol=1e-5, atol=1e-9)
     np.testing.assert_allclose(np.abs(grad).sum(), float(g["grad_abs_sum"]), rtol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------- second opinion for spconv_ref
+@pytest.mark.parametrize("kind,ks,st,pd", [("subm", (3, 3, 3), (1, 1, 1), (1, 1, 1)), ("spconv", (3, 3, 3), (2, 2, 2), (1, 1, 1)),
+                                           ("spconv", (3, 3, 3), (2, 2, 2), (0, 1, 1)), ("spconv", (3, 1, 1), (2, 1, 1), (0, 0, 0))])
+def test_spconv_restatement_equals_dense_conv3d(kind, ks, st, pd):
+    """spconv 1.x is absent (parity unpinned), so the restatement in oracle/spconv_ref.py is cross-checked against an INDEPENDENT
+    implementation: torch.nn.functional.conv3d on the densified (cropped) volume.
+      * SparseConv3d: the output set is every position reached by at least one active input, and the values equal the dense
+        cross-correlation there (everywhere else the dense result is exactly 0);
+      * SubMConv3d: the output set is the input set; values = dense cross-correlation (padding k//2) sampled at the active sites.
+    Covers the four (kernel, stride, padding) combinations of scn.py:106-149, 2 frames, ~12 % occupancy."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import spconv_ref as S
+    rng = np.random.default_rng(11)
+    B, shape, cin, cout = 2, (9, 20, 18), 5, 7
+    occ = rng.random((B,) + shape) < 0.12
+    coors = np.argwhere(occ).astype(np.int32)                       # ascending (b, z, y, x) = canonical order
+    feat = rng.standard_normal((len(coors), cin))
+    w = rng.standard_normal(ks + (cin, cout))                       # spconv layout [kz,ky,kx,Cin,Cout]
+    dense = np.zeros((B, cin) + shape)
+    dense[coors[:, 0], :, coors[:, 1], coors[:, 2], coors[:, 3]] = feat
+    wt = torch.from_numpy(w).permute(4, 3, 0, 1, 2).contiguous()    # conv3d layout [Cout,Cin,kz,ky,kx]
+    if kind == "subm":
+        out_coors, oshape = coors, shape
+        nbr = S.neighbor_table(coors, shape, coors, ks, (1, 1, 1), tuple(k // 2 for k in ks))
+        ref = F.conv3d(torch.from_numpy(dense), wt, None, 1, tuple(k // 2 for k in ks)).numpy()
+    else:
+        out_coors, oshape = S.strided_out_coors(coors, shape, ks, st, pd)
+        nbr = S.neighbor_table(coors, shape, out_coors, ks, st, pd)
+        ref = F.conv3d(torch.from_numpy(dense), wt, None, st, pd).numpy()
+        assert tuple(ref.shape[2:]) == oshape
+        # output set == positions reached by an active input == support of conv3d(occupancy, ones)
+        reach = F.conv3d(torch.from_numpy(occ[:, None].astype(np.float64)), torch.ones((1, 1) + ks, dtype=torch.float64), None, st, pd).numpy()[:, 0] > 0
+        assert np.array_equal(np.argwhere(reach).astype(np.int32), out_coors)
+        mask = np.zeros_like(reach)
+        mask[out_coors[:, 0], out_coors[:, 1], out_coors[:, 2], out_coors[:, 3]] = True
+        assert np.abs(ref[~np.broadcast_to(mask[:, None], ref.shape)]).max() == 0.0
+    got = S.conv_from_nbr(feat, nbr, w.reshape(-1, cin, cout), np.float64)
+    want = ref[out_coors[:, 0], :, out_coors[:, 1], out_coors[:, 2], out_coors[:, 3]]
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
+    # canonical pairs: every (in, out) pair satisfies pos_in = pos_out * stride - pad + k
+    for k, (pi, po) in enumerate(S.pairs_from_nbr(nbr)):
+        kz, r = divmod(k, ks[1] * ks[2])
+        ky, kx = divmod(r, ks[2])
+        s3 = (1, 1, 1) if kind == "subm" else st
+        p3 = tuple(q // 2 for q in ks) if kind == "subm" else pd
+        exp = out_coors[po, 1:] * np.array(s3) - np.array(p3) + np.array([kz, ky, kx])
+        assert np.array_equal(coors[pi, 1:], exp) and np.array_equal(coors[pi, 0], out_coors[po, 0])
