@@ -532,9 +532,7 @@ def stage_breakdown(e, clouds):
         ev[0].record(e.stream)
         ops.voxelize(e.d_points, e.d_off, e.vox)
         ev[1].record(e.stream)
-        dense = e.middle.forward(e.vox.mean, e.vox.coors, e.vox.num_voxels[e.batch:e.batch + 1])
-        ev[2].record(e.stream)
-        _, head = e.neck.forward(dense)
+        head = e.sparse_and_neck(mark=lambda label: ev[2].record(e.stream) if label == "dense" else None)
         ev[3].record(e.stream)
         ops.postprocess(head, e.anchors, None, e.post)
         ev[4].record(e.stream)

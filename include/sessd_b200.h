@@ -209,6 +209,33 @@ int sessd_bev_conv_h2(const float *d_in, const void *d_weight_h2, int cout_pad, 
 int sessd_bev_deconv_h2(const float *d_in, const void *d_weight_h2, int cout_pad, const float *d_scale,
                         const float *d_shift, const float *d_residual, float *d_out, int batch, int in_h, int in_w,
                         int cin, int cout, int relu, const float *d_amax_in, float *d_amax_out, void *stream);
+/* ------------------------------------------------------------------------------------------------
+ * BEV convs from PRE-SPLIT fp16 planes (csrc/bevconv_p2.cu): the neck's default path.  Activations travel between layers as
+ * __half [2 (hi|lo)][batch][H][W][C] planes with x = (hi + lo) / S, S an exact power of two; every plane tensor has a device-side
+ * info pair float[2] = {abs-max of the tensor (atomically raised by its producer; zero it once per frame), S}.  Same conv semantics
+ * as sessd_bev_conv / sessd_bev_deconv_tc (rpn_v1.py:135-210, mg_head_sessd.py:202-230): in_stride 1 or 2, <= 9 taps, cin % 64 == 0,
+ * cout % 8 == 0.  d_weight_h2 / d_scale as for sessd_bev_conv_h2.  gain / shift_max: |out| <= amax_in * gain + shift_max
+ * (+ amax of the residual) with gain = max_n sum_{tap,c} |w[tap][c][n] * bn_scale[n]|: the producer derives the OUTPUT scale from
+ * this bound before it writes the first element.  Outputs: fp32 NHWC (d_out_f32) and / or planes (d_out_planes + d_out_info). */
+int sessd_bev_conv_p2(const void *d_in_planes, const float *d_in_info, const void *d_weight_h2, int cout_pad, const float *d_scale,
+                      const float *d_shift, const float *d_residual, const float *d_resid_info, float gain, float shift_max,
+                      float *d_out_f32, void *d_out_planes, float *d_out_info, const sessd_conv_desc *desc, void *stream);
+int sessd_bev_deconv_p2(const void *d_in_planes, const float *d_in_info, const void *d_weight_h2, int cout_pad, const float *d_scale,
+                        const float *d_shift, const float *d_residual, const float *d_resid_info, float gain, float shift_max,
+                        float *d_out_f32, void *d_out_planes, float *d_out_info, int batch, int in_h, int in_w, int cin, int cout,
+                        int relu, void *stream);
+/* fp32 [n] -> planes [2][n] scaled from d_info[0] (the tensor's abs-max, e.g. from sessd_absmax); writes the scale to d_info[1] */
+int sessd_bev_split_planes(const float *d_x, long long n, float *d_info, void *d_planes, void *stream);
+/* CTAs per cluster sharing (TMA-multicasting) the weight tiles of sessd_bev_conv_p2: 1 or 2 (default) */
+void sessd_set_p2_cluster(int ctas_per_cluster);
+/* dense() (scn.py:184-187) straight into the planes the neck reads: d_amax = abs-max of the feature rows, d_info[2] <- {abs-max, S} */
+int sessd_sparse_to_dense_planes(const float *d_feat, int max_rows, const void *d_bitmap_index, int channels, sessd_grid grid,
+                                 const float *d_amax, float *d_info, void *d_planes, void *stream);
+/* sessd_ssfa_fuse that also (d_out nullable: only) writes the fused map as planes; d_info0 / d_info1 [2]: abs-max of x0 / x1 */
+int sessd_ssfa_fuse_planes(const float *d_x0, const float *d_x1, const float *d_w0, const float *d_w1, float s0, float t0, float s1,
+                           float t1, int num_pixels, int channels, float *d_out, const float *d_info0, const float *d_info1,
+                           float *d_out_info, void *d_planes, void *stream);
+
 /* profiling experiments only: ablation mask (1 no split work, 2 no MMAs, 4 no weight reloads, 8 no stores; results are garbage when
  * non-zero) and optional [ctas][8] int64 globaltimer stamps (start, split done, accumulators ready, end) */
 void sessd_set_h2_debug(int ablate_mask, void *d_stamps);

@@ -54,8 +54,7 @@ def group_rooflines(eng, clouds, iters=5):
             mark("start")
             ops.voxelize(eng.d_points, eng.d_off, eng.vox)
             mark("voxelize")
-            dense = eng.middle.forward(eng.vox.mean, eng.vox.coors, eng.vox.num_voxels[B:B + 1], mark=mark)
-            _, hd = eng.neck.forward(dense, mark=mark)
+            hd = eng.sparse_and_neck(mark=mark)
             ops.postprocess(hd, eng.anchors, None, eng.post)
             mark("post")
             st.synchronize()

@@ -14,6 +14,8 @@
 // register micro-tiles, A rows gathered with zero-filling cp.async (3-stage pipeline), fp32 FMA accumulation.
 // This SIMT version is the fp32 numerics baseline; the tcgen05 (3xTF32) version shares this interface.
 // Algorithmic bytes per layer: 4 (M Cin [read once per CTA column] + M Cout) ; FLOPs 2 M N K.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace sessd {
@@ -152,12 +154,22 @@ __global__ void __launch_bounds__(kCvThreads, 2) bev_conv_kernel(const float *__
     }
 }
 
-// SSFA tail (rpn_v1.py:229-233).  One warp per pixel; 128 channels = one float4 per lane.
+// SSFA tail (rpn_v1.py:229-233).  One warp per pixel; 128 channels = one float4 per lane.  Optionally also writes the result as
+// fp16 (hi, lo) planes for the head GEMM (sessd_bev_conv_p2): the output is a convex combination of x0 and x1, so max(amax0, amax1)
+// bounds it exactly.
 __global__ void __launch_bounds__(256) ssfa_fuse_kernel(const float *__restrict__ x0, const float *__restrict__ x1,
                                                         const float *__restrict__ w0, const float *__restrict__ w1, float s0, float t0,
-                                                        float s1, float t1, int num_pixels, int C, float *__restrict__ out) {
+                                                        float s1, float t1, int num_pixels, int C, float *__restrict__ out,
+                                                        const float *__restrict__ info0, const float *__restrict__ info1,
+                                                        float *__restrict__ out_info, __half *__restrict__ planes, long long plane_stride) {
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
+    float sp = 1.f;
+    if (planes) {
+        const float am = fmaxf(__ldg(info0), __ldg(info1));
+        sp = pow2_scale_for_bound(am);
+        if (blockIdx.x == 0 && threadIdx.x == 0) { out_info[0] = am; out_info[1] = sp; }
+    }
     for (int p = blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < num_pixels; p += gridDim.x * warps_per_block) {
         float d0 = 0.f, d1 = 0.f;
         for (int c = lane * 4; c < C; c += 128) {
@@ -180,7 +192,18 @@ __global__ void __launch_bounds__(256) ssfa_fuse_kernel(const float *__restrict_
             const float4 b = *reinterpret_cast<const float4 *>(x1 + (size_t)p * C + c);
             float4 r;
             r.x = a.x * a0 + b.x * a1; r.y = a.y * a0 + b.y * a1; r.z = a.z * a0 + b.z * a1; r.w = a.w * a0 + b.w * a1;
-            *reinterpret_cast<float4 *>(out + (size_t)p * C + c) = r;
+            if (out) *reinterpret_cast<float4 *>(out + (size_t)p * C + c) = r;
+            if (planes) {
+                const float q[4] = {r.x * sp, r.y * sp, r.z * sp, r.w * sp};
+                __align__(8) __half hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    hi[e] = __float2half_rn(q[e]);
+                    lo[e] = __float2half_rn(q[e] - __half2float(hi[e]));
+                }
+                *reinterpret_cast<uint2 *>(planes + (size_t)p * C + c) = *reinterpret_cast<const uint2 *>(hi);
+                *reinterpret_cast<uint2 *>(planes + plane_stride + (size_t)p * C + c) = *reinterpret_cast<const uint2 *>(lo);
+            }
         }
     }
 }
@@ -212,6 +235,18 @@ extern "C" int sessd_ssfa_fuse(const float *d_x0, const float *d_x1, const float
                                float t1, int num_pixels, int channels, float *d_out, void *stream) {
     if (!d_x0 || !d_x1 || !d_w0 || !d_w1 || !d_out || num_pixels < 1 || channels < 4 || channels % 4) return SESSD_EINVAL;
     SESSD_LAUNCH(ssfa_fuse_kernel, persistent_grid((long long)num_pixels * 32, 256), 256, 0, stream, d_x0, d_x1, d_w0, d_w1, s0, t0, s1, t1,
-                 num_pixels, channels, d_out);
+                 num_pixels, channels, d_out, nullptr, nullptr, nullptr, nullptr, 0ll);
+    return last_error();
+}
+
+// same, additionally (or only: d_out nullable) writing fp16 (hi, lo) planes [2][num_pixels][channels] + d_out_info = {bound, scale};
+// d_info0 / d_info1: [2] each, element 0 = abs-max of x0 / x1
+extern "C" int sessd_ssfa_fuse_planes(const float *d_x0, const float *d_x1, const float *d_w0, const float *d_w1, float s0, float t0, float s1,
+                                      float t1, int num_pixels, int channels, float *d_out, const float *d_info0, const float *d_info1,
+                                      float *d_out_info, void *d_planes, void *stream) {
+    if (!d_x0 || !d_x1 || !d_w0 || !d_w1 || !d_planes || !d_info0 || !d_info1 || !d_out_info || num_pixels < 1 || channels < 4 || channels % 4)
+        return SESSD_EINVAL;
+    SESSD_LAUNCH(ssfa_fuse_kernel, persistent_grid((long long)num_pixels * 32, 256), 256, 0, stream, d_x0, d_x1, d_w0, d_w1, s0, t0, s1, t1,
+                 num_pixels, channels, d_out, d_info0, d_info1, d_out_info, (__half *)d_planes, (long long)num_pixels * channels);
     return last_error();
 }

@@ -24,6 +24,19 @@ extern long long g_launches;   // counted per kernel launch (sessd_launch_count)
         if (_e != cudaSuccess) return (int)_e;                                                       \
     } while (0)
 
+// exact power-of-two scale that maps `bound` (> 0, finite) into [2^14, 2^15): the scale of fp16 (hi, lo) activation planes whose
+// elements are bounded by `bound` (1 when the bound is 0 / not finite).  x * S < 2^15 < 65504 for every |x| <= bound.
+__host__ __device__ __forceinline__ float pow2_scale_for_bound(float bound) {
+    union { float f; uint32_t u; } v;
+    v.f = bound;
+    const uint32_t e = (v.u >> 23) & 0xFFu;
+    if (e == 0 || e == 255) return 1.f;
+    int bits = 268 - (int)e;                                  // biased exponent of 2^(14 - (e - 127))
+    bits = bits < 2 ? 2 : (bits > 252 ? 252 : bits);
+    v.u = (uint32_t)bits << 23;
+    return v.f;
+}
+
 static inline int last_error() { return (int)cudaGetLastError(); }
 
 static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -17,6 +17,8 @@
 //              read (bit test + popc).  Level-1..4 bitmaps are 3 MB ... 18 KB per frame: L2 resident.
 // HBM traffic per build: reads 16 B/input row, writes 4*kvol B/output row (nbr) + 16 B/output row (coords); the
 // bitmap/hash probes hit L2.  All counts are device-resident (d_n), grids are persistent.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace sessd {
@@ -365,10 +367,18 @@ extern "C" int sessd_strided_rulebook(const int *d_in_coors, const int *d_n_in, 
 // the D z-slices of the cell come from the level's bitmap index (bit test + popcount rank).  NHWC [B, H, W, C*D], channel = c*D + d
 // (== NCDHW .view(N, C*D, H, W) of det3d/models/backbones/scn.py:184-187, channels-last).  Writes every output byte exactly once with
 // 16-byte stores; reads each feature row once.
+template <bool PLANES>
 __global__ void __launch_bounds__(256) dense_gather_kernel(const float *__restrict__ feat, BitmapIndex index, GridDims g, int C,
-                                                           int max_rows, float4 *__restrict__ out) {
+                                                           int max_rows, float4 *__restrict__ out, const float *__restrict__ amax,
+                                                           float *__restrict__ info, __half *__restrict__ planes, long long plane_stride) {
     const unsigned int cd4 = (unsigned int)(C * g.D) >> 2;
     const unsigned int total = (unsigned int)g.B * g.H * g.W * cd4;          // < 2^31 (checked by the host)
+    float s = 1.f;
+    if (PLANES) {
+        const float am = __ldg(amax);
+        s = pow2_scale_for_bound(am);
+        if (blockIdx.x == 0 && threadIdx.x == 0) { info[0] = am; info[1] = s; }
+    }
     for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
         const unsigned int cell = t / cd4;
         const int j = (int)(t - cell * cd4) * 4;
@@ -384,7 +394,19 @@ __global__ void __launch_bounds__(256) dense_gather_kernel(const float *__restri
             if (d != last_d) { row = index.find(lin_index(g, b, d, y, x)); last_d = d; }
             v[e] = (row >= 0 && row < max_rows) ? __ldg(&feat[(size_t)row * C + c]) : 0.f;    // rows past the capacity were dropped (status flag)
         }
-        out[t] = make_float4(v[0], v[1], v[2], v[3]);
+        if (PLANES) {
+            __align__(8) __half hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float a = v[e] * s;
+                hi[e] = __float2half_rn(a);
+                lo[e] = __float2half_rn(a - __half2float(hi[e]));
+            }
+            *reinterpret_cast<uint2 *>(planes + 4 * (size_t)t) = *reinterpret_cast<const uint2 *>(hi);
+            *reinterpret_cast<uint2 *>(planes + plane_stride + 4 * (size_t)t) = *reinterpret_cast<const uint2 *>(lo);
+        } else {
+            out[t] = make_float4(v[0], v[1], v[2], v[3]);
+        }
     }
 }
 
@@ -395,7 +417,23 @@ extern "C" int sessd_sparse_to_dense_indexed(const float *d_feat, int max_rows, 
     BitmapIndex idx{(const uint2 *)d_bitmap_index};
     const long long total = (long long)g.B * g.H * g.W * ((channels * g.D) >> 2);
     if (total >= (1ll << 31)) return SESSD_ECAPACITY;
-    SESSD_LAUNCH(dense_gather_kernel, persistent_grid(total, 256), 256, 0, stream, d_feat, idx, g, channels, max_rows, (float4 *)d_out);
+    SESSD_LAUNCH(dense_gather_kernel<false>, persistent_grid(total, 256), 256, 0, stream, d_feat, idx, g, channels, max_rows, (float4 *)d_out,
+                 nullptr, nullptr, nullptr, 0ll);
+    return last_error();
+}
+
+// dense() straight into the fp16 (hi, lo) planes [2][B][H][W][C*D] the BEV neck reads (sessd_bev_conv_p2): d_amax = abs-max of the feature
+// rows (raised by the producing sparse conv), d_info[2] receives {abs-max, scale}
+extern "C" int sessd_sparse_to_dense_planes(const float *d_feat, int max_rows, const void *d_bitmap_index, int channels, sessd_grid grid,
+                                            const float *d_amax, float *d_info, void *d_planes, void *stream) {
+    if (!d_feat || !d_bitmap_index || !d_amax || !d_info || !d_planes || channels < 1 || max_rows < 1 || ((channels * grid.shape[0]) & 3))
+        return SESSD_EINVAL;
+    const GridDims g = to_dims(grid);
+    BitmapIndex idx{(const uint2 *)d_bitmap_index};
+    const long long total = (long long)g.B * g.H * g.W * ((channels * g.D) >> 2);
+    if (total >= (1ll << 31)) return SESSD_ECAPACITY;
+    SESSD_LAUNCH(dense_gather_kernel<true>, persistent_grid(total, 256), 256, 0, stream, d_feat, idx, g, channels, max_rows, nullptr, d_amax,
+                 d_info, (__half *)d_planes, total * 4);
     return last_error();
 }
 

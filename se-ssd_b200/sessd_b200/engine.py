@@ -12,12 +12,13 @@ import numpy as np
 import torch
 
 from . import ops, synth
-from .runners import SpMiddleRunner, SSFARunner
+from .runners import SpMiddleRunner, SSFAPlanesRunner, SSFARunner
 
 
 class FrameEngine:
     def __init__(self, batch=1, max_points_per_frame=32768, voxel_size=synth.VOXEL_SIZE, pc_range=synth.PC_RANGE,
-                 max_points_per_voxel=5, max_voxels=20000, device="cuda", post_kwargs=None, growth=None, use_tc=True, sparse_split=None, rows_max_cin=None):
+                 max_points_per_voxel=5, max_voxels=20000, device="cuda", post_kwargs=None, growth=None, use_tc=True, sparse_split=None, rows_max_cin=None,
+                 neck="planes"):
         self.batch, self.device = int(batch), torch.device(device)
         self.max_points = int(max_points_per_frame) * self.batch
         self.vcfg = ops.make_voxel_cfg(voxel_size, pc_range, max_points_per_voxel, max_voxels)
@@ -30,7 +31,11 @@ class FrameEngine:
         self.d_off = torch.zeros((self.batch + 1,), dtype=torch.int32, device=dev)
         self.vox = ops.VoxelBuffers(self.vcfg, self.batch, self.max_points, dev, with_mean=True)
         self.middle = SpMiddleRunner(self.batch, self.batch * max_voxels, self.grid_xyz, 4, dev, growth=growth, use_tc=use_tc, split=sparse_split, rows_max_cin=rows_max_cin)
-        self.neck = SSFARunner(self.batch, (self.grid_xyz[1] // 8, self.grid_xyz[0] // 8), dev, use_tc=use_tc)
+        self.neck_planes = neck == "planes" and use_tc
+        if self.neck_planes:
+            self.neck = SSFAPlanesRunner(self.batch, (self.grid_xyz[1] // 8, self.grid_xyz[0] // 8), dev)
+        else:
+            self.neck = SSFARunner(self.batch, (self.grid_xyz[1] // 8, self.grid_xyz[0] // 8), dev, use_tc=use_tc)
         self.anchors = None
         pk = dict(batch=self.batch, head_stride=SSFARunner.HEAD_STRIDE)
         pk.update(post_kwargs or {})
@@ -60,11 +65,22 @@ class FrameEngine:
     def _device_pipeline(self):
         """All launches of one batch of frames on the current stream (capturable)."""
         ops.voxelize(self.d_points, self.d_off, self.vox)
-        n0 = self.vox.num_voxels[self.batch:self.batch + 1]
-        dense = self.middle.forward(self.vox.mean, self.vox.coors, n0)
-        _, head = self.neck.forward(dense)
+        head = self.sparse_and_neck()
         ops.postprocess_packed(head, self.anchors, self.frustum, self.post, self.d_result, self.d_meta,
                                self.vox.num_voxels[:self.batch], self.middle.status)
+
+    def sparse_and_neck(self, mark=None):
+        """sparse encoder + dense() + neck + head on the current stream; returns the head map.  mark(label) is called after every
+        launch group (profiling)."""
+        n0 = self.vox.num_voxels[self.batch:self.batch + 1]
+        if self.neck_planes:       # dense() writes the fp16 (hi, lo) planes of the neck input directly
+            self.neck.info.zero_()
+            self.middle.forward(self.vox.mean, self.vox.coors, n0, mark=mark, dense_planes=(self.neck.planes["x"], self.neck.info[0]))
+            _, head = self.neck.forward(None, mark=mark)
+        else:
+            dense = self.middle.forward(self.vox.mean, self.vox.coors, n0, mark=mark)
+            _, head = self.neck.forward(dense, mark=mark)
+        return head
 
     def _step_body(self):
         self.d_points.copy_(self.h_points, non_blocking=True)

@@ -323,6 +323,61 @@ def bev_deconv_h2(x, weight_h2, scale, shift, residual, out, relu=True, amax_in=
     return out
 
 
+# ---- BEV convs from pre-split fp16 planes (csrc/bevconv_p2.cu) ---------------------------------------------------------------
+def alloc_bev_planes(batch, h, w, c, device):
+    """fp16 (hi, lo) planes [2, B, H, W, C] of one activation tensor"""
+    return torch.zeros((2, batch, h, w, c), dtype=torch.float16, device=device)
+
+
+def conv_gain(wp, scale):
+    """max_n sum_{tap,c} |w[tap][c][n] * scale[n]| of a [taps, Cin, Cout] weight: |conv(x) * scale| <= max|x| * gain"""
+    g = wp.abs().sum(dim=(0, 1)) * scale.abs().to(wp.device)[: wp.shape[2]]
+    return float(g.max()) * (1.0 + 1e-5)
+
+
+def bev_conv_p2(in_planes, in_info, weight_h2, scale, shift, residual, resid_info, gain, shift_max, out_f32, out_planes, out_info, desc):
+    check(lib.sessd_bev_conv_p2(_p(in_planes), _p(in_info), _p(weight_h2), int(weight_h2.shape[2]), _p(scale), _p(shift), _p(residual),
+                                _p(resid_info), float(gain), float(shift_max), _p(out_f32), _p(out_planes), _p(out_info), C.byref(desc),
+                                _st()), "sessd_bev_conv_p2")
+
+
+def bev_deconv_p2(in_planes, in_info, weight_h2, scale, shift, residual, resid_info, gain, shift_max, out_f32, out_planes, out_info, relu=True):
+    _two, b, h, w, cin = in_planes.shape
+    cout = (out_f32 if out_f32 is not None else out_planes).shape[-1]
+    check(lib.sessd_bev_deconv_p2(_p(in_planes), _p(in_info), _p(weight_h2), int(weight_h2.shape[2]), _p(scale), _p(shift), _p(residual),
+                                  _p(resid_info), float(gain), float(shift_max), _p(out_f32), _p(out_planes), _p(out_info), int(b), int(h),
+                                  int(w), int(cin), int(cout), int(bool(relu)), _st()), "sessd_bev_deconv_p2")
+
+
+def set_p2_cluster(n):
+    """CTAs per cluster sharing the weight tiles of bev_conv_p2 through TMA multicast (1 or 2; default 2)."""
+    lib.sessd_set_p2_cluster(int(n))
+
+
+def bev_split_planes(x, info, planes):
+    """fp32 tensor -> planes with the scale from info[0] (its abs-max: call absmax(x, info[0:1]) first); info[1] <- scale"""
+    check(lib.sessd_bev_split_planes(_p(x), int(x.numel()), _p(info), _p(planes), _st()), "sessd_bev_split_planes")
+    return planes
+
+
+def planes_to_float(planes, info):
+    """(hi + lo) / S as fp32 (tests / debugging)"""
+    return (planes[0].float() + planes[1].float()) / info[1]
+
+
+def sparse_to_dense_planes(feat, bitmap_index, grid, amax, info, planes):
+    check(lib.sessd_sparse_to_dense_planes(_p(feat), int(feat.shape[0]), _p(bitmap_index), int(feat.shape[1]), grid, _p(amax), _p(info),
+                                           _p(planes), _st()), "sessd_sparse_to_dense_planes")
+    return planes
+
+
+def ssfa_fuse_planes(x0, x1, w0, w1, s0, t0, s1, t1, out, info0, info1, out_info, planes):
+    npix = x0.numel() // x0.shape[-1]
+    check(lib.sessd_ssfa_fuse_planes(_p(x0), _p(x1), _p(w0), _p(w1), float(s0), float(t0), float(s1), float(t1), int(npix), int(x0.shape[-1]),
+                                     _p(out), _p(info0), _p(info1), _p(out_info), _p(planes), _st()), "sessd_ssfa_fuse_planes")
+    return out
+
+
 def absmax(x, amax):
     """amax[0] = max(amax[0], max|x|) on the current stream."""
     check(lib.sessd_absmax(_p(x), int(x.numel()), _p(amax), _st()), "sessd_absmax")

@@ -126,9 +126,11 @@ class SpMiddleRunner:
                 tc = ops.pack_weight_tc(wp, p["cout"])
             self.weights.append((wp, sc, sh, tc))
 
-    def forward(self, feat0, coors0, n0, mark=None):
+    def forward(self, feat0, coors0, n0, mark=None, dense_planes=None):
         """feat0 [cap0, Cin] f32, coors0 [cap0,4] i32 (b,z,y,x), n0 [1] i32 (device).  Returns dense NHWC.
-        mark: optional callable(label) invoked after every launch group (profiling scripts record a CUDA event there)."""
+        mark: optional callable(label) invoked after every launch group (profiling scripts record a CUDA event there).
+        dense_planes: (planes [2,B,H,W,C*D] fp16, info [2] f32): dense() writes the fp16 (hi, lo) planes the BEV neck reads instead
+        of the fp32 map (returns the planes)."""
         mark = mark or (lambda label: None)
         assert self.weights is not None, "load_weights first"
         L0 = self.levels[0]
@@ -174,6 +176,12 @@ class SpMiddleRunner:
                 ops.split_h2(x, n_out, cap_out, self.amax[li:li + 1], self.planes[li])
                 mark("split:%d" % li)
         last = self.levels[-1]
+        if dense_planes is not None:
+            assert last["index_kind"] == 1 and self.use_h2
+            out = ops.sparse_to_dense_planes(x, last["index"], last["grid"], self.amax[len(self.plan) - 1:len(self.plan)], dense_planes[1],
+                                             dense_planes[0])
+            mark("dense")
+            return out
         if last["index_kind"] == 1 and self.DENSE_GATHER:
             out = ops.sparse_to_dense_indexed(x, last["index"], last["grid"], self.dense)
         else:
@@ -411,3 +419,135 @@ class SSFARunner:
         if "head:tc" in self.params:
             return ops.bev_conv_tc(x, self.params["head:tc"], None, hb, None, self.buf["head"], d)
         return ops.bev_conv(x, hw, None, hb, None, self.buf["head"], d)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class SSFAPlanesRunner:
+    """SSFA neck (rpn_v1.py:220-235) + the fused 128->22(+2 pad) head GEMM (mg_head_sessd.py:202-230) on csrc/bevconv_p2.cu:
+    activations travel between the layers as fp16 (hi, lo) planes written by the producing epilogue (the main loops are pure
+    TMA -> tcgen05), weight tiles are multicast over CTA pairs.  14 launches per forward: 13 convs (the stride-2 conv included)
+    + the attention fusion; + abs-max and split when the input arrives as fp32 (module API) instead of planes (FrameEngine)."""
+
+    HEAD_STRIDE = 24
+    # info slots (each {abs-max, scale}); the whole table is zeroed once per forward
+    SLOT = dict(x=0, b0a=1, b0b=2, x0=3, b1a=4, b1b=5, x1=6, t1=7, m0=8, m1=9, out=10, t0=11, o0=12, o1=13, head=14)
+
+    def __init__(self, batch, hw=(200, 176), device="cuda"):
+        self.batch, self.h, self.w, self.device = batch, int(hw[0]), int(hw[1]), torch.device(device)
+        h, w, h2, w2 = self.h, self.w, self.h // 2, self.w // 2
+        pl = lambda hh, ww, c: ops.alloc_bev_planes(batch, hh, ww, c, self.device)     # noqa: E731
+        z = lambda hh, ww, c: torch.zeros((batch, hh, ww, c), dtype=torch.float32, device=self.device)  # noqa: E731
+        self.planes = dict(x=pl(h, w, 128), b0a=pl(h, w, 128), b0b=pl(h, w, 128), x0=pl(h, w, 128), b1a=pl(h2, w2, 256), b1b=pl(h2, w2, 256),
+                           x1=pl(h2, w2, 256), t1=pl(h2, w2, 256), m0=pl(h, w, 128), m1=pl(h, w, 128), out=pl(h, w, 128))
+        self.buf = dict(t0=z(h, w, 128), o0=z(h, w, 128), o1=z(h, w, 128), out=z(h, w, 128), head=z(h, w, self.HEAD_STRIDE))
+        self.info = torch.zeros((16, 2), dtype=torch.float32, device=self.device)
+        self.params = None
+
+    def _info(self, name):
+        return self.info[self.SLOT[name]]
+
+    def load_state(self, ssfa_sd, head_sd=None, head_prefix="tasks.0.", bn_eps=BN_EPS):
+        dev = self.device
+        g = lambda k: ssfa_sd[k].to(dev, torch.float32)   # noqa: E731
+        P = {}
+
+        def bn(conv_name):
+            blk, idx = conv_name.rsplit(".", 1)
+            b = "%s.%d" % (blk, int(idx) + 1)
+            return fold_bn(g(b + ".weight"), g(b + ".bias"), g(b + ".running_mean"), g(b + ".running_var"), eps=bn_eps)
+
+        def pack(name, wp, taps, cout_pad):
+            sc, sh = bn(name)
+            planes, inv = ops.pack_weight_h2(wp, cout_pad)
+            P[name] = dict(w=planes, taps=taps, scale=(sc * inv[:sc.numel()]).contiguous(), shift=sh.contiguous(),
+                           gain=ops.conv_gain(wp, sc), shift_max=float(sh.abs().max()))
+
+        for name, pad in (("bottom_up_block_0.1", 1), ("bottom_up_block_0.4", 1), ("bottom_up_block_0.7", 1), ("bottom_up_block_1.0", 1),
+                          ("bottom_up_block_1.3", 1), ("bottom_up_block_1.6", 1), ("trans_0.0", 0), ("trans_1.0", 0), ("conv_0.0", 1),
+                          ("conv_1.0", 1)):
+            wp, taps = _pack_conv(g(name + ".weight"))
+            pack(name, wp, [(dy - pad, dx - pad) for dy, dx in taps], -(-wp.shape[2] // 128) * 128)
+        for name in ("deconv_block_0.0", "deconv_block_1.0"):       # plain 9-tap packing of W[cin][cout][ky][kx]
+            wd = g(name + ".weight")
+            pack(name, wd.permute(2, 3, 0, 1).reshape(9, wd.shape[0], wd.shape[1]).contiguous(), None, 128)
+        for name in ("w_0.0", "w_1.0"):
+            sc, sh = bn(name)
+            P[name] = (g(name + ".weight").reshape(-1).contiguous(), float(sc[0]), float(sh[0]))
+        if head_sd is not None:
+            hw, hb = pack_head(head_sd, head_prefix, dev, self.HEAD_STRIDE)
+            planes, inv = ops.pack_weight_h2(hw, 32)
+            P["head"] = dict(w=planes, taps=[(0, 0)], scale=inv[: self.HEAD_STRIDE].contiguous(), shift=hb.contiguous(),
+                             gain=ops.conv_gain(hw, torch.ones(self.HEAD_STRIDE, device=dev)), shift_max=float(hb.abs().max()))
+        self.params = P
+
+    def _conv(self, name, src, dst, in_hw, out_hw, cin, cout, stride=1, relu=True, f32=None):
+        """src: name of the input planes; dst: name of the output planes (or None); f32: name of an fp32 output buffer (or None)"""
+        q = self.params[name]
+        d = ops.conv_desc(self.batch, in_hw, cin, out_hw, cout, out_hw, q["taps"], in_stride=stride, relu=relu)
+        out_name = dst if dst is not None else f32
+        ops.bev_conv_p2(self.planes[src], self._info(src), q["w"], q["scale"], q["shift"], None, None, q["gain"], q["shift_max"],
+                        self.buf[f32] if f32 is not None else None, self.planes[dst] if dst is not None else None, self._info(out_name), d)
+
+    def _deconv(self, name, src, dst, residual=None):
+        q = self.params[name]
+        ops.bev_deconv_p2(self.planes[src], self._info(src), q["w"], q["scale"], q["shift"], self.buf[residual] if residual else None,
+                          self._info(residual) if residual else None, q["gain"], q["shift_max"], None, self.planes[dst], self._info(dst), True)
+
+    def forward(self, x=None, mark=None):
+        """x: NHWC fp32 [B,200,176,128] (converted to planes here) or None when self.planes['x'] / info slot 'x' were filled by the
+        producer (FrameEngine: dense() writes the planes directly).  Returns (neck out NHWC fp32, head NHWC fp32 [B,200,176,24])."""
+        assert self.params is not None, "load_state first"
+        mark = mark or (lambda label: None)
+        H, H2 = (self.h, self.w), (self.h // 2, self.w // 2)
+        if x is not None:
+            self.info.zero_()
+            ops.absmax(x, self.info[0, 0:1])
+            ops.bev_split_planes(x, self.info[0], self.planes["x"])
+
+        def conv(name, *a, **kw):
+            self._conv(name, *a, **kw)
+            mark("neck:" + name)
+
+        conv("bottom_up_block_0.1", "x", "b0a", H, H, 128, 128)
+        conv("bottom_up_block_0.4", "b0a", "b0b", H, H, 128, 128)
+        conv("bottom_up_block_0.7", "b0b", "x0", H, H, 128, 128)
+        conv("bottom_up_block_1.0", "x0", "b1a", H, H2, 128, 256, stride=2)
+        conv("bottom_up_block_1.3", "b1a", "b1b", H2, H2, 256, 256)
+        conv("bottom_up_block_1.6", "b1b", "x1", H2, H2, 256, 256)
+        conv("trans_0.0", "x0", None, H, H, 128, 128, f32="t0")
+        conv("trans_1.0", "x1", "t1", H2, H2, 256, 256)
+        self._deconv("deconv_block_0.0", "t1", "m0", residual="t0")
+        mark("neck:deconv_block_0.0")
+        self._deconv("deconv_block_1.0", "t1", "m1")
+        mark("neck:deconv_block_1.0")
+        conv("conv_0.0", "m0", None, H, H, 128, 128, f32="o0")
+        conv("conv_1.0", "m1", None, H, H, 128, 128, f32="o1")
+        w0, s0, t0 = self.params["w_0.0"]
+        w1, s1, t1 = self.params["w_1.0"]
+        ops.ssfa_fuse_planes(self.buf["o0"], self.buf["o1"], w0, w1, s0, t0, s1, t1, self.buf["out"], self._info("o0"), self._info("o1"),
+                             self._info("out"), self.planes["out"])
+        if "head" not in self.params:
+            mark("neck:fuse+head")
+            return self.buf["out"], None
+        self.head()
+        mark("neck:fuse+head")
+        return self.buf["out"], self.buf["head"]
+
+    def head(self):
+        H = (self.h, self.w)
+        self._conv("head", "out", None, H, H, 128, self.HEAD_STRIDE, relu=False, f32="head")
+        return self.buf["head"]
+
+    def activation(self, name):
+        """fp32 NHWC view of an intermediate tensor (tests): planes are converted back with their scale"""
+        if name in self.buf:
+            return self.buf[name]
+        return ops.planes_to_float(self.planes[name], self._info(name))
+
+    def bench_layer(self, name="bottom_up_block_0.4"):
+        H = (self.h, self.w)
+
+        def launch():
+            self._conv(name, "x0", "b0b", H, H, 128, 128)
+
+        return launch, "bev_conv_p2_kernel (tcgen05 kind::f16 from pre-split fp16 planes, two-term split, weight multicast)"

@@ -82,6 +82,7 @@ def kitti_car_anchors(feature_size=(1, 200, 176), anchor_range=(0, -40.0, -1.0, 
 # ---------------------------------------------------------------------------------------------------------------- bench weights
 _CALIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "bench_calib.json")
 BOX_HEAD_SCALE = 0.1
+IOU_HEAD_SCALE = 0.1
 EMPTY_LOGIT = -6.0        # classification logit of every anchor over empty space (sigmoid = 2.5e-3, far below the 0.3 threshold)
 
 
@@ -147,4 +148,8 @@ def bench_detector_state(cloud="ring", seed=0, alpha=None, gains=None):
     head = dict(head)
     for k in ("tasks.0.conv_box.weight", "tasks.0.conv_box.bias"):
         head[k] = head[k].float() * BOX_HEAD_SCALE
+    # IoU head: predictions around 0.5 +- 0.3 like a trained head (random init gives iou in [-3, 3]: (iou + 1) / 2 near 0 makes the
+    # rectified score x^4 ill-conditioned, relative differences of 1e-5 in the head become 3e-3 in the score)
+    head["tasks.0.conv_iou.weight"] = head["tasks.0.conv_iou.weight"].float() * IOU_HEAD_SCALE
+    head["tasks.0.conv_iou.bias"] = torch.full((2,), 0.5)
     return layers, ssfa, apply_cls_calibration(head, alpha)
