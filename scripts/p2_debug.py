@@ -167,7 +167,7 @@ if __name__ == "__main__":
         print("== step", st, flush=True)
         t0 = time.time()
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), st], timeout=180, capture_output=True, text=True)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), st], timeout=int(os.environ.get("P2_STEP_TIMEOUT", "120")), capture_output=True, text=True)
             print(r.stdout[-3000:], end="")
             if r.returncode != 0:
                 print(r.stderr[-1500:])
