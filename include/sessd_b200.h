@@ -121,12 +121,6 @@ int sessd_spconv_forward(const float *d_in_feat, int cin, const int *d_nbr, int 
                          int max_out, const float *d_weight, int cout, const float *d_scale, const float *d_shift,
                          int relu, float *d_out_feat, void *stream);
 
-/* Tensor-core variant (tcgen05, 3xTF32) for (Cin, Cout) in {(32,32), (32,64), (64,64)}: d_weight_split is
- * [2 (hi|lo)][kvol][Cout][Cin] (K-major), hi = tf32-truncated weights, lo = w - hi. */
-int sessd_spconv_forward_tc(const float *d_in_feat, int cin, const int *d_nbr, int kvol, const int *d_n_out,
-                            int max_out, const float *d_weight_split, int cout, const float *d_scale,
-                            const float *d_shift, int relu, float *d_out_feat, void *stream);
-
 /* dense(): out NHWC [batch, H, W, C*D] with channel index c*D + d (zero-filled by the call) */
 int sessd_sparse_to_dense(const float *d_feat, const int *d_coors, const int *d_n, int max_rows, int channels,
                           sessd_grid grid, float *d_out, void *stream);
@@ -135,28 +129,37 @@ int sessd_sparse_to_dense(const float *d_feat, const int *d_coors, const int *d_
 int sessd_sparse_to_dense_indexed(const float *d_feat, int max_rows, const void *d_bitmap_index, int channels, sessd_grid grid,
                                   float *d_out, void *stream);
 
-/* S4 (fp16-split tensor-core path with TMA gather; csrc/spconv_h2.cu).  Same contract as sessd_spconv_forward (spconv 1.x
- * gather -> GEMM -> scatter-add at det3d/models/backbones/scn.py:106-149, + folded BN + ReLU), but the input features are
- * read as fp16 (hi, lo) planes [plane_rows][2][cp] -- x = 2^-s (hi + lo), s chosen from *d_amax_in exactly like
- * sessd_bev_conv_h2 -- produced by sessd_split_h2 from the producing layer's fp32 rows; row `zero_row` of the planes must be
- * all zero (missing neighbours read it).  d_weight_h2: cp = 64: [kvol][2 (hi|lo)][cout][64] fp16, cp = 32:
- * [kvol][cout][hi 32 | lo 32] fp16 (Cin 16 zero-padded), every output channel scaled by a power of two 2^e[c];
- * d_scale[c] must be bn_scale[c] * 2^-e[c].  d_amax_out (nullable) receives the running abs-max of the output.
- * Supported (cp, cout): (32,16) (32,32) (32,64) (64,64). */
 /* S4, narrow layers (Cin <= 32; csrc/spconv_rows.cu): same contract and arguments as sessd_spconv_forward, fp32 SIMT, but the work is
  * proportional to the number of rulebook PAIRS instead of N_out x kvol row slots (a warp owns 8 output rows and visits only their valid
  * neighbours).  d_amax_out (nullable) receives the running abs-max of the output.  (Cin, Cout): (4,16) (16,16) (16,32) (32,32) (32,64). */
 int sessd_spconv_forward_rows(const float *d_in_feat, int cin, const int *d_nbr, int kvol, const int *d_n_out, int max_out,
                               const float *d_weight, int cout, const float *d_scale, const float *d_shift, int relu,
                               float *d_out_feat, float *d_amax_out, void *stream);
-/* pipeline depth of sessd_spconv_forward_h2: 0 / 1 = two CTAs per SM x 2-4 stages (default), 2 = one CTA per SM x 4-8 stages */
-void sessd_set_sp_h2_depth(int mode);
-int sessd_split_h2(const float *d_feat, const int *d_n, int max_rows, int channels, const float *d_amax, void *d_planes, int cp,
-                   void *stream);
+/* ... and the output also (d_out_feat nullable: only) as fp16 (hi, lo) planes [row][2][cpo] for the tensor-core layers: d_out_info =
+ * {abs-max of the output (atomicMax; zero it once per frame), plane scale S_out}; S_out = the power of two that maps the bound
+ * *d_amax_in * gain + shift_max into [2^14, 2^15) (d_amax_in = abs-max of the INPUT features, gain = max_n sum_{k,c} |w[k][c][n] bn_scale[n]|,
+ * shift_max = max_n |shift[n]|). */
+int sessd_spconv_forward_rows_planes(const float *d_in_feat, int cin, const int *d_nbr, int kvol, const int *d_n_out, int max_out,
+                                     const float *d_weight, int cout, const float *d_scale, const float *d_shift, int relu,
+                                     const float *d_amax_in, float gain, float shift_max, float *d_out_feat, void *d_out_planes, int cpo,
+                                     float *d_out_info, void *stream);
+/* S4, the default tensor-core path of the Cin >= 32 layers (csrc/spconv_cg.cu): pair-proportional operand traffic -- the rows of the
+ * neighbours that exist are copied by cp.async into the UMMA operand tiles (no row slot is spent on a missing neighbour), persistent CTAs,
+ * tcgen05 kind::f16 with the two-term fp16 split of spconv_h2.cu (same weight tiles: ops.pack_weight_sp_h2).  Same contract as
+ * sessd_spconv_forward (spconv 1.x gather -> GEMM -> scatter-add at det3d/models/backbones/scn.py:106-149, + folded BN + ReLU).
+ * d_in_planes [plane_rows][2][cp] fp16, x = (hi + lo) / d_in_info[1], d_in_info[0] = abs-max of the input tensor; outputs (each nullable, at
+ * least one): fp32 rows [max_out][cout]; planes [>= max_out][2][cout <= 32 ? 32 : 64] with d_out_info = {abs-max of the output (atomicMax; zero
+ * it once per frame), S_out}, S_out from the bound d_in_info[0] * gain + shift_max as above.  Supported (cp, cout): (32,32) (32,64) (64,64). */
+int sessd_spconv_forward_cg(const void *d_in_planes, int cp, int plane_rows, const float *d_in_info, const int *d_nbr, int kvol,
+                            const int *d_n_out, int max_out, const void *d_weight_h2, int cout, const float *d_scale, const float *d_shift,
+                            int relu, float gain, float shift_max, float *d_out_f32, void *d_out_planes, float *d_out_info, void *stream);
+/* 1: the gathered rows of sessd_spconv_forward_cg also allocate in L1 (cp.async.ca); default 0 (cp.async.cg) */
+void sessd_set_sp_cg_l1(int on);
+/* 1 (default): every CTA of sessd_spconv_forward_cg walks a tile's kernel offsets from a different starting point (de-phased weight streams:
+ * CTAs reading the same weight tile in lockstep keep only the L2 slices that hold it busy); 0: ascending offsets everywhere */
+void sessd_set_sp_cg_rotate(int on);
+/* *d_amax = max(*d_amax, max |d_feat[i]|) over the first *d_n rows of a [max_rows, channels] fp32 tensor */
 int sessd_absmax_rows(const float *d_feat, const int *d_n, int max_rows, int channels, float *d_amax, void *stream);
-int sessd_spconv_forward_h2(const void *d_in_planes, int cp, int plane_rows, int zero_row, const float *d_amax_in, const int *d_nbr,
-                            int kvol, const int *d_n_out, int max_out, const void *d_weight_h2, int cout, const float *d_scale,
-                            const float *d_shift, int relu, float *d_out_feat, float *d_amax_out, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * N1/H1: BEV neck (SSFA) + head.  Replaces the cuDNN conv/deconv + BatchNorm2d + ReLU blocks of
@@ -182,33 +185,6 @@ int sessd_bev_conv(const float *d_in, const float *d_weight /*[ntaps, cin, cout]
                    const float *d_shift, const float *d_residual /*nullable, same shape as out*/, float *d_out,
                    const sessd_conv_desc *desc, void *stream);
 
-/* Tensor-core variant (tcgen05 + TMEM + TMA, 3xTF32 split for fp32-level accuracy): same contract (in_stride 1 or 2).
- * d_weight_split [2 (hi|lo)][ntaps][cout_pad][cin]: hi = weights truncated to tf32, lo = w - hi; cout_pad is a multiple of the
- * N tile (128; 32 when cout <= 32). */
-int sessd_bev_conv_tc(const float *d_in, const float *d_weight_split, int cout_pad, const float *d_scale,
-                      const float *d_shift, const float *d_residual, float *d_out, const sessd_conv_desc *desc,
-                      void *stream);
-
-/* ConvTranspose2d(k3, s2, p1, op1) + BN + ReLU (+ residual) in one launch (four output-parity classes as blockIdx.z);
- * d_weight_split [2][9][cout_pad][cin], tap = ky*3+kx of W[cin][cout][ky][kx]; output [batch, 2*in_h, 2*in_w, cout] NHWC
- * (rpn_v1.py:183-195). */
-int sessd_bev_deconv_tc(const float *d_in, const float *d_weight_split, int cout_pad, const float *d_scale,
-                        const float *d_shift, const float *d_residual, float *d_out, int batch, int in_h, int in_w,
-                        int cin, int cout, int relu, void *stream);
-
-/* fp16-split tensor-core variant (tcgen05 kind::f16, A operand in tensor memory, one halo patch per channel chunk): same contract as
- * sessd_bev_conv_tc for in_stride == 1, cin % 64 == 0 and tap lists whose reach fits a 10x18-pixel patch (else SESSD_EINVAL: use
- * sessd_bev_conv_tc).  Every fp32 operand is represented exactly-scaled as fp16 hi + fp16 lo (>= 22 significand bits, same as 3xTF32).
- * d_weight_h2: __half [2 (hi|lo)][ntaps][cout_pad][cin] of 2^e[n]*w (per output channel n; max |2^e w| in [2^10, 2^11));
- * d_scale (required) = folded BN scale * 2^-e[n].
- * d_amax_in  (nullable): device scalar >= max|in| -- selects the activation scaling 2^s; NULL = no scaling (|in| must stay < 65504).
- * d_amax_out (nullable): device scalar, atomically raised to max|out| (the next layer's d_amax_in); zero it once per frame. */
-int sessd_bev_conv_h2(const float *d_in, const void *d_weight_h2, int cout_pad, const float *d_scale,
-                      const float *d_shift, const float *d_residual, float *d_out, const sessd_conv_desc *desc,
-                      const float *d_amax_in, float *d_amax_out, void *stream);
-int sessd_bev_deconv_h2(const float *d_in, const void *d_weight_h2, int cout_pad, const float *d_scale,
-                        const float *d_shift, const float *d_residual, float *d_out, int batch, int in_h, int in_w,
-                        int cin, int cout, int relu, const float *d_amax_in, float *d_amax_out, void *stream);
 /* ------------------------------------------------------------------------------------------------
  * BEV convs from PRE-SPLIT fp16 planes (csrc/bevconv_p2.cu): the neck's default path.  Activations travel between layers as
  * __half [2 (hi|lo)][batch][H][W][C] planes with x = (hi + lo) / S, S an exact power of two; every plane tensor has a device-side
@@ -226,8 +202,11 @@ int sessd_bev_deconv_p2(const void *d_in_planes, const float *d_in_info, const v
                         int relu, void *stream);
 /* fp32 [n] -> planes [2][n] scaled from d_info[0] (the tensor's abs-max, e.g. from sessd_absmax); writes the scale to d_info[1] */
 int sessd_bev_split_planes(const float *d_x, long long n, float *d_info, void *d_planes, void *stream);
-/* CTAs per cluster sharing (TMA-multicasting) the weight tiles of sessd_bev_conv_p2: 1 or 2 (default) */
+/* CTAs per cluster sharing (TMA-multicasting) the weight tiles of sessd_bev_conv_p2: 1 (default) or 2 */
 void sessd_set_p2_cluster(int ctas_per_cluster);
+/* 1 (default): every CTA of sessd_bev_conv_p2 starts its (channel chunk, tap) loop at a different point, so that the SMs do not stream
+ * the same 16 KB weight tile in lockstep (which keeps only the L2 slices holding that tile busy); 0: identical order everywhere */
+void sessd_set_p2_rotate(int on);
 /* dense() (scn.py:184-187) straight into the planes the neck reads: d_amax = abs-max of the feature rows, d_info[2] <- {abs-max, S} */
 int sessd_sparse_to_dense_planes(const float *d_feat, int max_rows, const void *d_bitmap_index, int channels, sessd_grid grid,
                                  const float *d_amax, float *d_info, void *d_planes, void *stream);
@@ -236,28 +215,9 @@ int sessd_ssfa_fuse_planes(const float *d_x0, const float *d_x1, const float *d_
                            float t1, int num_pixels, int channels, float *d_out, const float *d_info0, const float *d_info1,
                            float *d_out_info, void *d_planes, void *stream);
 
-/* profiling experiments only: ablation mask (1 no split work, 2 no MMAs, 4 no weight reloads, 8 no stores; results are garbage when
- * non-zero) and optional [ctas][8] int64 globaltimer stamps (start, split done, accumulators ready, end) */
-void sessd_set_h2_debug(int ablate_mask, void *d_stamps);
 /* *d_amax = max(*d_amax, max_i |d_x[i]|)  (for tensors produced by kernels without an abs-max epilogue) */
 int sessd_absmax(const float *d_x, long long n, float *d_amax, void *stream);
 
-/* tunable of sessd_bev_conv_tc: CTAs per thread-block cluster sharing the weight tiles through TMA multicast (1, 2 or 4) */
-void sessd_set_conv_cluster(int ctas_per_cluster);
-int sessd_get_conv_cluster(void);
-/* 1: A operand staged in shared memory, 2: A operand staged in tensor memory (less smem traffic) */
-void sessd_set_conv_variant(int variant);
-/* profiling experiments only: bit mask of pipeline stages to skip inside bev_conv_tc (results are garbage when non-zero) */
-void sessd_set_conv_ablate(int mask);
-/* profiling aid: sustained tcgen05.mma kind::tf32 rate (M=128, N=n) of one CTA per SM; mode bit0 = A from TMEM, bit1 = two rotating
- * accumulators; d_out[0..2] = issue cycles, cycles to retire, ns */
-int sessd_mma_probe(int n, int iters, int mode, long long *d_out, void *stream);
-/* profiling aid: handshake latencies in cycles (one CTA): d_out[0] tcgen05.commit->mbarrier, [1] two-warp mbarrier round trip,
- * [2] tcgen05.st x32 + wait, [3] / [4] one / four f16 MMAs (M128 N256 K16) + commit -> mbarrier, [5] tcgen05.ld x32 + wait,
- * [6] commit -> other warp -> arrive back round trip */
-int sessd_latency_probe(int iters, long long *d_out, void *stream);
-/* profiling experiments only: device buffer [ctas][8] int64 receiving per-CTA globaltimer stamps of bev_conv_tc (NULL = off) */
-void sessd_set_conv_debug_buffer(void *d_buf);
 
 /* SSFA tail (rpn_v1.py:229-233): w_k = BN(conv1x1_{128->1}(x_k)); softmax over the pair; weighted sum */
 int sessd_ssfa_fuse(const float *d_x0, const float *d_x1, const float *d_w0 /*[C]*/, const float *d_w1,

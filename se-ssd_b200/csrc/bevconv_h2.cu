@@ -368,25 +368,6 @@ __global__ void __launch_bounds__(kH2Threads, 1) bev_conv_h2_kernel(const __grid
     }
 }
 
-// running abs-max of a tensor (feeds the activation scaling of bev_conv_h2 for tensors produced by other kernels)
-__global__ void absmax_kernel(const float4 *__restrict__ x, long long n4, const float *__restrict__ tail, int ntail, float *__restrict__ amax) {
-    float m = 0.f;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        const float4 v = __ldg(x + i);
-        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-    }
-    if (blockIdx.x == 0 && (int)threadIdx.x < ntail) m = fmaxf(m, fabsf(tail[threadIdx.x]));
-    const unsigned w = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(m));
-    __shared__ unsigned s_m[32];
-    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = w;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        const unsigned v = threadIdx.x < (blockDim.x >> 5) ? s_m[threadIdx.x] : 0u;
-        const unsigned r = __reduce_max_sync(0xFFFFFFFFu, v);
-        if (threadIdx.x == 0 && r != 0u) atomicMax(reinterpret_cast<unsigned *>(amax), r);
-    }
-}
-
 static int g_h2_ablate = 0;
 static long long *g_h2_dbg = nullptr;
 
@@ -513,13 +494,3 @@ extern "C" int sessd_bev_deconv_h2(const float *d_in, const void *d_weight_h2, i
     return launch_h2(d_in, d_weight_h2, 9, cout_pad, d_scale, d_shift, d_residual, d_out, p, stream);
 }
 
-// *d_amax = max(*d_amax, max |x[i]|); x 16-byte aligned
-extern "C" int sessd_absmax(const float *d_x, long long n, float *d_amax, void *stream) {
-    if (!d_x || !d_amax || n < 0 || ((uintptr_t)d_x & 15)) return SESSD_EINVAL;
-    if (n == 0) return 0;
-    const long long n4 = n / 4;
-    const int blocks = (int)max(1LL, min((long long)148 * 8, (n4 + 255) / 256));
-    absmax_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(d_x), n4, d_x + n4 * 4, (int)(n - n4 * 4), d_amax);
-    ++g_launches;
-    return last_error();
-}

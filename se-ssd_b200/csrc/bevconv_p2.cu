@@ -48,7 +48,7 @@ struct P2Params {
     int ncopies, rows_v;
     int copy_u[kP2MaxCopies], copy_v[kP2MaxCopies];       // input coordinate of the copy's first element relative to (u0, v0) * in_stride
     int copy_bytes, patch_bytes, npatch;                  // bytes of one copy plane, of one patch buffer (ncopies x 2 planes), 1 or 2 buffers
-    int relu, n_tile, nblocks;
+    int relu, n_tile, nblocks, rotate;
     int tiles_u, tiles_v, tiles, tgroups, total;          // pixel tiles, tile groups (CS tiles each), work items = nclass * nblocks * tgroups
     int cls_order[4];
     const float *in_info;              // [2] = {abs-max of the input tensor, scale S_in of its planes}
@@ -151,7 +151,9 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
             int gcc = 0;
             for (int g = cluster_id; g < p.total; g += nclusters) {
                 const P2Item it = p2_decode<CS>(p, g, (int)crank);
-                for (int cc = 0; cc < nchunks; ++cc, ++gcc) {
+                const int rot_c = p.rotate ? cluster_id % nchunks : 0;
+                for (int c0 = 0; c0 < nchunks; ++c0, ++gcc) {
+                    const int cc = (c0 + rot_c) % nchunks;
                     const int pb = gcc % p.npatch;
                     const uint32_t ph = (uint32_t)(gcc / p.npatch) & 1u;
                     mbar_wait(&patch_empty[pb], ph ^ 1u);
@@ -173,8 +175,10 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
             const uint32_t so = crank * (uint32_t)rows * 64u;
             for (int g = cluster_id; g < p.total; g += nclusters) {
                 const P2Item it = p2_decode<CS>(p, g, (int)crank);
-                for (int cc = 0; cc < nchunks; ++cc)
-                    for (int tap = 0; tap < it.ntaps; ++tap, ++gbj) {
+                const int rot_c = p.rotate ? cluster_id % nchunks : 0, rot_t = p.rotate ? (cluster_id / nchunks) % it.ntaps : 0;
+                for (int c0 = 0; c0 < nchunks; ++c0)
+                    for (int t0 = 0; t0 < it.ntaps; ++t0, ++gbj) {
+                        const int cc = (c0 + rot_c) % nchunks, tap = (t0 + rot_t) % it.ntaps;
                         const int s = gbj % kP2BStages;
                         const uint32_t ph = (uint32_t)(gbj / kP2BStages) & 1u;
                         mbar_wait(&b_empty[s], ph ^ 1u);
@@ -213,13 +217,15 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
                     tc_fence_after();
                 }
                 int lbj = 0;
+                const int rot_t = p.rotate ? (cluster_id / nchunks) % ntaps : 0;
                 for (int cc = 0; cc < nchunks; ++cc, ++gcc) {
                     const int pb = gcc % p.npatch;
                     mbar_wait(&patch_full[pb], (uint32_t)(gcc / p.npatch) & 1u);
                     tc_fence_after();
                     const uint32_t pbase = patch_lo + (uint32_t)((pb * p.patch_bytes) >> 4);
 #pragma unroll 1
-                    for (int tap = 0; tap < ntaps; ++tap, ++gbj, ++lbj) {
+                    for (int t0 = 0; t0 < ntaps; ++t0, ++gbj, ++lbj) {
+                        const int tap = (t0 + rot_t) % ntaps;
                         const int S = gbj % kP2BStages, par = gbj & 1;
                         mbar_wait(&b_full[S], (uint32_t)(gbj / kP2BStages) & 1u);
                         tc_fence_after();
@@ -242,7 +248,7 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
                         }
                         if (CS == 1) tc_commit(&b_empty[S]);
                         else tc_commit_mc(&b_empty[S], kMask);                            // the stage is reusable in EVERY CTA of the cluster (peers multicast into it)
-                        if (tap == ntaps - 1) tc_commit(&patch_empty[pb]);
+                        if (t0 == ntaps - 1) tc_commit(&patch_empty[pb]);
                         if (lbj == nbj - 1) tc_commit(acc_full);
                     }
                 }
@@ -373,7 +379,9 @@ static int encode_map_nd(CUtensorMap *m, const void *base, int rank, const cuuin
     return r == CUDA_SUCCESS ? 0 : 700 + (int)r;
 }
 
-static int g_p2_cluster = 2;
+static int g_p2_cluster = 1;
+static int g_p2_rotate = 1;      // CTAs walk the (channel chunk, tap) loop from different starting points: 148 SMs streaming the SAME 16 KB weight tile in
+                                 // lockstep keep only the ~64 L2 slices that hold it busy
 
 // taps: per class (dy, dx, weight tap); fills the geometry of p and launches
 struct P2Taps { int n, dy[9], dx[9], w[9]; };
@@ -461,6 +469,7 @@ static int launch_p2(const void *d_in_planes, int in_h, int in_w, const float *d
         attr_done = true;
     }
     p.n_tile = n_tile;
+    p.rotate = g_p2_rotate;
     p.tiles_u = div_up(p.grid_u, kP2TileU);
     p.tiles_v = div_up(p.grid_v, kP2TileV);
     p.tiles = p.tiles_u * p.tiles_v * p.batch;
@@ -510,7 +519,9 @@ static int launch_p2(const void *d_in_planes, int in_h, int in_w, const float *d
 using namespace sessd;
 
 // CTAs per cluster sharing the weight tiles through TMA multicast (1 or 2; default 2)
-extern "C" void sessd_set_p2_cluster(int cs) { sessd::g_p2_cluster = cs == 1 ? 1 : 2; }
+extern "C" void sessd_set_p2_cluster(int cs) { sessd::g_p2_cluster = cs == 2 ? 2 : 1; }
+// 1 (default): every CTA starts the (channel chunk, tap) loop at a different point (de-phased weight streams); 0: all in the same order
+extern "C" void sessd_set_p2_rotate(int on) { sessd::g_p2_rotate = on ? 1 : 0; }
 
 // Conv2d (stride 1 or 2, arbitrary tap list) + folded BN + ReLU (+ residual) from fp16 (hi, lo) planes.
 //   d_in_planes  __half [2][batch][in_h][in_w][cin]; d_in_info [2] = {abs-max of the input, scale of its planes} (device);

@@ -1,0 +1,464 @@
+// spconv_cg.cu -- sparse 3-D convolution (SubM / strided, + folded BN + ReLU) on the tcgen05 tensor cores whose operand traffic is
+// proportional to the number of rulebook PAIRS: only the neighbour rows that exist are fetched.
+//
+// Replaces spconv 1.x's per-offset gather -> sgemm -> scatter-add used by det3d/models/backbones/scn.py:106-149 (SpMiddleFHD), like
+// spconv_h2.cu (same numerics: fp16 (hi, lo) planes with an exact power-of-two scale, three kind::f16 products per MAC, two main + one
+// cross TMEM accumulator summed in RN fp32; same weight tiles), but the 128-row A operand of a (tile, kernel offset) is no longer
+// fetched with 32-64 TMA gather4 instructions whose cost is per ROW SLOT, present or not (~5.5 clk per 128-byte row: at the 21 %
+// neighbour fill of the 32-channel layers 79 % of the row requests fetched zeros and the layer ran at 0.9 % of the tensor peak).  Here
+//   * the tile's neighbour table is compacted once into per-offset lists of (input row, tile row) pairs (shared memory, 13.8 KB);
+//   * eight producer warps copy the listed rows with 16-byte cp.async (LDGSTS: global/L2 -> shared, no registers, 2 clk per 128-byte row)
+//     straight into the K-major SWIZZLE_128B layout the UMMA descriptors address; rows without a neighbour are never touched;
+//   * a stage's missing rows must read as zeros: each warp remembers which of its rows hold data in every stage and clears (st.shared)
+//     only the rows that were valid for the stage's previous offset and are not for the new one -- the stages are zeroed once per CTA;
+//   * CTAs are persistent (two per SM: one tile's epilogue overlaps the other's main loop), so barrier / TMEM / zero-fill setup is paid
+//     once, not per 128 rows;
+//   * the epilogue writes the NEXT layer's operand format directly -- fp16 (hi, lo) planes scaled by a power of two derived from a
+//     rigorous bound |out| <= amax_in * G + max|shift| (G from the weights, host; amax_in measured by the producing layer's epilogue) --
+//     and raises the output's abs-max: the separate split kernel (one read + one write of every feature tensor) is gone.
+// Generic-proxy writes (cp.async, st.shared) become visible to the tensor core (async proxy) through fence.proxy.async executed by the
+// WRITING threads after cp.async.wait_group, before they arrive on the stage's mbarrier.
+// Warps: 0-7 producers then epilogue (TMEM lane quadrant = warp & 3, column half = warp >> 2), 8 weight-tile TMA, 9 MMA issue.
+#include <cuda_fp16.h>
+
+#include "tc_common.cuh"
+
+namespace sessd {
+
+constexpr int kCgBM = 128;
+constexpr int kCgMaxK = 27;
+constexpr int kCgProdWarps = 8;
+constexpr int kCgProdThreads = kCgProdWarps * 32;
+constexpr int kCgThreads = kCgProdThreads + 64;
+
+template <int CP, int COUT>
+struct CgCfg {
+    static constexpr bool kWide = (CP == 64);
+    static constexpr int kATile = (kWide ? 2 : 1) * kCgBM * 128;              // bytes: [hi tile ; lo tile] (wide) or one [hi | lo] tile
+    static constexpr int kBTile = (kWide ? 2 : 1) * COUT * 128;
+    static constexpr int kStage = kATile + (kBTile + 1023) / 1024 * 1024;
+    static constexpr int kStages = kWide ? 2 : (COUT <= 32 ? 4 : 3);
+    static constexpr int kLag = kStages - 1;                                  // cp.async groups a producer keeps in flight
+    static constexpr int kMeta = kCgBM * kCgMaxK * 4 /*lists*/ + kCgMaxK * 16 /*valid*/ + 32 * 4 /*cnt*/ + 33 * 4 /*klist, nact*/ +
+                                 kCgProdWarps * 4 * 4 /*dirty*/ + (3 * kStages + 1) * 8 /*barriers*/ + 24;
+    static constexpr int kSmem = kStages * kStage + kMeta + 1024;
+    static constexpr int kTmemCols = (3 * COUT <= 128) ? 128 : 256;
+    static constexpr int kCPO = COUT > 32 ? 64 : 32;                          // channels per plane row of the OUTPUT
+};
+
+struct CgArgs {
+    const __half *planes;              // input [rows][2][CP] fp16, x = (hi + lo) / in_info[1]
+    const float *in_info;              // {abs-max of the input tensor, its plane scale}
+    const int *nbr;                    // [max_out][kvol]
+    const int *d_n_out;
+    int kvol, max_out, relu, rotate;
+    const float *scale, *shift;        // folded BN (scale already times the per-channel weight exponent 2^-e)
+    float gain, shift_max;             // |out| <= amax_in * gain + shift_max
+    float *out_f32;                    // nullable [max_out][COUT]
+    __half *out_planes;                // nullable [max_out (+1)][2][kCPO]
+    float *out_info;                   // nullable {abs-max of the output (atomicMax), plane scale}
+};
+
+__host__ __device__ constexpr uint32_t cg_idesc_f16(int M, int N) {
+    return (1u << 4) /*C=F32*/ | (0u << 7) /*A=F16*/ | (0u << 10) /*B=F16*/ | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void cg_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int L1>
+__device__ __forceinline__ void cg_cp_async16(uint32_t smem_dst, const void *gsrc) {
+    if (L1)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
+    else
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cg_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cg_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cg_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void cg_sts_zero16(uint32_t saddr) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};\n" ::"r"(saddr), "r"(0) : "memory");
+}
+
+__device__ __forceinline__ void cg_tmem_ld16(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+template <int CP, int COUT, int L1>
+__global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_constant__ CUtensorMap map_w, const CgArgs a) {
+    using C = CgCfg<CP, COUT>;
+    const int n_out = min(*a.d_n_out, a.max_out);
+    const int ntiles = (n_out + kCgBM - 1) / kCgBM;
+    if ((int)blockIdx.x >= ntiles) return;                       // whole CTA leaves together (before any barrier / TMEM use)
+    const int kvol = a.kvol;
+
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *tiles = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint32_t *s_list = (uint32_t *)(tiles + C::kStages * C::kStage);      // [kvol][128]: (input row << 7) | tile row
+    uint32_t *s_valid = s_list + kCgBM * kCgMaxK;                        // [kvol][4]: 128-bit row mask per offset
+    int *s_cnt = (int *)(s_valid + kCgMaxK * 4);                         // [32]
+    int *s_klist = s_cnt + 32;                                           // [32] + nact
+    int *s_nact = s_klist + 32;
+    uint32_t *s_dirty = (uint32_t *)(s_nact + 1);                        // [8 warps][4 stages]: 16-bit mask of rows holding data
+    uint64_t *bars = (uint64_t *)(((uintptr_t)(s_dirty + kCgProdWarps * 4) + 7) & ~(uintptr_t)7);
+    uint64_t *full_a = bars, *full_b = bars + C::kStages, *empty = bars + 2 * C::kStages;
+    uint64_t *acc_full = bars + 3 * C::kStages;
+    uint32_t *tmem_slot = (uint32_t *)(acc_full + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tiles_u32 = smem_u32(tiles);
+
+    if (tid == 0) {
+        for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_a[s], kCgProdWarps); mbar_init(&full_b[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(C::kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    // every A tile starts as zeros (the B halves of the stages are always fully overwritten by the TMA)
+    for (int s = 0; s < C::kStages; ++s)
+        for (int o = tid * 16; o < C::kATile; o += kCgThreads * 16) cg_sts_zero16(tiles_u32 + (uint32_t)(s * C::kStage + o));
+    if (tid < kCgProdWarps * 4) s_dirty[tid] = 0u;
+    cg_fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const float amax_in = __ldg(a.in_info), s_in = __ldg(a.in_info + 1);
+    const float inv_act = 1.f / s_in;                            // exact: power of two
+    const float s_out = pow2_scale_for_bound(amax_in * a.gain + a.shift_max);
+    if (blockIdx.x == 0 && tid == 0 && a.out_info) a.out_info[1] = s_out;
+    float vmax = 0.f;
+    int gbase = 0, acc_it = 0;                                   // stage fills / accumulator hand-overs before this tile (all roles count alike)
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int row0 = tile * kCgBM;
+        const int rows = min(kCgBM, n_out - row0);
+        // ---------------------------------------------------------------- per-offset lists of the tile's (input row, tile row) pairs
+        if (tid < 32) s_cnt[tid] = 0;
+        if (tid < kCgMaxK * 4) s_valid[tid] = 0u;
+        __syncthreads();
+        {
+            const int nent = rows * kvol;                        // the tile's neighbour table is contiguous in global memory
+            const int *tn = a.nbr + (size_t)row0 * kvol;
+            for (int e = tid; e < nent; e += kCgThreads) {
+                const int v = __ldg(tn + e);
+                if (v >= 0) {
+                    const int r = (kvol == 27) ? e / 27 : e / kvol;
+                    const int k = e - r * kvol;
+                    const int pos = atomicAdd(&s_cnt[k], 1);
+                    s_list[k * kCgBM + pos] = ((uint32_t)v << 7) | (uint32_t)r;
+                    atomicOr(&s_valid[k * 4 + (r >> 5)], 1u << (r & 31));
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int c = 0;
+            for (int k = 0; k < kvol; ++k)
+                if (s_cnt[k] > 0) s_klist[c++] = k;
+            *s_nact = c;
+        }
+        __syncthreads();
+        const int nact = *s_nact;
+        // every CTA walks the tile's offsets from a different starting point: 296 CTAs streaming the SAME weight tile W[k] in lockstep would
+        // keep only the 16-64 L2 slices that hold it busy (the convoy bounds the layer, not the gather)
+        const int rot = (a.rotate && nact > 0) ? (int)((blockIdx.x * 11u + (unsigned)tile) % (unsigned)nact) : 0;
+
+        if (warp == 9) {
+            // ===================== MMA issue (one thread) =====================
+            if (lane == 0) {
+                const uint32_t idesc = cg_idesc_f16(kCgBM, COUT);
+                const uint32_t idesc2 = cg_idesc_f16(kCgBM, 2 * COUT);
+                const uint64_t desc_hi = ((uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29))) << 32;      // SBO | version | SWIZZLE_128B
+                const uint32_t tiles_lo = ((tiles_u32 >> 4) & 0x3FFFu) | (1u << 16);
+                const uint32_t acc_main0 = tmem_base, acc_cross = tmem_base + COUT, acc_main1 = tmem_base + 2 * COUT;
+                tc_fence_after();                                // the previous tile's epilogue read the accumulators before the CTA-wide sync
+                for (int j = 0; j < nact; ++j) {
+                    const int gj = gbase + j;
+                    const int s = gj % C::kStages;
+                    const uint32_t ph = (uint32_t)(gj / C::kStages) & 1u;
+                    mbar_wait(&full_b[s], ph);
+                    mbar_wait(&full_a[s], ph);
+                    tc_fence_after();
+                    const uint32_t st_lo = tiles_lo + (uint32_t)s * (C::kStage >> 4);
+                    const uint64_t dA = desc_hi | st_lo;
+                    const uint64_t dB = desc_hi | (st_lo + (C::kATile >> 4));
+                    if constexpr (C::kWide) {
+                        const uint64_t dAl = dA + ((kCgBM * 128) >> 4);
+                        const uint64_t dBh = dB + (((j & 1) ? COUT * 128 : 0) >> 4);       // the b_hi rows inside the [X ; Y] tile
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint32_t o = (uint32_t)(kk * 32) >> 4;
+                            if ((j & 1) == 0) {
+                                cg_mma_f16(acc_main0, dA + o, dB + o, idesc2, (j != 0 || kk != 0) ? 1u : 0u);    // [main0|cross] (+)= a_hi x [b_hi;b_lo]
+                            } else if (j == 1 && kk == 0) {
+                                cg_mma_f16(acc_cross, dA + o, dB + o, idesc, 1u);                                 // cross += a_hi x b_lo
+                                cg_mma_f16(acc_main1, dA + o, dBh + o, idesc, 0u);                                // main1  = a_hi x b_hi
+                            } else {
+                                cg_mma_f16(acc_cross, dA + o, dB + o, idesc2, 1u);                                // [cross|main1] += a_hi x [b_lo;b_hi]
+                            }
+                            cg_mma_f16(acc_cross, dAl + o, dBh + o, idesc, 1u);                                   // cross += a_lo x b_hi
+                        }
+                    } else {
+                        const uint32_t acc_main = (j & 1) ? acc_main1 : acc_main0;
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const uint32_t o = (uint32_t)(kk * 32) >> 4;
+                            cg_mma_f16(acc_main, dA + o, dB + o, idesc, (j >= 2 || kk != 0) ? 1u : 0u);           // main  (+)= a_hi x b_hi
+                            cg_mma_f16(acc_cross, dA + o, dB + 4 + o, idesc, (j != 0 || kk != 0) ? 1u : 0u);      // cross (+)= a_hi x b_lo
+                            cg_mma_f16(acc_cross, dA + 4 + o, dB + o, idesc, 1u);                                 // cross  += a_lo x b_hi
+                        }
+                    }
+                    tc_commit(&empty[s]);
+                    if (j == nact - 1) tc_commit(acc_full);
+                }
+            }
+            __syncwarp();
+        } else if (warp == 8) {
+            // ===================== weight tiles (TMA, one thread) =====================
+            if (lane == 0) {
+                for (int j = 0; j < nact; ++j) {
+                    const int gj = gbase + j;
+                    const int s = gj % C::kStages;
+                    const uint32_t ph = (uint32_t)(gj / C::kStages) & 1u;
+                    const int k = s_klist[j + rot < nact ? j + rot : j + rot - nact];
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    mbar_expect_tx(&full_b[s], C::kBTile);
+                    unsigned char *b_tile = tiles + s * C::kStage + C::kATile;
+                    if constexpr (C::kWide) {
+                        // [b_hi ; b_lo] on even steps, [b_lo ; b_hi] on odd steps (see the MMA issuer)
+                        tma_load_4d(b_tile + ((j & 1) ? COUT * 128 : 0), &map_w, &full_b[s], 0, 0, 0, k);
+                        tma_load_4d(b_tile + ((j & 1) ? 0 : COUT * 128), &map_w, &full_b[s], 0, 0, 1, k);
+                    } else {
+                        tma_load_4d(b_tile, &map_w, &full_b[s], 0, 0, 0, k);
+                    }
+                }
+            }
+            __syncwarp();
+        } else {
+            // ===================== producers: copy the rows that exist, clear the rows that stopped existing =====================
+            const int own = warp * 16;                                   // rows whose zero state this warp maintains
+            constexpr int kLanesPerRow = C::kWide ? 16 : 8;
+            constexpr int kRowsPerPass = kCgProdThreads / kLanesPerRow;
+            const int slot = tid / kLanesPerRow;
+            const int c = tid % kLanesPerRow;
+            const int half = c >> 3, cc = c & 7;                         // wide: chunk c of the 256-byte row = (hi | lo tile, 16-byte chunk)
+            for (int j = 0; j < nact; ++j) {
+                const int gj = gbase + j;
+                const int s = gj % C::kStages;
+                const uint32_t ph = (uint32_t)(gj / C::kStages) & 1u;
+                const int k = s_klist[j + rot < nact ? j + rot : j + rot - nact];
+                if (lane == 0) mbar_wait(&empty[s], ph ^ 1u);
+                __syncwarp();
+                const uint32_t a_base = tiles_u32 + (uint32_t)(s * C::kStage);
+                const uint32_t vs = (s_valid[k * 4 + (warp >> 1)] >> (16 * (warp & 1))) & 0xFFFFu;
+                const uint32_t z = s_dirty[warp * 4 + s] & ~vs;
+                __syncwarp();
+                if (lane == 0) s_dirty[warp * 4 + s] = vs;
+                if (z) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r16 = (lane >> 3) + 4 * i;
+                        if ((z >> r16) & 1u) {
+                            const uint32_t dst = a_base + (uint32_t)((own + r16) * 128 + (lane & 7) * 16);
+                            cg_sts_zero16(dst);
+                            if constexpr (C::kWide) cg_sts_zero16(dst + kCgBM * 128);
+                        }
+                    }
+                }
+                const int n = s_cnt[k];
+                const uint32_t *lst = s_list + k * kCgBM;
+                for (int i = slot; i < n; i += kRowsPerPass) {
+                    const uint32_t e = lst[i];
+                    const uint32_t r = e & 127u;
+                    const size_t src = (size_t)(e >> 7);
+                    if constexpr (C::kWide)
+                        cg_cp_async16<L1>(a_base + (uint32_t)half * (kCgBM * 128) + r * 128u + (((uint32_t)cc ^ (r & 7u)) << 4),
+                                          a.planes + src * 128 + half * 64 + cc * 8);
+                    else
+                        cg_cp_async16<L1>(a_base + r * 128u + (((uint32_t)cc ^ (r & 7u)) << 4), a.planes + src * 64 + cc * 8);
+                }
+                cg_cp_async_commit();
+                if (j >= C::kLag) {
+                    cg_cp_async_wait<C::kLag>();
+                    cg_fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_a[(gj - C::kLag) % C::kStages]);
+                }
+            }
+            cg_cp_async_wait<0>();
+            cg_fence_proxy_async();
+            __syncwarp();
+            if (lane == 0)
+                for (int j = (nact > C::kLag ? nact - C::kLag : 0); j < nact; ++j) mbar_arrive(&full_a[(gbase + j) % C::kStages]);
+
+            // ===================== epilogue: TMEM -> registers -> BN / ReLU -> planes and / or fp32 rows =====================
+            const int q = warp & 3, hcol = warp >> 2;
+            constexpr int kNcol = COUT / 2;                              // 16 or 32 channels per thread
+            const int r = q * 32 + lane;
+            float v[kNcol];
+            if (nact > 0) {
+                if (lane == 0) mbar_wait(acc_full, (uint32_t)acc_it & 1u);
+                __syncwarp();
+                tc_fence_after();
+                const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hcol * kNcol);
+#pragma unroll
+                for (int c0 = 0; c0 < kNcol; c0 += 16) {
+                    uint32_t m0[16], cr[16], m1[16];
+                    cg_tmem_ld16(lane_base + c0, m0);
+                    cg_tmem_ld16(lane_base + COUT + c0, cr);
+                    if (nact > 1) cg_tmem_ld16(lane_base + 2 * COUT + c0, m1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float t = __uint_as_float(m0[i]) + __uint_as_float(cr[i]);
+                        if (nact > 1) t += __uint_as_float(m1[i]);
+                        v[c0 + i] = t;
+                    }
+                }
+                tc_fence_before();                                       // the next tile's MMAs overwrite the accumulators after the CTA-wide sync
+            } else {
+#pragma unroll
+                for (int i = 0; i < kNcol; ++i) v[i] = 0.f;
+            }
+            if (r < rows) {
+                const size_t orow = (size_t)(row0 + r);
+#pragma unroll
+                for (int i = 0; i < kNcol; i += 8) {
+                    const int n = hcol * kNcol + i;
+                    float o[8];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float4 sc = *reinterpret_cast<const float4 *>(a.scale + n + 4 * h);
+                        float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (a.shift) sh = *reinterpret_cast<const float4 *>(a.shift + n + 4 * h);
+                        o[4 * h + 0] = fmaf(v[i + 4 * h + 0] * inv_act, sc.x, sh.x); o[4 * h + 1] = fmaf(v[i + 4 * h + 1] * inv_act, sc.y, sh.y);
+                        o[4 * h + 2] = fmaf(v[i + 4 * h + 2] * inv_act, sc.z, sh.z); o[4 * h + 3] = fmaf(v[i + 4 * h + 3] * inv_act, sc.w, sh.w);
+                    }
+                    if (a.relu) {
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) o[t] = fmaxf(o[t], 0.f);
+                    }
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) vmax = fmaxf(vmax, fabsf(o[t]));
+                    if (a.out_f32) {
+                        float *dst = a.out_f32 + orow * COUT + n;
+                        *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<float4 *>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                    }
+                    if (a.out_planes) {
+                        __align__(16) __half2 hi[4], lo[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const float x0 = o[2 * t] * s_out, x1 = o[2 * t + 1] * s_out;
+                            hi[t] = __floats2half2_rn(x0, x1);
+                            const float2 f = __half22float2(hi[t]);
+                            lo[t] = __floats2half2_rn(x0 - f.x, x1 - f.y);
+                        }
+                        __half *dst = a.out_planes + orow * (2 * C::kCPO) + n;
+                        *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hi);
+                        *reinterpret_cast<uint4 *>(dst + C::kCPO) = *reinterpret_cast<const uint4 *>(lo);
+                    }
+                }
+            }
+        }
+        gbase += nact;
+        acc_it += nact > 0 ? 1 : 0;
+        __syncthreads();                                         // lists are rebuilt next; every role is done reading them
+    }
+    if (warp < kCgProdWarps && a.out_info) {
+        const unsigned m = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(vmax));     // non-negative floats order like their bits
+        if (lane == 0 && m != 0u) atomicMax(reinterpret_cast<unsigned *>(a.out_info), m);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
+}
+
+static int g_cg_rotate = 1;
+static int g_cg_l1 = 0;            // 1: gathered rows also allocate in L1 (cp.async.ca)
+
+template <int CP, int COUT>
+static int launch_spconv_cg(const CgArgs &a, const void *w_h2, cudaStream_t st) {
+    using C = CgCfg<CP, COUT>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(spconv_cg_kernel<CP, COUT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(spconv_cg_kernel<CP, COUT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    CUtensorMap map_w;
+    int rc;
+    if (C::kWide) {       // [kvol][2 (hi|lo)][Cout][64]
+        const cuuint64_t dims[4] = {64, (cuuint64_t)COUT, 2, (cuuint64_t)a.kvol};
+        const cuuint32_t box[4] = {64, (cuuint32_t)COUT, 1, 1};
+        rc = encode_map_4d(&map_w, w_h2, dims, box, nullptr, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2);
+    } else {              // [kvol][Cout][b_hi 32 | b_lo 32]
+        const cuuint64_t dims[4] = {64, (cuuint64_t)COUT, 1, (cuuint64_t)a.kvol};
+        const cuuint32_t box[4] = {64, (cuuint32_t)COUT, 1, 1};
+        rc = encode_map_4d(&map_w, w_h2, dims, box, nullptr, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2);
+    }
+    if (rc) return rc;
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        SESSD_CUDA_TRY(cudaGetDevice(&dev));
+        SESSD_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int tiles = div_up(a.max_out, kCgBM);
+    const int grid = tiles < 2 * num_sms ? tiles : 2 * num_sms;          // persistent: two CTAs per SM
+    if (g_cg_l1)
+        SESSD_LAUNCH((spconv_cg_kernel<CP, COUT, 1>), grid, kCgThreads, C::kSmem, st, map_w, a);
+    else
+        SESSD_LAUNCH((spconv_cg_kernel<CP, COUT, 0>), grid, kCgThreads, C::kSmem, st, map_w, a);
+    return last_error();
+}
+
+}  // namespace sessd
+
+using namespace sessd;
+
+extern "C" void sessd_set_sp_cg_l1(int on) { sessd::g_cg_l1 = on ? 1 : 0; }
+extern "C" void sessd_set_sp_cg_rotate(int on) { sessd::g_cg_rotate = on ? 1 : 0; }
+
+// S4 (scn.py:106-149), pair-proportional tensor-core path.  d_in_planes [plane_rows][2][cp] fp16 with d_in_info = {abs-max, scale};
+// weights / d_scale from ops.pack_weight_sp_h2 (cp = 64: [kvol][2][Cout][64], cp = 32: [kvol][Cout][hi 32 | lo 32]; d_scale = BN scale *
+// 2^-e[c]); gain / shift_max bound the output (see the header).  Outputs (each nullable, at least one): fp32 rows [max_out][cout],
+// planes [>= max_out][2][cout <= 32 ? 32 : 64] + d_out_info = {abs-max (zero it once per frame), scale}.
+// Supported (cp, cout): (32,32), (32,64), (64,64).
+extern "C" int sessd_spconv_forward_cg(const void *d_in_planes, int cp, int plane_rows, const float *d_in_info, const int *d_nbr, int kvol,
+                                       const int *d_n_out, int max_out, const void *d_weight_h2, int cout, const float *d_scale,
+                                       const float *d_shift, int relu, float gain, float shift_max, float *d_out_f32, void *d_out_planes,
+                                       float *d_out_info, void *stream) {
+    if (!d_in_planes || !d_in_info || !d_nbr || !d_n_out || !d_weight_h2 || !d_scale || (!d_out_f32 && !d_out_planes) || max_out < 1 ||
+        kvol < 1 || kvol > kCgMaxK || plane_rows < 1 || plane_rows > (1 << 25))
+        return SESSD_EINVAL;
+    if (d_out_planes && !d_out_info) return SESSD_EINVAL;
+    CgArgs a;
+    a.planes = (const __half *)d_in_planes; a.in_info = d_in_info; a.nbr = d_nbr; a.d_n_out = d_n_out; a.kvol = kvol; a.max_out = max_out;
+    a.relu = relu; a.rotate = g_cg_rotate; a.scale = d_scale; a.shift = d_shift; a.gain = gain; a.shift_max = shift_max; a.out_f32 = d_out_f32;
+    a.out_planes = (__half *)d_out_planes; a.out_info = d_out_info;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cp == 32 && cout == 32) return launch_spconv_cg<32, 32>(a, d_weight_h2, st);
+    if (cp == 32 && cout == 64) return launch_spconv_cg<32, 64>(a, d_weight_h2, st);
+    if (cp == 64 && cout == 64) return launch_spconv_cg<64, 64>(a, d_weight_h2, st);
+    return SESSD_EINVAL;
+}

@@ -338,20 +338,6 @@ __global__ void __launch_bounds__(256) split_h2_kernel(const float *__restrict__
     }
 }
 
-// abs-max over the first *d_n rows of a [max_rows, channels] fp32 tensor (rows beyond the device-side count hold stale data)
-__global__ void __launch_bounds__(256) absmax_rows_kernel(const float *__restrict__ feat, const int *__restrict__ d_n, int max_rows, int channels,
-                                                          float *__restrict__ amax) {
-    const int n = min(*d_n, max_rows);
-    const long long total4 = ((long long)n * channels) >> 2;
-    float m = 0.f;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(feat) + i);
-        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-    }
-    const unsigned w = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(m));
-    if ((threadIdx.x & 31) == 0 && w != 0u) atomicMax(reinterpret_cast<unsigned *>(amax), w);
-}
-
 static int encode_map_2d_f16(CUtensorMap *m, const void *base, cuuint64_t cols, cuuint64_t rows, cuuint32_t box_cols) {
     EncodeTiledFn enc = get_tensor_map_encoder();
     if (!enc) return SESSD_EINVAL;
@@ -411,12 +397,6 @@ extern "C" int sessd_split_h2(const float *d_feat, const int *d_n, int max_rows,
     return last_error();
 }
 
-extern "C" int sessd_absmax_rows(const float *d_feat, const int *d_n, int max_rows, int channels, float *d_amax, void *stream) {
-    if (!d_feat || !d_n || !d_amax || max_rows < 1 || channels < 4 || (channels & 3)) return SESSD_EINVAL;
-    SESSD_LAUNCH(absmax_rows_kernel, persistent_grid(((long long)max_rows * channels) >> 2, 256), 256, 0, stream, d_feat, d_n, max_rows, channels,
-                 d_amax);
-    return last_error();
-}
 
 // d_in_planes: [plane_rows][2][cp] fp16 from sessd_split_h2 (row `zero_row` all zero); d_weight_h2 from the host packer
 // (ops.pack_weight_sp_h2): cp = 64: [kvol][2][Cout][64], cp = 32: [kvol][Cout][hi 32 | lo 32].  d_scale must already contain

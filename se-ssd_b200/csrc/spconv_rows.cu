@@ -17,6 +17,8 @@
 //     split of the next tensor-core layer).
 // Same contract and results as sessd_spconv_forward (fp32 FMA accumulation; only the summation order over offsets is the same too:
 // ascending k).  Algorithmic work: 2 P Cin Cout flops, 4 (P Cin + N_out Cout) + 4 kvol N_out bytes.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace sessd {
@@ -40,7 +42,8 @@ __global__ void __launch_bounds__(kRwThreads, 1) spconv_rows_kernel(const float 
                                                                     const int *__restrict__ d_n_out, int max_out,
                                                                     const float *__restrict__ weight, const float *__restrict__ scale,
                                                                     const float *__restrict__ shift, int relu, float *__restrict__ out_feat,
-                                                                    float *__restrict__ amax_out) {
+                                                                    float *__restrict__ amax_out, const float *__restrict__ amax_in, float gain,
+                                                                    float shift_max, __half *__restrict__ out_planes, int cpo) {
     using C = RwCfg<CIN, COUT>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *s_w = reinterpret_cast<float *>(smem_raw);                              // [kvol][CIN][COUT], resident for the CTA's lifetime
@@ -65,6 +68,13 @@ __global__ void __launch_bounds__(kRwThreads, 1) spconv_rows_kernel(const float 
         sh[j] = (shift && co < COUT) ? shift[co] : 0.f;
     }
     float wmax = 0.f;
+    // optional second output: the fp16 (hi, lo) planes [row][2][cpo] the tensor-core layers read, scaled by the power of two that maps
+    // the bound |out| <= amax_in * gain + shift_max into [2^14, 2^15) (same rule as spconv_cg.cu / bevconv_p2.cu); amax_out[1] <- scale
+    float s_out = 1.f;
+    if (out_planes) {
+        s_out = pow2_scale_for_bound(__ldg(amax_in) * gain + shift_max);
+        if (blockIdx.x == 0 && tid == 0) amax_out[1] = s_out;
+    }
 
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int row0 = tile * kRwRows;
@@ -123,7 +133,14 @@ __global__ void __launch_bounds__(kRwThreads, 1) spconv_rows_kernel(const float 
                     float o = fmaf(acc[j], sc[j], sh[j]);
                     if (relu) o = fmaxf(o, 0.f);
                     wmax = fmaxf(wmax, fabsf(o));
-                    out_feat[(size_t)(row0 + row) * COUT + co] = o;
+                    if (out_feat) out_feat[(size_t)(row0 + row) * COUT + co] = o;
+                    if (out_planes) {
+                        const float x = o * s_out;
+                        const __half hi = __float2half_rn(x);
+                        __half *dst = out_planes + (size_t)(row0 + row) * (2 * cpo) + co;
+                        dst[0] = hi;
+                        dst[cpo] = __float2half_rn(x - __half2float(hi));
+                    }
                 }
             }
         }
@@ -136,7 +153,8 @@ __global__ void __launch_bounds__(kRwThreads, 1) spconv_rows_kernel(const float 
 
 template <int CIN, int COUT>
 static int launch_rows(const float *in, const int *nbr, int kvol, const int *d_n, int max_out, const float *w, const float *sc, const float *sh,
-                       int relu, float *out, float *amax_out, cudaStream_t st) {
+                       int relu, float *out, float *amax_out, const float *amax_in, float gain, float shift_max, void *out_planes, int cpo,
+                       cudaStream_t st) {
     using C = RwCfg<CIN, COUT>;
     const size_t smem = C::smem(kvol);
     if (smem > 227 * 1024) return SESSD_ECAPACITY;
@@ -149,7 +167,8 @@ static int launch_rows(const float *in, const int *nbr, int kvol, const int *d_n
     const int tiles = div_up(max_out, kRwRows);
     const int per_sm = smem <= 100 * 1024 ? 2 : 1;                         // 1024 threads per CTA: at most two resident CTAs
     const int grid = tiles < per_sm * kNumSMs ? tiles : per_sm * kNumSMs;  // persistent
-    SESSD_LAUNCH((spconv_rows_kernel<CIN, COUT>), grid, kRwThreads, smem, st, in, nbr, kvol, d_n, max_out, w, sc, sh, relu, out, amax_out);
+    SESSD_LAUNCH((spconv_rows_kernel<CIN, COUT>), grid, kRwThreads, smem, st, in, nbr, kvol, d_n, max_out, w, sc, sh, relu, out, amax_out, amax_in,
+                 gain, shift_max, (__half *)out_planes, cpo);
     return last_error();
 }
 
@@ -157,19 +176,41 @@ static int launch_rows(const float *in, const int *nbr, int kvol, const int *d_n
 
 using namespace sessd;
 
-// Same arguments as sessd_spconv_forward plus d_amax_out (nullable): running abs-max of the output.  Supported (Cin, Cout): (4,16),
-// (16,16), (16,32), (32,32) -- the whole weight tensor must fit in shared memory.
-extern "C" int sessd_spconv_forward_rows(const float *d_in_feat, int cin, const int *d_nbr, int kvol, const int *d_n_out, int max_out,
-                                         const float *d_weight, int cout, const float *d_scale, const float *d_shift, int relu,
-                                         float *d_out_feat, float *d_amax_out, void *stream) {
-    if (!d_in_feat || !d_nbr || !d_n_out || !d_weight || !d_out_feat || max_out < 1 || kvol < 1 || kvol > kRwMaxK) return SESSD_EINVAL;
+static int rows_dispatch(const float *d_in_feat, int cin, const int *d_nbr, int kvol, const int *d_n_out, int max_out, const float *d_weight,
+                         int cout, const float *d_scale, const float *d_shift, int relu, float *d_out_feat, float *d_amax_out,
+                         const float *d_amax_in, float gain, float shift_max, void *d_out_planes, int cpo, void *stream) {
+    if (!d_in_feat || !d_nbr || !d_n_out || !d_weight || (!d_out_feat && !d_out_planes) || max_out < 1 || kvol < 1 || kvol > kRwMaxK)
+        return SESSD_EINVAL;
+    if (d_out_planes && (!d_amax_in || !d_amax_out || cpo < cout || (cpo != 32 && cpo != 64))) return SESSD_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
 #define RW_CASE(CI, CO) \
-    if (cin == CI && cout == CO) return launch_rows<CI, CO>(d_in_feat, d_nbr, kvol, d_n_out, max_out, d_weight, d_scale, d_shift, relu, d_out_feat, d_amax_out, st)
+    if (cin == CI && cout == CO) return launch_rows<CI, CO>(d_in_feat, d_nbr, kvol, d_n_out, max_out, d_weight, d_scale, d_shift, relu, d_out_feat, d_amax_out, d_amax_in, gain, shift_max, d_out_planes, cpo, st)
     RW_CASE(4, 16);
     RW_CASE(16, 16);
     RW_CASE(16, 32);
     RW_CASE(32, 32);
 #undef RW_CASE
     return SESSD_EINVAL;
+}
+
+// Same arguments as sessd_spconv_forward plus d_amax_out (nullable): running abs-max of the output.  Supported (Cin, Cout): (4,16),
+// (16,16), (16,32), (32,32) -- the whole weight tensor must fit in shared memory.
+extern "C" int sessd_spconv_forward_rows(const float *d_in_feat, int cin, const int *d_nbr, int kvol, const int *d_n_out, int max_out,
+                                         const float *d_weight, int cout, const float *d_scale, const float *d_shift, int relu,
+                                         float *d_out_feat, float *d_amax_out, void *stream) {
+    if (!d_out_feat) return SESSD_EINVAL;
+    return rows_dispatch(d_in_feat, cin, d_nbr, kvol, d_n_out, max_out, d_weight, cout, d_scale, d_shift, relu, d_out_feat, d_amax_out, nullptr,
+                         0.f, 0.f, nullptr, 0, stream);
+}
+
+// ... and the output also (d_out_feat nullable: only) as fp16 (hi, lo) planes [row][2][cpo] for the tensor-core layers: d_out_info =
+// {abs-max of the output (atomicMax; zero it once per frame), plane scale}; the scale comes from the bound *d_amax_in * gain + shift_max
+// (d_amax_in = abs-max of the INPUT features, gain = max_n sum_{k,c} |w[k][c][n] bn_scale[n]|, shift_max = max_n |shift[n]|).
+extern "C" int sessd_spconv_forward_rows_planes(const float *d_in_feat, int cin, const int *d_nbr, int kvol, const int *d_n_out, int max_out,
+                                                const float *d_weight, int cout, const float *d_scale, const float *d_shift, int relu,
+                                                const float *d_amax_in, float gain, float shift_max, float *d_out_feat, void *d_out_planes,
+                                                int cpo, float *d_out_info, void *stream) {
+    if (!d_out_planes) return SESSD_EINVAL;
+    return rows_dispatch(d_in_feat, cin, d_nbr, kvol, d_n_out, max_out, d_weight, cout, d_scale, d_shift, relu, d_out_feat, d_out_info, d_amax_in,
+                         gain, shift_max, d_out_planes, cpo, stream);
 }

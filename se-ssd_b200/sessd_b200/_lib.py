@@ -8,6 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "libsessd_b200.so")
+LAB_PATH = os.path.join(os.path.dirname(_HERE), "libsessd_b200_lab.so")
 
 
 class SessdError(RuntimeError):
@@ -57,34 +58,23 @@ SIGNATURES = {
     "sessd_rulebook_pairs_workspace_bytes": (_sz, [_i, _i]),
     "sessd_rulebook_pairs": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sessd_spconv_forward": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp]),
-    "sessd_spconv_forward_tc": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp]),
     "sessd_spconv_forward_rows": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
-    "sessd_set_sp_h2_depth": (None, [_i]),
-    "sessd_split_h2": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
+    "sessd_spconv_forward_rows_planes": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _f, _f, _vp, _vp, _i, _vp, _vp]),
+    "sessd_spconv_forward_cg": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _f, _f, _vp, _vp, _vp, _vp]),
+    "sessd_set_sp_cg_l1": (None, [_i]),
+    "sessd_set_sp_cg_rotate": (None, [_i]),
     "sessd_absmax_rows": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
-    "sessd_spconv_forward_h2": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "sessd_sparse_to_dense_indexed": (_i, [_vp, _i, _vp, _i, Grid, _vp, _vp]),
     "sessd_sparse_to_dense": (_i, [_vp, _vp, _vp, _i, _i, Grid, _vp, _vp]),
     "sessd_bev_conv": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(ConvDesc), _vp]),
-    "sessd_bev_conv_tc": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, C.POINTER(ConvDesc), _vp]),
-    "sessd_bev_deconv_tc": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
-    "sessd_bev_conv_h2": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, C.POINTER(ConvDesc), _vp, _vp, _vp]),
-    "sessd_bev_deconv_h2": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "sessd_bev_conv_p2": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, C.POINTER(ConvDesc), _vp]),
     "sessd_bev_deconv_p2": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "sessd_bev_split_planes": (_i, [_vp, _ll, _vp, _vp, _vp]),
     "sessd_set_p2_cluster": (None, [_i]),
+    "sessd_set_p2_rotate": (None, [_i]),
     "sessd_sparse_to_dense_planes": (_i, [_vp, _i, _vp, _i, Grid, _vp, _vp, _vp, _vp]),
     "sessd_ssfa_fuse_planes": (_i, [_vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "sessd_set_h2_debug": (None, [_i, _vp]),
     "sessd_absmax": (_i, [_vp, C.c_longlong, _vp, _vp]),
-    "sessd_set_conv_cluster": (None, [_i]),
-    "sessd_get_conv_cluster": (_i, []),
-    "sessd_mma_probe": (_i, [_i, _i, _i, _vp, _vp]),
-    "sessd_latency_probe": (_i, [_i, _vp, _vp]),
-    "sessd_set_conv_ablate": (None, [_i]),
-    "sessd_set_conv_variant": (None, [_i]),
-    "sessd_set_conv_debug_buffer": (None, [_vp]),
     "sessd_ssfa_fuse": (_i, [_vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _i, _vp, _vp]),
     "sessd_postprocess_workspace_bytes": (_sz, [C.POINTER(PostCfg)]),
     "sessd_postprocess": (_i, [_vp, _vp, _vp, C.POINTER(PostCfg), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -109,20 +99,64 @@ SIGNATURES = {
 }
 
 
-def _load():
-    if not os.path.exists(LIB_PATH):
+# include/sessd_b200_lab.h: non-default kernel variants and probes (libsessd_b200_lab.so; loaded on first use, by tests / lab scripts only)
+LAB_SIGNATURES = {
+    "sessd_spconv_forward_tc": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp]),
+    "sessd_set_sp_h2_depth": (None, [_i]),
+    "sessd_split_h2": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
+    "sessd_spconv_forward_h2": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "sessd_bev_conv_tc": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, C.POINTER(ConvDesc), _vp]),
+    "sessd_bev_deconv_tc": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "sessd_bev_conv_h2": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, C.POINTER(ConvDesc), _vp, _vp, _vp]),
+    "sessd_bev_deconv_h2": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "sessd_set_h2_debug": (None, [_i, _vp]),
+    "sessd_set_conv_cluster": (None, [_i]),
+    "sessd_get_conv_cluster": (_i, []),
+    "sessd_mma_probe": (_i, [_i, _i, _i, _vp, _vp]),
+    "sessd_latency_probe": (_i, [_i, _vp, _vp]),
+    "sessd_set_conv_ablate": (None, [_i]),
+    "sessd_set_conv_variant": (None, [_i]),
+    "sessd_set_conv_debug_buffer": (None, [_vp]),
+}
+
+
+def _load(path, signatures, mode=C.DEFAULT_MODE):
+    if not os.path.exists(path):
         raise ImportError(
             "sessd_b200: %s is missing -- the CUDA library has not been built (run `python se-ssd_b200/build.py`). "
-            "There is no CPU fallback." % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in SIGNATURES.items():
+            "There is no CPU fallback." % path)
+    lib = C.CDLL(path, mode=mode)
+    for name, (res, args) in signatures.items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
     return lib
 
 
-lib = _load()
+class _Libs:
+    """`lib.sessd_xxx` resolves in libsessd_b200.so (the product, loaded at import time); the names of LAB_SIGNATURES resolve in
+    libsessd_b200_lab.so, which is loaded the first time one of them is touched (the product path never does)."""
+
+    def __init__(self):
+        self._prod = _load(LIB_PATH, SIGNATURES, C.RTLD_GLOBAL)
+        self._lab = None
+
+    def lab(self):
+        if self._lab is None:
+            self._lab = _load(LAB_PATH, LAB_SIGNATURES)
+        return self._lab
+
+    @property
+    def lab_loaded(self):
+        return self._lab is not None
+
+    def __getattr__(self, name):
+        if name in LAB_SIGNATURES:
+            return getattr(self.lab(), name)
+        return getattr(self._prod, name)
+
+
+lib = _Libs()
 
 
 def check(rc, what):

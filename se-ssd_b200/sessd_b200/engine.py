@@ -18,7 +18,7 @@ from .runners import SpMiddleRunner, SSFAPlanesRunner, SSFARunner
 class FrameEngine:
     def __init__(self, batch=1, max_points_per_frame=32768, voxel_size=synth.VOXEL_SIZE, pc_range=synth.PC_RANGE,
                  max_points_per_voxel=5, max_voxels=20000, device="cuda", post_kwargs=None, growth=None, use_tc=True, sparse_split=None, rows_max_cin=None,
-                 neck="planes"):
+                 neck="planes", sparse_tc=None):
         self.batch, self.device = int(batch), torch.device(device)
         self.max_points = int(max_points_per_frame) * self.batch
         self.vcfg = ops.make_voxel_cfg(voxel_size, pc_range, max_points_per_voxel, max_voxels)
@@ -30,7 +30,8 @@ class FrameEngine:
         self.d_points = torch.zeros((self.max_points, 4), dtype=torch.float32, device=dev)
         self.d_off = torch.zeros((self.batch + 1,), dtype=torch.int32, device=dev)
         self.vox = ops.VoxelBuffers(self.vcfg, self.batch, self.max_points, dev, with_mean=True)
-        self.middle = SpMiddleRunner(self.batch, self.batch * max_voxels, self.grid_xyz, 4, dev, growth=growth, use_tc=use_tc, split=sparse_split, rows_max_cin=rows_max_cin)
+        self.middle = SpMiddleRunner(self.batch, self.batch * max_voxels, self.grid_xyz, 4, dev, growth=growth, use_tc=use_tc, split=sparse_split, rows_max_cin=rows_max_cin,
+                                     sparse_tc=sparse_tc)
         self.neck_planes = neck == "planes" and use_tc
         if self.neck_planes:
             self.neck = SSFAPlanesRunner(self.batch, (self.grid_xyz[1] // 8, self.grid_xyz[0] // 8), dev)

@@ -227,6 +227,35 @@ def spconv_forward_h2(in_planes, amax_in, nbr, n_out, max_out, weight_h2, scale,
     return out
 
 
+def spconv_forward_rows_planes(in_feat, nbr, n_out, max_out, weight, scale, shift, relu, amax_in, gain, shift_max, out, out_planes, out_info):
+    """spconv_forward_rows that also (out nullable: only) writes the output as fp16 (hi, lo) planes [rows, 2 * cpo] with
+    out_info = {abs-max (atomicMax), scale}; the scale is derived from the bound amax_in * gain + shift_max."""
+    kvol, cin, cout = weight.shape
+    check(lib.sessd_spconv_forward_rows_planes(_p(in_feat), int(cin), _p(nbr), int(kvol), _p(n_out), int(max_out), _p(weight), int(cout),
+                                               _p(scale), _p(shift), int(bool(relu)), _p(amax_in), float(gain), float(shift_max), _p(out),
+                                               _p(out_planes), int(out_planes.shape[1] // 2), _p(out_info), _st()),
+          "sessd_spconv_forward_rows_planes")
+    return out_planes
+
+
+def spconv_forward_cg(in_planes, in_info, nbr, n_out, max_out, weight_h2, scale, shift, relu, gain, shift_max, out, out_planes, out_info):
+    """Pair-proportional tensor-core sparse conv (csrc/spconv_cg.cu).  in_planes [rows, 2 * cp] fp16 with in_info = {abs-max, scale};
+    weight_h2 / scale from pack_weight_sp_h2 (scale = bn_scale * 2^-e); out (fp32 rows) and / or out_planes + out_info."""
+    cp = in_planes.shape[1] // 2
+    kvol = weight_h2.shape[0]
+    cout = weight_h2.shape[2] if cp == 64 else weight_h2.shape[1]
+    check(lib.sessd_spconv_forward_cg(_p(in_planes), int(cp), int(in_planes.shape[0]), _p(in_info), _p(nbr), int(kvol), _p(n_out), int(max_out),
+                                      _p(weight_h2), int(cout), _p(scale), _p(shift), int(bool(relu)), float(gain), float(shift_max), _p(out),
+                                      _p(out_planes), _p(out_info), _st()), "sessd_spconv_forward_cg")
+    return out if out is not None else out_planes
+
+
+def sparse_planes_to_float(planes, info, channels):
+    """(hi + lo) / S of sparse feature planes [rows, 2 * cp] as fp32 [rows, channels] (tests / debugging)"""
+    cp = planes.shape[1] // 2
+    return (planes[:, :channels].float() + planes[:, cp:cp + channels].float()) / info[1]
+
+
 def sparse_to_dense(feat, coors, n, max_rows, grid, out=None):
     c = feat.shape[1]
     d, h, w = grid.shape[0], grid.shape[1], grid.shape[2]
@@ -350,8 +379,13 @@ def bev_deconv_p2(in_planes, in_info, weight_h2, scale, shift, residual, resid_i
 
 
 def set_p2_cluster(n):
-    """CTAs per cluster sharing the weight tiles of bev_conv_p2 through TMA multicast (1 or 2; default 2)."""
+    """CTAs per cluster sharing the weight tiles of bev_conv_p2 through TMA multicast (1 or 2; default 1)."""
     lib.sessd_set_p2_cluster(int(n))
+
+
+def set_p2_rotate(on):
+    """1 (default): the CTAs of bev_conv_p2 walk the (channel chunk, tap) loop from different starting points (de-phased weight streams)"""
+    lib.sessd_set_p2_rotate(int(on))
 
 
 def bev_split_planes(x, info, planes):

@@ -29,12 +29,14 @@ class SpMiddleRunner:
     # active-site growth bounds per level relative to the level-0 capacity (uniform 20k cloud: 3.4 / 5.2 / 4.3 / 2.6)
     GROWTH = (1.0, 4.0, 6.0, 5.0, 3.0)
     SPLIT = "fp16"
+    SPARSE_TC = "cg"          # tensor-core kernel of the Cin >= 32 layers: "cg" = pair-proportional cp.async gather, planes written by the
+                              # producing layer's epilogue (csrc/spconv_cg.cu); "h2" = TMA gather4 + separate split kernel (csrc/spconv_h2.cu)
     ROWS_SHAPES = ((4, 16), (16, 16), (16, 32), (32, 32))     # (Cin, Cout) whose whole weight tensor fits in shared memory
     ROWS_MAX_CIN = 16         # layers with Cin <= this run on the pair-proportional SIMT kernel (0: tensor-core kernels wherever possible)
     DENSE_GATHER = True       # dense() as one gather pass through the last level's bitmap index (False: memset + scatter)
 
     def __init__(self, batch, max_voxels_total, input_shape_xyz=(1408, 1600, 40), num_input_features=4, device="cuda",
-                 growth=None, use_tc=True, split=None, rows_max_cin=None):
+                 growth=None, use_tc=True, split=None, rows_max_cin=None, sparse_tc=None, keep_f32=False):
         """use_tc: run the layers on the tcgen05 tensor cores; False = fp32 SIMT baseline for all layers.
         split: "fp16" = TMA-gather two-term fp16 split kernel (spconv_h2.cu) for every layer with Cin >= 16 (13 of 14 layers);
                "tf32" = 3xTF32 kernel with SIMT gather warps (spconv_tc.cu) for the Cin >= 32 layers.  Default: SPLIT."""
@@ -43,6 +45,9 @@ class SpMiddleRunner:
         self.split = split or self.SPLIT
         assert self.split in ("fp16", "tf32")
         self.use_h2 = self.use_tc and self.split == "fp16"
+        self.sparse_tc = sparse_tc or self.SPARSE_TC
+        assert self.sparse_tc in ("cg", "h2")
+        self.keep_f32 = bool(keep_f32)      # cg layers also write their fp32 rows (tests compare per-layer features)
         # per-layer kernel: "rows" = pair-proportional fp32 SIMT (narrow layers), "h2" = TMA-gather fp16-split tcgen05, "tc" = 3xTF32
         # tcgen05 with SIMT gather warps, "simt" = the dense output-stationary fp32 baseline
         self.rows_max_cin = (self.ROWS_MAX_CIN if rows_max_cin is None else int(rows_max_cin)) if self.use_tc else 0
@@ -85,6 +90,8 @@ class SpMiddleRunner:
         for p in self.plan:
             if self.use_tc and p["cin"] <= self.rows_max_cin and (p["cin"], p["cout"]) in self.ROWS_SHAPES:
                 p["impl"] = "rows"
+            elif self.use_h2 and p["cin"] >= 32 and self.sparse_tc == "cg":
+                p["impl"] = "cg"
             elif self.use_h2 and p["cin"] >= 16:
                 p["impl"] = "h2"
             elif self.use_tc and p["cin"] >= 32:
@@ -92,9 +99,22 @@ class SpMiddleRunner:
             else:
                 p["impl"] = "simt"
         for li, p in enumerate(self.plan[:-1]):
-            if self.plan[li + 1]["impl"] == "h2":
+            if self.plan[li + 1]["impl"] in ("h2", "cg"):
                 cp = 64 if p["cout"] > 32 else 32
                 self.planes[li] = ops.alloc_planes(self.levels[p["lout"]]["cap"], cp, self.device)
+                assert self.planes[li].shape[0] <= (1 << 25)
+        # {abs-max, plane scale} of every layer output (cg chain: written by the producing layer's epilogue)
+        self.info = torch.zeros((len(self.plan), 2), dtype=torch.float32, device=self.device)
+
+    def layer_output(self, li):
+        """fp32 rows [cap, Cout] of layer li's output after forward(): the fp32 buffer when the layer wrote it, else rebuilt from the fp16
+        (hi, lo) planes the next layer reads (exact: x = (hi + lo) / S) -- tests / debugging."""
+        p = self.plan[li]
+        nxt = self.plan[li + 1]["impl"] if li + 1 < len(self.plan) else None
+        planes_only = (not self.keep_f32) and nxt == "cg" and p["impl"] in ("cg", "rows")
+        if not planes_only:
+            return self.feats[li]
+        return ops.sparse_planes_to_float(self.planes[li][:-1], self.info[li], p["cout"])
 
     def _add_level(self, shape, cap, hash_index):
         grid = ops.make_grid(self.batch, shape)
@@ -119,11 +139,12 @@ class SpMiddleRunner:
             sc, sh = fold_bn(*[torch.as_tensor(l[k], device=self.device) for k in ("gamma", "beta", "mean", "var")], eps=float(l.get("eps", BN_EPS)))
             wp = w.reshape(-1, p["cin"], p["cout"]).contiguous()
             tc = None
-            if p["impl"] == "h2":
+            if p["impl"] in ("h2", "cg"):
                 tiles, inv = ops.pack_weight_sp_h2(wp, 64 if p["cin"] > 32 else 32)
-                tc = ("h2", tiles, (sc * inv).contiguous())
+                tc = (p["impl"], tiles, (sc * inv).contiguous())
             elif p["impl"] == "tc":
                 tc = ops.pack_weight_tc(wp, p["cout"])
+            p["gain"], p["shift_max"] = ops.conv_gain(wp, sc), float(sh.abs().max())
             self.weights.append((wp, sc, sh, tc))
 
     def forward(self, feat0, coors0, n0, mark=None, dense_planes=None):
@@ -141,6 +162,7 @@ class SpMiddleRunner:
         mark("hash_build")
         if self.use_h2:
             self.amax.zero_()
+            self.info.zero_()
         x = feat0
         for li, p in enumerate(self.plan):
             lin, lout = self.levels[p["lin"]], self.levels[p["lout"]]
@@ -158,9 +180,22 @@ class SpMiddleRunner:
                 n_out, cap_out = lout["n"], lout["cap"]
                 mark("rulebook:sp%d" % p["lout"])
             w, sc, sh, tc = self.weights[li]
-            if p["impl"] == "rows":
+            nxt = self.plan[li + 1]["impl"] if li + 1 < len(self.plan) else None
+            if p["impl"] == "rows" and nxt == "cg":
+                # last SIMT layer before the tensor-core chain: writes the planes the next layer reads (scale from the bound on its output)
+                ops.spconv_forward_rows_planes(x, p["nbr"], n_out, cap_out, w, sc, sh, True, self.info[li - 1, 0:1], p["gain"], p["shift_max"],
+                                               self.feats[li] if self.keep_f32 else None, self.planes[li], self.info[li])
+                x = self.feats[li]
+            elif p["impl"] == "rows":
+                need_amax = self.planes[li] is not None or (nxt == "rows" and li + 2 < len(self.plan) and self.plan[li + 2]["impl"] == "cg")
                 x = ops.spconv_forward_rows(x, p["nbr"], n_out, cap_out, w, sc, sh, True, self.feats[li],
-                                            self.amax[li:li + 1] if self.planes[li] is not None else None)
+                                            (self.info[li, 0:1] if nxt != "h2" else self.amax[li:li + 1]) if need_amax else None)
+            elif isinstance(tc, tuple) and tc[0] == "cg":
+                last = nxt != "cg"
+                ops.spconv_forward_cg(self.planes[li - 1], self.info[li - 1], p["nbr"], n_out, cap_out, tc[1], tc[2], sh, True, p["gain"],
+                                      p["shift_max"], self.feats[li] if (last or self.keep_f32) else None,
+                                      None if last else self.planes[li], self.info[li])
+                x = self.feats[li]
             elif isinstance(tc, tuple):
                 # fp16-split tensor-core layer: reads the (hi, lo) planes of its input, writes fp32 rows + the output's abs-max
                 x = ops.spconv_forward_h2(self.planes[li - 1], self.amax[li - 1:li], p["nbr"], n_out, cap_out, tc[1], tc[2], sh, True,
@@ -172,14 +207,14 @@ class SpMiddleRunner:
                 if self.planes[li] is not None:
                     ops.absmax_rows(x, n_out, cap_out, self.amax[li:li + 1])
             mark("conv:%d" % li)
-            if self.planes[li] is not None:
+            if self.planes[li] is not None and nxt == "h2":
                 ops.split_h2(x, n_out, cap_out, self.amax[li:li + 1], self.planes[li])
                 mark("split:%d" % li)
         last = self.levels[-1]
         if dense_planes is not None:
             assert last["index_kind"] == 1 and self.use_h2
-            out = ops.sparse_to_dense_planes(x, last["index"], last["grid"], self.amax[len(self.plan) - 1:len(self.plan)], dense_planes[1],
-                                             dense_planes[0])
+            amax_last = self.info[len(self.plan) - 1, 0:1] if self.plan[-1]["impl"] == "cg" else self.amax[len(self.plan) - 1:len(self.plan)]
+            out = ops.sparse_to_dense_planes(x, last["index"], last["grid"], amax_last, dense_planes[1], dense_planes[0])
             mark("dense")
             return out
         if last["index_kind"] == 1 and self.DENSE_GATHER:

@@ -91,9 +91,12 @@ def _weights(seed=3):
     return weights.split_detector_state(sd)
 
 
-@pytest.mark.parametrize("use_tc,split,rows", [(False, None, 0), (True, "tf32", 0), (True, "fp16", 0), (True, "fp16", 32), (True, "fp16", 16)],
-                         ids=["simt", "tcgen05-3xtf32", "tma-gather-fp16x2", "rows32+tma-gather", "rows16+tma-gather(default)"])
-def test_spmiddle_features_match_fp64_oracle(use_tc, split, rows):
+@pytest.mark.parametrize("use_tc,split,rows,kw", [(False, None, 0, {}), (True, "tf32", 0, {}), (True, "fp16", 0, dict(sparse_tc="h2")),
+                                                  (True, "fp16", 32, dict(sparse_tc="h2")), (True, "fp16", 16, dict(sparse_tc="h2")),
+                                                  (True, "fp16", 16, dict(sparse_tc="cg", keep_f32=True)), (True, "fp16", 16, {})],
+                         ids=["simt", "tcgen05-3xtf32", "tma-gather-fp16x2", "rows32+tma-gather", "rows16+tma-gather",
+                              "rows16+pair-gather+f32rows", "rows16+pair-gather(default)"])
+def test_spmiddle_features_match_fp64_oracle(use_tc, split, rows, kw):
     from oracle import spconv_ref as S
     from sessd_b200 import synth
     from sessd_b200.runners import SpMiddleRunner
@@ -105,13 +108,15 @@ def test_spmiddle_features_match_fp64_oracle(use_tc, split, rows):
                    var=l["var"].numpy()) for l in layers]
     trace = []
     ref = S.spmiddle_forward(feat, coors, 1, (1408, 1600, 40), params, np.float64, trace)   # [1,128,200,176]
-    r = SpMiddleRunner(1, n, device="cuda", use_tc=use_tc, split=split, rows_max_cin=rows)
+    r = SpMiddleRunner(1, n, device="cuda", use_tc=use_tc, split=split, rows_max_cin=rows, **kw)
     assert [p["impl"] for p in r.plan].count("rows") == {0: 0, 16: 3, 32: 5}[rows]
+    if use_tc and split == "fp16" and rows == 16:
+        assert [p["impl"] for p in r.plan].count(kw.get("sparse_tc", "cg")) == 11
     r.load_weights(layers)
     dense = r.forward(torch.from_numpy(feat).cuda(), torch.from_numpy(coors).cuda(), torch.tensor([n], dtype=torch.int32, device="cuda"))
     torch.cuda.synchronize()
     for li, t in enumerate(trace):
-        got = r.feats[li][: len(t["coors"])].cpu().numpy().astype(np.float64)
+        got = r.layer_output(li)[: len(t["coors"])].cpu().numpy().astype(np.float64)
         scale = np.abs(t["feat"]).max() + 1e-30
         assert np.abs(got - t["feat"]).max() / scale < 1e-5, "layer %d" % li
     got = dense.permute(0, 3, 1, 2).cpu().numpy().astype(np.float64)     # NHWC storage -> logical NCHW
@@ -150,7 +155,7 @@ def test_full_size_rulebook_symmetry_and_conv_properties():
     d1 = r.forward(vox.mean, vox.coors, n0).clone()
     torch.cuda.synchronize()
     assert int(r.status.item()) == 0
-    feats1 = [f.clone() for f in r.feats]
+    feats1 = [r.layer_output(li).clone() for li in range(len(r.plan))]
     # --- rulebooks
     seen = set()
     for p in r.plan:
@@ -178,8 +183,8 @@ def test_full_size_rulebook_symmetry_and_conv_properties():
     d2 = r.forward(vox.mean, vox.coors, n0)
     torch.cuda.synchronize()
     assert torch.equal(d1, d2)
-    for a, b in zip(feats1, r.feats):
-        assert torch.equal(a, b)
+    for li, a in enumerate(feats1):
+        assert torch.equal(a, r.layer_output(li))
     counts = [int((n0 if p["lout"] == 0 else r.levels[p["lout"]]["n"]).item()) for p in r.plan]
     for kw in (dict(split="tf32", rows_max_cin=0), dict(use_tc=False)):
         q = SpMiddleRunner(B, B * 200000, device="cuda", growth=(1.0, 8.0, 8.0, 8.0, 8.0), **kw)
@@ -213,7 +218,7 @@ def test_h2_sparse_conv_power_of_two_scaling_is_exact():
     p = r.plan[7]                                   # a 64 -> 64 SubM layer on level 2
     lv = r.levels[p["lout"]]
     n, cap = lv["n"], lv["cap"]
-    x = r.feats[6].clone()
+    x = r.layer_output(6).clone()
     w = torch.randn((27, 64, 64), device="cuda") * 0.05
     tiles, inv = ops.pack_weight_sp_h2(w, 64)
     sc = (torch.rand(64, device="cuda") + 0.5) * inv
@@ -232,6 +237,32 @@ def test_h2_sparse_conv_power_of_two_scaling_is_exact():
     assert nn > 100000
     assert torch.equal(outs[0][0][:nn] * 4.0, outs[1][0][:nn])
     assert outs[0][1] * 4.0 == outs[1][1]
+    # the pair-gather kernel (default): same property with the bound-derived scale, fp32 rows and plane outputs; and it agrees with the
+    # TMA-gather kernel to rounding
+    gain = ops.conv_gain(w, sc / inv)
+    cg = []
+    for mul in (1.0, 4.0):
+        xx = (x * mul).contiguous()
+        info = torch.zeros(2, device="cuda")
+        ops.absmax_rows(xx, n, cap, info[0:1])
+        planes = ops.alloc_planes(cap, 64, "cuda")
+        info[1] = 2.0 ** (14 - np.floor(np.log2(float(info[0]))))          # any exact power of two that keeps the planes in range
+        s = float(info[1])
+        hi = (xx * s).half()
+        planes[:cap, :64] = hi
+        planes[:cap, 64:] = (xx * s - hi.float()).half()
+        out = torch.zeros((cap, 64), device="cuda")
+        oplanes = ops.alloc_planes(cap, 64, "cuda")
+        oinfo = torch.zeros(2, device="cuda")
+        ops.spconv_forward_cg(planes, info, p["nbr"], n, cap, tiles, sc.contiguous(), None, True, gain, 0.0, out, oplanes, oinfo)
+        torch.cuda.synchronize()
+        back = ops.sparse_planes_to_float(oplanes[:-1], oinfo, 64)
+        assert float((back[:nn] - out[:nn]).abs().max()) <= 3e-7 * float(out[:nn].abs().max())
+        assert float(oinfo[0]) == float(out[:nn].abs().max())
+        cg.append((out, float(oinfo[0])))
+    assert torch.equal(cg[0][0][:nn] * 4.0, cg[1][0][:nn])
+    assert cg[0][1] * 4.0 == cg[1][1]
+    assert float((cg[0][0][:nn] - outs[0][0][:nn]).abs().max()) <= 2e-6 * float(outs[0][0][:nn].abs().max())
 
 
 # ---------------------------------------------------------------------------------------------------- BASELINE shapes
@@ -307,7 +338,7 @@ def test_features_uniform20k_match_fp64_oracle():
     trace = []
     ref = S.spmiddle_forward(feat, coors, 1, (1408, 1600, 40), params, np.float64, trace)
     for li, t in enumerate(trace):
-        got = r.feats[li][: len(t["coors"])].cpu().numpy().astype(np.float64)
+        got = r.layer_output(li)[: len(t["coors"])].cpu().numpy().astype(np.float64)
         scale = np.abs(t["feat"]).max() + 1e-30
         assert np.abs(got - t["feat"]).max() / scale < 1e-5, "layer %d" % li
     got = dense.permute(0, 3, 1, 2).cpu().numpy().astype(np.float64)

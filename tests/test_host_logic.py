@@ -14,15 +14,31 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_loads_and_exports_every_declared_symbol():
     from sessd_b200 import _lib
     hdr = open(os.path.join(ROOT, "include", "sessd_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)                                   # declarations only, not the prose
     declared = set(re.findall(r"\b(sessd_[a-z0-9_]+)\s*\(", hdr))
     assert len(declared) >= 25
     for name in declared:
-        assert hasattr(_lib.lib, name), name           # dlsym succeeds
-        assert name in _lib.SIGNATURES, name             # and the binding declares its signature
+        assert name in _lib.SIGNATURES, name             # the binding declares its signature
+        assert hasattr(_lib.lib._prod, name), name       # and dlsym succeeds in the PRODUCT library
+    assert not _lib.lib.lab_loaded                       # importing / using the product does not load the lab library
     assert "sm_100a" in _lib.version()
     # no compute calls here (no GPU in this container): argument validation only
     assert _lib.lib.sessd_voxelize_workspace_bytes(20000, 1, None) == 0
     assert _lib.lib.sessd_nms_workspace_bytes(1000) == 8 * (1000 * 16 + 64)
+
+
+def test_lab_library_exports_every_declared_symbol_and_nothing_of_the_product():
+    """include/sessd_b200_lab.h (non-default kernel variants + probes) lives in its own library; the product library exports none of it."""
+    import ctypes
+    from sessd_b200 import _lib
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "sessd_b200_lab.h")).read(), flags=re.S)
+    declared = set(re.findall(r"\b(sessd_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.LAB_SIGNATURES)
+    prod = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert not hasattr(prod, name), name
+        assert hasattr(_lib.lib, name), name             # resolves through the lazily loaded lab library
+    assert _lib.lib.lab_loaded
 
 
 def test_shared_library_is_sm100a_sass():
