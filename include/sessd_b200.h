@@ -204,9 +204,6 @@ int sessd_bev_deconv_p2(const void *d_in_planes, const float *d_in_info, const v
 int sessd_bev_split_planes(const float *d_x, long long n, float *d_info, void *d_planes, void *stream);
 /* CTAs per cluster sharing (TMA-multicasting) the weight tiles of sessd_bev_conv_p2: 1 (default) or 2 */
 void sessd_set_p2_cluster(int ctas_per_cluster);
-/* 1 (default): every CTA of sessd_bev_conv_p2 starts its (channel chunk, tap) loop at a different point, so that the SMs do not stream
- * the same 16 KB weight tile in lockstep (which keeps only the L2 slices holding that tile busy); 0: identical order everywhere */
-void sessd_set_p2_rotate(int on);
 /* dense() (scn.py:184-187) straight into the planes the neck reads: d_amax = abs-max of the feature rows, d_info[2] <- {abs-max, S} */
 int sessd_sparse_to_dense_planes(const float *d_feat, int max_rows, const void *d_bitmap_index, int channels, sessd_grid grid,
                                  const float *d_amax, float *d_info, void *d_planes, void *stream);

@@ -134,7 +134,6 @@ def main():
     from sessd_b200._lib import lib
     lib.sessd_set_sp_cg_l1(int(a.cg_l1))
     lib.sessd_set_sp_cg_rotate(int(a.rotate))
-    lib.sessd_set_p2_rotate(int(a.rotate))
     if a.shape == "stress":
         B, N = a.batch or 16, a.points or 200000
         clouds = [synth.uniform_cloud(1000 + f, N) for f in range(B)]

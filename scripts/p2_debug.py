@@ -138,10 +138,9 @@ def run_step(step):
             op = ops.alloc_bev_planes(1, hw[0], hw[1], cout, "cuda")
             of = torch.zeros((1, hw[0], hw[1], cout), device="cuda")
             amax = torch.zeros(2, device="cuda"); ops.absmax(x, amax[0:1])
-            variants = [("p2 cs1 rot planes-out", lambda: (ops.set_p2_cluster(1), ops.set_p2_rotate(1), ops.bev_conv_p2(xp, info, planes, sc, None, None, None, 30.0, 0.0, None, op, oinfo, d))),
-                        ("p2 cs1 norot planes-out", lambda: (ops.set_p2_cluster(1), ops.set_p2_rotate(0), ops.bev_conv_p2(xp, info, planes, sc, None, None, None, 30.0, 0.0, None, op, oinfo, d))),
-                        ("p2 cs2 rot planes-out", lambda: (ops.set_p2_cluster(2), ops.set_p2_rotate(1), ops.bev_conv_p2(xp, info, planes, sc, None, None, None, 30.0, 0.0, None, op, oinfo, d))),
-                        ("p2 cs1 rot fp32-out", lambda: (ops.set_p2_cluster(1), ops.set_p2_rotate(1), ops.bev_conv_p2(xp, info, planes, sc, None, None, None, 30.0, 0.0, of, None, oinfo, d)))]
+            variants = [("p2 cs1 planes-out", lambda: (ops.set_p2_cluster(1), ops.bev_conv_p2(xp, info, planes, sc, None, None, None, 30.0, 0.0, None, op, oinfo, d))),
+                                                ("p2 cs2 planes-out", lambda: (ops.set_p2_cluster(2), ops.bev_conv_p2(xp, info, planes, sc, None, None, None, 30.0, 0.0, None, op, oinfo, d))),
+                        ("p2 cs1 fp32-out", lambda: (ops.set_p2_cluster(1), ops.bev_conv_p2(xp, info, planes, sc, None, None, None, 30.0, 0.0, of, None, oinfo, d)))]
             if cin % 64 == 0 and cout >= 4:
                 variants.append(("h2 (in-kernel split)", lambda: ops.bev_conv_h2(x, planes, sc, None, None, of, d, amax[0:1], amax[1:2])))
             for name, fn in variants:

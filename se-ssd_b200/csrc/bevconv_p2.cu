@@ -48,7 +48,7 @@ struct P2Params {
     int ncopies, rows_v;
     int copy_u[kP2MaxCopies], copy_v[kP2MaxCopies];       // input coordinate of the copy's first element relative to (u0, v0) * in_stride
     int copy_bytes, patch_bytes, npatch;                  // bytes of one copy plane, of one patch buffer (ncopies x 2 planes), 1 or 2 buffers
-    int relu, n_tile, nblocks, rotate;
+    int relu, n_tile, nblocks;
     int tiles_u, tiles_v, tiles, tgroups, total;          // pixel tiles, tile groups (CS tiles each), work items = nclass * nblocks * tgroups
     int cls_order[4];
     const float *in_info;              // [2] = {abs-max of the input tensor, scale S_in of its planes}
@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
     uint64_t *patch_full = bars, *patch_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 4 + kP2BStages;
     uint64_t *acc_full = bars + 4 + 2 * kP2BStages, *acc_free = acc_full + 1;
     uint32_t *tmem_slot = (uint32_t *)(acc_free + 1);
+    uint32_t *s_aoff = tmem_slot + 2;                    // [4 classes][9 taps]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t crank = (CS > 1) ? cluster_cta_rank() : 0u;
@@ -145,93 +146,100 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Roles 0-2 run their loops with the WHOLE warp (warp-uniform trip counts and addresses stay in uniform registers) and issue the
+    // TMA / tcgen05 instructions from one elected lane.  Wrapping the loops in `if (lane == 0)` instead made every operand a vector
+    // register that has to be moved to the uniform file (R2UR) behind a divergence guard: ~890 clk per tap for 384 clk of MMA work --
+    // the issue thread, not the tensor pipe or the L2, bounded the first version (MMA thread busy 64 k of 73 k clk, waiting 8 k).
     if (warp == 0) {
         // ===================== activation patches: per (item, 32-channel chunk) ncopies x (hi, lo) boxes =====================
-        if (lane == 0) {
-            int gcc = 0;
-            for (int g = cluster_id; g < p.total; g += nclusters) {
-                const P2Item it = p2_decode<CS>(p, g, (int)crank);
-                const int rot_c = p.rotate ? cluster_id % nchunks : 0;
-                for (int c0 = 0; c0 < nchunks; ++c0, ++gcc) {
-                    const int cc = (c0 + rot_c) % nchunks;
-                    const int pb = gcc % p.npatch;
-                    const uint32_t ph = (uint32_t)(gcc / p.npatch) & 1u;
-                    mbar_wait(&patch_empty[pb], ph ^ 1u);
+        int pb = 0;
+        uint32_t pph = 0;
+        const uint32_t patches_u32 = smem_u32(patches);
+        for (int g = cluster_id; g < p.total; g += nclusters) {
+            const P2Item it = p2_decode<CS>(p, g, (int)crank);
+            const int bu = it.u0 * p.in_stride, bv = it.v0 * p.in_stride;
+            for (int cc = 0; cc < nchunks; ++cc) {
+                mbar_wait(&patch_empty[pb], pph ^ 1u);
+                if (elect_one()) {
                     mbar_expect_tx(&patch_full[pb], (uint32_t)p.patch_bytes);
-                    const uint32_t dst = smem_u32(patches) + (uint32_t)(pb * p.patch_bytes);
-                    for (int c = 0; c < p.ncopies; ++c) {
-                        const int cu = it.u0 * p.in_stride + p.copy_u[c], cv = it.v0 * p.in_stride + p.copy_v[c];
-                        tma_load_5d(dst + (uint32_t)((2 * c) * p.copy_bytes), &map_a, &patch_full[pb], cc * kP2Chunk, cu, cv, it.b, 0);
-                        tma_load_5d(dst + (uint32_t)((2 * c + 1) * p.copy_bytes), &map_a, &patch_full[pb], cc * kP2Chunk, cu, cv, it.b, 1);
+                    uint32_t dst = patches_u32 + (uint32_t)(pb * p.patch_bytes);
+                    for (int c = 0; c < p.ncopies; ++c, dst += 2u * (uint32_t)p.copy_bytes) {
+                        const int cu = bu + p.copy_u[c], cv = bv + p.copy_v[c];
+                        tma_load_5d(dst, &map_a, &patch_full[pb], cc * kP2Chunk, cu, cv, it.b, 0);
+                        tma_load_5d(dst + (uint32_t)p.copy_bytes, &map_a, &patch_full[pb], cc * kP2Chunk, cu, cv, it.b, 1);
                     }
                 }
+                __syncwarp();
+                if (++pb == p.npatch) { pb = 0; pph ^= 1u; }
             }
         }
     } else if (warp == 1) {
         // ===================== weight tiles: one [X ; Y] stage per (item, chunk, tap); this CTA fetches 1/CS of the rows =====================
-        if (lane == 0) {
-            int gbj = 0;
-            const int rows = p.n_tile / CS;
-            const uint32_t so = crank * (uint32_t)rows * 64u;
-            for (int g = cluster_id; g < p.total; g += nclusters) {
-                const P2Item it = p2_decode<CS>(p, g, (int)crank);
-                const int rot_c = p.rotate ? cluster_id % nchunks : 0, rot_t = p.rotate ? (cluster_id / nchunks) % it.ntaps : 0;
-                for (int c0 = 0; c0 < nchunks; ++c0)
-                    for (int t0 = 0; t0 < it.ntaps; ++t0, ++gbj) {
-                        const int cc = (c0 + rot_c) % nchunks, tap = (t0 + rot_t) % it.ntaps;
-                        const int s = gbj % kP2BStages;
-                        const uint32_t ph = (uint32_t)(gbj / kP2BStages) & 1u;
-                        mbar_wait(&b_empty[s], ph ^ 1u);
-                        mbar_expect_tx(&b_full[s], 2 * b_plane_bytes);
-                        unsigned char *st = tiles + s * kP2BStageBytes;
+        int S = 0;
+        uint32_t bph = 0, par = 0;
+        const int rows = p.n_tile / CS;
+        const uint32_t so = crank * (uint32_t)rows * 64u;
+        for (int g = cluster_id; g < p.total; g += nclusters) {
+            const P2Item it = p2_decode<CS>(p, g, (int)crank);
+            const int n0 = it.n0 + (CS > 1 ? (int)crank * rows : 0);
+            for (int cc = 0; cc < nchunks; ++cc)
+                for (int tap = 0; tap < it.ntaps; ++tap) {
+                    mbar_wait(&b_empty[S], bph ^ 1u);
+                    if (elect_one()) {
+                        mbar_expect_tx(&b_full[S], 2 * b_plane_bytes);
+                        unsigned char *st = tiles + S * kP2BStageBytes + so;
                         const int wtap = p.tap_w[it.cls][tap];
                         // [b_hi ; b_lo] on even stages, [b_lo ; b_hi] on odd stages (every item has an even stage count: running parity)
-                        const uint32_t hi_off = (gbj & 1) ? b_plane_bytes : 0u, lo_off = (gbj & 1) ? 0u : b_plane_bytes;
+                        const uint32_t hi_off = par ? b_plane_bytes : 0u, lo_off = par ? 0u : b_plane_bytes;
                         if (CS == 1) {
-                            tma_load_4d(st + hi_off, &map_b, &b_full[s], cc * kP2Chunk, it.n0, wtap, 0);
-                            tma_load_4d(st + lo_off, &map_b, &b_full[s], cc * kP2Chunk, it.n0, wtap, 1);
+                            tma_load_4d(st + hi_off, &map_b, &b_full[S], cc * kP2Chunk, n0, wtap, 0);
+                            tma_load_4d(st + lo_off, &map_b, &b_full[S], cc * kP2Chunk, n0, wtap, 1);
                         } else {
-                            tma_load_4d_mc(st + hi_off + so, &map_b, &b_full[s], cc * kP2Chunk, it.n0 + (int)crank * rows, wtap, 0, kMask);
-                            tma_load_4d_mc(st + lo_off + so, &map_b, &b_full[s], cc * kP2Chunk, it.n0 + (int)crank * rows, wtap, 1, kMask);
+                            tma_load_4d_mc(st + hi_off, &map_b, &b_full[S], cc * kP2Chunk, n0, wtap, 0, kMask);
+                            tma_load_4d_mc(st + lo_off, &map_b, &b_full[S], cc * kP2Chunk, n0, wtap, 1, kMask);
                         }
                     }
-            }
+                    __syncwarp();
+                    par ^= 1u;
+                    if (++S == kP2BStages) { S = 0; bph ^= 1u; }
+                }
         }
     } else if (warp == 2) {
-        // ===================== MMA issue (one thread) =====================
-        if (lane == 0) {
-            const uint32_t idesc1 = p2_idesc_f16(kP2BM, p.n_tile), idesc2 = p2_idesc_f16(kP2BM, 2 * p.n_tile);
-            const uint32_t acc_main0 = tmem_base, acc_cross = tmem_base + (uint32_t)p.n_tile, acc_main1 = tmem_base + 2 * (uint32_t)p.n_tile;
-            const uint64_t desc_hi = ((uint64_t)((512u >> 4) | (1u << 14) | (4u << 29))) << 32;      // SBO 512 B | version 1 | SWIZZLE_64B
-            const uint32_t lbo = 1u << 16;
-            const uint32_t tiles_lo = ((smem_u32(tiles) >> 4) & 0x3FFFu) | lbo;
-            const uint32_t patch_lo = ((smem_u32(patches) >> 4) & 0x3FFFu) | lbo;
-            const uint32_t plane_lo = b_plane_bytes >> 4;
-            int gbj = 0, gcc = 0, iter = 0;
-            for (int g = cluster_id; g < p.total; g += nclusters, ++iter) {
-                const int cls = p.cls_order[g / (p.nblocks * p.tgroups)];
-                const int ntaps = p.cls_ntaps[cls];
-                const int nbj = nchunks * ntaps;
-                if (iter > 0) {                          // the epilogue warps must have drained the previous item's accumulators
-                    mbar_wait(acc_free, (uint32_t)(iter - 1) & 1u);
-                    tc_fence_after();
-                }
-                int lbj = 0;
-                const int rot_t = p.rotate ? (cluster_id / nchunks) % ntaps : 0;
-                for (int cc = 0; cc < nchunks; ++cc, ++gcc) {
-                    const int pb = gcc % p.npatch;
-                    mbar_wait(&patch_full[pb], (uint32_t)(gcc / p.npatch) & 1u);
-                    tc_fence_after();
-                    const uint32_t pbase = patch_lo + (uint32_t)((pb * p.patch_bytes) >> 4);
+        // ===================== MMA issue (one elected lane; the warp walks the loops together) =====================
+        const uint32_t idesc1 = p2_idesc_f16(kP2BM, p.n_tile), idesc2 = p2_idesc_f16(kP2BM, 2 * p.n_tile);
+        const uint32_t acc_main0 = tmem_base, acc_cross = tmem_base + (uint32_t)p.n_tile, acc_main1 = tmem_base + 2 * (uint32_t)p.n_tile;
+        const uint64_t desc_hi = ((uint64_t)((512u >> 4) | (1u << 14) | (4u << 29))) << 32;      // SBO 512 B | version 1 | SWIZZLE_64B
+        const uint32_t lbo = 1u << 16;
+        const uint32_t tiles_lo = ((smem_u32(tiles) >> 4) & 0x3FFFu) | lbo;
+        const uint32_t patch_lo = ((smem_u32(patches) >> 4) & 0x3FFFu) | lbo;
+        const uint32_t plane_lo = b_plane_bytes >> 4;
+        const uint32_t copy_lo = (uint32_t)(p.copy_bytes >> 4), patch_sz = (uint32_t)(p.patch_bytes >> 4);
+        // operand offset of every (class, tap) inside a patch buffer, in 16-byte units
+        for (int idx = lane; idx < p.nclass * 9; idx += 32) {
+            const int c = idx / 9, t = idx - c * 9;
+            s_aoff[idx] = (uint32_t)((2 * p.tap_copy[c][t] * p.copy_bytes + p.tap_row[c][t] * 512) >> 4);
+        }
+        __syncwarp();
+        int S = 0, pb = 0, iter = 0;
+        uint32_t bph = 0, pph = 0, par = 0;
+        const int per_cls = p.nblocks * p.tgroups;
+        for (int g = cluster_id; g < p.total; g += nclusters, ++iter) {
+            const int cls = p.cls_order[g / per_cls];
+            const int ntaps = p.cls_ntaps[cls];
+            const int nbj = nchunks * ntaps;
+            const uint32_t *aoff = s_aoff + cls * 9;
+            if (iter > 0) mbar_wait(acc_free, (uint32_t)(iter - 1) & 1u);   // the epilogue warps drained the previous item's accumulators
+            int lbj = 0;
+            for (int cc = 0; cc < nchunks; ++cc) {
+                mbar_wait(&patch_full[pb], pph);
+                const uint32_t pbase = patch_lo + (uint32_t)pb * patch_sz;
 #pragma unroll 1
-                    for (int t0 = 0; t0 < ntaps; ++t0, ++gbj, ++lbj) {
-                        const int tap = (t0 + rot_t) % ntaps;
-                        const int S = gbj % kP2BStages, par = gbj & 1;
-                        mbar_wait(&b_full[S], (uint32_t)(gbj / kP2BStages) & 1u);
-                        tc_fence_after();
-                        const uint32_t a_off = (uint32_t)((2 * p.tap_copy[cls][tap] * p.copy_bytes + p.tap_row[cls][tap] * 512) >> 4);
-                        const uint64_t da_hi = desc_hi | (uint64_t)(pbase + a_off);
-                        const uint64_t da_lo = da_hi + (uint64_t)(p.copy_bytes >> 4);
+                for (int tap = 0; tap < ntaps; ++tap, ++lbj) {
+                    mbar_wait(&b_full[S], bph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t da_hi = desc_hi | (uint64_t)(pbase + aoff[tap]);
+                        const uint64_t da_lo = da_hi + (uint64_t)copy_lo;
                         const uint64_t dcat = desc_hi | (uint64_t)(tiles_lo + (uint32_t)(S * (kP2BStageBytes >> 4)));
                         const uint64_t dbhi = dcat + (par ? plane_lo : 0u);
                         const uint32_t d2 = par ? acc_cross : acc_main0;            // even stages: [main0|cross], odd stages: [cross|main1]
@@ -248,10 +256,14 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
                         }
                         if (CS == 1) tc_commit(&b_empty[S]);
                         else tc_commit_mc(&b_empty[S], kMask);                            // the stage is reusable in EVERY CTA of the cluster (peers multicast into it)
-                        if (t0 == ntaps - 1) tc_commit(&patch_empty[pb]);
+                        if (tap == ntaps - 1) tc_commit(&patch_empty[pb]);
                         if (lbj == nbj - 1) tc_commit(acc_full);
                     }
+                    __syncwarp();
+                    par ^= 1u;
+                    if (++S == kP2BStages) { S = 0; bph ^= 1u; }
                 }
+                if (++pb == p.npatch) { pb = 0; pph ^= 1u; }
             }
         }
     } else {
@@ -380,8 +392,6 @@ static int encode_map_nd(CUtensorMap *m, const void *base, int rank, const cuuin
 }
 
 static int g_p2_cluster = 1;
-static int g_p2_rotate = 1;      // CTAs walk the (channel chunk, tap) loop from different starting points: 148 SMs streaming the SAME 16 KB weight tile in
-                                 // lockstep keep only the ~64 L2 slices that hold it busy
 
 // taps: per class (dy, dx, weight tap); fills the geometry of p and launches
 struct P2Taps { int n, dy[9], dx[9], w[9]; };
@@ -437,7 +447,7 @@ static int launch_p2(const void *d_in_planes, int in_h, int in_w, const float *d
     }
     p.copy_bytes = p.rows_v * kP2TileU * 64;
     p.patch_bytes = p.ncopies * 2 * p.copy_bytes;
-    const int fixed = kP2BStages * kP2BStageBytes + 1024 + 256;
+    const int fixed = kP2BStages * kP2BStageBytes + 1024 + 512;
     p.npatch = (fixed + 2 * p.patch_bytes <= kP2MaxSmem) ? 2 : 1;
     const int smem = fixed + p.npatch * p.patch_bytes;
     if (smem > kP2MaxSmem) return SESSD_EINVAL;
@@ -469,7 +479,6 @@ static int launch_p2(const void *d_in_planes, int in_h, int in_w, const float *d
         attr_done = true;
     }
     p.n_tile = n_tile;
-    p.rotate = g_p2_rotate;
     p.tiles_u = div_up(p.grid_u, kP2TileU);
     p.tiles_v = div_up(p.grid_v, kP2TileV);
     p.tiles = p.tiles_u * p.tiles_v * p.batch;
@@ -520,8 +529,7 @@ using namespace sessd;
 
 // CTAs per cluster sharing the weight tiles through TMA multicast (1 or 2; default 2)
 extern "C" void sessd_set_p2_cluster(int cs) { sessd::g_p2_cluster = cs == 2 ? 2 : 1; }
-// 1 (default): every CTA starts the (channel chunk, tap) loop at a different point (de-phased weight streams); 0: all in the same order
-extern "C" void sessd_set_p2_rotate(int on) { sessd::g_p2_rotate = on ? 1 : 0; }
+
 
 // Conv2d (stride 1 or 2, arbitrary tap list) + folded BN + ReLU (+ residual) from fp16 (hi, lo) planes.
 //   d_in_planes  __half [2][batch][in_h][in_w][cin]; d_in_info [2] = {abs-max of the input, scale of its planes} (device);

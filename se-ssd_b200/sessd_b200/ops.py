@@ -383,11 +383,6 @@ def set_p2_cluster(n):
     lib.sessd_set_p2_cluster(int(n))
 
 
-def set_p2_rotate(on):
-    """1 (default): the CTAs of bev_conv_p2 walk the (channel chunk, tap) loop from different starting points (de-phased weight streams)"""
-    lib.sessd_set_p2_rotate(int(on))
-
-
 def bev_split_planes(x, info, planes):
     """fp32 tensor -> planes with the scale from info[0] (its abs-max: call absmax(x, info[0:1]) first); info[1] <- scale"""
     check(lib.sessd_bev_split_planes(_p(x), int(x.numel()), _p(info), _p(planes), _st()), "sessd_bev_split_planes")
