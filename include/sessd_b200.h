@@ -155,9 +155,6 @@ int sessd_spconv_forward_cg(const void *d_in_planes, int cp, int plane_rows, con
                             int relu, float gain, float shift_max, float *d_out_f32, void *d_out_planes, float *d_out_info, void *stream);
 /* 1: the gathered rows of sessd_spconv_forward_cg also allocate in L1 (cp.async.ca); default 0 (cp.async.cg) */
 void sessd_set_sp_cg_l1(int on);
-/* 1 (default): every CTA of sessd_spconv_forward_cg walks a tile's kernel offsets from a different starting point (de-phased weight streams:
- * CTAs reading the same weight tile in lockstep keep only the L2 slices that hold it busy); 0: ascending offsets everywhere */
-void sessd_set_sp_cg_rotate(int on);
 /* *d_amax = max(*d_amax, max |d_feat[i]|) over the first *d_n rows of a [max_rows, channels] fp32 tensor */
 int sessd_absmax_rows(const float *d_feat, const int *d_n, int max_rows, int channels, float *d_amax, void *stream);
 
@@ -202,7 +199,8 @@ int sessd_bev_deconv_p2(const void *d_in_planes, const float *d_in_info, const v
                         int relu, void *stream);
 /* fp32 [n] -> planes [2][n] scaled from d_info[0] (the tensor's abs-max, e.g. from sessd_absmax); writes the scale to d_info[1] */
 int sessd_bev_split_planes(const float *d_x, long long n, float *d_info, void *d_planes, void *stream);
-/* CTAs per cluster sharing (TMA-multicasting) the weight tiles of sessd_bev_conv_p2: 1 (default) or 2 */
+/* sessd_bev_conv_p2 / sessd_bev_deconv_p2: 0 (default) = CTA pairs (tcgen05 cta_group::2: one MMA spans two SMs, each CTA stages half of
+ * every weight tile) for the layers with long K loops, single CTAs for the 1x1 convs; 1 / 2 = force single CTAs / pairs */
 void sessd_set_p2_cluster(int ctas_per_cluster);
 /* dense() (scn.py:184-187) straight into the planes the neck reads: d_amax = abs-max of the feature rows, d_info[2] <- {abs-max, S} */
 int sessd_sparse_to_dense_planes(const float *d_feat, int max_rows, const void *d_bitmap_index, int channels, sessd_grid grid,

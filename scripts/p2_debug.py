@@ -140,7 +140,7 @@ def run_step(step):
             amax = torch.zeros(2, device="cuda"); ops.absmax(x, amax[0:1])
             variants = [("p2 cs1 planes-out", lambda: (ops.set_p2_cluster(1), ops.bev_conv_p2(xp, info, planes, sc, None, None, None, 30.0, 0.0, None, op, oinfo, d))),
                                                 ("p2 cs2 planes-out", lambda: (ops.set_p2_cluster(2), ops.bev_conv_p2(xp, info, planes, sc, None, None, None, 30.0, 0.0, None, op, oinfo, d))),
-                        ("p2 cs1 fp32-out", lambda: (ops.set_p2_cluster(1), ops.bev_conv_p2(xp, info, planes, sc, None, None, None, 30.0, 0.0, of, None, oinfo, d)))]
+                        ("p2 auto fp32-out", lambda: (ops.set_p2_cluster(0), ops.bev_conv_p2(xp, info, planes, sc, None, None, None, 30.0, 0.0, of, None, oinfo, d)))]
             if cin % 64 == 0 and cout >= 4:
                 variants.append(("h2 (in-kernel split)", lambda: ops.bev_conv_h2(x, planes, sc, None, None, of, d, amax[0:1], amax[1:2])))
             for name, fn in variants:

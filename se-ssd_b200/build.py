@@ -19,7 +19,7 @@ LAB_OUT = os.path.join(HERE, "libsessd_b200_lab.so")
 LAB = {"mma_probe.cu", "bevconv_tc.cu", "bevconv_h2.cu", "spconv_tc.cu", "spconv_h2.cu"}
 OBJ = os.path.join(HERE, "build")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("SESSD_DEFINES", "").split()
 NO_FMA = {"iou3d.cu", "postproc.cu", "assign.cu", "odiou.cu"}
 
 

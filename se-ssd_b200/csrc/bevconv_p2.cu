@@ -30,8 +30,9 @@ namespace sessd {
 constexpr int kP2TileU = 8, kP2TileV = 16, kP2BM = 128;
 constexpr int kP2Chunk = 32;                              // channels per stage = one 64-byte SWIZZLE_64B row
 constexpr int kP2MaxCopies = 6, kP2MaxRowsV = 18;
-constexpr int kP2BStages = 6;
+constexpr int kP2BStages = 6, kP2MaxBStages = 12;
 constexpr int kP2BStageBytes = 2 * 128 * 64;              // [X ; Y] planes, up to 128 rows of 64 B each
+constexpr int kP2BRing = kP2BStages * kP2BStageBytes;     // bytes of the weight-stage ring (pair mode: twice as many stages of half the size)
 constexpr int kP2Threads = 352;                           // 11 warps
 constexpr int kP2EpiWarps = 8;
 constexpr int kP2MaxSmem = 227 * 1024;
@@ -49,6 +50,7 @@ struct P2Params {
     int copy_u[kP2MaxCopies], copy_v[kP2MaxCopies];       // input coordinate of the copy's first element relative to (u0, v0) * in_stride
     int copy_bytes, patch_bytes, npatch;                  // bytes of one copy plane, of one patch buffer (ncopies x 2 planes), 1 or 2 buffers
     int relu, n_tile, nblocks;
+    int bstages, bstage_bytes;         // weight-stage ring: count and bytes per stage
     int tiles_u, tiles_v, tiles, tgroups, total;          // pixel tiles, tile groups (CS tiles each), work items = nclass * nblocks * tgroups
     int cls_order[4];
     const float *in_info;              // [2] = {abs-max of the input tensor, scale S_in of its planes}
@@ -56,6 +58,7 @@ struct P2Params {
     float gain, shift_max;             // bound of the output: amax_in * gain + shift_max (+ amax_resid)
     float *out_info;                   // [2] = {running abs-max of the output (atomicMax), S_out}
     long long out_plane_stride;        // elements between the hi and the lo plane of the output
+    long long *dbg;                    // SESSD_P2_PROFILE only
 };
 
 __host__ __device__ constexpr uint32_t p2_idesc_f16(int M, int N) {
@@ -78,7 +81,61 @@ __device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const CUtensorMap
         : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) variants: the MMA spans two SMs (M = 256: 128 pixels per CTA), each CTA stages only HALF of every weight
+// tile (N/2 rows) and its own activation patch; all loads signal the LEADER's (cluster rank 0) mbarriers.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;          // shared::cluster address of the same offset in the even CTA of the pair
+
+__device__ __forceinline__ void p2_mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t smem_dst, const CUtensorMap *map, uint64_t *leader_bar, int c0, int c1, int c2, int c3,
+                                                 int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n" ::"r"(
+            smem_dst),
+        "l"(map), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t smem_dst, const CUtensorMap *map, uint64_t *leader_bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(
+            smem_dst),
+        "l"(map), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(rank)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t *bar) {      // arrives on the barrier at this offset in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
 struct P2Item { int cls, n0, b, u0, v0, ntaps; };
+
+// -DSESSD_P2_PROFILE: per-CTA cycle counters of the waits of every role ([ctas][8] int64 via sessd_set_p2_dbg; lab measurements only)
+#ifdef SESSD_P2_PROFILE
+#define P2_WAIT(slot, stmt)                                                                              \
+    do {                                                                                                 \
+        const long long _t0 = clock64();                                                                 \
+        stmt;                                                                                            \
+        if (p.dbg && lane == 0) p.dbg[(size_t)blockIdx.x * 8 + (slot)] += clock64() - _t0;               \
+    } while (0)
+#else
+#define P2_WAIT(slot, stmt) stmt
+#endif
 template <int CS>
 __device__ __forceinline__ P2Item p2_decode(const P2Params &p, int g, int crank) {
     P2Item it;
@@ -115,34 +172,41 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
                                                                    __half *__restrict__ out_planes, P2Params p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *tiles = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    unsigned char *patches = tiles + kP2BStages * kP2BStageBytes;
+    unsigned char *patches = tiles + kP2BRing;
     uint64_t *bars = (uint64_t *)(patches + p.npatch * p.patch_bytes);
-    uint64_t *patch_full = bars, *patch_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 4 + kP2BStages;
-    uint64_t *acc_full = bars + 4 + 2 * kP2BStages, *acc_free = acc_full + 1;
+    uint64_t *patch_full = bars, *patch_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 4 + kP2MaxBStages;
+    uint64_t *acc_full = bars + 4 + 2 * kP2MaxBStages, *acc_free = acc_full + 1;
     uint32_t *tmem_slot = (uint32_t *)(acc_free + 1);
     uint32_t *s_aoff = tmem_slot + 2;                    // [4 classes][9 taps]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t crank = (CS > 1) ? cluster_cta_rank() : 0u;
-    constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
+    constexpr bool kPair = (CS == 2);
     const int cluster_id = blockIdx.x / CS, nclusters = gridDim.x / CS;
     const int nchunks = p.cin / kP2Chunk;
-    const uint32_t b_plane_bytes = (uint32_t)p.n_tile * 64u;
+    const uint32_t b_plane_bytes = (uint32_t)(p.n_tile / CS) * 64u;      // bytes of the b_hi (or b_lo) rows THIS CTA stages per (tap, chunk)
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(&patch_full[s], 1); mbar_init(&patch_empty[s], 1); }
-        for (int s = 0; s < kP2BStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], CS); }
+        // pair mode: the leader's "full" barriers collect one arrival per CTA (the leader's carries the byte count of BOTH CTAs' loads)
+        for (int s = 0; s < 2; ++s) { mbar_init(&patch_full[s], CS); mbar_init(&patch_empty[s], 1); }
+        for (int s = 0; s < p.bstages; ++s) { mbar_init(&b_full[s], CS); mbar_init(&b_empty[s], 1); }
         mbar_init(acc_full, 1);
-        mbar_init(acc_free, kP2EpiWarps);
+        mbar_init(acc_free, kP2EpiWarps * CS);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
+    if (kPair) cluster_sync_all();         // both CTAs are resident before the pair-wide TMEM allocation
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+        if (kPair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (CS > 1) cluster_sync_all();        // peers' barriers must be initialised before any multicast / remote arrive
+    if (kPair) cluster_sync_all();         // the peer's barriers are initialised before any remote arrive / peer-signalling load
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -159,14 +223,20 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
             const P2Item it = p2_decode<CS>(p, g, (int)crank);
             const int bu = it.u0 * p.in_stride, bv = it.v0 * p.in_stride;
             for (int cc = 0; cc < nchunks; ++cc) {
-                mbar_wait(&patch_empty[pb], pph ^ 1u);
+                P2_WAIT(7, mbar_wait(&patch_empty[pb], pph ^ 1u));
                 if (elect_one()) {
-                    mbar_expect_tx(&patch_full[pb], (uint32_t)p.patch_bytes);
+                    if (!kPair || crank == 0) mbar_expect_tx(&patch_full[pb], (uint32_t)(CS * p.patch_bytes));
+                    else mbar_arrive_remote(&patch_full[pb], 0);
                     uint32_t dst = patches_u32 + (uint32_t)(pb * p.patch_bytes);
                     for (int c = 0; c < p.ncopies; ++c, dst += 2u * (uint32_t)p.copy_bytes) {
                         const int cu = bu + p.copy_u[c], cv = bv + p.copy_v[c];
-                        tma_load_5d(dst, &map_a, &patch_full[pb], cc * kP2Chunk, cu, cv, it.b, 0);
-                        tma_load_5d(dst + (uint32_t)p.copy_bytes, &map_a, &patch_full[pb], cc * kP2Chunk, cu, cv, it.b, 1);
+                        if (kPair) {
+                            tma_load_5d_pair(dst, &map_a, &patch_full[pb], cc * kP2Chunk, cu, cv, it.b, 0);
+                            tma_load_5d_pair(dst + (uint32_t)p.copy_bytes, &map_a, &patch_full[pb], cc * kP2Chunk, cu, cv, it.b, 1);
+                        } else {
+                            tma_load_5d(dst, &map_a, &patch_full[pb], cc * kP2Chunk, cu, cv, it.b, 0);
+                            tma_load_5d(dst + (uint32_t)p.copy_bytes, &map_a, &patch_full[pb], cc * kP2Chunk, cu, cv, it.b, 1);
+                        }
                     }
                 }
                 __syncwarp();
@@ -174,39 +244,41 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
             }
         }
     } else if (warp == 1) {
-        // ===================== weight tiles: one [X ; Y] stage per (item, chunk, tap); this CTA fetches 1/CS of the rows =====================
+        // ===================== weight tiles: one stage per (item, chunk, tap) =====================
+        // single CTA: [b_hi ; b_lo] (128 + 128 rows) on even stages, [b_lo ; b_hi] on odd stages (every item has an even stage count);
+        // pair: this CTA's half of the output channels, always [b_hi half ; b_lo half] (64 + 64 rows)
         int S = 0;
         uint32_t bph = 0, par = 0;
         const int rows = p.n_tile / CS;
-        const uint32_t so = crank * (uint32_t)rows * 64u;
         for (int g = cluster_id; g < p.total; g += nclusters) {
             const P2Item it = p2_decode<CS>(p, g, (int)crank);
-            const int n0 = it.n0 + (CS > 1 ? (int)crank * rows : 0);
+            const int n0 = it.n0 + (kPair ? (int)crank * rows : 0);
             for (int cc = 0; cc < nchunks; ++cc)
                 for (int tap = 0; tap < it.ntaps; ++tap) {
-                    mbar_wait(&b_empty[S], bph ^ 1u);
+                    P2_WAIT(6, mbar_wait(&b_empty[S], bph ^ 1u));
                     if (elect_one()) {
-                        mbar_expect_tx(&b_full[S], 2 * b_plane_bytes);
-                        unsigned char *st = tiles + S * kP2BStageBytes + so;
+                        unsigned char *st = tiles + S * p.bstage_bytes;
                         const int wtap = p.tap_w[it.cls][tap];
-                        // [b_hi ; b_lo] on even stages, [b_lo ; b_hi] on odd stages (every item has an even stage count: running parity)
-                        const uint32_t hi_off = par ? b_plane_bytes : 0u, lo_off = par ? 0u : b_plane_bytes;
-                        if (CS == 1) {
+                        if (kPair) {
+                            if (crank == 0) mbar_expect_tx(&b_full[S], 4 * b_plane_bytes);
+                            else mbar_arrive_remote(&b_full[S], 0);
+                            tma_load_4d_pair(smem_u32(st), &map_b, &b_full[S], cc * kP2Chunk, n0, wtap, 0);
+                            tma_load_4d_pair(smem_u32(st) + b_plane_bytes, &map_b, &b_full[S], cc * kP2Chunk, n0, wtap, 1);
+                        } else {
+                            mbar_expect_tx(&b_full[S], 2 * b_plane_bytes);
+                            const uint32_t hi_off = par ? b_plane_bytes : 0u, lo_off = par ? 0u : b_plane_bytes;
                             tma_load_4d(st + hi_off, &map_b, &b_full[S], cc * kP2Chunk, n0, wtap, 0);
                             tma_load_4d(st + lo_off, &map_b, &b_full[S], cc * kP2Chunk, n0, wtap, 1);
-                        } else {
-                            tma_load_4d_mc(st + hi_off, &map_b, &b_full[S], cc * kP2Chunk, n0, wtap, 0, kMask);
-                            tma_load_4d_mc(st + lo_off, &map_b, &b_full[S], cc * kP2Chunk, n0, wtap, 1, kMask);
                         }
                     }
                     __syncwarp();
                     par ^= 1u;
-                    if (++S == kP2BStages) { S = 0; bph ^= 1u; }
+                    if (++S == p.bstages) { S = 0; bph ^= 1u; }
                 }
         }
-    } else if (warp == 2) {
-        // ===================== MMA issue (one elected lane; the warp walks the loops together) =====================
-        const uint32_t idesc1 = p2_idesc_f16(kP2BM, p.n_tile), idesc2 = p2_idesc_f16(kP2BM, 2 * p.n_tile);
+    } else if (warp == 2 && (!kPair || crank == 0)) {
+        // ===================== MMA issue (one elected lane; the warp walks the loops together; pair mode: the leader CTA only) =========
+        const uint32_t idesc1 = p2_idesc_f16(kP2BM * CS, p.n_tile), idesc2 = p2_idesc_f16(kP2BM * CS, 2 * p.n_tile);
         const uint32_t acc_main0 = tmem_base, acc_cross = tmem_base + (uint32_t)p.n_tile, acc_main1 = tmem_base + 2 * (uint32_t)p.n_tile;
         const uint64_t desc_hi = ((uint64_t)((512u >> 4) | (1u << 14) | (4u << 29))) << 32;      // SBO 512 B | version 1 | SWIZZLE_64B
         const uint32_t lbo = 1u << 16;
@@ -223,26 +295,53 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
         int S = 0, pb = 0, iter = 0;
         uint32_t bph = 0, pph = 0, par = 0;
         const int per_cls = p.nblocks * p.tgroups;
+#ifdef SESSD_P2_PROFILE
+        const long long t_begin = clock64();
+#endif
         for (int g = cluster_id; g < p.total; g += nclusters, ++iter) {
             const int cls = p.cls_order[g / per_cls];
             const int ntaps = p.cls_ntaps[cls];
             const int nbj = nchunks * ntaps;
             const uint32_t *aoff = s_aoff + cls * 9;
-            if (iter > 0) mbar_wait(acc_free, (uint32_t)(iter - 1) & 1u);   // the epilogue warps drained the previous item's accumulators
+            if (iter > 0) P2_WAIT(0, mbar_wait(acc_free, (uint32_t)(iter - 1) & 1u));   // the epilogue warps drained the previous item's accumulators
             int lbj = 0;
             for (int cc = 0; cc < nchunks; ++cc) {
-                mbar_wait(&patch_full[pb], pph);
+                P2_WAIT(1, mbar_wait(&patch_full[pb], pph));
                 const uint32_t pbase = patch_lo + (uint32_t)pb * patch_sz;
 #pragma unroll 1
                 for (int tap = 0; tap < ntaps; ++tap, ++lbj) {
-                    mbar_wait(&b_full[S], bph);
+                    P2_WAIT(2, mbar_wait(&b_full[S], bph));
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t da_hi = desc_hi | (uint64_t)(pbase + aoff[tap]);
                         const uint64_t da_lo = da_hi + (uint64_t)copy_lo;
-                        const uint64_t dcat = desc_hi | (uint64_t)(tiles_lo + (uint32_t)(S * (kP2BStageBytes >> 4)));
+                        const uint64_t dcat = desc_hi | (uint64_t)(tiles_lo + (uint32_t)(S * (p.bstage_bytes >> 4)));
                         const uint64_t dbhi = dcat + (par ? plane_lo : 0u);
                         const uint32_t d2 = par ? acc_cross : acc_main0;            // even stages: [main0|cross], odd stages: [cross|main1]
+                        if constexpr (kPair) {
+                            // TMEM columns (per CTA: its 128 pixels x all columns), h = n_tile / 2:
+                            //   [0, 2 n_tile)  = [main0 c<h | cross c<h | main0 c>=h | cross c>=h]: even taps, ONE N = 2 n_tile product
+                            //                    a_hi x [b_hi half ; b_lo half] (the two CTAs' halves are concatenated along N)
+                            //   [2 n_tile, 3 n_tile) = main1: odd taps, a_hi x b_hi  (two main accumulators halve the length of the truncating
+                            //                    accumulation chains, like the single-CTA path)
+                            //   [3 n_tile, 4 n_tile) = cross2: a_lo x b_hi (every tap) and a_hi x b_lo (odd taps)
+                            const uint32_t acc_m1 = tmem_base + 2 * (uint32_t)p.n_tile, acc_c2 = tmem_base + 3 * (uint32_t)p.n_tile;
+                            const uint64_t dblo = dcat + (uint64_t)plane_lo;
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                const uint32_t ko = (uint32_t)(k * 2);
+                                if (!par) {
+                                    p2_mma_f16_pair(tmem_base, da_hi + ko, dcat + ko, idesc2, (lbj | k) != 0);
+                                } else {
+                                    p2_mma_f16_pair(acc_m1, da_hi + ko, dcat + ko, idesc1, (lbj != 1) || k != 0);
+                                    p2_mma_f16_pair(acc_c2, da_hi + ko, dblo + ko, idesc1, 1);
+                                }
+                                p2_mma_f16_pair(acc_c2, da_lo + ko, dcat + ko, idesc1, (lbj | k) != 0);
+                            }
+                            tc_commit_pair(&b_empty[S]);
+                            if (tap == ntaps - 1) tc_commit_pair(&patch_empty[pb]);
+                            if (lbj == nbj - 1) tc_commit_pair(acc_full);
+                        } else {
 #pragma unroll
                         for (int k = 0; k < 2; ++k) {                                  // K = 16 per instruction = 32 bytes of the 64-byte row
                             const uint32_t ko = (uint32_t)(k * 2);
@@ -254,19 +353,22 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
                             }
                             p2_mma_f16(acc_cross, da_lo + ko, dbhi + ko, idesc1, 1);      // cross += a_lo x b_hi
                         }
-                        if (CS == 1) tc_commit(&b_empty[S]);
-                        else tc_commit_mc(&b_empty[S], kMask);                            // the stage is reusable in EVERY CTA of the cluster (peers multicast into it)
+                        tc_commit(&b_empty[S]);
                         if (tap == ntaps - 1) tc_commit(&patch_empty[pb]);
                         if (lbj == nbj - 1) tc_commit(acc_full);
+                        }
                     }
                     __syncwarp();
                     par ^= 1u;
-                    if (++S == kP2BStages) { S = 0; bph ^= 1u; }
+                    if (++S == p.bstages) { S = 0; bph ^= 1u; }
                 }
                 if (++pb == p.npatch) { pb = 0; pph ^= 1u; }
             }
         }
-    } else {
+#ifdef SESSD_P2_PROFILE
+        if (p.dbg && lane == 0) { p.dbg[(size_t)blockIdx.x * 8 + 3] = clock64() - t_begin; p.dbg[(size_t)blockIdx.x * 8 + 4] = iter; }
+#endif
+    } else if (warp >= 3) {
         // ===================== epilogue warps (3-10): TMEM -> registers, release the accumulators, BN / ReLU / residual / stores
         const int q = warp & 3;                          // TMEM lane quadrant this warp may access
         const int half = (warp - 3) >> 2;                // warps 3-6: first half of the N tile's columns, 7-10: second half
@@ -284,25 +386,38 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
         for (int g = cluster_id; g < p.total; g += nclusters, ++iter) {
             const P2Item it = p2_decode<CS>(p, g, (int)crank);
             float v[64];
-            if (lane == 0) mbar_wait(acc_full, (uint32_t)iter & 1u);
+            if (lane == 0) { if (warp == 3) P2_WAIT(5, mbar_wait(acc_full, (uint32_t)iter & 1u)); else mbar_wait(acc_full, (uint32_t)iter & 1u); }
             __syncwarp();
             tc_fence_after();
-            const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * ncol);
+            // single CTA: [main0 | cross | main1], n_tile columns each; pair: [main c<h | cross c<h | main c>=h | cross c>=h | cross2], h = ncol
+            const uint32_t lane0 = tmem_base + ((uint32_t)(q * 32) << 16);
+            const uint32_t lane_base = lane0 + (uint32_t)(kPair ? half * 2 * ncol : half * ncol);
+            const uint32_t off_cr = (uint32_t)(kPair ? ncol : p.n_tile);
+            const uint32_t base_m1 = kPair ? lane0 + 2 * (uint32_t)p.n_tile + (uint32_t)(half * ncol) : lane_base + 2 * (uint32_t)p.n_tile;
+            const uint32_t base_c2 = lane0 + 3 * (uint32_t)p.n_tile + (uint32_t)(half * ncol);       // pair mode only
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 16) {
                 if (c0 < ncol) {
                     uint32_t m0[16], cr[16], m1[16];
                     p2_tmem_ld16(lane_base + c0, m0);
-                    p2_tmem_ld16(lane_base + (uint32_t)p.n_tile + c0, cr);
-                    p2_tmem_ld16(lane_base + 2 * (uint32_t)p.n_tile + c0, m1);
+                    p2_tmem_ld16(lane_base + off_cr + c0, cr);
+                    p2_tmem_ld16(base_m1 + c0, m1);
+                    uint32_t c2[16];
+                    if (kPair) p2_tmem_ld16(base_c2 + c0, c2);
                     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[c0 + i] = (__uint_as_float(m0[i]) + __uint_as_float(cr[i])) + __uint_as_float(m1[i]);
+                    for (int i = 0; i < 16; ++i) {
+                        if (kPair) v[c0 + i] = (__uint_as_float(m0[i]) + __uint_as_float(m1[i])) + (__uint_as_float(cr[i]) + __uint_as_float(c2[i]));
+                        else v[c0 + i] = (__uint_as_float(m0[i]) + __uint_as_float(cr[i])) + __uint_as_float(m1[i]);
+                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_free);        // the next item's MMAs may overwrite the accumulators now
+            if (lane == 0) {                             // the next item's MMAs may overwrite the accumulators now
+                if (kPair && crank != 0) mbar_arrive_remote(acc_free, 0);
+                else mbar_arrive(acc_free);
+            }
             const int gu = it.u0 + lu, gv = it.v0 + lv;
             if (it.b < p.batch && gu < p.grid_u && gv < p.grid_v) {
                 const int ou = gu * p.out_stride + p.cls_off_u[it.cls], ov = gv * p.out_stride + p.cls_off_v[it.cls];
@@ -359,8 +474,11 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
     }
     tc_fence_before();
     __syncthreads();
-    if (CS > 1) cluster_sync_all();        // nobody exits while a peer may still multicast into / arrive on this CTA
-    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
+    if (kPair) cluster_sync_all();         // nobody exits while the peer may still arrive on / load for this CTA
+    if (warp == 2) {
+        if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
+    }
 }
 
 // fp32 rows [rows][C] -> fp16 (hi, lo) planes [2][rows][C] with the scale taken from info[0] (exact abs-max of the tensor); writes info[1]
@@ -391,7 +509,8 @@ static int encode_map_nd(CUtensorMap *m, const void *base, int rank, const cuuin
     return r == CUDA_SUCCESS ? 0 : 700 + (int)r;
 }
 
-static int g_p2_cluster = 1;
+static long long *g_p2_dbg = nullptr;
+static int g_p2_cluster = 0;      // 0: CTA pairs (cta_group::2) for the layers with long K loops, single CTAs for the rest; 1 / 2: force
 
 // taps: per class (dy, dx, weight tap); fills the geometry of p and launches
 struct P2Taps { int n, dy[9], dx[9], w[9]; };
@@ -447,11 +566,16 @@ static int launch_p2(const void *d_in_planes, int in_h, int in_w, const float *d
     }
     p.copy_bytes = p.rows_v * kP2TileU * 64;
     p.patch_bytes = p.ncopies * 2 * p.copy_bytes;
-    const int fixed = kP2BStages * kP2BStageBytes + 1024 + 512;
+    const int fixed = kP2BRing + 1024 + 512;
     p.npatch = (fixed + 2 * p.patch_bytes <= kP2MaxSmem) ? 2 : 1;
     const int smem = fixed + p.npatch * p.patch_bytes;
     if (smem > kP2MaxSmem) return SESSD_EINVAL;
-    const int cs = (g_p2_cluster == 2 && n_tile / 2 >= 8) ? 2 : 1;
+    // CTA pairs halve the weight bytes every SM pulls from the L2 and stages in shared memory (the two resources that bound the 3x3
+    // layers); the short K loops (1x1 convs: 4-8 tap-chunks per item) are dominated by per-item latencies, where a pair only adds
+    // cross-CTA handshakes (measured: 3x3 128->128 45.9 -> 39.7 us, 3x3 256->256 65.5 -> 51.2 us; 1x1 128->128 22.6 -> 23.6 us)
+    int kloop = 0;
+    for (int c = 0; c < p.nclass; ++c) kloop = max(kloop, cls[c].n * (p.cin / kP2Chunk));
+    const int cs = (g_p2_cluster == 2 || (g_p2_cluster == 0 && kloop >= 16)) ? 2 : 1;
     CUtensorMap map_a, map_b;
     {   // planes [2][B][H][W][C] fp16 viewed as {C, U, V, B, plane}
         const cuuint64_t row_w = (cuuint64_t)p.cin * 2, row_h = (cuuint64_t)in_w * p.cin * 2;
@@ -479,6 +603,9 @@ static int launch_p2(const void *d_in_planes, int in_h, int in_w, const float *d
         attr_done = true;
     }
     p.n_tile = n_tile;
+    p.bstage_bytes = 2 * (n_tile / cs) * 64;
+    p.bstages = kP2BRing / p.bstage_bytes < kP2MaxBStages ? kP2BRing / p.bstage_bytes : kP2MaxBStages;
+    p.dbg = g_p2_dbg;
     p.tiles_u = div_up(p.grid_u, kP2TileU);
     p.tiles_v = div_up(p.grid_v, kP2TileV);
     p.tiles = p.tiles_u * p.tiles_v * p.batch;
@@ -527,9 +654,13 @@ static int launch_p2(const void *d_in_planes, int in_h, int in_w, const float *d
 
 using namespace sessd;
 
-// CTAs per cluster sharing the weight tiles through TMA multicast (1 or 2; default 2)
-extern "C" void sessd_set_p2_cluster(int cs) { sessd::g_p2_cluster = cs == 2 ? 2 : 1; }
+// 0 (default): CTA pairs (tcgen05 cta_group::2, each CTA stages half of every weight tile) where the K loop is long; 1 / 2: force
+extern "C" void sessd_set_p2_cluster(int cs) { sessd::g_p2_cluster = (cs == 1 || cs == 2) ? cs : 0; }
 
+
+#ifdef SESSD_P2_PROFILE
+extern "C" void sessd_set_p2_dbg(void *d) { sessd::g_p2_dbg = (long long *)d; }
+#endif
 
 // Conv2d (stride 1 or 2, arbitrary tap list) + folded BN + ReLU (+ residual) from fp16 (hi, lo) planes.
 //   d_in_planes  __half [2][batch][in_h][in_w][cin]; d_in_info [2] = {abs-max of the input, scale of its planes} (device);

@@ -52,7 +52,7 @@ struct CgArgs {
     const float *in_info;              // {abs-max of the input tensor, its plane scale}
     const int *nbr;                    // [max_out][kvol]
     const int *d_n_out;
-    int kvol, max_out, relu, rotate;
+    int kvol, max_out, relu;
     const float *scale, *shift;        // folded BN (scale already times the per-channel weight exponent 2^-e)
     float gain, shift_max;             // |out| <= amax_in * gain + shift_max
     float *out_f32;                    // nullable [max_out][COUT]
@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
     const float s_out = pow2_scale_for_bound(amax_in * a.gain + a.shift_max);
     if (blockIdx.x == 0 && tid == 0 && a.out_info) a.out_info[1] = s_out;
     float vmax = 0.f;
-    int gbase = 0, acc_it = 0;                                   // stage fills / accumulator hand-overs before this tile (all roles count alike)
+    int st0 = 0, acc_it = 0;                                     // stage of this tile's first fill / accumulator hand-overs so far (all roles
+    uint32_t ph0 = 0;                                            // count alike); ph0 = phase bit of stage st0
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int row0 = tile * kCgBM;
@@ -175,26 +176,23 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
         }
         __syncthreads();
         const int nact = *s_nact;
-        // every CTA walks the tile's offsets from a different starting point: 296 CTAs streaming the SAME weight tile W[k] in lockstep would
-        // keep only the 16-64 L2 slices that hold it busy (the convoy bounds the layer, not the gather)
-        const int rot = (a.rotate && nact > 0) ? (int)((blockIdx.x * 11u + (unsigned)tile) % (unsigned)nact) : 0;
 
+        // stage index / phase of this tile's first fill (all roles advance them alike)
         if (warp == 9) {
-            // ===================== MMA issue (one thread) =====================
-            if (lane == 0) {
-                const uint32_t idesc = cg_idesc_f16(kCgBM, COUT);
-                const uint32_t idesc2 = cg_idesc_f16(kCgBM, 2 * COUT);
-                const uint64_t desc_hi = ((uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29))) << 32;      // SBO | version | SWIZZLE_128B
-                const uint32_t tiles_lo = ((tiles_u32 >> 4) & 0x3FFFu) | (1u << 16);
-                const uint32_t acc_main0 = tmem_base, acc_cross = tmem_base + COUT, acc_main1 = tmem_base + 2 * COUT;
-                tc_fence_after();                                // the previous tile's epilogue read the accumulators before the CTA-wide sync
-                for (int j = 0; j < nact; ++j) {
-                    const int gj = gbase + j;
-                    const int s = gj % C::kStages;
-                    const uint32_t ph = (uint32_t)(gj / C::kStages) & 1u;
-                    mbar_wait(&full_b[s], ph);
-                    mbar_wait(&full_a[s], ph);
-                    tc_fence_after();
+            // ===================== MMA issue (one elected lane; the warp walks the loop together: operands stay in uniform registers) ===
+            const uint32_t idesc = cg_idesc_f16(kCgBM, COUT);
+            const uint32_t idesc2 = cg_idesc_f16(kCgBM, 2 * COUT);
+            const uint64_t desc_hi = ((uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29))) << 32;      // SBO | version | SWIZZLE_128B
+            const uint32_t tiles_lo = ((tiles_u32 >> 4) & 0x3FFFu) | (1u << 16);
+            const uint32_t acc_main0 = tmem_base, acc_cross = tmem_base + COUT, acc_main1 = tmem_base + 2 * COUT;
+            tc_fence_after();                                    // the previous tile's epilogue read the accumulators before the CTA-wide sync
+            int s = st0;
+            uint32_t ph = ph0;
+            for (int j = 0; j < nact; ++j) {
+                mbar_wait(&full_b[s], ph);
+                mbar_wait(&full_a[s], ph);
+                tc_fence_after();
+                if (elect_one()) {
                     const uint32_t st_lo = tiles_lo + (uint32_t)s * (C::kStage >> 4);
                     const uint64_t dA = desc_hi | st_lo;
                     const uint64_t dB = desc_hi | (st_lo + (C::kATile >> 4));
@@ -227,17 +225,17 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
                     tc_commit(&empty[s]);
                     if (j == nact - 1) tc_commit(acc_full);
                 }
+                __syncwarp();
+                if (++s == C::kStages) { s = 0; ph ^= 1u; }
             }
-            __syncwarp();
         } else if (warp == 8) {
-            // ===================== weight tiles (TMA, one thread) =====================
-            if (lane == 0) {
-                for (int j = 0; j < nact; ++j) {
-                    const int gj = gbase + j;
-                    const int s = gj % C::kStages;
-                    const uint32_t ph = (uint32_t)(gj / C::kStages) & 1u;
-                    const int k = s_klist[j + rot < nact ? j + rot : j + rot - nact];
-                    mbar_wait(&empty[s], ph ^ 1u);
+            // ===================== weight tiles (TMA, one elected lane) =====================
+            int s = st0;
+            uint32_t ph = ph0;
+            for (int j = 0; j < nact; ++j) {
+                const int k = s_klist[j];
+                mbar_wait(&empty[s], ph ^ 1u);
+                if (elect_one()) {
                     mbar_expect_tx(&full_b[s], C::kBTile);
                     unsigned char *b_tile = tiles + s * C::kStage + C::kATile;
                     if constexpr (C::kWide) {
@@ -248,8 +246,9 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
                         tma_load_4d(b_tile, &map_w, &full_b[s], 0, 0, 0, k);
                     }
                 }
+                __syncwarp();
+                if (++s == C::kStages) { s = 0; ph ^= 1u; }
             }
-            __syncwarp();
         } else {
             // ===================== producers: copy the rows that exist, clear the rows that stopped existing =====================
             const int own = warp * 16;                                   // rows whose zero state this warp maintains
@@ -258,11 +257,10 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
             const int slot = tid / kLanesPerRow;
             const int c = tid % kLanesPerRow;
             const int half = c >> 3, cc = c & 7;                         // wide: chunk c of the 256-byte row = (hi | lo tile, 16-byte chunk)
+            int s = st0;
+            uint32_t ph = ph0;
             for (int j = 0; j < nact; ++j) {
-                const int gj = gbase + j;
-                const int s = gj % C::kStages;
-                const uint32_t ph = (uint32_t)(gj / C::kStages) & 1u;
-                const int k = s_klist[j + rot < nact ? j + rot : j + rot - nact];
+                const int k = s_klist[j];
                 if (lane == 0) mbar_wait(&empty[s], ph ^ 1u);
                 __syncwarp();
                 const uint32_t a_base = tiles_u32 + (uint32_t)(s * C::kStage);
@@ -297,6 +295,7 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
                 // asynchronous arrival: this thread's share of the stage is complete when its cp.asyncs have landed (no thread waits for data:
                 // up to kStages fills are in flight per CTA, bounded only by the MMA releasing the stages)
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&full_a[s])) : "memory");
+                if (++s == C::kStages) { s = 0; ph ^= 1u; }
             }
 
             // ===================== epilogue: TMEM -> registers -> BN / ReLU -> planes and / or fp32 rows =====================
@@ -369,7 +368,11 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
                 }
             }
         }
-        gbase += nact;
+        {   // advance the ring position by this tile's fills
+            const int adv = st0 + nact;
+            ph0 ^= (uint32_t)(adv / C::kStages) & 1u;
+            st0 = adv % C::kStages;
+        }
         acc_it += nact > 0 ? 1 : 0;
         __syncthreads();                                         // lists are rebuilt next; every role is done reading them
     }
@@ -382,7 +385,6 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
     if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
 }
 
-static int g_cg_rotate = 1;
 static int g_cg_l1 = 0;            // 1: gathered rows also allocate in L1 (cp.async.ca)
 
 template <int CP, int COUT>
@@ -427,7 +429,6 @@ static int launch_spconv_cg(const CgArgs &a, const void *w_h2, cudaStream_t st) 
 using namespace sessd;
 
 extern "C" void sessd_set_sp_cg_l1(int on) { sessd::g_cg_l1 = on ? 1 : 0; }
-extern "C" void sessd_set_sp_cg_rotate(int on) { sessd::g_cg_rotate = on ? 1 : 0; }
 
 // S4 (scn.py:106-149), pair-proportional tensor-core path.  d_in_planes [plane_rows][2][cp] fp16 with d_in_info = {abs-max, scale};
 // weights / d_scale from ops.pack_weight_sp_h2 (cp = 64: [kvol][2][Cout][64], cp = 32: [kvol][Cout][hi 32 | lo 32]; d_scale = BN scale *
@@ -444,7 +445,7 @@ extern "C" int sessd_spconv_forward_cg(const void *d_in_planes, int cp, int plan
     if (d_out_planes && !d_out_info) return SESSD_EINVAL;
     CgArgs a;
     a.planes = (const __half *)d_in_planes; a.in_info = d_in_info; a.nbr = d_nbr; a.d_n_out = d_n_out; a.kvol = kvol; a.max_out = max_out;
-    a.relu = relu; a.rotate = g_cg_rotate; a.scale = d_scale; a.shift = d_shift; a.gain = gain; a.shift_max = shift_max; a.out_f32 = d_out_f32;
+    a.relu = relu; a.scale = d_scale; a.shift = d_shift; a.gain = gain; a.shift_max = shift_max; a.out_f32 = d_out_f32;
     a.out_planes = (__half *)d_out_planes; a.out_info = d_out_info;
     cudaStream_t st = (cudaStream_t)stream;
     if (cp == 32 && cout == 32) return launch_spconv_cg<32, 32>(a, d_weight_h2, st);

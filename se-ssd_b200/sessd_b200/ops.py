@@ -379,7 +379,7 @@ def bev_deconv_p2(in_planes, in_info, weight_h2, scale, shift, residual, resid_i
 
 
 def set_p2_cluster(n):
-    """CTAs per cluster sharing the weight tiles of bev_conv_p2 through TMA multicast (1 or 2; default 1)."""
+    """bev_conv_p2: 0 (default) = CTA pairs (cta_group::2) where the K loop is long, 1 / 2 = force single CTAs / pairs."""
     lib.sessd_set_p2_cluster(int(n))
 
 
