@@ -105,6 +105,11 @@ int sessd_strided_rulebook(const int *d_in_coors, const int *d_n_in, int max_in,
                            sessd_grid out_grid, void *d_out_bitmap /*uint2[words]*/, void *d_scan_scratch,
                            int *d_out_coors, int *d_n_out, int max_out, int *d_nbr, int *d_status, void *stream);
 
+/* nbr table -> per-tile pair lists for sessd_spconv_forward_cg: one record of sessd_tile_list_stride(kvol) uint32 per 128 output rows:
+ * [0,32) pair count per kernel offset, [32, 32 + 4 kvol) 128-bit row mask per offset, [160, ...) the pairs grouped by offset, each
+ * (input row << 7) | tile row, ascending tile row (deterministic).  d_tiles: uint32 [ceil(max_out / 128)][stride].  kvol <= 27. */
+int sessd_tile_list_stride(int kvol);
+int sessd_rulebook_tile_lists(const int *d_nbr, int kvol, const int *d_n_out, int max_out, void *d_tiles, void *stream);
 /* canonical spconv-style pairs from a nbr table: pairs_in/out [kvol, max_rows], pair_num [kvol] */
 size_t sessd_rulebook_pairs_workspace_bytes(int max_rows, int kvol);
 int sessd_rulebook_pairs(const int *d_nbr, const int *d_n_out, int max_rows, int kvol, int *d_pairs_in,
@@ -147,10 +152,11 @@ int sessd_spconv_forward_rows_planes(const float *d_in_feat, int cin, const int 
  * neighbours that exist are copied by cp.async into the UMMA operand tiles (no row slot is spent on a missing neighbour), persistent CTAs,
  * tcgen05 kind::f16 with the two-term fp16 split of spconv_h2.cu (same weight tiles: ops.pack_weight_sp_h2).  Same contract as
  * sessd_spconv_forward (spconv 1.x gather -> GEMM -> scatter-add at det3d/models/backbones/scn.py:106-149, + folded BN + ReLU).
+ * The rulebook is passed as d_tiles = the per-tile pair lists sessd_rulebook_tile_lists() makes from the nbr table (once per rulebook).
  * d_in_planes [plane_rows][2][cp] fp16, x = (hi + lo) / d_in_info[1], d_in_info[0] = abs-max of the input tensor; outputs (each nullable, at
  * least one): fp32 rows [max_out][cout]; planes [>= max_out][2][cout <= 32 ? 32 : 64] with d_out_info = {abs-max of the output (atomicMax; zero
  * it once per frame), S_out}, S_out from the bound d_in_info[0] * gain + shift_max as above.  Supported (cp, cout): (32,32) (32,64) (64,64). */
-int sessd_spconv_forward_cg(const void *d_in_planes, int cp, int plane_rows, const float *d_in_info, const int *d_nbr, int kvol,
+int sessd_spconv_forward_cg(const void *d_in_planes, int cp, int plane_rows, const float *d_in_info, const void *d_tiles, int kvol,
                             const int *d_n_out, int max_out, const void *d_weight_h2, int cout, const float *d_scale, const float *d_shift,
                             int relu, float gain, float shift_max, float *d_out_f32, void *d_out_planes, float *d_out_info, void *stream);
 /* 1: the gathered rows of sessd_spconv_forward_cg also allocate in L1 (cp.async.ca); default 0 (cp.async.cg) */

@@ -78,6 +78,9 @@ int sessd_mma_probe(int n, int iters, int mode, long long *d_out, void *stream);
 /* profiling aid: handshake latencies in cycles (one CTA): d_out[0] tcgen05.commit->mbarrier, [1] two-warp mbarrier round trip,
  * [2] tcgen05.st x32 + wait, [3] / [4] one / four f16 MMAs (M128 N256 K16) + commit -> mbarrier, [5] tcgen05.ld x32 + wait,
  * [6] commit -> other warp -> arrive back round trip */
+/* kind::f16 SS probe: d_out[0] = issue cycles, [1] = cycles until retired for `iters` back-to-back M128 x N x K16 MMAs; mode & 3: 0 / 1 / 2 =
+ * one / two / four accumulators in rotation, mode & 4: SWIZZLE_64B operand descriptors */
+int sessd_mma_probe_f16(int n, int iters, int mode, long long *d_out, void *stream);
 int sessd_latency_probe(int iters, long long *d_out, void *stream);
 /* profiling experiments only: device buffer [ctas][8] int64 receiving per-CTA globaltimer stamps of bev_conv_tc (NULL = off) */
 void sessd_set_conv_debug_buffer(void *d_buf);

@@ -60,6 +60,71 @@ extern "C" int sessd_mma_probe(int n, int iters, int mode, long long *d_out, voi
     return last_error();
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// kind::f16 SS probe: cycles per tcgen05.mma (M = 128, N = n, K = 16) when `iters` of them are issued back to back by one elected lane in
+// warp-uniform control flow (the way the product kernels issue).  mode & 3: 0 = one accumulator (dependent chain), 1 = two, 2 = four
+// accumulators in rotation; mode & 4: SWIZZLE_64B descriptors (64-byte rows) instead of SWIZZLE_128B.
+namespace sessd {
+__global__ void __launch_bounds__(128, 1) mma_probe_f16_kernel(int n, int iters, int mode, long long *out) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *tiles = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(tiles)[i] = 0x3c003c00u;   // fp16 1.0 pairs
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (warp == 0) {
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const bool sw64 = (mode & 4) != 0;
+        const uint64_t desc_hi = sw64 ? ((uint64_t)((512u >> 4) | (1u << 14) | (4u << 29))) << 32 : ((uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29))) << 32;
+        const uint32_t a_lo = ((smem_u32(tiles) >> 4) & 0x3FFFu) | (1u << 16), b_lo = (((smem_u32(tiles) + 16384) >> 4) & 0x3FFFu) | (1u << 16);
+        const int nacc = 1 << (mode & 3);
+        const int kmask = sw64 ? 1 : 3;
+        long long c0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            const uint32_t k = (uint32_t)(i & kmask) * 2u;                       // 32-byte K steps inside the swizzled row
+            const uint32_t acc = tmem + (uint32_t)((i & (nacc - 1)) * (nacc == 4 ? 128 : 256));
+            if (elect_one()) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(acc),
+                    "l"(desc_hi | (uint64_t)(a_lo + k)), "l"(desc_hi | (uint64_t)(b_lo + k)), "r"(idesc), "r"(1)
+                    : "memory");
+            }
+            __syncwarp();
+        }
+        if (elect_one()) tc_commit(&bar);
+        __syncwarp();
+        long long c1 = clock64();
+        mbar_wait(&bar, 0);
+        long long c2 = clock64();
+        if (blockIdx.x == 0 && threadIdx.x == 0) { out[0] = c1 - c0; out[1] = c2 - c0; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512) : "memory");
+}
+}  // namespace sessd
+
+extern "C" int sessd_mma_probe_f16(int n, int iters, int mode, long long *d_out, void *stream) {
+    using namespace sessd;
+    if (n < 16 || n > 256 || (n & 15) || ((mode & 3) == 2 && n > 128) || ((mode & 3) == 1 && n > 256) || (mode & 3) == 3) return SESSD_EINVAL;
+    static bool done = false;
+    if (!done) { SESSD_CUDA_TRY(cudaFuncSetAttribute(mma_probe_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); done = true; }
+    SESSD_LAUNCH(mma_probe_f16_kernel, kNumSMs, 128, 64 * 1024, stream, n, iters, mode, d_out);
+    return last_error();
+}
+
 // ---------------------------------------------------------------------------------------------------------------------------------
 // Latency probe for the producer/consumer handshakes of the tensor-core kernels (one CTA, clock64 cycles averaged over `iters`):
 //   out[0] tcgen05.commit (nothing outstanding) -> mbarrier phase observed by the committing thread

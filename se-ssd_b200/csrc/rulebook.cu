@@ -273,6 +273,57 @@ __global__ void __launch_bounds__(kPairRows) pair_write_kernel(const int *__rest
 
 static GridDims to_dims(sessd_grid g) { GridDims d; d.B = g.batch; d.D = g.shape[0]; d.H = g.shape[1]; d.W = g.shape[2]; return d; }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Tile lists: the neighbour table regrouped for the pair-proportional tensor-core conv (spconv_cg.cu).  One record per tile of 128
+// output rows: [0, 32) pair count per kernel offset, [32, 32 + 4 kvol) 128-bit row mask per offset, [160, 160 + pairs) the pairs of
+// offset 0, then of offset 1, ... each (input row << 7) | tile row, ascending tile row.  Built once per rulebook (a SubM rulebook serves
+// 2-3 layers); deterministic (warp ballots + popcount ranks, no atomics).
+constexpr int kTlRows = 128, kTlHeader = 160;
+__host__ __device__ constexpr int tile_list_stride(int kvol) { return kTlHeader + kTlRows * kvol; }
+
+template <int KV>
+__global__ void __launch_bounds__(kTlRows) tile_lists_kernel(const int *__restrict__ nbr, int kvol_, const int *__restrict__ d_n_out, int max_out,
+                                                             unsigned int *__restrict__ tiles) {
+    const int kvol = KV ? KV : kvol_;
+    const int n_out = min(*d_n_out, max_out);
+    const int row0 = blockIdx.x * kTlRows;
+    if (row0 >= n_out) return;
+    __shared__ unsigned int s_mask[32][4];
+    __shared__ int s_off[33];
+    const int r = threadIdx.x, warp = r >> 5, lane = r & 31;
+    const bool live = row0 + r < n_out;
+    int v[KV ? KV : 27];
+    const int *src = nbr + (size_t)(row0 + r) * kvol;
+#pragma unroll
+    for (int k = 0; k < (KV ? KV : 27); ++k) {
+        v[k] = (k < kvol && live) ? __ldg(src + k) : -1;
+        const unsigned int m = __ballot_sync(0xffffffffu, v[k] >= 0);
+        if (lane == 0 && k < kvol) s_mask[k][warp] = m;
+    }
+    __syncthreads();
+    if (r < 32) {                                        // exclusive prefix of the per-offset counts (kvol <= 27 < 32)
+        int c = 0;
+        if (r < kvol) c = __popc(s_mask[r][0]) + __popc(s_mask[r][1]) + __popc(s_mask[r][2]) + __popc(s_mask[r][3]);
+        const int incl = warp_incl_scan(c, lane);
+        s_off[r + 1] = incl;
+        if (r == 0) s_off[0] = 0;
+    }
+    __syncthreads();
+    unsigned int *rec = tiles + (size_t)blockIdx.x * tile_list_stride(kvol);
+    if (r < 32) rec[r] = (unsigned int)(s_off[r + 1] - s_off[r]);
+    for (int e = r; e < kvol * 4; e += kTlRows) rec[32 + e] = s_mask[e >> 2][e & 3];
+    const unsigned int lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int k = 0; k < (KV ? KV : 27); ++k) {
+        if (k < kvol && v[k] >= 0) {
+            int pos = s_off[k] + __popc(s_mask[k][warp] & lt);
+            for (int w = 0; w < warp; ++w) pos += __popc(s_mask[k][w]);
+            rec[kTlHeader + pos] = ((unsigned int)v[k] << 7) | (unsigned int)r;
+        }
+    }
+}
+
 }  // namespace sessd
 
 using namespace sessd;
@@ -452,5 +503,21 @@ extern "C" int sessd_rulebook_pairs(const int *d_nbr, const int *d_n_out, int ma
     SESSD_LAUNCH(pair_count_kernel, nblk, kPairRows, sizeof(int) * kvol, st, d_nbr, d_n_out, max_rows, kvol, block_counts);
     SESSD_LAUNCH(pair_offsets_kernel, kvol, 32, 0, st, d_n_out, max_rows, kvol, block_counts, d_pair_num);
     SESSD_LAUNCH(pair_write_kernel, nblk, kPairRows, 0, st, d_nbr, d_n_out, max_rows, kvol, block_counts, d_pairs_in, d_pairs_out);
+    return last_error();
+}
+
+// words per tile record of sessd_rulebook_tile_lists (128 output rows per tile)
+extern "C" int sessd_tile_list_stride(int kvol) { return tile_list_stride(kvol); }
+
+// nbr table -> per-tile pair lists for sessd_spconv_forward_cg (see tile_lists_kernel).  d_tiles: uint32 [ceil(max_out / 128)][stride].
+extern "C" int sessd_rulebook_tile_lists(const int *d_nbr, int kvol, const int *d_n_out, int max_out, void *d_tiles, void *stream) {
+    if (!d_nbr || !d_n_out || !d_tiles || kvol < 1 || kvol > 27 || max_out < 1) return SESSD_EINVAL;
+    const int nblk = div_up(max_out, kTlRows);
+    if (kvol == 27)
+        SESSD_LAUNCH((tile_lists_kernel<27>), nblk, kTlRows, 0, stream, d_nbr, kvol, d_n_out, max_out, (unsigned int *)d_tiles);
+    else if (kvol == 3)
+        SESSD_LAUNCH((tile_lists_kernel<3>), nblk, kTlRows, 0, stream, d_nbr, kvol, d_n_out, max_out, (unsigned int *)d_tiles);
+    else
+        SESSD_LAUNCH((tile_lists_kernel<0>), nblk, kTlRows, 0, stream, d_nbr, kvol, d_n_out, max_out, (unsigned int *)d_tiles);
     return last_error();
 }

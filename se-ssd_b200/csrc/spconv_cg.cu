@@ -6,7 +6,9 @@
 // cross TMEM accumulator summed in RN fp32; same weight tiles), but the 128-row A operand of a (tile, kernel offset) is no longer
 // fetched with 32-64 TMA gather4 instructions whose cost is per ROW SLOT, present or not (~5.5 clk per 128-byte row: at the 21 %
 // neighbour fill of the 32-channel layers 79 % of the row requests fetched zeros and the layer ran at 0.9 % of the tensor peak).  Here
-//   * the tile's neighbour table is compacted once into per-offset lists of (input row, tile row) pairs (shared memory, 13.8 KB);
+//   * the rulebook is regrouped ONCE per build (sessd_rulebook_tile_lists; a SubM rulebook serves 2-3 layers) into per-tile, per-offset
+//     lists of (input row, tile row) pairs + row masks; a tile's record (~3-8 KB) is copied to shared memory (compacting the neighbour
+//     table inside this kernel with shared-memory atomics cost 14.7 k clk per tile, a third of the tile's time);
 //   * eight producer warps copy the listed rows with 16-byte cp.async (LDGSTS: global/L2 -> shared, no registers, 2 clk per 128-byte row)
 //     straight into the K-major SWIZZLE_128B layout the UMMA descriptors address; rows without a neighbour are never touched;
 //   * a stage's missing rows must read as zeros: each warp remembers which of its rows hold data in every stage and clears (st.shared)
@@ -40,7 +42,7 @@ struct CgCfg {
     static constexpr int kBTile = (kWide ? 2 : 1) * COUT * 128;
     static constexpr int kStage = kATile + (kBTile + 1023) / 1024 * 1024;
     static constexpr int kStages = kWide ? 2 : (COUT <= 32 ? 4 : 3);
-    static constexpr int kMeta = kCgBM * kCgMaxK * 4 /*lists*/ + kCgMaxK * 16 /*valid*/ + 32 * 4 /*cnt*/ + 33 * 4 /*klist, nact*/ +
+    static constexpr int kMeta = kCgBM * kCgMaxK * 4 /*lists*/ + kCgMaxK * 16 /*valid*/ + 32 * 4 /*cnt*/ + 33 * 4 /*klist, nact*/ + 32 * 4 /*off*/ +
                                  kCgProdWarps * 4 * 4 /*dirty*/ + (3 * kStages + 1) * 8 /*barriers*/ + 24;
     static constexpr int kSmem = kStages * kStage + kMeta + 1024;
     static constexpr int kTmemCols = (3 * COUT <= 128) ? 128 : 256;
@@ -50,7 +52,8 @@ struct CgCfg {
 struct CgArgs {
     const __half *planes;              // input [rows][2][CP] fp16, x = (hi + lo) / in_info[1]
     const float *in_info;              // {abs-max of the input tensor, its plane scale}
-    const int *nbr;                    // [max_out][kvol]
+    const unsigned int *tiles;         // per-tile pair lists (sessd_rulebook_tile_lists), tile_stride words per tile
+    int tile_stride;
     const int *d_n_out;
     int kvol, max_out, relu;
     const float *scale, *shift;        // folded BN (scale already times the per-channel weight exponent 2^-e)
@@ -58,6 +61,7 @@ struct CgArgs {
     float *out_f32;                    // nullable [max_out][COUT]
     __half *out_planes;                // nullable [max_out (+1)][2][kCPO]
     float *out_info;                   // nullable {abs-max of the output (atomicMax), plane scale}
+    long long *dbg;                    // SESSD_CG_PROFILE only
 };
 
 __host__ __device__ constexpr uint32_t cg_idesc_f16(int M, int N) {
@@ -95,6 +99,19 @@ __device__ __forceinline__ void cg_tmem_ld16(uint32_t taddr, uint32_t *r) {
         : "memory");
 }
 
+// -DSESSD_CG_PROFILE: per-CTA cycle counters ([ctas][16] int64 via sessd_set_cg_dbg; lab measurements only)
+//   0 mma wait full_b, 1 mma wait full_a, 2 mma loop total, 3 tiles, 4 wload wait empty, 5 producer(w0) wait empty, 6 producer(w0) loop total,
+//   7 epilogue wait acc_full (w0), 8 epilogue total (w0), 9 list build (t0), 10 kernel total (t0), 11 stage fills
+#ifdef SESSD_CG_PROFILE
+#define CG_T(var) const long long var = clock64()
+#define CG_ADD(slot, t0) do { if (a.dbg) a.dbg[(size_t)blockIdx.x * 16 + (slot)] += clock64() - (t0); } while (0)
+#define CG_WAIT(slot, cond, stmt) do { const long long _t = clock64(); stmt; if ((cond) && a.dbg) a.dbg[(size_t)blockIdx.x * 16 + (slot)] += clock64() - _t; } while (0)
+#else
+#define CG_T(var)
+#define CG_ADD(slot, t0)
+#define CG_WAIT(slot, cond, stmt) stmt
+#endif
+
 template <int CP, int COUT, int L1>
 __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_constant__ CUtensorMap map_w, const CgArgs a) {
     using C = CgCfg<CP, COUT>;
@@ -102,6 +119,7 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
     const int ntiles = (n_out + kCgBM - 1) / kCgBM;
     if ((int)blockIdx.x >= ntiles) return;                       // whole CTA leaves together (before any barrier / TMEM use)
     const int kvol = a.kvol;
+    CG_T(t_kernel);
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char *tiles = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -110,7 +128,8 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
     int *s_cnt = (int *)(s_valid + kCgMaxK * 4);                         // [32]
     int *s_klist = s_cnt + 32;                                           // [32] + nact
     int *s_nact = s_klist + 32;
-    uint32_t *s_dirty = (uint32_t *)(s_nact + 1);                        // [8 warps][4 stages]: 16-bit mask of rows holding data
+    int *s_off = s_nact + 1;                                             // [32] first list entry of every offset
+    uint32_t *s_dirty = (uint32_t *)(s_off + 32);                        // [8 warps][4 stages]: 16-bit mask of rows holding data
     uint64_t *bars = (uint64_t *)(((uintptr_t)(s_dirty + kCgProdWarps * 4) + 7) & ~(uintptr_t)7);
     uint64_t *full_a = bars, *full_b = bars + C::kStages, *empty = bars + 2 * C::kStages;
     uint64_t *acc_full = bars + 3 * C::kStages;
@@ -149,33 +168,27 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int row0 = tile * kCgBM;
         const int rows = min(kCgBM, n_out - row0);
-        // ---------------------------------------------------------------- per-offset lists of the tile's (input row, tile row) pairs
-        if (tid < 32) s_cnt[tid] = 0;
-        if (tid < kCgMaxK * 4) s_valid[tid] = 0u;
-        __syncthreads();
+        // ---------------------------------------------------------------- the tile's per-offset pair lists (built once per rulebook by
+        // sessd_rulebook_tile_lists: counts, row masks, (input row << 7 | tile row) entries grouped by offset) -> shared memory
+        CG_T(t_list);
         {
-            const int nent = rows * kvol;                        // the tile's neighbour table is contiguous in global memory
-            const int *tn = a.nbr + (size_t)row0 * kvol;
-            for (int e = tid; e < nent; e += kCgThreads) {
-                const int v = __ldg(tn + e);
-                if (v >= 0) {
-                    const int r = (kvol == 27) ? e / 27 : e / kvol;
-                    const int k = e - r * kvol;
-                    const int pos = atomicAdd(&s_cnt[k], 1);
-                    s_list[k * kCgBM + pos] = ((uint32_t)v << 7) | (uint32_t)r;
-                    atomicOr(&s_valid[k * 4 + (r >> 5)], 1u << (r & 31));
-                }
+            const unsigned int *rec = a.tiles + (size_t)tile * (size_t)a.tile_stride;
+            const int c = (int)__ldg(rec + lane);                        // every warp ranks the 32 counts itself: no extra block-wide sync
+            const int incl = warp_incl_scan(c, lane);
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (warp == 0) {
+                s_cnt[lane] = c;
+                s_off[lane] = incl - c;
+                const unsigned int m = __ballot_sync(0xffffffffu, c > 0);
+                if (c > 0) s_klist[__popc(m & ((1u << lane) - 1u))] = lane;
+                if (lane == 0) *s_nact = __popc(m);
             }
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int c = 0;
-            for (int k = 0; k < kvol; ++k)
-                if (s_cnt[k] > 0) s_klist[c++] = k;
-            *s_nact = c;
+            if (tid < kvol * 4) s_valid[tid] = __ldg(rec + 32 + tid);
+            for (int e = tid; e < total; e += kCgThreads) s_list[e] = __ldg(rec + 160 + e);
         }
         __syncthreads();
         const int nact = *s_nact;
+        if (tid == 0) { CG_ADD(9, t_list); }
 
         // stage index / phase of this tile's first fill (all roles advance them alike)
         if (warp == 9) {
@@ -188,9 +201,10 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
             tc_fence_after();                                    // the previous tile's epilogue read the accumulators before the CTA-wide sync
             int s = st0;
             uint32_t ph = ph0;
+            CG_T(t_mma);
             for (int j = 0; j < nact; ++j) {
-                mbar_wait(&full_b[s], ph);
-                mbar_wait(&full_a[s], ph);
+                CG_WAIT(0, lane == 0, mbar_wait(&full_b[s], ph));
+                CG_WAIT(1, lane == 0, mbar_wait(&full_a[s], ph));
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t st_lo = tiles_lo + (uint32_t)s * (C::kStage >> 4);
@@ -228,13 +242,17 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
                 __syncwarp();
                 if (++s == C::kStages) { s = 0; ph ^= 1u; }
             }
+            if (lane == 0) { CG_ADD(2, t_mma); }
+#ifdef SESSD_CG_PROFILE
+            if (lane == 0 && a.dbg) { a.dbg[(size_t)blockIdx.x * 16 + 3] += 1; a.dbg[(size_t)blockIdx.x * 16 + 11] += nact; }
+#endif
         } else if (warp == 8) {
             // ===================== weight tiles (TMA, one elected lane) =====================
             int s = st0;
             uint32_t ph = ph0;
             for (int j = 0; j < nact; ++j) {
                 const int k = s_klist[j];
-                mbar_wait(&empty[s], ph ^ 1u);
+                CG_WAIT(4, lane == 0, mbar_wait(&empty[s], ph ^ 1u));
                 if (elect_one()) {
                     mbar_expect_tx(&full_b[s], C::kBTile);
                     unsigned char *b_tile = tiles + s * C::kStage + C::kATile;
@@ -259,9 +277,10 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
             const int half = c >> 3, cc = c & 7;                         // wide: chunk c of the 256-byte row = (hi | lo tile, 16-byte chunk)
             int s = st0;
             uint32_t ph = ph0;
+            CG_T(t_prod);
             for (int j = 0; j < nact; ++j) {
                 const int k = s_klist[j];
-                if (lane == 0) mbar_wait(&empty[s], ph ^ 1u);
+                if (lane == 0) CG_WAIT(5, warp == 0, mbar_wait(&empty[s], ph ^ 1u));
                 __syncwarp();
                 const uint32_t a_base = tiles_u32 + (uint32_t)(s * C::kStage);
                 const uint32_t vs = (s_valid[k * 4 + (warp >> 1)] >> (16 * (warp & 1))) & 0xFFFFu;
@@ -281,7 +300,7 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
                     cg_fence_proxy_async();                              // the clears are generic-proxy writes the tensor core will read
                 }
                 const int n = s_cnt[k];
-                const uint32_t *lst = s_list + k * kCgBM;
+                const uint32_t *lst = s_list + s_off[k];
                 for (int i = slot; i < n; i += kRowsPerPass) {
                     const uint32_t e = lst[i];
                     const uint32_t r = e & 127u;
@@ -298,13 +317,15 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
                 if (++s == C::kStages) { s = 0; ph ^= 1u; }
             }
 
+            if (tid == 0) { CG_ADD(6, t_prod); }
+            CG_T(t_epi);
             // ===================== epilogue: TMEM -> registers -> BN / ReLU -> planes and / or fp32 rows =====================
             const int q = warp & 3, hcol = warp >> 2;
             constexpr int kNcol = COUT / 2;                              // 16 or 32 channels per thread
             const int r = q * 32 + lane;
             float v[kNcol];
             if (nact > 0) {
-                if (lane == 0) mbar_wait(acc_full, (uint32_t)acc_it & 1u);
+                if (lane == 0) CG_WAIT(7, warp == 0, mbar_wait(acc_full, (uint32_t)acc_it & 1u));
                 __syncwarp();
                 tc_fence_after();
                 const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hcol * kNcol);
@@ -367,6 +388,7 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
                     }
                 }
             }
+            if (tid == 0) { CG_ADD(8, t_epi); }
         }
         {   // advance the ring position by this tile's fills
             const int adv = st0 + nact;
@@ -380,11 +402,13 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
         const unsigned m = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(vmax));     // non-negative floats order like their bits
         if (lane == 0 && m != 0u) atomicMax(reinterpret_cast<unsigned *>(a.out_info), m);
     }
+    if (tid == 0) { CG_ADD(10, t_kernel); }
     tc_fence_before();
     __syncthreads();
     if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
 }
 
+static long long *g_cg_dbg = nullptr;
 static int g_cg_l1 = 0;            // 1: gathered rows also allocate in L1 (cp.async.ca)
 
 template <int CP, int COUT>
@@ -428,6 +452,9 @@ static int launch_spconv_cg(const CgArgs &a, const void *w_h2, cudaStream_t st) 
 
 using namespace sessd;
 
+#ifdef SESSD_CG_PROFILE
+extern "C" void sessd_set_cg_dbg(void *d) { sessd::g_cg_dbg = (long long *)d; }
+#endif
 extern "C" void sessd_set_sp_cg_l1(int on) { sessd::g_cg_l1 = on ? 1 : 0; }
 
 // S4 (scn.py:106-149), pair-proportional tensor-core path.  d_in_planes [plane_rows][2][cp] fp16 with d_in_info = {abs-max, scale};
@@ -435,18 +462,18 @@ extern "C" void sessd_set_sp_cg_l1(int on) { sessd::g_cg_l1 = on ? 1 : 0; }
 // 2^-e[c]); gain / shift_max bound the output (see the header).  Outputs (each nullable, at least one): fp32 rows [max_out][cout],
 // planes [>= max_out][2][cout <= 32 ? 32 : 64] + d_out_info = {abs-max (zero it once per frame), scale}.
 // Supported (cp, cout): (32,32), (32,64), (64,64).
-extern "C" int sessd_spconv_forward_cg(const void *d_in_planes, int cp, int plane_rows, const float *d_in_info, const int *d_nbr, int kvol,
+extern "C" int sessd_spconv_forward_cg(const void *d_in_planes, int cp, int plane_rows, const float *d_in_info, const void *d_tiles, int kvol,
                                        const int *d_n_out, int max_out, const void *d_weight_h2, int cout, const float *d_scale,
                                        const float *d_shift, int relu, float gain, float shift_max, float *d_out_f32, void *d_out_planes,
                                        float *d_out_info, void *stream) {
-    if (!d_in_planes || !d_in_info || !d_nbr || !d_n_out || !d_weight_h2 || !d_scale || (!d_out_f32 && !d_out_planes) || max_out < 1 ||
+    if (!d_in_planes || !d_in_info || !d_tiles || !d_n_out || !d_weight_h2 || !d_scale || (!d_out_f32 && !d_out_planes) || max_out < 1 ||
         kvol < 1 || kvol > kCgMaxK || plane_rows < 1 || plane_rows > (1 << 25))
         return SESSD_EINVAL;
     if (d_out_planes && !d_out_info) return SESSD_EINVAL;
     CgArgs a;
-    a.planes = (const __half *)d_in_planes; a.in_info = d_in_info; a.nbr = d_nbr; a.d_n_out = d_n_out; a.kvol = kvol; a.max_out = max_out;
+    a.planes = (const __half *)d_in_planes; a.in_info = d_in_info; a.tiles = (const unsigned int *)d_tiles; a.tile_stride = 160 + 128 * kvol; a.d_n_out = d_n_out; a.kvol = kvol; a.max_out = max_out;
     a.relu = relu; a.scale = d_scale; a.shift = d_shift; a.gain = gain; a.shift_max = shift_max; a.out_f32 = d_out_f32;
-    a.out_planes = (__half *)d_out_planes; a.out_info = d_out_info;
+    a.out_planes = (__half *)d_out_planes; a.out_info = d_out_info; a.dbg = g_cg_dbg;
     cudaStream_t st = (cudaStream_t)stream;
     if (cp == 32 && cout == 32) return launch_spconv_cg<32, 32>(a, d_weight_h2, st);
     if (cp == 32 && cout == 64) return launch_spconv_cg<32, 64>(a, d_weight_h2, st);

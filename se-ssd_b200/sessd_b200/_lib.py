@@ -55,6 +55,8 @@ SIGNATURES = {
     "sessd_scan_scratch_bytes": (_sz, [_sz]),
     "sessd_subm_rulebook": (_i, [_vp, _vp, _i, Grid, _I3, _i, _vp, _i, _vp, _vp]),
     "sessd_strided_rulebook": (_i, [_vp, _vp, _i, Grid, _i, _vp, _i, _I3, _I3, _I3, Grid, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "sessd_tile_list_stride": (_i, [_i]),
+    "sessd_rulebook_tile_lists": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "sessd_rulebook_pairs_workspace_bytes": (_sz, [_i, _i]),
     "sessd_rulebook_pairs": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sessd_spconv_forward": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp]),
@@ -111,6 +113,7 @@ LAB_SIGNATURES = {
     "sessd_set_conv_cluster": (None, [_i]),
     "sessd_get_conv_cluster": (_i, []),
     "sessd_mma_probe": (_i, [_i, _i, _i, _vp, _vp]),
+    "sessd_mma_probe_f16": (_i, [_i, _i, _i, _vp, _vp]),
     "sessd_latency_probe": (_i, [_i, _vp, _vp]),
     "sessd_set_conv_ablate": (None, [_i]),
     "sessd_set_conv_variant": (None, [_i]),

@@ -238,13 +238,26 @@ def spconv_forward_rows_planes(in_feat, nbr, n_out, max_out, weight, scale, shif
     return out_planes
 
 
-def spconv_forward_cg(in_planes, in_info, nbr, n_out, max_out, weight_h2, scale, shift, relu, gain, shift_max, out, out_planes, out_info):
+def alloc_tile_lists(max_out, kvol, device):
+    """buffer of the per-tile pair lists of one rulebook (rulebook_tile_lists)"""
+    return torch.zeros((-(-int(max_out) // 128), int(lib.sessd_tile_list_stride(int(kvol)))), dtype=torch.int32, device=device)
+
+
+def rulebook_tile_lists(nbr, n_out, max_out, tiles):
+    """nbr table [max_out, kvol] -> per-tile pair lists (counts, row masks, (input row << 7 | tile row) grouped by kernel offset): the
+    rulebook format of spconv_forward_cg.  Once per rulebook build."""
+    check(lib.sessd_rulebook_tile_lists(_p(nbr), int(nbr.shape[1]), _p(n_out), int(max_out), _p(tiles), _st()), "sessd_rulebook_tile_lists")
+    return tiles
+
+
+def spconv_forward_cg(in_planes, in_info, tiles, n_out, max_out, weight_h2, scale, shift, relu, gain, shift_max, out, out_planes, out_info):
     """Pair-proportional tensor-core sparse conv (csrc/spconv_cg.cu).  in_planes [rows, 2 * cp] fp16 with in_info = {abs-max, scale};
-    weight_h2 / scale from pack_weight_sp_h2 (scale = bn_scale * 2^-e); out (fp32 rows) and / or out_planes + out_info."""
+    tiles from rulebook_tile_lists; weight_h2 / scale from pack_weight_sp_h2 (scale = bn_scale * 2^-e); out (fp32 rows) and / or
+    out_planes + out_info."""
     cp = in_planes.shape[1] // 2
     kvol = weight_h2.shape[0]
     cout = weight_h2.shape[2] if cp == 64 else weight_h2.shape[1]
-    check(lib.sessd_spconv_forward_cg(_p(in_planes), int(cp), int(in_planes.shape[0]), _p(in_info), _p(nbr), int(kvol), _p(n_out), int(max_out),
+    check(lib.sessd_spconv_forward_cg(_p(in_planes), int(cp), int(in_planes.shape[0]), _p(in_info), _p(tiles), int(kvol), _p(n_out), int(max_out),
                                       _p(weight_h2), int(cout), _p(scale), _p(shift), int(bool(relu)), float(gain), float(shift_max), _p(out),
                                       _p(out_planes), _p(out_info), _st()), "sessd_spconv_forward_cg")
     return out if out is not None else out_planes

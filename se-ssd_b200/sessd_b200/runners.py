@@ -103,6 +103,16 @@ class SpMiddleRunner:
                 cp = 64 if p["cout"] > 32 else 32
                 self.planes[li] = ops.alloc_planes(self.levels[p["lout"]]["cap"], cp, self.device)
                 assert self.planes[li].shape[0] <= (1 << 25)
+        # per-tile pair lists of every rulebook a cg layer reads (one per nbr table; a SubM rulebook is shared by its layers)
+        for p in self.plan:
+            p["tiles"] = None
+        by_nbr = {}
+        for p in self.plan:
+            if p["impl"] == "cg":
+                key = p["nbr"].data_ptr()
+                if key not in by_nbr:
+                    by_nbr[key] = ops.alloc_tile_lists(p["nbr"].shape[0], p["nbr"].shape[1], self.device)
+                p["tiles"] = by_nbr[key]
         # {abs-max, plane scale} of every layer output (cg chain: written by the producing layer's epilogue)
         self.info = torch.zeros((len(self.plan), 2), dtype=torch.float32, device=self.device)
 
@@ -171,6 +181,9 @@ class SpMiddleRunner:
             if p["kind"] == "subm":
                 if p["first"]:
                     ops.subm_rulebook(lin["coors"], n_in, cap_in, lin["grid"], p["ks"], lin["index_kind"], lin["index"], p["nbr"])
+                    tl = next((q["tiles"] for q in self.plan if q.get("key") == p["key"] and q["tiles"] is not None), None)
+                    if tl is not None:
+                        ops.rulebook_tile_lists(p["nbr"], n_in, cap_in, tl)
                     mark("rulebook:%s" % p["key"])
                 n_out, cap_out = n_in, cap_in
             else:
@@ -178,6 +191,8 @@ class SpMiddleRunner:
                                      p["pd"], lout["grid"], lout["index"], lout["scratch"], lout["coors"], lout["n"], lout["cap"],
                                      p["nbr"], self.status)
                 n_out, cap_out = lout["n"], lout["cap"]
+                if p["tiles"] is not None:
+                    ops.rulebook_tile_lists(p["nbr"], n_out, cap_out, p["tiles"])
                 mark("rulebook:sp%d" % p["lout"])
             w, sc, sh, tc = self.weights[li]
             nxt = self.plan[li + 1]["impl"] if li + 1 < len(self.plan) else None
@@ -192,7 +207,7 @@ class SpMiddleRunner:
                                             (self.info[li, 0:1] if nxt != "h2" else self.amax[li:li + 1]) if need_amax else None)
             elif isinstance(tc, tuple) and tc[0] == "cg":
                 last = nxt != "cg"
-                ops.spconv_forward_cg(self.planes[li - 1], self.info[li - 1], p["nbr"], n_out, cap_out, tc[1], tc[2], sh, True, p["gain"],
+                ops.spconv_forward_cg(self.planes[li - 1], self.info[li - 1], p["tiles"], n_out, cap_out, tc[1], tc[2], sh, True, p["gain"],
                                       p["shift_max"], self.feats[li] if (last or self.keep_f32) else None,
                                       None if last else self.planes[li], self.info[li])
                 x = self.feats[li]

@@ -240,6 +240,7 @@ def test_h2_sparse_conv_power_of_two_scaling_is_exact():
     # the pair-gather kernel (default): same property with the bound-derived scale, fp32 rows and plane outputs; and it agrees with the
     # TMA-gather kernel to rounding
     gain = ops.conv_gain(w, sc / inv)
+    tl = ops.rulebook_tile_lists(p["nbr"], n, cap, ops.alloc_tile_lists(cap, 27, "cuda"))
     cg = []
     for mul in (1.0, 4.0):
         xx = (x * mul).contiguous()
@@ -254,7 +255,7 @@ def test_h2_sparse_conv_power_of_two_scaling_is_exact():
         out = torch.zeros((cap, 64), device="cuda")
         oplanes = ops.alloc_planes(cap, 64, "cuda")
         oinfo = torch.zeros(2, device="cuda")
-        ops.spconv_forward_cg(planes, info, p["nbr"], n, cap, tiles, sc.contiguous(), None, True, gain, 0.0, out, oplanes, oinfo)
+        ops.spconv_forward_cg(planes, info, tl, n, cap, tiles, sc.contiguous(), None, True, gain, 0.0, out, oplanes, oinfo)
         torch.cuda.synchronize()
         back = ops.sparse_planes_to_float(oplanes[:-1], oinfo, 64)
         assert float((back[:nn] - out[:nn]).abs().max()) <= 3e-7 * float(out[:nn].abs().max())
@@ -343,3 +344,34 @@ def test_features_uniform20k_match_fp64_oracle():
         assert np.abs(got - t["feat"]).max() / scale < 1e-5, "layer %d" % li
     got = dense.permute(0, 3, 1, 2).cpu().numpy().astype(np.float64)
     assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-5
+
+
+def test_tile_lists_regroup_the_neighbour_table_exactly():
+    """sessd_rulebook_tile_lists (the rulebook format of the pair-gather conv) vs a numpy regrouping of the same nbr table: counts, row masks
+    and the (input row << 7 | tile row) entries per offset in ascending tile row -- bit-exact, SubM (kvol 27) and the (3,1,1) layer (kvol 3)."""
+    from sessd_b200 import ops, synth
+    r, _feat, coors, _layers, _dense = _frame_through_runner(synth.ring_cloud(3, 20000))
+    for p in (r.plan[3], r.plan[6], r.plan[13]):
+        n = int((r.levels[p["lout"]]["n"]).item())
+        kvol = p["nbr"].shape[1]
+        cap = p["nbr"].shape[0]
+        tl = ops.rulebook_tile_lists(p["nbr"], r.levels[p["lout"]]["n"], cap, ops.alloc_tile_lists(cap, kvol, "cuda"))
+        torch.cuda.synchronize()
+        nbr = p["nbr"][:n].cpu().numpy()
+        rec = tl.cpu().numpy().view(np.uint32)
+        stride = rec.shape[1]
+        assert stride == 160 + 128 * kvol
+        for t in range(-(-n // 128)):
+            rows = nbr[t * 128:(t + 1) * 128]
+            pos = 160
+            for k in range(kvol):
+                valid = np.nonzero(rows[:, k] >= 0)[0]
+                assert rec[t, k] == len(valid), (t, k)
+                mask = np.zeros(4, np.uint32)
+                for rr in valid:
+                    mask[rr >> 5] |= np.uint32(1) << np.uint32(rr & 31)
+                assert np.array_equal(rec[t, 32 + 4 * k:36 + 4 * k], mask), (t, k)
+                want = (rows[valid, k].astype(np.uint32) << np.uint32(7)) | valid.astype(np.uint32)
+                assert np.array_equal(rec[t, pos:pos + len(valid)], want), (t, k)
+                pos += len(valid)
+            assert not rec[t, kvol:32].any()
