@@ -131,7 +131,7 @@ struct P2Item { int cls, n0, b, u0, v0, ntaps; };
     do {                                                                                                 \
         const long long _t0 = clock64();                                                                 \
         stmt;                                                                                            \
-        if (p.dbg && lane == 0) p.dbg[(size_t)blockIdx.x * 8 + (slot)] += clock64() - _t0;               \
+        p2_acc[slot] += clock64() - _t0;                                                                 \
     } while (0)
 #else
 #define P2_WAIT(slot, stmt) stmt
@@ -180,6 +180,9 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
     uint32_t *s_aoff = tmem_slot + 2;                    // [4 classes][9 taps]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef SESSD_P2_PROFILE
+    long long p2_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // per-thread wait counters, written once at the end
+#endif
     const uint32_t crank = (CS > 1) ? cluster_cta_rank() : 0u;
     constexpr bool kPair = (CS == 2);
     const int cluster_id = blockIdx.x / CS, nclusters = gridDim.x / CS;
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
             }
         }
 #ifdef SESSD_P2_PROFILE
-        if (p.dbg && lane == 0) { p.dbg[(size_t)blockIdx.x * 8 + 3] = clock64() - t_begin; p.dbg[(size_t)blockIdx.x * 8 + 4] = iter; }
+        p2_acc[3] = clock64() - t_begin; p2_acc[4] = iter;
 #endif
     } else if (warp >= 3) {
         // ===================== epilogue warps (3-10): TMEM -> registers, release the accumulators, BN / ReLU / residual / stores
@@ -472,6 +475,15 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
             if (lane == 0 && m != 0u) atomicMax(reinterpret_cast<unsigned *>(p.out_info), m);
         }
     }
+#ifdef SESSD_P2_PROFILE
+    if (p.dbg && lane == 0 && warp <= 3) {
+        long long *d = p.dbg + (size_t)blockIdx.x * 8;
+        if (warp == 0) d[7] = p2_acc[7];
+        if (warp == 1) d[6] = p2_acc[6];
+        if (warp == 2) { d[0] = p2_acc[0]; d[1] = p2_acc[1]; d[2] = p2_acc[2]; d[3] = p2_acc[3]; d[4] = p2_acc[4]; }
+        if (warp == 3) d[5] = p2_acc[5];
+    }
+#endif
     tc_fence_before();
     __syncthreads();
     if (kPair) cluster_sync_all();         // nobody exits while the peer may still arrive on / load for this CTA

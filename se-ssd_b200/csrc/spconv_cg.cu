@@ -18,10 +18,9 @@
 //   * the epilogue writes the NEXT layer's operand format directly -- fp16 (hi, lo) planes scaled by a power of two derived from a
 //     rigorous bound |out| <= amax_in * G + max|shift| (G from the weights, host; amax_in measured by the producing layer's epilogue) --
 //     and raises the output's abs-max: the separate split kernel (one read + one write of every feature tensor) is gone.
-// A stage is handed to the MMA issuer by cp.async.mbarrier.arrive.noinc: every producer thread's arrival on the stage's mbarrier is
-// triggered by the completion of its own copies (the st.shared clears precede it in program order), so no thread ever waits for data and
-// kStages fills stay in flight per CTA (a first version that waited on cp.async.wait_group before a manual arrive serialised
-// fill -> MMA -> release -> fill: 9.1 ms instead of the TMA-gather kernel's 9.7 ms on the 32-channel stress layers).
+// Each stage has its own producer group (8 / kStages warps): the group copies, waits for ITS copies (cp.async.wait_all), makes them and
+// the clears visible to the async proxy (fence.proxy.async by the writing threads) and arrives on the stage's mbarrier, while the other
+// groups' fills are in flight -- kStages fills per CTA overlap and nobody hands data over on behalf of another thread.
 // Warps: 0-7 producers then epilogue (TMEM lane quadrant = warp & 3, column half = warp >> 2), 8 weight-tile TMA, 9 MMA issue.
 #include <cuda_fp16.h>
 
@@ -41,7 +40,7 @@ struct CgCfg {
     static constexpr int kATile = (kWide ? 2 : 1) * kCgBM * 128;              // bytes: [hi tile ; lo tile] (wide) or one [hi | lo] tile
     static constexpr int kBTile = (kWide ? 2 : 1) * COUT * 128;
     static constexpr int kStage = kATile + (kBTile + 1023) / 1024 * 1024;
-    static constexpr int kStages = kWide ? 2 : (COUT <= 32 ? 4 : 3);
+    static constexpr int kStages = kWide ? 2 : 4;                             // must divide the 8 producer warps (one group per stage)
     static constexpr int kMeta = kCgBM * kCgMaxK * 4 /*lists*/ + kCgMaxK * 16 /*valid*/ + 32 * 4 /*cnt*/ + 33 * 4 /*klist, nact*/ + 32 * 4 /*off*/ +
                                  kCgProdWarps * 4 * 4 /*dirty*/ + (3 * kStages + 1) * 8 /*barriers*/ + 24;
     static constexpr int kSmem = kStages * kStage + kMeta + 1024;
@@ -55,7 +54,7 @@ struct CgArgs {
     const unsigned int *tiles;         // per-tile pair lists (sessd_rulebook_tile_lists), tile_stride words per tile
     int tile_stride;
     const int *d_n_out;
-    int kvol, max_out, relu;
+    int kvol, max_out, relu, nofence;
     const float *scale, *shift;        // folded BN (scale already times the per-channel weight exponent 2^-e)
     float gain, shift_max;             // |out| <= amax_in * gain + shift_max
     float *out_f32;                    // nullable [max_out][COUT]
@@ -104,8 +103,8 @@ __device__ __forceinline__ void cg_tmem_ld16(uint32_t taddr, uint32_t *r) {
 //   7 epilogue wait acc_full (w0), 8 epilogue total (w0), 9 list build (t0), 10 kernel total (t0), 11 stage fills
 #ifdef SESSD_CG_PROFILE
 #define CG_T(var) const long long var = clock64()
-#define CG_ADD(slot, t0) do { if (a.dbg) a.dbg[(size_t)blockIdx.x * 16 + (slot)] += clock64() - (t0); } while (0)
-#define CG_WAIT(slot, cond, stmt) do { const long long _t = clock64(); stmt; if ((cond) && a.dbg) a.dbg[(size_t)blockIdx.x * 16 + (slot)] += clock64() - _t; } while (0)
+#define CG_ADD(slot, t0) do { cg_acc[slot] += clock64() - (t0); } while (0)
+#define CG_WAIT(slot, cond, stmt) do { const long long _t = clock64(); stmt; if (cond) cg_acc[slot] += clock64() - _t; } while (0)
 #else
 #define CG_T(var)
 #define CG_ADD(slot, t0)
@@ -119,6 +118,9 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
     const int ntiles = (n_out + kCgBM - 1) / kCgBM;
     if ((int)blockIdx.x >= ntiles) return;                       // whole CTA leaves together (before any barrier / TMEM use)
     const int kvol = a.kvol;
+#ifdef SESSD_CG_PROFILE
+    long long cg_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};      // per-thread counters, written once at the end (no memory traffic in the loops)
+#endif
     CG_T(t_kernel);
 
     extern __shared__ unsigned char smem_raw[];
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
     const uint32_t tiles_u32 = smem_u32(tiles);
 
     if (tid == 0) {
-        for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_a[s], kCgProdThreads); mbar_init(&full_b[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_a[s], kCgProdWarps / C::kStages); mbar_init(&full_b[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -150,7 +152,6 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
     // every A tile starts as zeros (the B halves of the stages are always fully overwritten by the TMA)
     for (int s = 0; s < C::kStages; ++s)
         for (int o = tid * 16; o < C::kATile; o += kCgThreads * 16) cg_sts_zero16(tiles_u32 + (uint32_t)(s * C::kStage + o));
-    if (tid < kCgProdWarps * 4) s_dirty[tid] = 0u;
     cg_fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
     const float s_out = pow2_scale_for_bound(amax_in * a.gain + a.shift_max);
     if (blockIdx.x == 0 && tid == 0 && a.out_info) a.out_info[1] = s_out;
     float vmax = 0.f;
+    uint32_t dirty[2] = {0u, 0u};                                // rows of this warp's share of its stage that hold data (producer warps)
     int st0 = 0, acc_it = 0;                                     // stage of this tile's first fill / accumulator hand-overs so far (all roles
     uint32_t ph0 = 0;                                            // count alike); ph0 = phase bit of stage st0
 
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
             }
             if (lane == 0) { CG_ADD(2, t_mma); }
 #ifdef SESSD_CG_PROFILE
-            if (lane == 0 && a.dbg) { a.dbg[(size_t)blockIdx.x * 16 + 3] += 1; a.dbg[(size_t)blockIdx.x * 16 + 11] += nact; }
+            if (lane == 0) { cg_acc[3] += 1; cg_acc[11] += nact; }
 #endif
         } else if (warp == 8) {
             // ===================== weight tiles (TMA, one elected lane) =====================
@@ -269,35 +271,45 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
             }
         } else {
             // ===================== producers: copy the rows that exist, clear the rows that stopped existing =====================
-            const int own = warp * 16;                                   // rows whose zero state this warp maintains
+            // One producer GROUP per stage (kStages groups of 8 / kStages warps): a group fills only "its" stage, waits for its own copies
+            // (cp.async.wait_all), fences them into the async proxy and arrives; the other groups' fills are in flight meanwhile.  (With
+            // every warp working on every fill and cp.async.mbarrier.arrive.noinc as the hand-over, a warp's next shared-memory access
+            // queued behind the arrival, i.e. behind its outstanding copies: ~900 clk = one L2 round trip per fill, serialised.)
+            constexpr int kGroupWarps = kCgProdWarps / C::kStages;       // 2 (four stages) or 4 (two stages)
+            constexpr int kGroupThreads = kGroupWarps * 32;
+            constexpr int kOwnRows = kCgBM / kGroupWarps;                // rows of the stage whose zero state this warp maintains: 64 or 32
+            constexpr int kOwnWords = kOwnRows / 32;
             constexpr int kLanesPerRow = C::kWide ? 16 : 8;
-            constexpr int kRowsPerPass = kCgProdThreads / kLanesPerRow;
-            const int slot = tid / kLanesPerRow;
-            const int c = tid % kLanesPerRow;
+            constexpr int kRowsPerPass = kGroupThreads / kLanesPerRow;
+            const int grp = warp / kGroupWarps, gw = warp % kGroupWarps;
+            const int gtid = tid - grp * kGroupThreads;
+            const int slot = gtid / kLanesPerRow;
+            const int c = gtid % kLanesPerRow;
             const int half = c >> 3, cc = c & 7;                         // wide: chunk c of the 256-byte row = (hi | lo tile, 16-byte chunk)
-            int s = st0;
-            uint32_t ph = ph0;
+            const uint32_t a_base = tiles_u32 + (uint32_t)(grp * C::kStage);
             CG_T(t_prod);
-            for (int j = 0; j < nact; ++j) {
+            // this tile's fills that land in stage `grp`: j = j0, j0 + kStages, ...; the phase bit of fill j follows the ring position
+            for (int j = (grp - st0 + C::kStages) % C::kStages; j < nact; j += C::kStages) {
+                const uint32_t ph = ph0 ^ ((uint32_t)((st0 + j) / C::kStages) & 1u);
                 const int k = s_klist[j];
-                if (lane == 0) CG_WAIT(5, warp == 0, mbar_wait(&empty[s], ph ^ 1u));
+                if (lane == 0) CG_WAIT(5, warp == 0, mbar_wait(&empty[grp], ph ^ 1u));
                 __syncwarp();
-                const uint32_t a_base = tiles_u32 + (uint32_t)(s * C::kStage);
-                const uint32_t vs = (s_valid[k * 4 + (warp >> 1)] >> (16 * (warp & 1))) & 0xFFFFu;
-                const uint32_t z = s_dirty[warp * 4 + s] & ~vs;
-                __syncwarp();
-                if (lane == 0) s_dirty[warp * 4 + s] = vs;
-                if (z) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r16 = (lane >> 3) + 4 * i;
-                        if ((z >> r16) & 1u) {
-                            const uint32_t dst = a_base + (uint32_t)((own + r16) * 128 + (lane & 7) * 16);
-                            cg_sts_zero16(dst);
-                            if constexpr (C::kWide) cg_sts_zero16(dst + kCgBM * 128);
+                for (int w = 0; w < kOwnWords; ++w) {
+                    const uint32_t vs = s_valid[k * 4 + gw * kOwnWords + w];
+                    const uint32_t z = dirty[w] & ~vs;                     // rows that hold data of the stage's previous offset and get none now
+                    dirty[w] = vs;
+                    if (z) {
+#pragma unroll
+                        for (int q4 = 0; q4 < 8; ++q4) {
+                            const int r32 = q4 * 4 + (lane >> 3);
+                            if ((z >> r32) & 1u) {
+                                const uint32_t dst = a_base + (uint32_t)((gw * kOwnRows + w * 32 + r32) * 128 + (lane & 7) * 16);
+                                cg_sts_zero16(dst);
+                                if constexpr (C::kWide) cg_sts_zero16(dst + kCgBM * 128);
+                            }
                         }
                     }
-                    cg_fence_proxy_async();                              // the clears are generic-proxy writes the tensor core will read
                 }
                 const int n = s_cnt[k];
                 const uint32_t *lst = s_list + s_off[k];
@@ -311,10 +323,10 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
                     else
                         cg_cp_async16<L1>(a_base + r * 128u + (((uint32_t)cc ^ (r & 7u)) << 4), a.planes + src * 64 + cc * 8);
                 }
-                // asynchronous arrival: this thread's share of the stage is complete when its cp.asyncs have landed (no thread waits for data:
-                // up to kStages fills are in flight per CTA, bounded only by the MMA releasing the stages)
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&full_a[s])) : "memory");
-                if (++s == C::kStages) { s = 0; ph ^= 1u; }
+                asm volatile("cp.async.wait_all;\n" ::: "memory");
+                if (!a.nofence) cg_fence_proxy_async();                  // copies and clears (generic proxy) -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_a[grp]);
             }
 
             if (tid == 0) { CG_ADD(6, t_prod); }
@@ -403,6 +415,14 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
         if (lane == 0 && m != 0u) atomicMax(reinterpret_cast<unsigned *>(a.out_info), m);
     }
     if (tid == 0) { CG_ADD(10, t_kernel); }
+#ifdef SESSD_CG_PROFILE
+    if (a.dbg && lane == 0 && (warp == 0 || warp >= 8)) {
+        long long *d = a.dbg + (size_t)blockIdx.x * 16;
+        if (warp == 9) { d[0] = cg_acc[0]; d[1] = cg_acc[1]; d[2] = cg_acc[2]; d[3] = cg_acc[3]; d[11] = cg_acc[11]; }
+        if (warp == 8) d[4] = cg_acc[4];
+        if (warp == 0) { d[5] = cg_acc[5]; d[6] = cg_acc[6]; d[7] = cg_acc[7]; d[8] = cg_acc[8]; d[9] = cg_acc[9]; d[10] = cg_acc[10]; }
+    }
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
@@ -441,7 +461,7 @@ static int launch_spconv_cg(const CgArgs &a, const void *w_h2, cudaStream_t st) 
     }
     const int tiles = div_up(a.max_out, kCgBM);
     const int grid = tiles < 2 * num_sms ? tiles : 2 * num_sms;          // persistent: two CTAs per SM
-    if (g_cg_l1)
+    if (g_cg_l1 & 1)
         SESSD_LAUNCH((spconv_cg_kernel<CP, COUT, 1>), grid, kCgThreads, C::kSmem, st, map_w, a);
     else
         SESSD_LAUNCH((spconv_cg_kernel<CP, COUT, 0>), grid, kCgThreads, C::kSmem, st, map_w, a);
@@ -455,7 +475,7 @@ using namespace sessd;
 #ifdef SESSD_CG_PROFILE
 extern "C" void sessd_set_cg_dbg(void *d) { sessd::g_cg_dbg = (long long *)d; }
 #endif
-extern "C" void sessd_set_sp_cg_l1(int on) { sessd::g_cg_l1 = on ? 1 : 0; }
+extern "C" void sessd_set_sp_cg_l1(int on) { sessd::g_cg_l1 = on & 3; }
 
 // S4 (scn.py:106-149), pair-proportional tensor-core path.  d_in_planes [plane_rows][2][cp] fp16 with d_in_info = {abs-max, scale};
 // weights / d_scale from ops.pack_weight_sp_h2 (cp = 64: [kvol][2][Cout][64], cp = 32: [kvol][Cout][hi 32 | lo 32]; d_scale = BN scale *
@@ -472,7 +492,7 @@ extern "C" int sessd_spconv_forward_cg(const void *d_in_planes, int cp, int plan
     if (d_out_planes && !d_out_info) return SESSD_EINVAL;
     CgArgs a;
     a.planes = (const __half *)d_in_planes; a.in_info = d_in_info; a.tiles = (const unsigned int *)d_tiles; a.tile_stride = 160 + 128 * kvol; a.d_n_out = d_n_out; a.kvol = kvol; a.max_out = max_out;
-    a.relu = relu; a.scale = d_scale; a.shift = d_shift; a.gain = gain; a.shift_max = shift_max; a.out_f32 = d_out_f32;
+    a.relu = relu; a.nofence = (g_cg_l1 >> 1) & 1; a.scale = d_scale; a.shift = d_shift; a.gain = gain; a.shift_max = shift_max; a.out_f32 = d_out_f32;
     a.out_planes = (__half *)d_out_planes; a.out_info = d_out_info; a.dbg = g_cg_dbg;
     cudaStream_t st = (cudaStream_t)stream;
     if (cp == 32 && cout == 32) return launch_spconv_cg<32, 32>(a, d_weight_h2, st);
