@@ -351,6 +351,17 @@ int sessd_head_loss(const float *d_head, const float *d_anchors, const int *d_la
                     float pos_cls_weight, float neg_cls_weight, float w_cls, float w_loc, float w_dir, float *d_losses,
                     float *d_grad_head, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training step, optimiser side, over flat fp32 arenas (csrc/train.cu):
+ * sessd_axpby  -- d_y = a d_y + b d_x: the teacher's exponential moving average of det3d/torchie/trainer/trainer_sessd.py:315-318 in one
+ *                 launch (a = alpha, b = 1 - alpha), and the 1 / world_size scaling after the gradient all-reduce
+ *                 (det3d/core/utils/dist_utils.py:8-29) with d_x = NULL;
+ * sessd_adamw_step -- Adam with decoupled weight decay (the fastai true_wd step of det3d/solver/fastai_optim.py == torch.optim.AdamW).
+ * ------------------------------------------------------------------------------------------------ */
+int sessd_axpby(float *d_y, const float *d_x, float a, float b, long long n, void *stream);
+int sessd_adamw_step(float *d_param, const float *d_grad, float *d_exp_avg, float *d_exp_avg_sq, long long n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int step, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,14 +19,14 @@ timeout 900 python scripts/kernel_rooflines.py --shape stress > $OUT/roofline_st
 fi
 if [ -z "$SKIP_NCU" ]; then
 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches.csv python scripts/profile_frame.py --frames 2 --cloud ${CLOUD:-ring} > $OUT/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
-for K in ${NCU_KERNELS:-bev_conv_h2_kernel spconv_h2_kernel}; do
+for K in ${NCU_KERNELS:-bev_conv_p2_kernel spconv_cg_kernel}; do
 timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:$K -s ${NCU_SKIP:-2} -c ${NCU_COUNT:-2} -f -o $OUT/prof_$K python scripts/profile_frame.py --frames 1 --cloud ${CLOUD:-ring} > $OUT/ncu_$K.log 2>&1; echo "ncu $K rc=$?"
 done
 fi
 if [ -n "$NCU_STRESS" ]; then
 # stress-shape captures (BASELINE config #5 shape on one GPU), first pass of scripts/kernel_rooflines.py:
 #  (a) the tensor-core sparse conv: launches 0..3 = layers 3, 4 (32->32), 5 (32->64), 6 (64->64)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:spconv_h2_kernel -s 0 -c 4 -f -o $OUT/prof_stress_spconv_h2 python scripts/kernel_rooflines.py --shape stress --iters 1 > $OUT/ncu_stress.log 2>&1; echo "ncu stress rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:spconv_cg_kernel -s 0 -c 4 -f -o $OUT/prof_stress_spconv_cg python scripts/kernel_rooflines.py --shape stress --iters 1 > $OUT/ncu_stress.log 2>&1; echo "ncu stress rc=$?"
 #  (b) the bandwidth-bound kernels: voxeliser, rulebook, narrow-layer conv, split, dense(), NMS mask
-timeout 900 ncu --set full --clock-control none -k regex:"vox_|hash_build|nbr_kernel|mark_outputs|enumerate_kernel|spconv_rows|split_h2|dense_gather|post_mask" -c 14 -f -o $OUT/prof_stress_hbm python scripts/kernel_rooflines.py --shape stress --iters 1 > $OUT/ncu_stress_hbm.log 2>&1; echo "ncu stress hbm rc=$?"
+timeout 900 ncu --set full --clock-control none -k regex:"vox_|hash_build|nbr_kernel|mark_outputs|enumerate_kernel|tile_lists|spconv_rows|dense_gather|post_mask" -c 16 -f -o $OUT/prof_stress_hbm python scripts/kernel_rooflines.py --shape stress --iters 1 > $OUT/ncu_stress_hbm.log 2>&1; echo "ncu stress hbm rc=$?"
 fi

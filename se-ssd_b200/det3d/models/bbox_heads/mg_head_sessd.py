@@ -8,6 +8,7 @@
   (box_torch_ops.py:536, mg_head_sessd.py:1026) and clips polygons on one CPU thread.
 * ``loss``     : training is a "next" row; raises NotImplementedError."""
 import logging
+import math
 
 import numpy as np
 import torch
@@ -127,8 +128,92 @@ class MultiGroupHead(nn.Module):
         return [task(x) for task in self.tasks]
 
     def loss(self, example, preds_dicts, preds_ema=None, **kwargs):
-        raise NotImplementedError("MultiGroupHead.loss: the SE-SSD training step (consistency + ODIoU losses) is a 'next' row; the "
-                                  "supervised terms (focal cls, sin-difference smooth-L1, direction CE) are available as loss_supervised()")
+        raise NotImplementedError("MultiGroupHead.loss: the assembled SE-SSD loss needs the backward of the encoder / neck (a 'next' row); "
+                                  "its terms are available separately: loss_supervised() (focal cls, sin-difference smooth-L1, direction CE, "
+                                  "IoU prediction, ODIoU) and consistency_loss() (student / teacher)")
+
+    # ------------------------------------------------------------------------------------------------------------------ teacher / student
+    @staticmethod
+    def _smooth_l1(diff, sigma=3.0):
+        """elementwise value of WeightedSmoothL1Loss (losses.py:180-191): 0.5 (sigma d)^2 below 1 / sigma^2, |d| - 0.5 / sigma^2 above"""
+        a, cut = diff.abs(), 1.0 / (sigma * sigma)
+        return torch.where(a <= cut, 0.5 * (a * sigma) ** 2, a - 0.5 * cut)
+
+    def nn_distance(self, box1, box2, iou_thres=0.7, return_loss="10"):
+        """Mutual nearest-neighbour matching of two box sets by rotated BEV IoU and the sin-difference smooth-L1 between matched boxes
+        (reference mg_head_sessd.py:573-611).  box1 [N,7] (student, carries the gradient), box2 [M,7].  Returns (loss, idx1, idx2, mask1,
+        mask2) with the reference's meaning, or five Nones when nothing overlaps by more than ``iou_thres``.  The IoU matrix is the device
+        kernel behind det3d.core.iou3d.iou3d_utils.boxes_iou_bev_gpu; it only selects pairs (no gradient flows through it there either)."""
+        from det3d.core.iou3d import iou3d_utils
+        if return_loss not in ("10", "01", "11"):
+            raise NotImplementedError
+        iou = iou3d_utils.boxes_iou_bev_gpu(box1.detach().contiguous(), box2.detach().contiguous())
+        mask1, mask2 = iou.max(dim=1).values > iou_thres, iou.max(dim=0).values > iou_thres
+        sub = iou[mask1][:, mask2]
+        if sub.shape[0] == 0 or sub.shape[1] == 0:
+            return [None] * 5
+        idx1, idx2 = sub.argmax(dim=1), sub.argmax(dim=0)            # partner of every kept box1 / of every kept box2
+        kept1, kept2 = box1[mask1], box2[mask2]
+
+        def pair_loss(a, b):                                         # add_sin_difference (:39-44) + smooth-L1, mean over the 7 codes
+            d = torch.cat([a[:, :-1] - b[:, :-1], torch.sin(a[:, -1:]) * torch.cos(b[:, -1:]) - torch.cos(a[:, -1:]) * torch.sin(b[:, -1:])], -1)
+            return self._smooth_l1(d, float(self.loss_reg._sigma)).sum(-1) / 7.0
+
+        loss1 = pair_loss(kept1, kept2[idx1]) if return_loss[0] == "1" else None
+        loss2 = pair_loss(kept2, kept1[idx2]) if return_loss[1] == "1" else None
+        if return_loss == "10":
+            val = loss1.sum() / loss1.shape[0]
+        elif return_loss == "01":
+            val = loss2.sum() / loss2.shape[0]
+        else:
+            val = (loss1.sum() + loss2.sum()) / (loss1.shape[0] + loss2.shape[0])
+        return val, idx1, idx2, mask1, mask2
+
+    def consistency_loss(self, preds_stu, preds_tea, example):
+        """SE-SSD consistency loss between the student's and the teacher's predictions (reference mg_head_sessd.py:622-703): per frame,
+        both heads' boxes are decoded, filtered (sigmoid score >= 0.3, centre inside the post-processing range), the teacher's boxes are
+        carried into the student's augmentation frame (flip, global rotation, scale: ``example['transformation']``), matched by
+        ``nn_distance`` and compared: box smooth-L1 + score smooth-L1 (sigmoid scores) + IoU-head smooth-L1 ((x+1)/2), summed over frames
+        and divided by the batch size.  (The reference also evaluates a direction term and leaves it out of the sum; it is not computed
+        here.)  Differentiable w.r.t. ``preds_stu`` through torch autograd; runs on the device (the matching uses the CUDA IoU kernel)."""
+        from det3d.core.bbox import box_torch_ops
+        stu, tea = preds_stu[0], preds_tea[0]
+        batch = stu["box_preds"].shape[0]
+        anchors = example["anchors"][0][0].reshape(-1, self.box_n_dim).to(stu["box_preds"].device).float()
+        dev = stu["box_preds"].device
+        lo = torch.tensor(self.post_center_range[:3], dtype=torch.float32, device=dev)
+        hi = torch.tensor(self.post_center_range[3:], dtype=torch.float32, device=dev)
+
+        def candidates(p, f):
+            boxes = box_torch_ops.second_box_decode(p["box_preds"][f].reshape(-1, self.box_n_dim), anchors)
+            cls = p["cls_preds"][f].reshape(-1, 1)
+            keep = (torch.sigmoid(cls).squeeze(-1) >= 0.3) & (boxes[:, :3] >= lo).all(1) & (boxes[:, :3] <= hi).all(1)
+            return boxes[keep], cls[keep], p["iou_preds"][f].reshape(-1, 1)[keep]
+
+        total = torch.zeros(1, dtype=torch.float32, device=dev)
+        sigma = 3.0                                                      # loss_score_consistency / loss_iou_consistency (:489-490)
+        for f in range(batch):
+            sb, scls, siou = candidates(stu, f)
+            tb, tcls, tiou = candidates(tea, f)
+            if sb.shape[0] == 0 or tb.shape[0] == 0:
+                continue
+            t = example["transformation"][f]
+            tb = tb.detach().clone()
+            if t["flipped"]:
+                tb[:, 1] = -tb[:, 1]
+                tb[:, 6] = math.pi - tb[:, 6]
+            c, s = math.cos(t["noise_rotation"]), math.sin(t["noise_rotation"])
+            x, y = tb[:, 0].clone(), tb[:, 1].clone()
+            tb[:, 0], tb[:, 1] = x * c + y * s, y * c - x * s             # rotation_points_single_angle(axis=2) (box_torch_ops.py:331-345)
+            tb[:, 6] += t["noise_rotation"]
+            tb[:, :6] *= t["noise_scale"]
+            box_loss, idx1, _idx2, mask1, mask2 = self.nn_distance(sb, tb)
+            if box_loss is None:
+                continue
+            score_loss = self._smooth_l1(torch.sigmoid(scls[mask1]) - torch.sigmoid(tcls[mask2][idx1]).detach(), sigma).mean()
+            iou_loss = self._smooth_l1((siou[mask1] + 1) * 0.5 - ((tiou[mask2][idx1] + 1) * 0.5).detach(), sigma).mean()
+            total = total + box_loss + score_loss + iou_loss
+        return total / batch
 
     def loss_supervised(self, example, preds_dicts, with_grad=True, with_odiou=False):
         """Supervised terms of ``loss`` (reference mg_head_sessd.py:706-768 without the teacher / ODIoU parts) for the

@@ -94,6 +94,8 @@ SIGNATURES = {
     "sessd_odiou_pairs_host": (_i, [_vp, _vp, _i, _vp, _vp]),
     "sessd_iou_pred_loss_workspace_bytes": (_sz, [_i]),
     "sessd_iou_pred_loss": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _sz, _vp]),
+    "sessd_axpby": (_i, [_vp, _vp, _f, _f, _ll, _vp]),
+    "sessd_adamw_step": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _vp]),
     "sessd_assign_workspace_bytes": (_sz, [_i, _i, _i]),
     "sessd_assign_targets": (_i, [_vp, _i, _vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }

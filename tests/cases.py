@@ -147,3 +147,59 @@ def checkpoint_model(seed):
         m.bn.running_var.copy_(torch.rand(16, generator=g) + 0.5)
         m.bn.num_batches_tracked.fill_(seed)
     return m
+
+
+def consistency_case():
+    """Student / teacher head outputs of two frames for the SE-SSD consistency loss: ~60 objects per frame predicted by both models at
+    different anchors (teacher in its own augmentation frame: flip / global rotation / scale undone by the loss), plus unmatched and
+    out-of-range predictions.  Returns (preds_stu, preds_tea) as dicts of [2, A, k] float32 arrays, anchors [A, 7], the two transformation
+    dicts and the number of planted objects."""
+    import torch
+    from oracle import anchors as oa
+    anc = oa.create_anchors_3d_range().reshape(-1, 7).astype(np.float32)
+    A = anc.shape[0]
+    rng = np.random.default_rng(2024)
+    trans = [dict(flipped=False, noise_rotation=0.031, noise_scale=1.02), dict(flipped=True, noise_rotation=-0.044, noise_scale=0.97)]
+
+    def encode(b, a):                                              # second_box_encode (box_np_ops.py), per pair
+        diag = np.sqrt(a[:, 3] ** 2 + a[:, 4] ** 2)
+        return np.stack([(b[:, 0] - a[:, 0]) / diag, (b[:, 1] - a[:, 1]) / diag, (b[:, 2] - a[:, 2]) / a[:, 5], np.log(b[:, 3] / a[:, 3]),
+                         np.log(b[:, 4] / a[:, 4]), np.log(b[:, 5] / a[:, 5]), b[:, 6] - a[:, 6]], 1).astype(np.float32)
+
+    out = []
+    for f in range(2):
+        n = 60
+        boxes = np.stack([rng.uniform(5, 65, n), rng.uniform(-35, 35, n), rng.uniform(-1.6, -0.6, n), rng.uniform(1.5, 1.8, n),
+                          rng.uniform(3.6, 4.4, n), rng.uniform(1.4, 1.7, n), rng.uniform(-3.1, 3.1, n)], 1).astype(np.float32)
+        t = trans[f]
+        # the same objects in the teacher's frame: undo scale, rotation and flip (inverse of mg_head_sessd.py:668-673)
+        tb = boxes.copy()
+        tb[:, :6] /= np.float32(t["noise_scale"])
+        tb[:, 6] -= np.float32(t["noise_rotation"])
+        c, s = np.cos(-t["noise_rotation"]), np.sin(-t["noise_rotation"])
+        x, y = tb[:, 0].copy(), tb[:, 1].copy()
+        tb[:, 0], tb[:, 1] = x * c + y * s, -x * s + y * c
+        if t["flipped"]:
+            tb[:, 1] = -tb[:, 1]
+            tb[:, 6] = np.float32(np.pi) - tb[:, 6]
+        preds = []
+        for who, bx in (("stu", boxes), ("tea", tb)):
+            g = np.random.default_rng(100 * f + (1 if who == "stu" else 2))
+            box = (g.normal(0, 0.05, (A, 7))).astype(np.float32)
+            cls = np.full((A, 1), -5.0, np.float32) + g.normal(0, 0.2, (A, 1)).astype(np.float32)
+            dr = g.normal(0, 1, (A, 2)).astype(np.float32)
+            iou = g.uniform(-1, 1, (A, 1)).astype(np.float32)
+            idx = g.choice(A, n + 25, replace=False)
+            noisy = bx + g.normal(0, 1, bx.shape).astype(np.float32) * np.float32([0.08, 0.08, 0.03, 0.03, 0.06, 0.03, 0.03])
+            noisy[:6] += np.float32([1.5, 1.2, 0, 0, 0, 0, 0.6])       # six objects whose two predictions overlap too little to match
+            box[idx[:n]] = encode(noisy, anc[idx[:n]])
+            cls[idx[:n], 0] = g.uniform(0.0, 3.0, n).astype(np.float32)
+            cls[idx[n:n + 15], 0] = g.uniform(-0.7, 2.0, 15).astype(np.float32)   # confident predictions without a partner
+            far = idx[n + 15:]
+            box[far, 2] = np.float32(9.0)                                # decoded z above the post-processing range
+            cls[far, 0] = np.float32(2.0)
+            preds.append(dict(box_preds=box, cls_preds=cls, dir_cls_preds=dr, iou_preds=iou))
+        out.append(preds)
+    stu = {k: np.stack([out[0][0][k], out[1][0][k]], 0) for k in out[0][0]}
+    tea = {k: np.stack([out[0][1][k], out[1][1][k]], 0) for k in out[0][1]}
+    return stu, tea, anc, trans

@@ -258,6 +258,56 @@ def gen_loss():
     print("loss: cls", cl.sum((1, 2)).tolist(), "loc", loc.sum((1, 2)).tolist(), "dir", dl.sum(1).tolist(), "total", float(total))
 
 
+def gen_consistency():
+    """SE-SSD consistency loss of the REFERENCE (mg_head_sessd.py:573-703: nn_distance + consistency_loss, run unmodified on the CPU): the
+    rotated BEV IoU inside comes from the reference's own iou3d_cpu.cpp (oracle/_ref) behind the reference's boxes3d_to_bev_torch, `.cuda()`
+    is a no-op here.  Stores the loss and d(loss)/d(student predictions)."""
+    import types
+    from cases import consistency_case
+    _stub("det3d.models.losses.utils", weight_reduce_loss=None)
+    losses = sys.modules.get("det3d.models.losses.losses") or _load("det3d.models.losses.losses", "det3d/models/losses/losses.py")
+    mg = sys.modules.get("det3d.models.bbox_heads.mg_head_sessd") or _load("det3d.models.bbox_heads.mg_head_sessd",
+                                                                           "det3d/models/bbox_heads/mg_head_sessd.py")
+    bt = sys.modules.get("det3d.core.bbox.box_torch_ops") or _load("det3d.core.bbox.box_torch_ops", "det3d/core/bbox/box_torch_ops.py")
+    iu = _load("det3d.core.iou3d.utils", "det3d/core/iou3d/utils.py")
+    ref = obuild.load_ref() or (obuild.build_ref() and obuild.load_ref())
+
+    def boxes_iou_bev_gpu(a, b):
+        a5, b5 = iu.boxes3d_to_bev_torch(a.detach(), "wlh", False).contiguous(), iu.boxes3d_to_bev_torch(b.detach(), "wlh", False).contiguous()
+        out = torch.zeros(a5.shape[0], b5.shape[0])
+        ref.boxes_iou_bev_cpu(a5, b5, out)
+        return out
+
+    mg.iou3d_utils = types.SimpleNamespace(boxes_iou_bev_gpu=boxes_iou_bev_gpu)
+    mg.box_torch_ops = bt
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    stu_np, tea_np, anc, trans = consistency_case()
+    stu = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in stu_np.items()}
+    tea = {k: torch.from_numpy(v).clone() for k, v in tea_np.items()}
+    head = types.SimpleNamespace(
+        box_coder=types.SimpleNamespace(decode_torch=lambda enc, a: bt.second_box_decode(enc, a, False, False)),
+        post_center_range=torch.tensor([0, -40.0, -5.0, 70.4, 40.0, 5.0]),
+        loss_reg=losses.WeightedSmoothL1Loss(sigma=3.0, code_weights=[1.0] * 7, codewise=True, loss_weight=2.0),
+        loss_iou_consistency=losses.WeightedSmoothL1Loss(sigma=3.0, code_weights=None, codewise=True, loss_weight=1.0),
+        loss_score_consistency=losses.WeightedSmoothL1Loss(sigma=3.0, code_weights=None, codewise=True, loss_weight=1.0),
+        loss_dir_consistency=torch.nn.MSELoss(reduction="mean"))
+    head.nn_distance = types.MethodType(mg.MultiGroupHead.nn_distance, head)
+    example = dict(transformation=trans, annos_raw=[None, None], anchors=[torch.from_numpy(anc)[None, None].expand(1, 2, -1, -1)])
+    # example["anchors"][0][0] must be the [A, 7] anchor table
+    example["anchors"] = [[torch.from_numpy(anc)]]
+    loss = mg.MultiGroupHead.consistency_loss(head, [stu], [tea], example)
+    loss.sum().backward()
+    g = {k: v.grad.numpy() for k, v in stu.items() if v.grad is not None}
+    nz = np.nonzero(np.abs(g["box_preds"]).sum(-1).reshape(-1))[0]
+    np.savez_compressed(os.path.join(HERE, "consistency_case.npz"), loss=loss.detach().numpy().astype(np.float32),
+                        grad_rows=nz.astype(np.int32), grad_box=g["box_preds"].reshape(-1, 7)[nz], grad_cls=g["cls_preds"].reshape(-1)[nz],
+                        grad_iou=g["iou_preds"].reshape(-1)[nz], grad_box_abs_sum=np.float64(np.abs(g["box_preds"]).sum()),
+                        grad_cls_abs_sum=np.float64(np.abs(g["cls_preds"]).sum()), grad_iou_abs_sum=np.float64(np.abs(g["iou_preds"]).sum()),
+                        grad_dir_is_none=np.bool_("dir_cls_preds" not in g or not np.abs(g.get("dir_cls_preds", 0)).sum()))
+    print("consistency: loss", loss.tolist(), "rows with gradient", len(nz), "grad sums", float(np.abs(g["box_preds"]).sum()),
+          float(np.abs(g["cls_preds"]).sum()), float(np.abs(g["iou_preds"]).sum()))
+
+
 def gen_odiou():
     """ODIoU loss of the REFERENCE (det3d/models/losses/odious.py, imported where it lies; runs on the CPU): per-pair value and the gradient
     w.r.t. the predicted box through the reference's own custom autograd Functions."""
@@ -331,5 +381,7 @@ if __name__ == "__main__":
         gen_loss()
     if not only or "wire" in only:
         gen_wire()
+    if "consistency" in only:        # patches torch.Tensor.cuda: run on its own (`make_golden.py consistency`)
+        gen_consistency()
     if not only or "models" in only:
         gen_models()
