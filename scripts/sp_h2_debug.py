@@ -44,7 +44,7 @@ def run(cin, cout, kvol, n_in, n_out, density, relu=True, reps=0):
     amax = torch.zeros((2,), device=dev)
     ops.absmax_rows(feat, d_nin, cap_in, amax[0:1])
     ops.split_h2(feat, d_nin, cap_in, amax[0:1], planes)
-    tiles, inv = ops.pack_weight_sp_h2(w, cp)
+    tiles, inv = ops.pack_weight_sp_h2(w, cp, layout="h2")
     out = torch.full((cap_out, cout), -7.0, device=dev)
     ops.spconv_forward_h2(planes, amax[0:1], nbr, d_nout, cap_out, tiles, (sc * inv).contiguous(), sh, relu, out, amax[1:2])
     torch.cuda.synchronize()

@@ -72,7 +72,7 @@ def run(cin, cout, kvol, n_in, n_out, density, relu=True, reps=0):
             am = torch.zeros((2,), device=dev)
             feat2 = torch.nan_to_num(feat)
             ops.absmax_rows(feat2, d_nin, cap_in, am[0:1]); ops.split_h2(feat2, d_nin, cap_in, am[0:1], planes)
-            tiles, inv = ops.pack_weight_sp_h2(w, cp)
+            tiles, inv = ops.pack_weight_sp_h2(w, cp, layout="h2")
             scl = (sc * inv).contiguous()
             t_h2 = timeit(lambda: ops.spconv_forward_h2(planes, am[0:1], nbr, d_nout, cap_out, tiles, scl, sh, relu, simt, am[1:2]), reps)
             msg += " | TMA-gather h2 %.4f ms" % t_h2

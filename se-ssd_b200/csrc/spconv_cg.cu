@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
             const uint32_t idesc = cg_idesc_f16(kCgBM, COUT);
             const uint32_t idesc2 = cg_idesc_f16(kCgBM, 2 * COUT);
             const uint64_t desc_hi = ((uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29))) << 32;      // SBO | version | SWIZZLE_128B
+            const uint64_t desc_b64 = ((uint64_t)((512u >> 4) | (1u << 14) | (4u << 29))) << 32;      // narrow weight stages: SWIZZLE_64B rows
             const uint32_t tiles_lo = ((tiles_u32 >> 4) & 0x3FFFu) | (1u << 16);
             const uint32_t acc_main0 = tmem_base, acc_cross = tmem_base + COUT, acc_main1 = tmem_base + 2 * COUT;
             tc_fence_after();                                    // the previous tile's epilogue read the accumulators before the CTA-wide sync
@@ -229,13 +230,23 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
                             cg_mma_f16(acc_cross, dAl + o, dBh + o, idesc, 1u);                                   // cross += a_lo x b_hi
                         }
                     } else {
-                        const uint32_t acc_main = (j & 1) ? acc_main1 : acc_main0;
+                        // narrow: A line = [hi 32 | lo 32] halves (SWIZZLE_128B); B stage = [b_hi rows ; b_lo rows] of 64 bytes each (SWIZZLE_64B),
+                        // [b_lo ; b_hi] on odd offsets: one N = 2 COUT product gives main and the a_hi x b_lo cross term together (4 instead of
+                        // 6 MMAs per offset: the A-operand reads from shared memory bound these layers)
+                        const uint64_t dBn = desc_b64 | (st_lo + (C::kATile >> 4));
+                        const uint64_t dBh = dBn + (((j & 1) ? COUT * 64 : 0) >> 4);
 #pragma unroll
                         for (int kk = 0; kk < 2; ++kk) {
                             const uint32_t o = (uint32_t)(kk * 32) >> 4;
-                            cg_mma_f16(acc_main, dA + o, dB + o, idesc, (j >= 2 || kk != 0) ? 1u : 0u);           // main  (+)= a_hi x b_hi
-                            cg_mma_f16(acc_cross, dA + o, dB + 4 + o, idesc, (j != 0 || kk != 0) ? 1u : 0u);      // cross (+)= a_hi x b_lo
-                            cg_mma_f16(acc_cross, dA + 4 + o, dB + o, idesc, 1u);                                 // cross  += a_lo x b_hi
+                            if ((j & 1) == 0) {
+                                cg_mma_f16(acc_main0, dA + o, dBn + o, idesc2, (j != 0 || kk != 0) ? 1u : 0u);   // [main0|cross] (+)= a_hi x [b_hi;b_lo]
+                            } else if (j == 1 && kk == 0) {
+                                cg_mma_f16(acc_cross, dA + o, dBn + o, idesc, 1u);                                // cross += a_hi x b_lo
+                                cg_mma_f16(acc_main1, dA + o, dBh + o, idesc, 0u);                                // main1  = a_hi x b_hi
+                            } else {
+                                cg_mma_f16(acc_cross, dA + o, dBn + o, idesc2, 1u);                               // [cross|main1] += a_hi x [b_lo;b_hi]
+                            }
+                            cg_mma_f16(acc_cross, dA + 4 + o, dBh + o, idesc, 1u);                                // cross += a_lo x b_hi
                         }
                     }
                     tc_commit(&empty[s]);
@@ -263,7 +274,8 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
                         tma_load_4d(b_tile + ((j & 1) ? COUT * 128 : 0), &map_w, &full_b[s], 0, 0, 0, k);
                         tma_load_4d(b_tile + ((j & 1) ? 0 : COUT * 128), &map_w, &full_b[s], 0, 0, 1, k);
                     } else {
-                        tma_load_4d(b_tile, &map_w, &full_b[s], 0, 0, 0, k);
+                        tma_load_4d(b_tile + ((j & 1) ? COUT * 64 : 0), &map_w, &full_b[s], 0, 0, 0, k);
+                        tma_load_4d(b_tile + ((j & 1) ? 0 : COUT * 64), &map_w, &full_b[s], 0, 0, 1, k);
                     }
                 }
                 __syncwarp();
@@ -447,10 +459,16 @@ static int launch_spconv_cg(const CgArgs &a, const void *w_h2, cudaStream_t st) 
         const cuuint64_t dims[4] = {64, (cuuint64_t)COUT, 2, (cuuint64_t)a.kvol};
         const cuuint32_t box[4] = {64, (cuuint32_t)COUT, 1, 1};
         rc = encode_map_4d(&map_w, w_h2, dims, box, nullptr, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2);
-    } else {              // [kvol][Cout][b_hi 32 | b_lo 32]
-        const cuuint64_t dims[4] = {64, (cuuint64_t)COUT, 1, (cuuint64_t)a.kvol};
-        const cuuint32_t box[4] = {64, (cuuint32_t)COUT, 1, 1};
-        rc = encode_map_4d(&map_w, w_h2, dims, box, nullptr, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2);
+    } else {              // [kvol][2 (hi|lo)][Cout][32]: 64-byte rows, SWIZZLE_64B
+        EncodeTiledFn enc = get_tensor_map_encoder();
+        if (!enc) return SESSD_EINVAL;
+        const cuuint64_t dims[4] = {32, (cuuint64_t)COUT, 2, (cuuint64_t)a.kvol};
+        const cuuint64_t strides[3] = {64, (cuuint64_t)COUT * 64, (cuuint64_t)COUT * 128};
+        const cuuint32_t box[4] = {32, (cuuint32_t)COUT, 1, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(w_h2), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        rc = r == CUDA_SUCCESS ? 0 : 700 + (int)r;
     }
     if (rc) return rc;
     static int num_sms = 0;
@@ -478,7 +496,7 @@ extern "C" void sessd_set_cg_dbg(void *d) { sessd::g_cg_dbg = (long long *)d; }
 extern "C" void sessd_set_sp_cg_l1(int on) { sessd::g_cg_l1 = on & 3; }
 
 // S4 (scn.py:106-149), pair-proportional tensor-core path.  d_in_planes [plane_rows][2][cp] fp16 with d_in_info = {abs-max, scale};
-// weights / d_scale from ops.pack_weight_sp_h2 (cp = 64: [kvol][2][Cout][64], cp = 32: [kvol][Cout][hi 32 | lo 32]; d_scale = BN scale *
+// weights / d_scale from ops.pack_weight_sp_h2 (cp = 64: [kvol][2][Cout][64], cp = 32: [kvol][2][Cout][32]; d_scale = BN scale *
 // 2^-e[c]); gain / shift_max bound the output (see the header).  Outputs (each nullable, at least one): fp32 rows [max_out][cout],
 // planes [>= max_out][2][cout <= 32 ? 32 : 64] + d_out_info = {abs-max (zero it once per frame), scale}.
 // Supported (cp, cout): (32,32), (32,64), (64,64).

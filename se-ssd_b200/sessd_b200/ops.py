@@ -172,10 +172,11 @@ def spconv_forward_tc(in_feat, nbr, n_out, max_out, weight_split, scale, shift, 
     return out
 
 
-def pack_weight_sp_h2(wp, cp):
-    """[kvol, Cin, Cout] (spconv layout, flattened offsets) -> (fp16 weight tiles for sessd_spconv_forward_h2, 2^-e[Cout]).
+def pack_weight_sp_h2(wp, cp, layout="cg"):
+    """[kvol, Cin, Cout] (spconv layout, flattened offsets) -> (fp16 weight tiles of the tensor-core sparse convs, 2^-e[Cout]).
     Every output channel is scaled by the power of two that puts its largest |w| into [2^10, 2^11); hi = fp16_rn(2^e w),
-    lo = fp16_rn(2^e w - hi).  cp = 64: [kvol, 2, Cout, 64]; cp = 32: [kvol, Cout, 64] with hi in columns [0, Cin), lo in [32, 32+Cin)."""
+    lo = fp16_rn(2^e w - hi).  cp = 64: [kvol, 2, Cout, 64]; cp = 32: layout "cg" (sessd_spconv_forward_cg): [kvol, 2, Cout, 32] (hi rows, then
+    lo rows), layout "h2" (lab sessd_spconv_forward_h2): [kvol, Cout, 64] with hi in columns [0, Cin), lo in [32, 32+Cin)."""
     kvol, cin, cout = wp.shape
     assert cp in (32, 64) and cin <= cp and (cp == 32 or cin == 64)
     wt = wp.permute(0, 2, 1).contiguous().to(torch.float32)                      # [kvol, Cout, Cin]
@@ -187,6 +188,9 @@ def pack_weight_sp_h2(wp, cp):
     lo = (ws - hi.to(torch.float32)).to(torch.float16)
     if cp == 64:
         tiles = torch.stack([hi, lo], 1).contiguous()                            # [kvol, 2, Cout, 64]
+    elif layout == "cg":
+        assert cin == 32
+        tiles = torch.stack([hi, lo], 1).contiguous()                            # [kvol, 2, Cout, 32]
     else:
         tiles = torch.zeros((kvol, cout, 64), dtype=torch.float16, device=wp.device)
         tiles[:, :, :cin] = hi
@@ -256,7 +260,7 @@ def spconv_forward_cg(in_planes, in_info, tiles, n_out, max_out, weight_h2, scal
     out_planes + out_info."""
     cp = in_planes.shape[1] // 2
     kvol = weight_h2.shape[0]
-    cout = weight_h2.shape[2] if cp == 64 else weight_h2.shape[1]
+    cout = weight_h2.shape[2]
     check(lib.sessd_spconv_forward_cg(_p(in_planes), int(cp), int(in_planes.shape[0]), _p(in_info), _p(tiles), int(kvol), _p(n_out), int(max_out),
                                       _p(weight_h2), int(cout), _p(scale), _p(shift), int(bool(relu)), float(gain), float(shift_max), _p(out),
                                       _p(out_planes), _p(out_info), _st()), "sessd_spconv_forward_cg")

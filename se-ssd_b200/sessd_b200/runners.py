@@ -150,7 +150,7 @@ class SpMiddleRunner:
             wp = w.reshape(-1, p["cin"], p["cout"]).contiguous()
             tc = None
             if p["impl"] in ("h2", "cg"):
-                tiles, inv = ops.pack_weight_sp_h2(wp, 64 if p["cin"] > 32 else 32)
+                tiles, inv = ops.pack_weight_sp_h2(wp, 64 if p["cin"] > 32 else 32, layout=p["impl"])
                 tc = (p["impl"], tiles, (sc * inv).contiguous())
             elif p["impl"] == "tc":
                 tc = ops.pack_weight_tc(wp, p["cout"])

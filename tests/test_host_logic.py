@@ -135,16 +135,16 @@ def test_sparse_fp16_split_weight_packing_layout_and_precision():
     to fp16-split precision (22+ significand bits)."""
     from sessd_b200 import ops
     g = torch.Generator().manual_seed(3)
-    for cin, cout, cp in ((64, 64, 64), (32, 32, 32), (32, 64, 32), (16, 32, 32)):
+    for cin, cout, cp, layout in ((64, 64, 64, "cg"), (32, 32, 32, "cg"), (32, 64, 32, "cg"), (32, 32, 32, "h2"), (16, 32, 32, "h2")):
         w = torch.randn(27, cin, cout, generator=g) * torch.logspace(-3, 1, cout)[None, None, :]      # channel scales over 4 decades
-        tiles, inv = ops.pack_weight_sp_h2(w, cp)
+        tiles, inv = ops.pack_weight_sp_h2(w, cp, layout=layout)
         assert tiles.dtype == torch.float16 and inv.shape == (cout,)
         ex = torch.log2(inv)
         assert torch.equal(ex, ex.round())                                   # exact powers of two
         scaled = w.permute(0, 2, 1) / inv[None, :, None]                     # [kvol, cout, cin] * 2^e
         assert float(scaled.abs().amax()) < 2048.0 and float(scaled.abs().amax(dim=(0, 2)).min()) >= 1024.0
-        if cp == 64:
-            assert tuple(tiles.shape) == (27, 2, cout, 64)
+        if cp == 64 or layout == "cg":                                       # [kvol, 2 (hi | lo), Cout, Cin]: the pair-gather kernel's tiles
+            assert tuple(tiles.shape) == (27, 2, cout, cin)
             hi, lo = tiles[:, 0].float(), tiles[:, 1].float()
         else:
             assert tuple(tiles.shape) == (27, cout, 64)
