@@ -22,14 +22,19 @@ for (cin, cout, hw, k) in ((128, 128, (200, 176), 3), (256, 256, (100, 88), 3), 
     xp, info = p2_debug.to_planes(x)
     oinfo = torch.zeros(2, device="cuda")
     op = ops.alloc_bev_planes(1, hw[0], hw[1], cout, "cuda")
-    dbg = torch.zeros((148, 8), dtype=torch.int64, device="cuda")
+    dbg = torch.zeros((2 * 148, 8), dtype=torch.int64, device="cuda")
     for it in range(3):
         dbg.zero_()
         fn(C.c_void_p(dbg.data_ptr()))
         ops.bev_conv_p2(xp, info, planes, sc, None, None, None, 30.0, 0.0, None, op, oinfo, d)
         torch.cuda.synchronize()
     fn(C.c_void_p(0))
-    m = dbg.double().cpu()
+    m = dbg[:148].double().cpu()
+    tl = dbg[148:].double().cpu()
+    lead = tl[:, 1] > 0
+    tn = ["setup done", "MMA loop start", "MMA loop end", "first acc_full seen", "last epilogue done", "-", "before teardown"]
+    print("   timeline (clk since kernel entry, mean over CTAs; MMA rows: leaders only): " + "  ".join(
+        "%s %.0f" % (tn[i], (tl[lead, i] if i in (1, 2) else tl[:, i]).mean()) for i in (0, 1, 2, 3, 4, 6)))
     names = ["mma:wait acc_free", "mma:wait patch_full", "mma:wait b_full", "mma:total", "items", "epi:wait acc_full", "wload:wait b_empty", "pload:wait patch_empty"]
     print("conv %dx%d %d->%d k%d" % (hw[0], hw[1], cin, cout, k))
     for i, n in enumerate(names):

@@ -140,6 +140,8 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef SESSD_P2_PROFILE
     long long p2_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // per-thread wait counters, written once at the end
+    const long long p2_t0 = clock64();                   // timeline (second [ctas][8] block of dbg): 0 setup done, 1 MMA loop start, 2 MMA loop end,
+    long long p2_tl[8] = {0, 0, 0, 0, 0, 0, 0, 0};       // 3 first acc_full seen, 4 last epilogue done, 5 teardown done (clk since kernel entry)
 #endif
     const uint32_t crank = (CS > 1) ? cluster_cta_rank() : 0u;
     constexpr bool kPair = (CS == 2);
@@ -170,6 +172,9 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
     if (kPair) cluster_sync_all();         // the peer's barriers are initialised before any remote arrive / peer-signalling load
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+#ifdef SESSD_P2_PROFILE
+    p2_tl[0] = clock64() - p2_t0;
+#endif
 
     // Roles 0-2 run their loops with the WHOLE warp (warp-uniform trip counts and addresses stay in uniform registers) and issue the
     // TMA / tcgen05 instructions from one elected lane.  Wrapping the loops in `if (lane == 0)` instead made every operand a vector
@@ -258,6 +263,7 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
         const int per_cls = p.nblocks * p.tgroups;
 #ifdef SESSD_P2_PROFILE
         const long long t_begin = clock64();
+        p2_tl[1] = t_begin - p2_t0;
 #endif
         for (int g = cluster_id; g < p.total; g += nclusters, ++iter) {
             const int cls = p.cls_order[g / per_cls];
@@ -327,7 +333,7 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
             }
         }
 #ifdef SESSD_P2_PROFILE
-        p2_acc[3] = clock64() - t_begin; p2_acc[4] = iter;
+        p2_acc[3] = clock64() - t_begin; p2_acc[4] = iter; p2_tl[2] = clock64() - p2_t0;
 #endif
     } else if (warp >= 3) {
         // ===================== epilogue warps (3-10): TMEM -> registers, release the accumulators, BN / ReLU / residual / stores
@@ -350,6 +356,9 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
             if (lane == 0) { if (warp == 3) P2_WAIT(5, mbar_wait(acc_full, (uint32_t)iter & 1u)); else mbar_wait(acc_full, (uint32_t)iter & 1u); }
             __syncwarp();
             tc_fence_after();
+#ifdef SESSD_P2_PROFILE
+            if (iter == 0) p2_tl[3] = clock64() - p2_t0;
+#endif
             // single CTA: [main0 | cross | main1], n_tile columns each; pair: [main c<h | cross c<h | main c>=h | cross c>=h | cross2], h = ncol
             const uint32_t lane0 = tmem_base + ((uint32_t)(q * 32) << 16);
             const uint32_t lane_base = lane0 + (uint32_t)(kPair ? half * 2 * ncol : half * ncol);
@@ -428,6 +437,9 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
                 }
             }
         }
+#ifdef SESSD_P2_PROFILE
+        p2_tl[4] = clock64() - p2_t0;
+#endif
         if (p.out_info) {
             const unsigned m = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(vmax));     // non-negative floats order like their bits
             if (lane == 0 && m != 0u) atomicMax(reinterpret_cast<unsigned *>(p.out_info), m);
@@ -440,6 +452,10 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
         if (warp == 1) d[6] = p2_acc[6];
         if (warp == 2) { d[0] = p2_acc[0]; d[1] = p2_acc[1]; d[2] = p2_acc[2]; d[3] = p2_acc[3]; d[4] = p2_acc[4]; }
         if (warp == 3) d[5] = p2_acc[5];
+        long long *tl = p.dbg + (size_t)gridDim.x * 8 + (size_t)blockIdx.x * 8;
+        if (warp == 0) tl[0] = p2_tl[0];
+        if (warp == 2) { tl[1] = p2_tl[1]; tl[2] = p2_tl[2]; }
+        if (warp == 3) { tl[3] = p2_tl[3]; tl[4] = p2_tl[4]; tl[6] = clock64() - p2_t0; }
     }
 #endif
     tc_fence_before();
