@@ -201,10 +201,48 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(Load load, Sto
     }
 }
 
+// Small inputs (a frame's point list, the bitmaps of the coarse levels): ONE launch of one 1024-thread CTA that walks the items in chunks with a
+// running carry -- the three-launch scan costs ~12 us of launch latency per use at batch 1, more than the work itself.
+constexpr int kScanSmallThreads = 1024;
+constexpr long long kScanSmallMax = 16 * 1024;          // capacity (items) up to which the one-CTA scan is used (measured: 5.5 k / 2.2 k bitmap words -6 us, 48 k words +30 us)
+
+template <class Load, class Store>
+__global__ void __launch_bounds__(kScanSmallThreads) scan_small_kernel(Load load, Store store, const int *__restrict__ d_n, long long n_mul,
+                                                                       int *__restrict__ d_total) {
+    __shared__ int sm[40];
+    const long long n = d_n ? (long long)(*d_n) * n_mul : n_mul;
+    int carry = 0;
+    for (long long base = 0; base < n; base += (long long)kScanSmallThreads * kScanItems) {
+        int v[kScanItems];
+        int s = 0;
+        const long long first = base + (long long)threadIdx.x * kScanItems;
+#pragma unroll
+        for (int j = 0; j < kScanItems; ++j) {
+            const long long i = first + j;
+            v[j] = (i < n) ? load(i) : 0;
+            s += v[j];
+        }
+        int tot;
+        int ex = block_excl_scan(s, sm, &tot) + carry;
+#pragma unroll
+        for (int j = 0; j < kScanItems; ++j) {
+            const long long i = first + j;
+            if (i < n) store(i, ex, v[j]);
+            ex += v[j];
+        }
+        carry += tot;
+    }
+    if (threadIdx.x == 0 && d_total) *d_total = carry;
+}
+
 // host driver.  scratch: ints[ceil(cap/kScanTile) + 1].  d_n * n_mul items; cap = capacity in items.
 template <class Load, class Store>
 static inline void device_scan(Load load, Store store, const int *d_n, long long n_mul, long long cap_items,
                                int *scratch, int *d_total, cudaStream_t st) {
+    if (cap_items <= kScanSmallMax) {
+        SESSD_LAUNCH((scan_small_kernel<Load, Store>), 1, kScanSmallThreads, 0, st, load, store, d_n, n_mul, d_total);
+        return;
+    }
     int tiles = (int)((cap_items + kScanTile - 1) / kScanTile);
     if (tiles < 1) tiles = 1;
     SESSD_LAUNCH((scan_reduce_kernel<Load>), tiles, kScanThreads, 0, st, load, d_n, n_mul, scratch);

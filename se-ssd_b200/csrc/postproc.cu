@@ -226,41 +226,51 @@ __device__ __forceinline__ float standup_iou_pos(const float *bn, const float *q
     return 0.f;
 }
 
-// one CTA per 64x64 tile of the upper triangle; 512 threads = 8 rows x 64 columns per pass, bits gathered with warp ballots
-constexpr int kMaskThreads = 512;
+// one CTA per 32x32 tile of the upper triangle (a frame's ~400 candidates = 91 tiles: one wave; 64x64 tiles gave 28 CTAs with eight serial
+// polygon clips per thread, 40 us); 256 threads = 8 rows x 32 columns per pass, one warp = one row: its ballot is a 32-bit half of the row's
+// 64-bit mask word
+constexpr int kMaskThreads = 256, kMaskTile = 32;
 __global__ void __launch_bounds__(kMaskThreads) post_mask_kernel(PostWs w, int K, float thresh, int ge) {
     const int b = blockIdx.z;
     const int rb = blockIdx.y, cb = blockIdx.x;
-    if (cb < rb) return;
     const int m = min(w.ncand[b], K);
-    if (rb * 64 >= m || cb * 64 >= m) return;
+    if (rb * kMaskTile >= m || cb * kMaskTile >= m) return;
     const int col_blocks = (K + 63) / 64;
-    __shared__ RotBox s_col[64];
-    __shared__ RotBox s_row[64];
-    __shared__ float s_csu[64 * 4];
-    __shared__ float s_rsu[64 * 4];
-    const int ncol = min(m - cb * 64, 64), nrow = min(m - rb * 64, 64);
+    if (cb < rb) {
+        // below the diagonal nothing is read -- except the low half of the 64-bit diagonal word of the rows in the upper half of a 64-row
+        // block (the scan loads whole words): zero it
+        if ((rb & 1) && cb == rb - 1) {
+            const int r = threadIdx.x;
+            if (r < kMaskTile && rb * kMaskTile + r < m)
+                reinterpret_cast<unsigned int *>(w.mask + ((size_t)b * K + rb * kMaskTile + r) * col_blocks + (cb >> 1))[0] = 0u;
+        }
+        return;
+    }
+    __shared__ RotBox s_col[kMaskTile];
+    __shared__ RotBox s_row[kMaskTile];
+    __shared__ float s_csu[kMaskTile * 4];
+    __shared__ float s_rsu[kMaskTile * 4];
+    const int ncol = min(m - cb * kMaskTile, kMaskTile), nrow = min(m - rb * kMaskTile, kMaskTile);
     const size_t fb = (size_t)b * K;
-    if ((int)threadIdx.x < 64) {
+    if ((int)threadIdx.x < kMaskTile) {
         const int t = threadIdx.x;
         if (t < ncol) {
-            s_col[t] = w.srot[fb + cb * 64 + t];
+            s_col[t] = w.srot[fb + cb * kMaskTile + t];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) s_csu[t * 4 + k] = w.ssu[(fb + cb * 64 + t) * 4 + k];
+            for (int k = 0; k < 4; ++k) s_csu[t * 4 + k] = w.ssu[(fb + cb * kMaskTile + t) * 4 + k];
         }
-    } else if (threadIdx.x < 128) {
-        const int t = threadIdx.x - 64;
+    } else if (threadIdx.x < 2 * kMaskTile) {
+        const int t = threadIdx.x - kMaskTile;
         if (t < nrow) {
-            s_row[t] = w.srot[fb + rb * 64 + t];
+            s_row[t] = w.srot[fb + rb * kMaskTile + t];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) s_rsu[t * 4 + k] = w.ssu[(fb + rb * 64 + t) * 4 + k];
+            for (int k = 0; k < 4; ++k) s_rsu[t * 4 + k] = w.ssu[(fb + rb * kMaskTile + t) * 4 + k];
         }
     }
     __syncthreads();
-    const int j = threadIdx.x & 63;           // column within the tile
-    const int half = j >> 5;                  // which 32-bit half of the 64-bit mask word this warp produces
-    for (int r0 = 0; r0 < 64; r0 += kMaskThreads / 64) {
-        const int r = r0 + (threadIdx.x >> 6);
+    const int j = threadIdx.x & 31;           // column within the tile
+    for (int r0 = 0; r0 < kMaskTile; r0 += kMaskThreads / 32) {
+        const int r = r0 + (threadIdx.x >> 5);
         bool hit = false;
         if (r < nrow && j < ncol && (rb != cb || j > r)) {
             if (standup_iou_pos(s_rsu + r * 4, s_csu + j * 4) > 0.0f) {            // nms_cpu.h:104-105
@@ -269,8 +279,8 @@ __global__ void __launch_bounds__(kMaskThreads) post_mask_kernel(PostWs w, int K
             }
         }
         const unsigned int bits = __ballot_sync(0xffffffffu, hit);
-        if ((threadIdx.x & 31) == 0 && r < nrow)
-            reinterpret_cast<unsigned int *>(w.mask + (fb + rb * 64 + r) * col_blocks + cb)[half] = bits;
+        if (j == 0 && r < nrow)
+            reinterpret_cast<unsigned int *>(w.mask + (fb + rb * kMaskTile + r) * col_blocks + (cb >> 1))[cb & 1] = bits;
     }
 }
 
@@ -468,7 +478,7 @@ static int postprocess_impl(const float *d_head, const float *d_anchors, const f
     SESSD_LAUNCH(post_select_kernel, g2, 256, 0, st, w.cand, w.ncand, A, K, w.sel);
     dim3 g3(div_up(K, 128), B);
     SESSD_LAUNCH(post_prepare_kernel, g3, 128, 0, st, d_head, d_anchors, *cfg, w);
-    const int cb = (K + 63) / 64;
+    const int cb = (K + kMaskTile - 1) / kMaskTile;
     dim3 g4(cb, cb, B);
     SESSD_LAUNCH(post_mask_kernel, g4, kMaskThreads, 0, st, w, K, cfg->nms_iou_thresh, cfg->nms_ge);
     const size_t sm = finalize_smem(K, P);
@@ -513,7 +523,7 @@ extern "C" int sessd_rotate_nms(const float *d_boxes5, const float *d_scores, co
     dim3 g2(div_up(max_boxes, 256), 1);
     SESSD_LAUNCH(post_select_kernel, g2, 256, 0, st, w.cand, w.ncand, max_boxes, pre_max, w.sel);
     SESSD_LAUNCH(nms_prepare_kernel, div_up(pre_max, 128), 128, 0, st, d_boxes5, pre_max, w);
-    const int cb = (pre_max + 63) / 64;
+    const int cb = (pre_max + kMaskTile - 1) / kMaskTile;
     dim3 g4(cb, cb, 1);
     SESSD_LAUNCH(post_mask_kernel, g4, kMaskThreads, 0, st, w, pre_max, iou_thresh, ge);
     const size_t sm = finalize_smem(pre_max, post_max);
