@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--frames-per-step", type=int, default=None, help="default 512 (frame workloads: >= 5 s timed at 20 steps), 16 (stress)")
     ap.add_argument("--streams", type=int, default=None, help="concurrent engines; default 12 (frame workloads), 1 (stress)")
     ap.add_argument("--pool", type=int, default=16, help="distinct synthetic frames per rank")
+    ap.add_argument("--cg-deep", type=int, default=None, help="sparse conv pipeline: 1 deep / one CTA per SM, 0 two CTAs per SM (default: the engine's choice)")
     ap.add_argument("--quick", action="store_true", help="skip the e2e / roofline / cpu_baseline / extra legs (tuning runs)")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra.uniform20k / extra.stress sub-records")
     return ap.parse_args()
@@ -318,6 +319,9 @@ def run_ours(args):
     S = args.streams or (1 if wl == "stress" else 12)
     F = args.frames_per_step or (16 if wl == "stress" else 512)
     F = max(B, F // B * B)
+    if args.cg_deep is not None:
+        from sessd_b200 import ops as _ops
+        _ops.set_sp_cg_deep(args.cg_deep)
     rig = Rig(wl, S, args.pool, rank, world, dev)
     rig.prime_offsets()
 

@@ -159,8 +159,8 @@ int sessd_spconv_forward_rows_planes(const float *d_in_feat, int cin, const int 
 int sessd_spconv_forward_cg(const void *d_in_planes, int cp, int plane_rows, const float *d_in_info, const void *d_tiles, int kvol,
                             const int *d_n_out, int max_out, const void *d_weight_h2, int cout, const float *d_scale, const float *d_shift,
                             int relu, float gain, float shift_max, float *d_out_f32, void *d_out_planes, float *d_out_info, void *stream);
-/* 1: the gathered rows of sessd_spconv_forward_cg also allocate in L1 (cp.async.ca); default 0 (cp.async.cg) */
-void sessd_set_sp_cg_l1(int on);
+/* 1: deep pipeline (twice the stages, one CTA per SM) for launches with fewer tiles than SMs (single frames); 0 (default): two CTAs per SM */
+void sessd_set_sp_cg_deep(int on);
 /* *d_amax = max(*d_amax, max |d_feat[i]|) over the first *d_n rows of a [max_rows, channels] fp32 tensor */
 int sessd_absmax_rows(const float *d_feat, const int *d_n, int max_rows, int channels, float *d_amax, void *stream);
 

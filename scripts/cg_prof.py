@@ -1,5 +1,5 @@
 """Per-role cycle counters of spconv_cg_kernel per layer at the stress / frame shape (library built with SESSD_DEFINES=-DSESSD_CG_PROFILE).
-    SESSD_DEFINES=-DSESSD_CG_PROFILE python se-ssd_b200/build.py --force && python scripts/cg_prof.py [stress|frame] [cg_l1]"""
+    SESSD_DEFINES=-DSESSD_CG_PROFILE python se-ssd_b200/build.py --force && python scripts/cg_prof.py [stress|frame] [deep]"""
 import os, sys, ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "se-ssd_b200"))
@@ -9,7 +9,7 @@ from sessd_b200 import ops
 from sessd_b200._lib import lib
 from sessd_b200.engine import FrameEngine
 shape = sys.argv[1] if len(sys.argv) > 1 else "stress"
-lib.sessd_set_sp_cg_l1(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+lib.sessd_set_sp_cg_deep(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 fn = lib._prod.sessd_set_cg_dbg; fn.restype = None; fn.argtypes = [C.c_void_p]
 if shape == "stress":
     B, N = 16, 200000

@@ -128,10 +128,10 @@ def main():
     ap.add_argument("--points", type=int, default=None)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--sparse-tc", default=None, choices=["cg", "h2"], help="tensor-core kernel of the Cin >= 32 sparse layers (default: the runner's)")
-    ap.add_argument("--cg-l1", type=int, default=0, help="1: cp.async.ca (gathered rows allocate in L1)")
+    ap.add_argument("--cg-deep", type=int, default=0, help="1: deep pipeline, one CTA per SM")
     a = ap.parse_args()
     from sessd_b200._lib import lib
-    lib.sessd_set_sp_cg_l1(int(a.cg_l1))
+    lib.sessd_set_sp_cg_deep(int(a.cg_deep))
     if a.shape == "stress":
         B, N = a.batch or 16, a.points or 200000
         clouds = [synth.uniform_cloud(1000 + f, N) for f in range(B)]
@@ -147,7 +147,7 @@ def main():
     out = group_rooflines(eng, clouds, a.iters)
     out["shape"] = a.shape
     out["sparse_tc"] = eng.middle.sparse_tc
-    out["cg_l1"] = int(a.cg_l1)
+    out["cg_deep"] = int(a.cg_deep)
     print(json.dumps(out))
 
 

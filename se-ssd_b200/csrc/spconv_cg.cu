@@ -34,13 +34,15 @@ constexpr int kCgProdWarps = 8;
 constexpr int kCgProdThreads = kCgProdWarps * 32;
 constexpr int kCgThreads = kCgProdThreads + 64;
 
-template <int CP, int COUT>
+// DEEP = 1: twice the stages, one CTA per SM -- for launches whose tiles do not fill the machine twice over (a single frame: ~100 tiles on 148 SMs), where
+// a CTA is alone on its SM anyway and the layer's time is the serial chain of its tile's fills (latency-bound): more fills in flight shorten it
+template <int CP, int COUT, int DEEP = 0>
 struct CgCfg {
     static constexpr bool kWide = (CP == 64);
     static constexpr int kATile = (kWide ? 2 : 1) * kCgBM * 128;              // bytes: [hi tile ; lo tile] (wide) or one [hi | lo] tile
     static constexpr int kBTile = (kWide ? 2 : 1) * COUT * 128;
     static constexpr int kStage = kATile + (kBTile + 1023) / 1024 * 1024;
-    static constexpr int kStages = kWide ? 2 : 4;                             // must divide the 8 producer warps (one group per stage)
+    static constexpr int kStages = (kWide ? 2 : 4) * (DEEP ? 2 : 1);           // must divide the 8 producer warps (one group per stage)
     static constexpr int kMeta = kCgBM * kCgMaxK * 4 /*lists*/ + kCgMaxK * 16 /*valid*/ + 32 * 4 /*cnt*/ + 33 * 4 /*klist, nact*/ + 32 * 4 /*off*/ +
                                  kCgProdWarps * 4 * 4 /*dirty*/ + (3 * kStages + 1) * 8 /*barriers*/ + 24;
     static constexpr int kSmem = kStages * kStage + kMeta + 1024;
@@ -54,7 +56,7 @@ struct CgArgs {
     const unsigned int *tiles;         // per-tile pair lists (sessd_rulebook_tile_lists), tile_stride words per tile
     int tile_stride;
     const int *d_n_out;
-    int kvol, max_out, relu, nofence;
+    int kvol, max_out, relu;
     const float *scale, *shift;        // folded BN (scale already times the per-channel weight exponent 2^-e)
     float gain, shift_max;             // |out| <= amax_in * gain + shift_max
     float *out_f32;                    // nullable [max_out][COUT]
@@ -76,12 +78,9 @@ __device__ __forceinline__ void cg_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
         : "memory");
 }
 
-template <int L1>
+// 16-byte global -> shared copy that bypasses L1 (allocating the gathered rows in L1 was measured: no hits worth the footprint)
 __device__ __forceinline__ void cg_cp_async16(uint32_t smem_dst, const void *gsrc) {
-    if (L1)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
-    else
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cg_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void cg_sts_zero16(uint32_t saddr) {
@@ -111,9 +110,9 @@ __device__ __forceinline__ void cg_tmem_ld16(uint32_t taddr, uint32_t *r) {
 #define CG_WAIT(slot, cond, stmt) stmt
 #endif
 
-template <int CP, int COUT, int L1>
-__global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_constant__ CUtensorMap map_w, const CgArgs a) {
-    using C = CgCfg<CP, COUT>;
+template <int CP, int COUT, int DEEP>
+__global__ void __launch_bounds__(kCgThreads, DEEP ? 1 : 2) spconv_cg_kernel(const __grid_constant__ CUtensorMap map_w, const CgArgs a) {
+    using C = CgCfg<CP, COUT, DEEP>;
     const int n_out = min(*a.d_n_out, a.max_out);
     const int ntiles = (n_out + kCgBM - 1) / kCgBM;
     if ((int)blockIdx.x >= ntiles) return;                       // whole CTA leaves together (before any barrier / TMEM use)
@@ -163,7 +162,7 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
     const float s_out = pow2_scale_for_bound(amax_in * a.gain + a.shift_max);
     if (blockIdx.x == 0 && tid == 0 && a.out_info) a.out_info[1] = s_out;
     float vmax = 0.f;
-    uint32_t dirty[2] = {0u, 0u};                                // rows of this warp's share of its stage that hold data (producer warps)
+    uint32_t dirty[4] = {0u, 0u, 0u, 0u};                        // rows of this warp's share of its stage that hold data (producer warps)
     int st0 = 0, acc_it = 0;                                     // stage of this tile's first fill / accumulator hand-overs so far (all roles
     uint32_t ph0 = 0;                                            // count alike); ph0 = phase bit of stage st0
 
@@ -330,13 +329,13 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
                     const uint32_t r = e & 127u;
                     const size_t src = (size_t)(e >> 7);
                     if constexpr (C::kWide)
-                        cg_cp_async16<L1>(a_base + (uint32_t)half * (kCgBM * 128) + r * 128u + (((uint32_t)cc ^ (r & 7u)) << 4),
+                        cg_cp_async16(a_base + (uint32_t)half * (kCgBM * 128) + r * 128u + (((uint32_t)cc ^ (r & 7u)) << 4),
                                           a.planes + src * 128 + half * 64 + cc * 8);
                     else
-                        cg_cp_async16<L1>(a_base + r * 128u + (((uint32_t)cc ^ (r & 7u)) << 4), a.planes + src * 64 + cc * 8);
+                        cg_cp_async16(a_base + r * 128u + (((uint32_t)cc ^ (r & 7u)) << 4), a.planes + src * 64 + cc * 8);
                 }
                 asm volatile("cp.async.wait_all;\n" ::: "memory");
-                if (!a.nofence) cg_fence_proxy_async();                  // copies and clears (generic proxy) -> visible to the tensor core
+                cg_fence_proxy_async();                                  // copies and clears (generic proxy) -> visible to the tensor core (measured: free)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full_a[grp]);
             }
@@ -441,15 +440,14 @@ __global__ void __launch_bounds__(kCgThreads, 2) spconv_cg_kernel(const __grid_c
 }
 
 static long long *g_cg_dbg = nullptr;
-static int g_cg_l1 = 0;            // 1: gathered rows also allocate in L1 (cp.async.ca)
+static int g_cg_deep = 0;          // 1: deep pipeline, one CTA per SM (sessd_set_sp_cg_deep)
 
-template <int CP, int COUT>
+template <int CP, int COUT, int DEEP>
 static int launch_spconv_cg(const CgArgs &a, const void *w_h2, cudaStream_t st) {
-    using C = CgCfg<CP, COUT>;
+    using C = CgCfg<CP, COUT, DEEP>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(spconv_cg_kernel<CP, COUT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(spconv_cg_kernel<CP, COUT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+        cudaError_t e = cudaFuncSetAttribute(spconv_cg_kernel<CP, COUT, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
         if (e != cudaSuccess) return (int)e;
         attr_done = true;
     }
@@ -478,11 +476,9 @@ static int launch_spconv_cg(const CgArgs &a, const void *w_h2, cudaStream_t st) 
         SESSD_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     const int tiles = div_up(a.max_out, kCgBM);
-    const int grid = tiles < 2 * num_sms ? tiles : 2 * num_sms;          // persistent: two CTAs per SM
-    if (g_cg_l1 & 1)
-        SESSD_LAUNCH((spconv_cg_kernel<CP, COUT, 1>), grid, kCgThreads, C::kSmem, st, map_w, a);
-    else
-        SESSD_LAUNCH((spconv_cg_kernel<CP, COUT, 0>), grid, kCgThreads, C::kSmem, st, map_w, a);
+    const int per_sm = DEEP ? 1 : 2;
+    const int grid = tiles < per_sm * num_sms ? tiles : per_sm * num_sms;        // persistent
+    SESSD_LAUNCH((spconv_cg_kernel<CP, COUT, DEEP>), grid, kCgThreads, C::kSmem, st, map_w, a);
     return last_error();
 }
 
@@ -493,7 +489,9 @@ using namespace sessd;
 #ifdef SESSD_CG_PROFILE
 extern "C" void sessd_set_cg_dbg(void *d) { sessd::g_cg_dbg = (long long *)d; }
 #endif
-extern "C" void sessd_set_sp_cg_l1(int on) { sessd::g_cg_l1 = on & 3; }
+// 1: twice the stages and one CTA per SM (launches with fewer tiles than SMs, e.g. single frames: the serial fill chain of a tile is latency-bound);
+// 0 (default): two CTAs per SM (many tiles: throughput)
+extern "C" void sessd_set_sp_cg_deep(int on) { sessd::g_cg_deep = on ? 1 : 0; }
 
 // S4 (scn.py:106-149), pair-proportional tensor-core path.  d_in_planes [plane_rows][2][cp] fp16 with d_in_info = {abs-max, scale};
 // weights / d_scale from ops.pack_weight_sp_h2 (cp = 64: [kvol][2][Cout][64], cp = 32: [kvol][2][Cout][32]; d_scale = BN scale *
@@ -510,11 +508,14 @@ extern "C" int sessd_spconv_forward_cg(const void *d_in_planes, int cp, int plan
     if (d_out_planes && !d_out_info) return SESSD_EINVAL;
     CgArgs a;
     a.planes = (const __half *)d_in_planes; a.in_info = d_in_info; a.tiles = (const unsigned int *)d_tiles; a.tile_stride = 160 + 128 * kvol; a.d_n_out = d_n_out; a.kvol = kvol; a.max_out = max_out;
-    a.relu = relu; a.nofence = (g_cg_l1 >> 1) & 1; a.scale = d_scale; a.shift = d_shift; a.gain = gain; a.shift_max = shift_max; a.out_f32 = d_out_f32;
+    a.relu = relu; a.scale = d_scale; a.shift = d_shift; a.gain = gain; a.shift_max = shift_max; a.out_f32 = d_out_f32;
     a.out_planes = (__half *)d_out_planes; a.out_info = d_out_info; a.dbg = g_cg_dbg;
     cudaStream_t st = (cudaStream_t)stream;
-    if (cp == 32 && cout == 32) return launch_spconv_cg<32, 32>(a, d_weight_h2, st);
-    if (cp == 32 && cout == 64) return launch_spconv_cg<32, 64>(a, d_weight_h2, st);
-    if (cp == 64 && cout == 64) return launch_spconv_cg<64, 64>(a, d_weight_h2, st);
+#define SESSD_CG_CASE(CPV, CO) \
+    if (cp == CPV && cout == CO) return g_cg_deep ? launch_spconv_cg<CPV, CO, 1>(a, d_weight_h2, st) : launch_spconv_cg<CPV, CO, 0>(a, d_weight_h2, st);
+    SESSD_CG_CASE(32, 32)
+    SESSD_CG_CASE(32, 64)
+    SESSD_CG_CASE(64, 64)
+#undef SESSD_CG_CASE
     return SESSD_EINVAL;
 }

@@ -267,6 +267,11 @@ def spconv_forward_cg(in_planes, in_info, tiles, n_out, max_out, weight_h2, scal
     return out if out is not None else out_planes
 
 
+def set_sp_cg_deep(on):
+    """spconv_forward_cg: 1 = deep pipeline, one CTA per SM (launches with fewer tiles than SMs: single frames); 0 = two CTAs per SM"""
+    lib.sessd_set_sp_cg_deep(int(on))
+
+
 def sparse_planes_to_float(planes, info, channels):
     """(hi + lo) / S of sparse feature planes [rows, 2 * cp] as fp32 [rows, channels] (tests / debugging)"""
     cp = planes.shape[1] // 2
