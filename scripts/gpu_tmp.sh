@@ -1,6 +1,12 @@
 #!/bin/bash
 OUT=gpurun_out/${1:-tmp}
 mkdir -p $OUT
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 scripts/ddp_allreduce_check.py > $OUT/ddp_allreduce_n2.json 2> $OUT/ddp_allreduce_n2.err; echo "ddp rc=$?"; tail -2 $OUT/ddp_allreduce_n2.json; tail -3 $OUT/ddp_allreduce_n2.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus 2 --steps 6 --warmup 3 --no-extra > $OUT/bench_n2.json 2> $OUT/bench_n2.err; echo "bench n2 rc=$?"; python -c "
-import json;d=json.loads(open('$OUT/bench_n2.json').read().strip().splitlines()[-1]);print({k:d[k] for k in ('value','n_gpus','ms_per_step')}, d['e2e']['value'])"
+for D in 0 1; do
+timeout 600 python scripts/kernel_rooflines.py --shape frame-uniform --iters 5 --cg-deep $D > $OUT/roof_uniform_$D.json 2> $OUT/roof_uniform_$D.err; echo "roof rc=$?"
+python - <<PY
+import json
+d=json.load(open("$OUT/roof_uniform_$D.json"))
+print("uniform deep=$D total_ms", d["total_ms"], d["active_sites"], " ".join("%s=%.3f"%(g["group"].replace("neck:","n:").replace("rulebook:","rb:"),g["ms"]) for g in d["groups"] if not g["group"].startswith("neck")), "neck=%.3f"%sum(g["ms"] for g in d["groups"] if g["group"].startswith("neck")))
+PY
+done
+timeout 600 python scripts/cg_prof.py frame 0 > /dev/null 2>&1

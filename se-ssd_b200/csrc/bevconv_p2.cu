@@ -1,7 +1,7 @@
 // bevconv_p2.cu -- BEV conv / deconv (+BN+ReLU+residual) on the 5th-gen tensor cores from PRE-SPLIT fp16 planes.
 //
 // Replaces the cuDNN conv blocks of det3d/models/necks/rpn_v1.py:135-210 and the 1x1 head convs of
-// det3d/models/bbox_heads/mg_head_sessd.py:202-230 (fp32 in, fp32 out, fp32 accumulate).  Same numerics as bevconv_h2.cu
+// det3d/models/bbox_heads/mg_head_sessd.py:202-230 (fp32 in, fp32 out, fp32 accumulate).  Same numerics as the lab library's bevconv_h2.cu
 // (x = (x_hi + x_lo) / S with fp16 hi / lo and an exact power-of-two scale S: 22+ significand bits; three kind::f16 products per MAC
 // accumulated in fp32 TMEM: a_hi*b_hi -> main0 / main1 alternating, a_hi*b_lo + a_lo*b_hi -> cross, summed in RN fp32 by the epilogue),
 // but the activations TRAVEL BETWEEN LAYERS as fp16 (hi, lo) planes [2][B*H*W][C] written by the producing layer's epilogue, so that
@@ -12,14 +12,19 @@
 //     |out| <= amax_in * G + max|shift| (+ amax_residual), G = max_n sum_k |w[k][n]| |bn_scale[n]| (host, at weight-load time) and
 //     amax_in = the measured abs-max of the input (device scalar, raised by the producer's epilogue).  The bound maps into
 //     [2^14, 2^15): fp16 keeps 22 bits of every element down to 2^-17 of the bound, far more slack than the bound is loose;
-//   * the weight tiles ([b_hi ; b_lo], 16 KB per (tap, 32-channel chunk)) are the dominant L2 -> SM traffic (589 KB per 128-pixel tile
-//     of a 3x3 128->128 layer = 162 MB per layer = 23 us at the ~7 TB/s the L2 delivers): a CLUSTER of two CTAs works on two
-//     neighbouring pixel tiles and each CTA TMA-multicasts half of every weight tile to both.
+//   * the weight tiles ([b_hi ; b_lo], 16 KB per (tap, 32-channel chunk)) are the dominant L2 -> SM traffic (589 KB per 128-pixel tile of
+//     a 3x3 128->128 layer against ~23 B/clk/SM the L2 delivers).  TMA multicast across a cluster of two did not help (every SM still
+//     receives every byte); CTA PAIRS do: with tcgen05 cta_group::2 ONE MMA spans two SMs (M = 256: 128 pixels per CTA) and each CTA stages
+//     only HALF of every weight tile (the N halves are concatenated by the instruction); all loads signal the leader's mbarriers
+//     (cp.async.bulk.tensor...cta_group::2), the leader's commits arrive in both CTAs.  Used where the K loop is long (3x3, stride-2, deconv);
+//     the 1x1 convs stay single-CTA;
+//   * the three loops (patch TMA, weight TMA, MMA issue) run warp-uniform with one ELECTED issuing lane, so descriptors and addresses stay
+//     in uniform registers (an `if (lane == 0)` around the loop made the issue thread, not the tensor pipe, the bottleneck).
 // Geometry: tile = 8 (u) x 16 (v) output pixels = 128 MMA rows, row = v*8 + u, so that one 8-row swizzle group = 8 consecutive u.
 // For every distinct tap shift along u (and v parity, strided convs) ONE copy of the input patch [v rows][8 u][32 channels] is
 // TMA-loaded per plane: a tap then addresses a canonical K-major SWIZZLE_64B operand at copy + v_shift * 512 B (group stride 512 B):
 // plain descriptors, no base-offset tricks.  u / v are mapped to (y, x) or (x, y), whichever tiles the map with fewer tiles.
-// Warps: 0 patch TMA, 1 weight TMA (multicast), 2 MMA issue, 3-10 epilogue (TMEM -> registers -> BN/ReLU/residual -> fp32 and / or
+// Warps: 0 patch TMA, 1 weight TMA, 2 MMA issue (pair mode: the leader CTA's only), 3-10 epilogue (TMEM -> registers -> BN/ReLU/residual -> fp32 and / or
 // fp16 planes + running abs-max).
 #include <cuda_fp16.h>
 

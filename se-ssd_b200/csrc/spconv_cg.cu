@@ -2,17 +2,20 @@
 // proportional to the number of rulebook PAIRS: only the neighbour rows that exist are fetched.
 //
 // Replaces spconv 1.x's per-offset gather -> sgemm -> scatter-add used by det3d/models/backbones/scn.py:106-149 (SpMiddleFHD), like
-// spconv_h2.cu (same numerics: fp16 (hi, lo) planes with an exact power-of-two scale, three kind::f16 products per MAC, two main + one
-// cross TMEM accumulator summed in RN fp32; same weight tiles), but the 128-row A operand of a (tile, kernel offset) is no longer
-// fetched with 32-64 TMA gather4 instructions whose cost is per ROW SLOT, present or not (~5.5 clk per 128-byte row: at the 21 %
-// neighbour fill of the 32-channel layers 79 % of the row requests fetched zeros and the layer ran at 0.9 % of the tensor peak).  Here
+// the lab library's spconv_h2.cu (same numerics: fp16 (hi, lo) planes with an exact power-of-two scale, three kind::f16 products per MAC,
+// two main + one cross TMEM accumulator summed in RN fp32), but the 128-row A operand of a (tile, kernel offset) is no longer fetched
+// with 32-64 TMA gather4 instructions whose cost is per ROW SLOT, present or not (~5.5 clk per 128-byte row: at the 21 % neighbour fill of
+// the 32-channel layers 79 % of the row requests fetched zeros and the layer ran at 0.9 % of the tensor peak).  Here
 //   * the rulebook is regrouped ONCE per build (sessd_rulebook_tile_lists; a SubM rulebook serves 2-3 layers) into per-tile, per-offset
 //     lists of (input row, tile row) pairs + row masks; a tile's record (~3-8 KB) is copied to shared memory (compacting the neighbour
 //     table inside this kernel with shared-memory atomics cost 14.7 k clk per tile, a third of the tile's time);
 //   * eight producer warps copy the listed rows with 16-byte cp.async (LDGSTS: global/L2 -> shared, no registers, 2 clk per 128-byte row)
 //     straight into the K-major SWIZZLE_128B layout the UMMA descriptors address; rows without a neighbour are never touched;
-//   * a stage's missing rows must read as zeros: each warp remembers which of its rows hold data in every stage and clears (st.shared)
-//     only the rows that were valid for the stage's previous offset and are not for the new one -- the stages are zeroed once per CTA;
+//   * a stage's missing rows must read as zeros: each producer warp remembers (registers) which of its rows of its stage hold data and
+//     clears (st.shared) only the rows that were valid for the stage's previous offset and are not for the new one -- the stages are
+//     zeroed once per CTA;
+//   * the 32-channel layers stage the weights as [b_hi rows ; b_lo rows] of 64 bytes (SWIZZLE_64B) so that one N = 2 Cout product gives
+//     the main and the a_hi x b_lo cross term (4 instead of 6 MMAs per offset: an SS-form MMA costs max(math, operand bytes / 128 B/clk));
 //   * CTAs are persistent (two per SM: one tile's epilogue overlaps the other's main loop), so barrier / TMEM / zero-fill setup is paid
 //     once, not per 128 rows;
 //   * the epilogue writes the NEXT layer's operand format directly -- fp16 (hi, lo) planes scaled by a power of two derived from a
@@ -44,7 +47,7 @@ struct CgCfg {
     static constexpr int kStage = kATile + (kBTile + 1023) / 1024 * 1024;
     static constexpr int kStages = (kWide ? 2 : 4) * (DEEP ? 2 : 1);           // must divide the 8 producer warps (one group per stage)
     static constexpr int kMeta = kCgBM * kCgMaxK * 4 /*lists*/ + kCgMaxK * 16 /*valid*/ + 32 * 4 /*cnt*/ + 33 * 4 /*klist, nact*/ + 32 * 4 /*off*/ +
-                                 kCgProdWarps * 4 * 4 /*dirty*/ + (3 * kStages + 1) * 8 /*barriers*/ + 24;
+                                 (3 * kStages + 1) * 8 /*barriers*/ + 24;
     static constexpr int kSmem = kStages * kStage + kMeta + 1024;
     static constexpr int kTmemCols = (3 * COUT <= 128) ? 128 : 256;
     static constexpr int kCPO = COUT > 32 ? 64 : 32;                          // channels per plane row of the OUTPUT
@@ -130,8 +133,7 @@ __global__ void __launch_bounds__(kCgThreads, DEEP ? 1 : 2) spconv_cg_kernel(con
     int *s_klist = s_cnt + 32;                                           // [32] + nact
     int *s_nact = s_klist + 32;
     int *s_off = s_nact + 1;                                             // [32] first list entry of every offset
-    uint32_t *s_dirty = (uint32_t *)(s_off + 32);                        // [8 warps][4 stages]: 16-bit mask of rows holding data
-    uint64_t *bars = (uint64_t *)(((uintptr_t)(s_dirty + kCgProdWarps * 4) + 7) & ~(uintptr_t)7);
+    uint64_t *bars = (uint64_t *)(((uintptr_t)(s_off + 32) + 7) & ~(uintptr_t)7);
     uint64_t *full_a = bars, *full_b = bars + C::kStages, *empty = bars + 2 * C::kStages;
     uint64_t *acc_full = bars + 3 * C::kStages;
     uint32_t *tmem_slot = (uint32_t *)(acc_full + 1);
