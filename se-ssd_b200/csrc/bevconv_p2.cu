@@ -299,32 +299,34 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
                             //   [3 n_tile, 4 n_tile) = cross2: a_lo x b_hi (every tap) and a_hi x b_lo (odd taps)
                             const uint32_t acc_m1 = tmem_base + 2 * (uint32_t)p.n_tile, acc_c2 = tmem_base + 3 * (uint32_t)p.n_tile;
                             const uint64_t dblo = dcat + (uint64_t)plane_lo;
-#pragma unroll
-                            for (int k = 0; k < 2; ++k) {
-                                const uint32_t ko = (uint32_t)(k * 2);
-                                if (!par) {
-                                    tc_mma_f16_pair(tmem_base, da_hi + ko, dcat + ko, idesc2, (lbj | k) != 0);
-                                } else {
-                                    tc_mma_f16_pair(acc_m1, da_hi + ko, dcat + ko, idesc1, (lbj != 1) || k != 0);
-                                    tc_mma_f16_pair(acc_c2, da_hi + ko, dblo + ko, idesc1, 1);
-                                }
-                                tc_mma_f16_pair(acc_c2, da_lo + ko, dcat + ko, idesc1, (lbj | k) != 0);
+                            // all K steps of one product before the next product (see the single-CTA path below)
+                            if (!par) {
+                                tc_mma_f16_pair(tmem_base, da_hi, dcat, idesc2, lbj != 0);
+                                tc_mma_f16_pair(tmem_base, da_hi + 2, dcat + 2, idesc2, 1);
+                            } else {
+                                tc_mma_f16_pair(acc_m1, da_hi, dcat, idesc1, lbj != 1);
+                                tc_mma_f16_pair(acc_m1, da_hi + 2, dcat + 2, idesc1, 1);
+                                tc_mma_f16_pair(acc_c2, da_hi, dblo, idesc1, 1);
+                                tc_mma_f16_pair(acc_c2, da_hi + 2, dblo + 2, idesc1, 1);
                             }
+                            tc_mma_f16_pair(acc_c2, da_lo, dcat, idesc1, lbj != 0);
+                            tc_mma_f16_pair(acc_c2, da_lo + 2, dcat + 2, idesc1, 1);
                             tc_commit_pair(&b_empty[S]);
                             if (tap == ntaps - 1) tc_commit_pair(&patch_empty[pb]);
                             if (lbj == nbj - 1) tc_commit_pair(acc_full);
                         } else {
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) {                                  // K = 16 per instruction = 32 bytes of the 64-byte row
-                            const uint32_t ko = (uint32_t)(k * 2);
-                            if (lbj == 1 && k == 0) {
-                                p2_mma_f16(acc_cross, da_hi, dcat, idesc1, 1);            // cross += a_hi x b_lo
-                                p2_mma_f16(acc_main1, da_hi, dbhi, idesc1, 0);            // main1  = a_hi x b_hi (first write)
-                            } else {
-                                p2_mma_f16(d2, da_hi + ko, dcat + ko, idesc2, (lbj | k) != 0);   // [main|cross] (+)= a_hi x [b_hi;b_lo]
-                            }
-                            p2_mma_f16(acc_cross, da_lo + ko, dbhi + ko, idesc1, 1);      // cross += a_lo x b_hi
+                        // K = 16 per instruction = 32 bytes of the 64-byte row.  Both K steps of one product are issued before the next product:
+                        // consecutive MMAs of one shape into one accumulator pipeline, a switch to a product whose accumulator columns overlap the
+                        // previous one's drains the pipe
+                        if (lbj == 1) {
+                            p2_mma_f16(acc_main1, da_hi, dbhi, idesc1, 0);                // main1  = a_hi x b_hi (first write)
+                            p2_mma_f16(acc_cross, da_hi, dcat, idesc1, 1);                // cross += a_hi x b_lo
+                        } else {
+                            p2_mma_f16(d2, da_hi, dcat, idesc2, lbj != 0);                // [main|cross] (+)= a_hi x [b_hi;b_lo]
                         }
+                        p2_mma_f16(d2, da_hi + 2, dcat + 2, idesc2, 1);
+                        p2_mma_f16(acc_cross, da_lo, dbhi, idesc1, 1);                    // cross += a_lo x b_hi
+                        p2_mma_f16(acc_cross, da_lo + 2, dbhi + 2, idesc1, 1);
                         tc_commit(&b_empty[S]);
                         if (tap == ntaps - 1) tc_commit(&patch_empty[pb]);
                         if (lbj == nbj - 1) tc_commit(acc_full);

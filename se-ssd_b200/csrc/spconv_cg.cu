@@ -217,38 +217,44 @@ __global__ void __launch_bounds__(kCgThreads, DEEP ? 1 : 2) spconv_cg_kernel(con
                     if constexpr (C::kWide) {
                         const uint64_t dAl = dA + ((kCgBM * 128) >> 4);
                         const uint64_t dBh = dB + (((j & 1) ? COUT * 128 : 0) >> 4);       // the b_hi rows inside the [X ; Y] tile
+                        // all K steps of one product first, then the next product: consecutive MMAs of one shape into one accumulator pipeline,
+                        // a switch to a product whose accumulator columns OVERLAP the previous one's drains the pipe (one switch per offset, not per K step)
+                        if ((j & 1) == 0) {
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const uint32_t o = (uint32_t)(kk * 32) >> 4;
-                            if ((j & 1) == 0) {
-                                cg_mma_f16(acc_main0, dA + o, dB + o, idesc2, (j != 0 || kk != 0) ? 1u : 0u);    // [main0|cross] (+)= a_hi x [b_hi;b_lo]
-                            } else if (j == 1 && kk == 0) {
-                                cg_mma_f16(acc_cross, dA + o, dB + o, idesc, 1u);                                 // cross += a_hi x b_lo
-                                cg_mma_f16(acc_main1, dA + o, dBh + o, idesc, 0u);                                // main1  = a_hi x b_hi
-                            } else {
-                                cg_mma_f16(acc_cross, dA + o, dB + o, idesc2, 1u);                                // [cross|main1] += a_hi x [b_lo;b_hi]
+                            for (int kk = 0; kk < 4; ++kk)
+                                cg_mma_f16(acc_main0, dA + 2 * kk, dB + 2 * kk, idesc2, (j != 0 || kk != 0) ? 1u : 0u);      // [main0|cross] (+)= a_hi x [b_hi;b_lo]
+                        } else {
+                            if (j == 1) {
+                                cg_mma_f16(acc_main1, dA, dBh, idesc, 0u);                                                 // main1  = a_hi x b_hi
+                                cg_mma_f16(acc_cross, dA, dB, idesc, 1u);                                                  // cross += a_hi x b_lo
                             }
-                            cg_mma_f16(acc_cross, dAl + o, dBh + o, idesc, 1u);                                   // cross += a_lo x b_hi
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                if (j != 1 || kk != 0) cg_mma_f16(acc_cross, dA + 2 * kk, dB + 2 * kk, idesc2, 1u);         // [cross|main1] += a_hi x [b_lo;b_hi]
                         }
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) cg_mma_f16(acc_cross, dAl + 2 * kk, dBh + 2 * kk, idesc, 1u);        // cross += a_lo x b_hi
                     } else {
                         // narrow: A line = [hi 32 | lo 32] halves (SWIZZLE_128B); B stage = [b_hi rows ; b_lo rows] of 64 bytes each (SWIZZLE_64B),
                         // [b_lo ; b_hi] on odd offsets: one N = 2 COUT product gives main and the a_hi x b_lo cross term together (4 instead of
                         // 6 MMAs per offset: the A-operand reads from shared memory bound these layers)
                         const uint64_t dBn = desc_b64 | (st_lo + (C::kATile >> 4));
                         const uint64_t dBh = dBn + (((j & 1) ? COUT * 64 : 0) >> 4);
+                        if ((j & 1) == 0) {
 #pragma unroll
-                        for (int kk = 0; kk < 2; ++kk) {
-                            const uint32_t o = (uint32_t)(kk * 32) >> 4;
-                            if ((j & 1) == 0) {
-                                cg_mma_f16(acc_main0, dA + o, dBn + o, idesc2, (j != 0 || kk != 0) ? 1u : 0u);   // [main0|cross] (+)= a_hi x [b_hi;b_lo]
-                            } else if (j == 1 && kk == 0) {
-                                cg_mma_f16(acc_cross, dA + o, dBn + o, idesc, 1u);                                // cross += a_hi x b_lo
-                                cg_mma_f16(acc_main1, dA + o, dBh + o, idesc, 0u);                                // main1  = a_hi x b_hi
-                            } else {
-                                cg_mma_f16(acc_cross, dA + o, dBn + o, idesc2, 1u);                               // [cross|main1] += a_hi x [b_lo;b_hi]
+                            for (int kk = 0; kk < 2; ++kk)
+                                cg_mma_f16(acc_main0, dA + 2 * kk, dBn + 2 * kk, idesc2, (j != 0 || kk != 0) ? 1u : 0u);   // [main0|cross] (+)= a_hi x [b_hi;b_lo]
+                        } else {
+                            if (j == 1) {
+                                cg_mma_f16(acc_main1, dA, dBh, idesc, 0u);                                                 // main1  = a_hi x b_hi
+                                cg_mma_f16(acc_cross, dA, dBn, idesc, 1u);                                                 // cross += a_hi x b_lo
                             }
-                            cg_mma_f16(acc_cross, dA + 4 + o, dBh + o, idesc, 1u);                                // cross += a_lo x b_hi
+#pragma unroll
+                            for (int kk = 0; kk < 2; ++kk)
+                                if (j != 1 || kk != 0) cg_mma_f16(acc_cross, dA + 2 * kk, dBn + 2 * kk, idesc2, 1u);        // [cross|main1] += a_hi x [b_lo;b_hi]
                         }
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) cg_mma_f16(acc_cross, dA + 4 + 2 * kk, dBh + 2 * kk, idesc, 1u);     // cross += a_lo x b_hi
                     }
                     tc_commit(&empty[s]);
                     if (j == nact - 1) tc_commit(acc_full);
