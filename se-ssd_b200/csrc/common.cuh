@@ -174,13 +174,26 @@ static __global__ void __launch_bounds__(1024) scan_tiles_kernel(const int *__re
     if (threadIdx.x == 0 && d_total) *d_total = carry;
 }
 
-template <class Load, class Store>
+// SELF_PREFIX: tile_sums holds the raw per-tile sums of scan_reduce_kernel and every CTA adds up the sums of the tiles before it itself (a few
+// hundred ints) -- saves the one-CTA scan_tiles launch for mid-sized inputs (two launches instead of three); the last tile writes the total.
+template <class Load, class Store, bool SELF_PREFIX>
 __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(Load load, Store store, const int *__restrict__ d_n,
-                                                                  long long n_mul, const int *__restrict__ tile_sums) {
+                                                                  long long n_mul, const int *__restrict__ tile_sums, int *__restrict__ d_total) {
     __shared__ int sm[40];
     const long long n = d_n ? (long long)(*d_n) * n_mul : n_mul;
     const long long base = (long long)blockIdx.x * kScanTile;
+    if (SELF_PREFIX && n <= 0 && blockIdx.x == 0 && threadIdx.x == 0 && d_total) *d_total = 0;
     if (base >= n) return;
+    int tile_off = 0;
+    if (SELF_PREFIX) {
+        int part = 0;
+        for (int t = threadIdx.x; t < (int)blockIdx.x; t += kScanThreads) part += tile_sums[t];
+        int tot;
+        block_excl_scan(part, sm, &tot);
+        tile_off = tot;
+    } else {
+        tile_off = tile_sums[blockIdx.x];
+    }
     // thread owns kScanItems consecutive items (blocked arrangement keeps the scan order trivial)
     int v[kScanItems];
     int s = 0;
@@ -192,18 +205,20 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(Load load, Sto
         s += v[j];
     }
     int tot;
-    int ex = block_excl_scan(s, sm, &tot) + tile_sums[blockIdx.x];
+    int ex = block_excl_scan(s, sm, &tot) + tile_off;
 #pragma unroll
     for (int j = 0; j < kScanItems; ++j) {
         long long i = first + j;
         if (i < n) store(i, ex, v[j]);
         ex += v[j];
     }
+    if (SELF_PREFIX && d_total && threadIdx.x == 0 && base + kScanTile >= n) *d_total = tile_off + tot;     // the last tile
 }
 
 // Small inputs (a frame's point list, the bitmaps of the coarse levels): ONE launch of one 1024-thread CTA that walks the items in chunks with a
 // running carry -- the three-launch scan costs ~12 us of launch latency per use at batch 1, more than the work itself.
 constexpr int kScanSmallThreads = 1024;
+constexpr int kScanSelfPrefixTiles = 1024;               // up to this many tiles every apply CTA sums the preceding tile sums itself
 constexpr long long kScanSmallMax = 16 * 1024;          // capacity (items) up to which the one-CTA scan is used (measured: 5.5 k / 2.2 k bitmap words -6 us, 48 k words +30 us)
 
 template <class Load, class Store>
@@ -246,8 +261,12 @@ static inline void device_scan(Load load, Store store, const int *d_n, long long
     int tiles = (int)((cap_items + kScanTile - 1) / kScanTile);
     if (tiles < 1) tiles = 1;
     SESSD_LAUNCH((scan_reduce_kernel<Load>), tiles, kScanThreads, 0, st, load, d_n, n_mul, scratch);
+    if (tiles <= kScanSelfPrefixTiles) {
+        SESSD_LAUNCH((scan_apply_kernel<Load, Store, true>), tiles, kScanThreads, 0, st, load, store, d_n, n_mul, scratch, d_total);
+        return;
+    }
     SESSD_LAUNCH(scan_tiles_kernel, 1, 1024, 0, st, d_n, n_mul, scratch, d_total);
-    SESSD_LAUNCH((scan_apply_kernel<Load, Store>), tiles, kScanThreads, 0, st, load, store, d_n, n_mul, scratch);
+    SESSD_LAUNCH((scan_apply_kernel<Load, Store, false>), tiles, kScanThreads, 0, st, load, store, d_n, n_mul, scratch, d_total);
 }
 
 static inline size_t scan_scratch_bytes(long long cap_items) {

@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(256) enumerate_kernel(const uint2 *__restrict_
         *d_n_out = tot < max_out ? tot : max_out;
         if (tot > max_out && d_status) atomicOr(d_status, 1);
     }
+    const bool small = nwords < (1ll << 27);
     for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (long long)gridDim.x * blockDim.x) {
         const uint2 e = bitmap[w];
         unsigned int bits = e.x;
@@ -194,11 +195,19 @@ __global__ void __launch_bounds__(256) enumerate_kernel(const uint2 *__restrict_
             const int b = __ffs(bits) - 1;
             bits &= bits - 1;
             if (pos < max_out) {
-                unsigned long long lin = (unsigned long long)w * 32 + b;
-                const int x = (int)(lin % gout.W); lin /= gout.W;
-                const int y = (int)(lin % gout.H); lin /= gout.H;
-                const int z = (int)(lin % gout.D); lin /= gout.D;
-                out_coors[pos] = make_int4((int)lin, z, y, x);
+                if (small) {                               // < 2^32 cells (every level below the input grid): 32-bit divisions
+                    unsigned int lin = (unsigned int)w * 32u + (unsigned int)b;
+                    const unsigned int q1 = lin / (unsigned int)gout.W, x = lin - q1 * (unsigned int)gout.W;
+                    const unsigned int q2 = q1 / (unsigned int)gout.H, y = q1 - q2 * (unsigned int)gout.H;
+                    const unsigned int q3 = q2 / (unsigned int)gout.D, z = q2 - q3 * (unsigned int)gout.D;
+                    out_coors[pos] = make_int4((int)q3, (int)z, (int)y, (int)x);
+                } else {
+                    unsigned long long lin = (unsigned long long)w * 32 + b;
+                    const int x = (int)(lin % gout.W); lin /= gout.W;
+                    const int y = (int)(lin % gout.H); lin /= gout.H;
+                    const int z = (int)(lin % gout.D); lin /= gout.D;
+                    out_coors[pos] = make_int4((int)lin, z, y, x);
+                }
             }
             ++pos;
         }
