@@ -6,7 +6,8 @@
 * ``predict``  : decode -> sigmoid -> threshold -> IoU-rectified score -> top-k -> rotated NMS -> frustum filter -> direction fix
   -> range mask in five kernels with no host round trip (sessd_postprocess); the reference syncs to the host twice per frame
   (box_torch_ops.py:536, mg_head_sessd.py:1026) and clips polygons on one CPU thread.
-* ``loss``     : training is a "next" row; raises NotImplementedError."""
+* ``loss``     : the assembled SE-SSD head loss (supervised terms + ODIoU on the device, consistency loss against the teacher); value and
+  gradient w.r.t. the packed head tensor.  The encoder / neck backward below it is a "next" row."""
 import logging
 import math
 
@@ -20,6 +21,20 @@ from sessd_b200.runners import HeadRunner
 
 from ..builder import build_loss
 from ..registry import HEADS
+
+
+class _HeadLossFn(torch.autograd.Function):
+    """Scalar loss whose value and gradient w.r.t. the packed head tensor were both produced by the device loss kernels."""
+
+    @staticmethod
+    def forward(ctx, packed, value, grad):
+        ctx.save_for_backward(grad)
+        return value.detach().reshape(()).clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (grad,) = ctx.saved_tensors
+        return grad_out * grad, None, None
 
 
 @HEADS.register_module
@@ -127,10 +142,76 @@ class MultiGroupHead(nn.Module):
     def forward(self, x):
         return [task(x) for task in self.tasks]
 
+    def _supervision_mask(self, example, batch, device):
+        if "ssl_labeled" in example:
+            return (torch.as_tensor(example["ssl_labeled"]) == 1).to(device)
+        return torch.ones(batch, dtype=torch.bool, device=device)
+
+    def _supervised_terms(self, example, preds_dict, keys, with_odiou):
+        """One pass of the supervised terms over the supervised frames of ``preds_dict``: (values dict, loss scalar wired to the packed head
+        tensor through ``_HeadLossFn``).  ``keys`` = the example entries to read (anchors, labels, reg_targets -- or their ``_raw`` twins for
+        the teacher, mg_head_sessd.py:810-830)."""
+        k_anc, k_lab, k_reg = keys
+        packed = preds_dict["_packed"]
+        mask = self._supervision_mask(example, packed.shape[0], packed.device)
+        sel = packed if bool(mask.all()) else packed[mask]
+        ex = dict(anchors=[example[k_anc][0][mask.to(example[k_anc][0].device)]], labels=[example[k_lab][0]], reg_targets=[example[k_reg][0]])
+        out = self.loss_supervised(ex, [dict(_packed=sel.detach())], with_grad=True, with_odiou=with_odiou)
+        b = sel.shape[0]
+        labels = ex["labels"][0]
+        head = sel.detach().reshape(b, -1, sel.shape[-1])
+        box = head[..., :2 * self.box_n_dim].reshape(b, -1, self.box_n_dim)
+        tgt = ex["reg_targets"][0].float()
+        pos = labels > 0
+        w = pos.float() / pos.sum(1, keepdim=True).clamp(min=1).float()
+        d = torch.cat([box[..., :-1] - tgt[..., :-1], torch.sin(box[..., -1:]) * torch.cos(tgt[..., -1:]) - torch.cos(box[..., -1:]) * torch.sin(tgt[..., -1:])], -1)
+        elem = (self._smooth_l1(d, float(self.loss_reg._sigma)) * w[..., None]).sum((0, 1)) / b      # analysis only (:752)
+        value = out["cls_loss_reduced"] + out["dir_loss_reduced"] + out["iou_pred_loss"]
+        if with_odiou:
+            value = value + out["ious_loss"]
+        grad = out["grad_head"]
+        if sel is not packed:                                         # scatter the supervised frames' gradient back into the full batch
+            full = torch.zeros_like(packed)
+            full[mask] = grad
+            grad = full
+        out["loc_loss_elem"] = [e.cpu() for e in elem]
+        out["num_pos"], out["num_neg"] = (labels > 0)[0].sum(), (labels == 0)[0].sum()
+        return out, _HeadLossFn.apply(packed, value, grad)
+
     def loss(self, example, preds_dicts, preds_ema=None, **kwargs):
-        raise NotImplementedError("MultiGroupHead.loss: the assembled SE-SSD loss needs the backward of the encoder / neck (a 'next' row); "
-                                  "its terms are available separately: loss_supervised() (focal cls, sin-difference smooth-L1, direction CE, "
-                                  "IoU prediction, ODIoU) and consistency_loss() (student / teacher)")
+        """The SE-SSD head loss (reference mg_head_sessd.py:706-808), single-task car head: ``loss`` = focal cls + ODIoU box loss +
+        direction CE + IoU-prediction smooth-L1 on the supervised frames (the smooth-L1 box term is reported, not summed, as in the
+        reference :781), plus ``consistency_loss`` against the teacher's predictions (added by the trainer with the ramp-up weight,
+        trainer_sessd.py:267) and the teacher's own supervised terms on the raw targets (``*_ema``, :810-884).  Values and the gradient
+        w.r.t. the packed head tensor come from one device pass (csrc/headloss.cu, odiou.cu); ``loss`` is a torch scalar whose backward
+        hands that gradient to ``preds_dicts[0]['_packed']``'s graph, and ``consistency_loss`` is differentiable through
+        ``box_preds / cls_preds / iou_preds`` by torch autograd.  Returns the reference's key -> [per-task value] dict.  The backward of the
+        encoder / neck below the head tensor is a 'next' row: a head tensor produced by ``Head.forward`` carries no graph."""
+        if len(preds_dicts) != 1:
+            raise NotImplementedError("the fused loss kernels are built for the single-task (car) head")
+        merged = {}
+        if preds_ema is not None:
+            merged["consistency_loss"] = [self.consistency_loss(preds_dicts, preds_ema, example)]
+        out, loss = self._supervised_terms(example, preds_dicts[0], ("anchors", "labels", "reg_targets"), with_odiou=True)
+        cpu = lambda v: v.detach().cpu()                                                     # noqa: E731
+        merged.update(loss=[loss], cls_loss_reduced=[cpu(out["cls_loss_reduced"])], loc_loss_reduced=[cpu(out["loc_loss_reduced"])],
+                      dir_loss_reduced=[cpu(out["dir_loss_reduced"])], iou_pred_loss=[cpu(out["iou_pred_loss"])],
+                      loc_loss_elem=[out["loc_loss_elem"]], cls_pos_loss=[cpu(out["cls_pos_loss"])], cls_neg_loss=[cpu(out["cls_neg_loss"])],
+                      ious_loss=[cpu(out["ious_loss"])], num_pos=[out["num_pos"]], num_neg=[out["num_neg"]])
+        if preds_ema is not None:
+            for k, v in self.get_model_ema_loss(example, preds_ema).items():
+                merged[k] = [v[0]]
+        return merged
+
+    def get_model_ema_loss(self, example, preds_dicts):
+        """The teacher's supervised terms on the un-augmented targets (``labels_raw`` / ``reg_targets_raw`` / ``anchors_raw``), reported only
+        (reference mg_head_sessd.py:810-890; no ODIoU term there)."""
+        out, loss = self._supervised_terms(example, preds_dicts[0], ("anchors_raw", "labels_raw", "reg_targets_raw"), with_odiou=False)
+        cpu = lambda v: v.detach().cpu()                                                     # noqa: E731
+        return dict(loss_ema=[cpu(loss)], cls_loss_reduced_ema=[cpu(out["cls_loss_reduced"])], loc_loss_reduced_ema=[cpu(out["loc_loss_reduced"])],
+                    dir_loss_reduced_ema=[cpu(out["dir_loss_reduced"])], iou_pred_loss_ema=[cpu(out["iou_pred_loss"])],
+                    loc_loss_elem_ema=[out["loc_loss_elem"]], cls_pos_loss_ema=[cpu(out["cls_pos_loss"])],
+                    cls_neg_loss_ema=[cpu(out["cls_neg_loss"])], num_pos_ema=[out["num_pos"]], num_neg_ema=[out["num_neg"]])
 
     # ------------------------------------------------------------------------------------------------------------------ teacher / student
     @staticmethod
