@@ -99,6 +99,18 @@ struct P2Item { int cls, n0, b, u0, v0, ntaps; };
 #else
 #define P2_WAIT(slot, stmt) stmt
 #endif
+// 256-bit global accesses (sm_100: LDG / STG .256): one full 32-byte sector per lane, half the LSU wavefronts of two 16-byte accesses
+__device__ __forceinline__ void p2_st256(void *ptr, const uint32_t *a, const uint32_t *b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(ptr), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]),
+                 "r"(b[1]), "r"(b[2]), "r"(b[3])
+                 : "memory");
+}
+__device__ __forceinline__ void p2_ld256(const void *ptr, float *r) {
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+                 : "l"(ptr));
+}
+
 template <int CS>
 __device__ __forceinline__ P2Item p2_decode(const P2Params &p, int g, int crank) {
     P2Item it;
@@ -356,6 +368,7 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
         const float s_out = pow2_scale_for_bound(bound);
         if (blockIdx.x == 0 && warp == 3 && lane == 0 && p.out_info) p.out_info[1] = s_out;
         float vmax = 0.f;
+        const bool wide = (p.cout & 15) == 0 && (p.out_plane_stride & 15) == 0;     // plane rows are 32-byte aligned per 16-channel group
         int iter = 0;
         for (int g = cluster_id; g < p.total; g += nclusters, ++iter) {
             const P2Item it = p2_decode<CS>(p, g, (int)crank);
@@ -400,6 +413,7 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
                 const int ou = gu * p.out_stride + p.cls_off_u[it.cls], ov = gv * p.out_stride + p.cls_off_v[it.cls];
                 const int oy = p.u_is_x ? ov : ou, ox = p.u_is_x ? ou : ov;
                 const size_t opix = ((size_t)it.b * p.out_h + (size_t)oy) * p.out_w + (size_t)ox;
+                uint32_t hprev[4] = {0u, 0u, 0u, 0u}, lprev[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
                 for (int i = 0; i < 64; i += 8) {
                     const int n = it.n0 + half * ncol + i;
@@ -419,15 +433,14 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
                             for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
                         }
                         if (resid) {
-                            const float4 r0 = *reinterpret_cast<const float4 *>(resid + off), r1 = *reinterpret_cast<const float4 *>(resid + off + 4);
-                            o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w; o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
+                            float rr[8];
+                            p2_ld256(resid + off, rr);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o[j] += rr[j];
                         }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) vmax = fmaxf(vmax, fabsf(o[j]));
-                        if (out_f32) {
-                            *reinterpret_cast<float4 *>(out_f32 + off) = make_float4(o[0], o[1], o[2], o[3]);
-                            *reinterpret_cast<float4 *>(out_f32 + off + 4) = make_float4(o[4], o[5], o[6], o[7]);
-                        }
+                        if (out_f32) p2_st256(out_f32 + off, reinterpret_cast<const uint32_t *>(o), reinterpret_cast<const uint32_t *>(o) + 4);
                         if (out_planes) {
                             __align__(16) __half2 hi[4], lo[4];
 #pragma unroll
@@ -437,8 +450,16 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
                                 const float2 f = __half22float2(hi[j]);
                                 lo[j] = __floats2half2_rn(x0 - f.x, x1 - f.y);
                             }
-                            *reinterpret_cast<uint4 *>(out_planes + off) = *reinterpret_cast<const uint4 *>(hi);
-                            *reinterpret_cast<uint4 *>(out_planes + p.out_plane_stride + off) = *reinterpret_cast<const uint4 *>(lo);
+                            if (!wide) {
+                                *reinterpret_cast<uint4 *>(out_planes + off) = *reinterpret_cast<const uint4 *>(hi);
+                                *reinterpret_cast<uint4 *>(out_planes + p.out_plane_stride + off) = *reinterpret_cast<const uint4 *>(lo);
+                            } else if ((i & 8) == 0) {       // first half of a 16-channel group: keep it for the 32-byte store
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) { hprev[j] = *reinterpret_cast<const uint32_t *>(&hi[j]); lprev[j] = *reinterpret_cast<const uint32_t *>(&lo[j]); }
+                            } else {
+                                p2_st256(out_planes + off - 8, hprev, reinterpret_cast<const uint32_t *>(hi));
+                                p2_st256(out_planes + p.out_plane_stride + off - 8, lprev, reinterpret_cast<const uint32_t *>(lo));
+                            }
                         }
                     }
                 }

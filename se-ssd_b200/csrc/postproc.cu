@@ -293,10 +293,14 @@ __device__ int greedy_scan(const unsigned long long *__restrict__ mask, int m, i
     const int nblk = (m + 63) / 64;
     for (int j = threadIdx.x; j < col_blocks; j += blockDim.x) remv[j] = 0;
     if (threadIdx.x == 0) s_misc[0] = 0;
+    // the diagonal word of row (64 b + t) is fetched one block ahead, so its L2 round trip overlaps the previous block's scan
+    unsigned long long dcur = 0;
+    if ((int)threadIdx.x < min(64, m)) dcur = mask[(size_t)threadIdx.x * col_blocks];
     __syncthreads();
     for (int b = 0; b < nblk; ++b) {
         const int rows = min(64, m - b * 64);
-        if ((int)threadIdx.x < rows) diag[threadIdx.x] = mask[(size_t)(b * 64 + threadIdx.x) * col_blocks + b];
+        if ((int)threadIdx.x < rows) diag[threadIdx.x] = dcur;
+        if (b + 1 < nblk && (int)threadIdx.x < min(64, m - (b + 1) * 64)) dcur = mask[(size_t)((b + 1) * 64 + threadIdx.x) * col_blocks + b + 1];
         __syncthreads();
         if (threadIdx.x == 0) {
             unsigned long long cur = remv[b], kb = 0;
@@ -310,12 +314,12 @@ __device__ int greedy_scan(const unsigned long long *__restrict__ mask, int m, i
         const unsigned long long kb = *s_kb;
         if (s_misc[0] >= max_keep) break;
         for (int j = b + 1 + threadIdx.x; j < nblk; j += blockDim.x) {
-            unsigned long long acc = remv[j], bits = kb;
-            while (bits) {
-                const int t = __ffsll((long long)bits) - 1;
-                bits &= bits - 1;
-                acc |= mask[(size_t)(b * 64 + t) * col_blocks + j];
-            }
+            // predicated, unrolled: the loads of all kept rows are in flight together (one L2 round trip per block, not one per kept row)
+            unsigned long long acc = remv[j];
+            const unsigned long long *col = mask + (size_t)(b * 64) * col_blocks + j;
+#pragma unroll 16
+            for (int t = 0; t < 64; ++t)
+                if ((kb >> t) & 1ull) acc |= col[(size_t)t * col_blocks];
             remv[j] = acc;
         }
         __syncthreads();
