@@ -99,18 +99,6 @@ struct P2Item { int cls, n0, b, u0, v0, ntaps; };
 #else
 #define P2_WAIT(slot, stmt) stmt
 #endif
-// 256-bit global accesses (sm_100: LDG / STG .256): one full 32-byte sector per lane, half the LSU wavefronts of two 16-byte accesses
-__device__ __forceinline__ void p2_st256(void *ptr, const uint32_t *a, const uint32_t *b) {
-    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(ptr), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]),
-                 "r"(b[1]), "r"(b[2]), "r"(b[3])
-                 : "memory");
-}
-__device__ __forceinline__ void p2_ld256(const void *ptr, float *r) {
-    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
-                 : "l"(ptr));
-}
-
 template <int CS>
 __device__ __forceinline__ P2Item p2_decode(const P2Params &p, int g, int crank) {
     P2Item it;
@@ -155,6 +143,8 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
     uint32_t *s_aoff = tmem_slot + 2;                    // [4 classes][9 taps]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) prefetch_tensormap(&map_a);    // descriptor fetches overlap barrier init / TMEM allocation / cluster syncs
+    if (threadIdx.x == 32) prefetch_tensormap(&map_b);
 #ifdef SESSD_P2_PROFILE
     long long p2_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // per-thread wait counters, written once at the end
     const long long p2_t0 = clock64();                   // timeline (second [ctas][8] block of dbg): 0 setup done, 1 MMA loop start, 2 MMA loop end,
@@ -434,13 +424,13 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
                         }
                         if (resid) {
                             float rr[8];
-                            p2_ld256(resid + off, rr);
+                            ldg256(resid + off, rr);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) o[j] += rr[j];
                         }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) vmax = fmaxf(vmax, fabsf(o[j]));
-                        if (out_f32) p2_st256(out_f32 + off, reinterpret_cast<const uint32_t *>(o), reinterpret_cast<const uint32_t *>(o) + 4);
+                        if (out_f32) stg256(out_f32 + off, reinterpret_cast<const uint32_t *>(o), reinterpret_cast<const uint32_t *>(o) + 4);
                         if (out_planes) {
                             __align__(16) __half2 hi[4], lo[4];
 #pragma unroll
@@ -457,8 +447,8 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) { hprev[j] = *reinterpret_cast<const uint32_t *>(&hi[j]); lprev[j] = *reinterpret_cast<const uint32_t *>(&lo[j]); }
                             } else {
-                                p2_st256(out_planes + off - 8, hprev, reinterpret_cast<const uint32_t *>(hi));
-                                p2_st256(out_planes + p.out_plane_stride + off - 8, lprev, reinterpret_cast<const uint32_t *>(lo));
+                                stg256(out_planes + off - 8, hprev, reinterpret_cast<const uint32_t *>(hi));
+                                stg256(out_planes + p.out_plane_stride + off - 8, lprev, reinterpret_cast<const uint32_t *>(lo));
                             }
                         }
                     }

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(kCgThreads, DEEP ? 1 : 2) spconv_cg_kernel(con
     long long cg_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};      // per-thread counters, written once at the end (no memory traffic in the loops)
 #endif
     CG_T(t_kernel);
+    if (threadIdx.x == 8 * 32) prefetch_tensormap(&map_w);       // the weight-TMA warp's first load finds the descriptor cached
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char *tiles = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -381,6 +382,7 @@ __global__ void __launch_bounds__(kCgThreads, DEEP ? 1 : 2) spconv_cg_kernel(con
             }
             if (r < rows) {
                 const size_t orow = (size_t)(row0 + r);
+                uint32_t hprev[4] = {0u, 0u, 0u, 0u}, lprev[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
                 for (int i = 0; i < kNcol; i += 8) {
                     const int n = hcol * kNcol + i;
@@ -399,11 +401,7 @@ __global__ void __launch_bounds__(kCgThreads, DEEP ? 1 : 2) spconv_cg_kernel(con
                     }
 #pragma unroll
                     for (int t = 0; t < 8; ++t) vmax = fmaxf(vmax, fabsf(o[t]));
-                    if (a.out_f32) {
-                        float *dst = a.out_f32 + orow * COUT + n;
-                        *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-                        *reinterpret_cast<float4 *>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
-                    }
+                    if (a.out_f32) stg256(a.out_f32 + orow * COUT + n, reinterpret_cast<const uint32_t *>(o), reinterpret_cast<const uint32_t *>(o) + 4);
                     if (a.out_planes) {
                         __align__(16) __half2 hi[4], lo[4];
 #pragma unroll
@@ -413,9 +411,15 @@ __global__ void __launch_bounds__(kCgThreads, DEEP ? 1 : 2) spconv_cg_kernel(con
                             const float2 f = __half22float2(hi[t]);
                             lo[t] = __floats2half2_rn(x0 - f.x, x1 - f.y);
                         }
+                        // 32-byte stores (one full sector per lane): the first 8 channels of a 16-channel group wait for the second
                         __half *dst = a.out_planes + orow * (2 * C::kCPO) + n;
-                        *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hi);
-                        *reinterpret_cast<uint4 *>(dst + C::kCPO) = *reinterpret_cast<const uint4 *>(lo);
+                        if ((i & 8) == 0) {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) { hprev[t] = *reinterpret_cast<const uint32_t *>(&hi[t]); lprev[t] = *reinterpret_cast<const uint32_t *>(&lo[t]); }
+                        } else {
+                            stg256(dst - 8, hprev, reinterpret_cast<const uint32_t *>(hi));
+                            stg256(dst - 8 + C::kCPO, lprev, reinterpret_cast<const uint32_t *>(lo));
+                        }
                     }
                 }
             }

@@ -89,6 +89,23 @@ __device__ __forceinline__ uint32_t cluster_cta_rank() {
     return r;
 }
 
+// 256-bit global accesses (sm_100: LDG / STG .256): one full 32-byte sector per lane, half the LSU wavefronts of two 16-byte accesses
+__device__ __forceinline__ void stg256(void *ptr, const uint32_t *a, const uint32_t *b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(ptr), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]),
+                 "r"(b[1]), "r"(b[2]), "r"(b[3])
+                 : "memory");
+}
+__device__ __forceinline__ void ldg256(const void *ptr, float *r) {
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+                 : "l"(ptr));
+}
+
+// bring a kernel-parameter tensor map into the descriptor cache before the first TMA that uses it (hides the descriptor fetch behind the setup)
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *m) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+
 // true in exactly one lane of a fully converged warp; the code it guards stays in warp-uniform control flow
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
