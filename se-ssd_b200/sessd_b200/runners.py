@@ -600,4 +600,4 @@ class SSFAPlanesRunner:
         def launch():
             self._conv(name, "x0", "b0b", H, H, 128, 128)
 
-        return launch, "bev_conv_p2_kernel (tcgen05 kind::f16 from pre-split fp16 planes, two-term split, weight multicast)"
+        return launch, "bev_conv_p2_kernel (tcgen05 kind::f16 from pre-split fp16 planes, two-term split, CTA pairs: cta_group::2)"
