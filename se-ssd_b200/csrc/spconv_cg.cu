@@ -178,6 +178,11 @@ __global__ void __launch_bounds__(kCgThreads, DEEP ? 1 : 2) spconv_cg_kernel(con
         {
             const unsigned int *rec = a.tiles + (size_t)tile * (size_t)a.tile_stride;
             const int c = (int)__ldg(rec + lane);                        // every warp ranks the 32 counts itself: no extra block-wide sync
+            // the first list entries are requested together with the counts (one L2 round trip instead of two for tiles of <= 1280 pairs;
+            // the record is 160 + 128 kvol words long, so the speculative reads stay inside it)
+            unsigned int spec[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) spec[u] = (tid + u * kCgThreads < 128 * kvol) ? __ldg(rec + 160 + tid + u * kCgThreads) : 0u;
             const int incl = warp_incl_scan(c, lane);
             const int total = __shfl_sync(0xffffffffu, incl, 31);
             if (warp == 0) {
@@ -188,7 +193,10 @@ __global__ void __launch_bounds__(kCgThreads, DEEP ? 1 : 2) spconv_cg_kernel(con
                 if (lane == 0) *s_nact = __popc(m);
             }
             if (tid < kvol * 4) s_valid[tid] = __ldg(rec + 32 + tid);
-            for (int e = tid; e < total; e += kCgThreads) s_list[e] = __ldg(rec + 160 + e);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (tid + u * kCgThreads < total) s_list[tid + u * kCgThreads] = spec[u];
+            for (int e = tid + 4 * kCgThreads; e < total; e += kCgThreads) s_list[e] = __ldg(rec + 160 + e);
         }
         __syncthreads();
         const int nact = *s_nact;
@@ -333,16 +341,23 @@ __global__ void __launch_bounds__(kCgThreads, DEEP ? 1 : 2) spconv_cg_kernel(con
                 }
                 const int n = s_cnt[k];
                 const uint32_t *lst = s_list + s_off[k];
-                for (int i = slot; i < n; i += kRowsPerPass) {
-                    const uint32_t e = lst[i];
+                auto copy_row = [&](uint32_t e) {
                     const uint32_t r = e & 127u;
                     const size_t src = (size_t)(e >> 7);
                     if constexpr (C::kWide)
                         cg_cp_async16(a_base + (uint32_t)half * (kCgBM * 128) + r * 128u + (((uint32_t)cc ^ (r & 7u)) << 4),
-                                          a.planes + src * 128 + half * 64 + cc * 8);
+                                      a.planes + src * 128 + half * 64 + cc * 8);
                     else
                         cg_cp_async16(a_base + r * 128u + (((uint32_t)cc ^ (r & 7u)) << 4), a.planes + src * 64 + cc * 8);
+                };
+                // four list entries per round: the shared-memory reads of a round are in flight together (the copies are `asm volatile`
+                // with a memory clobber, so the compiler keeps every read behind the previous copy otherwise: one LDS latency per row)
+                int i = slot;
+                for (; i + 3 * kRowsPerPass < n; i += 4 * kRowsPerPass) {
+                    const uint32_t e0 = lst[i], e1 = lst[i + kRowsPerPass], e2 = lst[i + 2 * kRowsPerPass], e3 = lst[i + 3 * kRowsPerPass];
+                    copy_row(e0); copy_row(e1); copy_row(e2); copy_row(e3);
                 }
+                for (; i < n; i += kRowsPerPass) copy_row(lst[i]);
                 asm volatile("cp.async.wait_all;\n" ::: "memory");
                 cg_fence_proxy_async();                                  // copies and clears (generic proxy) -> visible to the tensor core (measured: free)
                 __syncwarp();
