@@ -11,7 +11,7 @@
 //     and stay there: no per-offset staging, no block-wide synchronisation in the main loop;
 //   * per tile of 128 output rows the neighbour table is staged in shared memory; lane k of a warp holds nbr[row][k], a ballot gives
 //     the row's valid offsets, and the warp walks them in ascending k: the input row is one coalesced 16-128 byte segment (lane c
-//     holds channel c; the rows of up to 6 pairs are in flight together), acc[cout] += in[c] * W[k][c][cout] with the input value broadcast
+//     holds channel c; the first pair of each of the warp's 4 rows is requested up front, further pairs 4 at a time), acc[cout] += in[c] * W[k][c][cout] with the input value broadcast
 //     by warp shuffle and the weights read as consecutive lanes = consecutive output channels (conflict-free);
 //   * epilogue per row: folded BatchNorm1d scale / shift + ReLU, coalesced row store, running abs-max of the output (feeds the fp16
 //     split of the next tensor-core layer).
@@ -28,13 +28,13 @@ constexpr int kRwWarps = 32;
 constexpr int kRwThreads = kRwWarps * 32;
 constexpr int kRwRpw = kRwRows / kRwWarps;          // rows per warp
 constexpr int kRwMaxK = 27;
-constexpr int kRwBatch = 6;                         // input rows in flight per warp
+constexpr int kRwBatch = 4;                         // input rows in flight per warp beyond the prefetched first pair of each row
 
 template <int CIN, int COUT>
 struct RwCfg {
     static constexpr int kJ = (COUT + 31) / 32;                  // output channels per lane
     static constexpr int kWFloats = CIN * COUT;                  // per kernel offset
-    static constexpr size_t smem(int kvol) { return (size_t)kvol * kWFloats * 4 + (size_t)kRwRows * kRwMaxK * 4 + 64; }
+    static constexpr size_t smem(int kvol) { return (size_t)kvol * kWFloats * 4 + 2 * (size_t)kRwRows * kRwMaxK * 4 + 64; }   // weights + two neighbour tables
 };
 
 template <int CIN, int COUT>
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kRwThreads, 1) spconv_rows_kernel(const float 
     using C = RwCfg<CIN, COUT>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *s_w = reinterpret_cast<float *>(smem_raw);                              // [kvol][CIN][COUT], resident for the CTA's lifetime
-    int *s_nbr = reinterpret_cast<int *>(s_w + (size_t)kvol * C::kWFloats);        // [128][kvol]
+    int *s_nbr = reinterpret_cast<int *>(s_w + (size_t)kvol * C::kWFloats);        // [2][128][kvol]
 
     const int n_out = min(*d_n_out, max_out);
     const int tiles = (n_out + kRwRows - 1) / kRwRows;
@@ -76,53 +76,86 @@ __global__ void __launch_bounds__(kRwThreads, 1) spconv_rows_kernel(const float 
         if (blockIdx.x == 0 && tid == 0) amax_out[1] = s_out;
     }
 
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    // the tile's neighbour table is contiguous in global memory; the NEXT tile's table is copied (cp.async) while this one is processed
+    auto stage_nbr = [&](int t, int b) {
+        const int r0 = t * kRwRows;
+        const int nent = min(kRwRows, n_out - r0) * kvol;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_nbr + b * (kRwRows * kRwMaxK));
+        const int *src = nbr + (size_t)r0 * kvol;
+        for (int e = tid; e < nent; e += kRwThreads)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst + 4u * (uint32_t)e), "l"(src + e) : "memory");
+    };
+    int buf = 0;
+    stage_nbr(blockIdx.x, 0);
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, buf ^= 1) {
         const int row0 = tile * kRwRows;
         const int rows = min(kRwRows, n_out - row0);
-        __syncthreads();                      // previous tile's s_nbr fully consumed (and s_w written, first iteration)
-        const int nent = rows * kvol;         // the tile's neighbour table is contiguous in global memory
-        for (int e = tid; e < nent; e += kRwThreads) s_nbr[e] = __ldg(&nbr[(size_t)row0 * kvol + e]);
-        __syncthreads();
-        // each warp walks the valid (row, offset) pairs of its rows; no block-wide synchronisation inside
-#pragma unroll 1
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+        __syncthreads();                      // this tile's table landed; every warp is done with the other buffer (and s_w is written, first iteration)
+        if (tile + (int)gridDim.x < tiles) stage_nbr(tile + (int)gridDim.x, buf ^ 1);
+        const int *s_nbr_t = s_nbr + buf * (kRwRows * kRwMaxK);
+        // each warp walks the valid (row, offset) pairs of its rows; no block-wide synchronisation inside.  The input row of the FIRST pair
+        // of each of the warp's rows is requested up front (on these layers most rows have one to three pairs: with one row at a time the
+        // warp sat through one L2 / HBM round trip per row)
+        int mine[kRwRpw];                                                        // lane k holds nbr[row][k]
+        unsigned int m[kRwRpw];
+        float v0[kRwRpw];
+#pragma unroll
+        for (int r = 0; r < kRwRpw; ++r) {
+            const int row = warp * kRwRpw + r;
+            mine[r] = (row < rows && lane < kvol) ? s_nbr_t[row * kvol + lane] : -1;
+            m[r] = __ballot_sync(0xffffffffu, mine[r] >= 0);
+            v0[r] = 0.f;
+            if (m[r]) {                                                          // warp-uniform
+                const int src = __shfl_sync(0xffffffffu, mine[r], __ffs(m[r]) - 1);
+                if (lane < CIN) v0[r] = __ldg(&in_feat[(size_t)src * CIN + lane]);
+            }
+        }
+#pragma unroll
         for (int r = 0; r < kRwRpw; ++r) {
             const int row = warp * kRwRpw + r;
             if (row >= rows) break;                                              // warp-uniform
-            const int mine = (lane < kvol) ? s_nbr[row * kvol + lane] : -1;      // lane k holds nbr[row][k]
-            unsigned int m = __ballot_sync(0xffffffffu, mine >= 0);
             float acc[C::kJ];
 #pragma unroll
             for (int j = 0; j < C::kJ; ++j) acc[j] = 0.f;
-            // up to kRwBatch pairs at a time: all their input rows are requested back to back (independent loads), then multiplied
-            while (m) {
+            auto mac = [&](int k, float v) {                                     // acc[cout] += in[c] * W[k][c][cout], c ascending
+                const float *sw = s_w + (size_t)k * C::kWFloats;
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) {
+                    const float a = __shfl_sync(0xffffffffu, v, c);
+#pragma unroll
+                    for (int j = 0; j < C::kJ; ++j) {
+                        const int co = lane + 32 * j;
+                        const float wv = sw[c * COUT + (COUT >= 32 ? co : (co & (COUT - 1)))];
+                        acc[j] = fmaf(a, wv, acc[j]);
+                    }
+                }
+            };
+            unsigned int mr = m[r];
+            if (mr) {
+                mac(__ffs(mr) - 1, v0[r]);
+                mr &= mr - 1;
+            }
+            // the row's remaining pairs, up to kRwBatch at a time: their input rows are requested back to back, then multiplied (ascending k)
+            while (mr) {
                 int ks[kRwBatch];
                 float vs[kRwBatch];
 #pragma unroll
                 for (int i = 0; i < kRwBatch; ++i) {
                     ks[i] = -1;
                     vs[i] = 0.f;
-                    if (m) {                                                     // warp-uniform
-                        const int k = __ffs(m) - 1;
-                        m &= m - 1;
+                    if (mr) {                                                    // warp-uniform
+                        const int k = __ffs(mr) - 1;
+                        mr &= mr - 1;
                         ks[i] = k;
-                        const int src = __shfl_sync(0xffffffffu, mine, k);
+                        const int src = __shfl_sync(0xffffffffu, mine[r], k);
                         if (lane < CIN) vs[i] = __ldg(&in_feat[(size_t)src * CIN + lane]);
                     }
                 }
 #pragma unroll
                 for (int i = 0; i < kRwBatch; ++i) {
                     if (ks[i] < 0) break;
-                    const float *sw = s_w + (size_t)ks[i] * C::kWFloats;
-#pragma unroll
-                    for (int c = 0; c < CIN; ++c) {
-                        const float a = __shfl_sync(0xffffffffu, vs[i], c);
-#pragma unroll
-                        for (int j = 0; j < C::kJ; ++j) {
-                            const int co = lane + 32 * j;
-                            const float wv = sw[c * COUT + (COUT >= 32 ? co : (co & (COUT - 1)))];
-                            acc[j] = fmaf(a, wv, acc[j]);
-                        }
-                    }
+                    mac(ks[i], vs[i]);
                 }
             }
             // epilogue: folded BatchNorm1d (eval) + ReLU, one coalesced segment per row
