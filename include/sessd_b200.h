@@ -208,9 +208,6 @@ int sessd_bev_split_planes(const float *d_x, long long n, float *d_info, void *d
 /* sessd_bev_conv_p2 / sessd_bev_deconv_p2: 0 (default) = CTA pairs (tcgen05 cta_group::2: one MMA spans two SMs, each CTA stages half of
  * every weight tile) for the layers with long K loops, single CTAs for the 1x1 convs; 1 / 2 = force single CTAs / pairs */
 void sessd_set_p2_cluster(int ctas_per_cluster);
-/* 1 (default): 1x1 convs (one block of output channels, <= 12 weight stages) load their weight stages once per CTA and keep them in shared
- * memory; 0: stream them per item like the 3x3 layers */
-void sessd_set_p2_wres(int on);
 /* dense() (scn.py:184-187) straight into the planes the neck reads: d_amax = abs-max of the feature rows, d_info[2] <- {abs-max, S} */
 int sessd_sparse_to_dense_planes(const float *d_feat, int max_rows, const void *d_bitmap_index, int channels, sessd_grid grid,
                                  const float *d_amax, float *d_info, void *d_planes, void *stream);

@@ -56,7 +56,6 @@ struct P2Params {
     int copy_bytes, patch_bytes, npatch;                  // bytes of one copy plane, of one patch buffer (ncopies x 2 planes), 1 or 2 buffers
     int relu, n_tile, nblocks;
     int bstages, bstage_bytes;         // weight-stage ring: count and bytes per stage
-    int wres, bring;                   // 1: the layer's weight stages stay resident in shared memory (loaded once per CTA); bytes of the ring
     int tiles_u, tiles_v, tiles, tgroups, total;          // pixel tiles, tile groups (CS tiles each), work items = nclass * nblocks * tgroups
     int cls_order[4];
     const float *in_info;              // [2] = {abs-max of the input tensor, scale S_in of its planes}
@@ -136,7 +135,7 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
                                                                    __half *__restrict__ out_planes, P2Params p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *tiles = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    unsigned char *patches = tiles + p.bring;
+    unsigned char *patches = tiles + kP2BRing;
     uint64_t *bars = (uint64_t *)(patches + p.npatch * p.patch_bytes);
     uint64_t *patch_full = bars, *patch_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 4 + kP2MaxBStages;
     uint64_t *acc_full = bars + 4 + 2 * kP2MaxBStages, *acc_free = acc_full + 1;
@@ -225,7 +224,6 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
         uint32_t bph = 0, par = 0;
         const int rows = p.n_tile / CS;
         for (int g = cluster_id; g < p.total; g += nclusters) {
-            if (p.wres && g != cluster_id) break;        // resident weights (1x1 convs): every item reads the stages the first one loaded
             const P2Item it = p2_decode<CS>(p, g, (int)crank);
             const int n0 = it.n0 + (kPair ? (int)crank * rows : 0);
             for (int cc = 0; cc < nchunks; ++cc)
@@ -286,7 +284,7 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
                 const uint32_t pbase = patch_lo + (uint32_t)pb * patch_sz;
 #pragma unroll 1
                 for (int tap = 0; tap < ntaps; ++tap, ++lbj) {
-                    if (!p.wres || iter == 0) P2_WAIT(2, mbar_wait(&b_full[S], bph));
+                    P2_WAIT(2, mbar_wait(&b_full[S], bph));
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t da_hi = desc_hi | (uint64_t)(pbase + aoff[tap]);
@@ -331,7 +329,7 @@ __global__ void __launch_bounds__(kP2Threads, 1) bev_conv_p2_kernel(const __grid
                         p2_mma_f16(d2, da_hi + 2, dcat + 2, idesc2, 1);
                         p2_mma_f16(acc_cross, da_lo, dbhi, idesc1, 1);                    // cross += a_lo x b_hi
                         p2_mma_f16(acc_cross, da_lo + 2, dbhi + 2, idesc1, 1);
-                        if (!p.wres) tc_commit(&b_empty[S]);
+                        tc_commit(&b_empty[S]);
                         if (tap == ntaps - 1) tc_commit(&patch_empty[pb]);
                         if (lbj == nbj - 1) tc_commit(acc_full);
                         }
@@ -516,7 +514,6 @@ static int encode_map_nd(CUtensorMap *m, const void *base, int rank, const cuuin
 }
 
 static long long *g_p2_dbg = nullptr;
-static int g_p2_wres = 1;         // 1: 1x1 convs keep their weight stages resident in shared memory (sessd_set_p2_wres)
 static int g_p2_cluster = 0;      // 0: CTA pairs (cta_group::2) for the layers with long K loops, single CTAs for the rest; 1 / 2: force
 
 // taps: per class (dy, dx, weight tap); fills the geometry of p and launches
@@ -573,23 +570,16 @@ static int launch_p2(const void *d_in_planes, int in_h, int in_w, const float *d
     }
     p.copy_bytes = p.rows_v * kP2TileU * 64;
     p.patch_bytes = p.ncopies * 2 * p.copy_bytes;
+    const int fixed = kP2BRing + 1024 + 512;
+    p.npatch = (fixed + 2 * p.patch_bytes <= kP2MaxSmem) ? 2 : 1;
+    const int smem = fixed + p.npatch * p.patch_bytes;
+    if (smem > kP2MaxSmem) return SESSD_EINVAL;
     // CTA pairs halve the weight bytes every SM pulls from the L2 and stages in shared memory (the two resources that bound the 3x3
     // layers); the short K loops (1x1 convs: 4-8 tap-chunks per item) are dominated by per-item latencies, where a pair only adds
     // cross-CTA handshakes (measured: 3x3 128->128 45.9 -> 39.7 us, 3x3 256->256 65.5 -> 51.2 us; 1x1 128->128 22.6 -> 23.6 us)
     int kloop = 0;
     for (int c = 0; c < p.nclass; ++c) kloop = max(kloop, cls[c].n * (p.cin / kP2Chunk));
     const int cs = (g_p2_cluster == 2 || (g_p2_cluster == 0 && kloop >= 16)) ? 2 : 1;
-    // 1x1 convs (one class, one block of output channels, a handful of stages): the whole weight set of the layer fits the ring, so it is
-    // loaded once per CTA and stays -- these layers move 64 KB of weights + 64 KB of activations in and 64 KB out per 128-pixel item and
-    // sit on the L2 <-> SM fabric (~24 B/clk/SM), not on the tensor pipe
-    p.bstage_bytes = 2 * (n_tile / cs) * 64;
-    p.wres = (g_p2_wres && cs == 1 && p.nclass == 1 && cout_pad == n_tile && kloop <= kP2MaxBStages &&
-              kloop * p.bstage_bytes + 1024 + 512 + 2 * p.patch_bytes <= kP2MaxSmem) ? 1 : 0;
-    p.bring = p.wres ? kloop * p.bstage_bytes : kP2BRing;
-    const int fixed = p.bring + 1024 + 512;
-    p.npatch = (fixed + 2 * p.patch_bytes <= kP2MaxSmem) ? 2 : 1;
-    const int smem = fixed + p.npatch * p.patch_bytes;
-    if (smem > kP2MaxSmem) return SESSD_EINVAL;
     CUtensorMap map_a, map_b;
     {   // planes [2][B][H][W][C] fp16 viewed as {C, U, V, B, plane}
         const cuuint64_t row_w = (cuuint64_t)p.cin * 2, row_h = (cuuint64_t)in_w * p.cin * 2;
@@ -617,7 +607,8 @@ static int launch_p2(const void *d_in_planes, int in_h, int in_w, const float *d
         attr_done = true;
     }
     p.n_tile = n_tile;
-    p.bstages = p.wres ? kloop : (kP2BRing / p.bstage_bytes < kP2MaxBStages ? kP2BRing / p.bstage_bytes : kP2MaxBStages);
+    p.bstage_bytes = 2 * (n_tile / cs) * 64;
+    p.bstages = kP2BRing / p.bstage_bytes < kP2MaxBStages ? kP2BRing / p.bstage_bytes : kP2MaxBStages;
     p.dbg = g_p2_dbg;
     p.tiles_u = div_up(p.grid_u, kP2TileU);
     p.tiles_v = div_up(p.grid_v, kP2TileV);
@@ -669,7 +660,6 @@ using namespace sessd;
 
 // 0 (default): CTA pairs (tcgen05 cta_group::2, each CTA stages half of every weight tile) where the K loop is long; 1 / 2: force
 extern "C" void sessd_set_p2_cluster(int cs) { sessd::g_p2_cluster = (cs == 1 || cs == 2) ? cs : 0; }
-extern "C" void sessd_set_p2_wres(int on) { sessd::g_p2_wres = on ? 1 : 0; }
 
 
 #ifdef SESSD_P2_PROFILE

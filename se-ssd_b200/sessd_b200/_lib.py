@@ -72,7 +72,6 @@ SIGNATURES = {
     "sessd_bev_deconv_p2": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "sessd_bev_split_planes": (_i, [_vp, _ll, _vp, _vp, _vp]),
     "sessd_set_p2_cluster": (None, [_i]),
-    "sessd_set_p2_wres": (None, [_i]),
     "sessd_sparse_to_dense_planes": (_i, [_vp, _i, _vp, _i, Grid, _vp, _vp, _vp, _vp]),
     "sessd_ssfa_fuse_planes": (_i, [_vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sessd_absmax": (_i, [_vp, C.c_longlong, _vp, _vp]),

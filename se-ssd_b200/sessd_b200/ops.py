@@ -405,11 +405,6 @@ def set_p2_cluster(n):
     lib.sessd_set_p2_cluster(int(n))
 
 
-def set_p2_wres(on):
-    """bev_conv_p2, 1x1 convs: 1 (default) = weight stages loaded once per CTA and kept in shared memory; 0 = streamed per item."""
-    lib.sessd_set_p2_wres(int(bool(on)))
-
-
 def bev_split_planes(x, info, planes):
     """fp32 tensor -> planes with the scale from info[0] (its abs-max: call absmax(x, info[0:1]) first); info[1] <- scale"""
     check(lib.sessd_bev_split_planes(_p(x), int(x.numel()), _p(info), _p(planes), _st()), "sessd_bev_split_planes")
