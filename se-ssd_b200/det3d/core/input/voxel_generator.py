@@ -9,15 +9,12 @@ from sessd_b200 import ops
 
 class VoxelGenerator:
     def __init__(self, voxel_size, point_cloud_range, max_num_points, max_voxels=20000):
-        point_cloud_range = np.array(point_cloud_range, dtype=np.float32)
-        voxel_size = np.array(voxel_size, dtype=np.float32)
-        grid_size = np.round((point_cloud_range[3:] - point_cloud_range[:3]) / voxel_size).astype(np.int64)
-        self._voxel_size = voxel_size
-        self._point_cloud_range = point_cloud_range
-        self._max_num_points = max_num_points
-        self._max_voxels = max_voxels
-        self._grid_size = grid_size
-        self._cfgs = {}
+        self._point_cloud_range = np.asarray(point_cloud_range, dtype=np.float32).copy()
+        self._voxel_size = np.asarray(voxel_size, dtype=np.float32).copy()
+        extent = self._point_cloud_range[3:] - self._point_cloud_range[:3]
+        self._grid_size = np.round(extent / self._voxel_size).astype(np.int64)          # (x, y, z) cells, :17-18
+        self._max_num_points, self._max_voxels = max_num_points, max_voxels
+        self._cfgs = {}                                                                  # one device config per point feature count
 
     def _cfg(self, num_feat):
         if num_feat not in self._cfgs:
@@ -40,18 +37,8 @@ class VoxelGenerator:
             buffers = ops.VoxelBuffers(self._cfg(points.shape[1]), batch, max(int(points.shape[0]), 1), points.device)
         return ops.voxelize(points, frame_offsets, buffers)
 
-    @property
-    def voxel_size(self):
-        return self._voxel_size
-
-    @property
-    def max_num_points_per_voxel(self):
-        return self._max_num_points
-
-    @property
-    def point_cloud_range(self):
-        return self._point_cloud_range
-
-    @property
-    def grid_size(self):
-        return self._grid_size
+    # read-only views of the constructor arguments (same names as the reference's properties)
+    voxel_size = property(lambda self: self._voxel_size)
+    max_num_points_per_voxel = property(lambda self: self._max_num_points)
+    point_cloud_range = property(lambda self: self._point_cloud_range)
+    grid_size = property(lambda self: self._grid_size)
