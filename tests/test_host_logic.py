@@ -223,3 +223,33 @@ def test_bench_parity_matcher_by_anchor_index():
     m = b.match_detections(got, ref_boxes, ref_scores, np.array([5, 9, 13]))
     assert m["n_matched"] == 2 and m["max_abs_box_diff"] == 0.0 and m["same_order"]
     assert sorted((u["side"], u["anchor"]) for u in m["unmatched"]) == [("gpu", 11), ("oracle", 13)]
+
+
+def test_c_abi_rejects_null_arguments_before_touching_the_device():
+    """every compute entry point validates its arguments first and returns SESSD_EINVAL (-1) -- it never exits the
+    process (the reference's CHECK_ERROR does, iou3d.cpp:13-21) and needs no GPU to say so.  All-null / all-zero calls; the pairwise IoU
+    entries and the host ODIoU evaluator treat n = m = 0 as an empty, successful call (like the reference on empty box sets)."""
+    import ctypes as C
+    from sessd_b200._lib import SIGNATURES, lib
+    empty_ok = {"sessd_boxes_overlap_bev", "sessd_boxes_aligned_overlap_bev", "sessd_boxes_iou_bev", "sessd_boxes_iou3d", "sessd_odiou_pairs_host"}
+    not_compute = {"sessd_launch_count", "sessd_tile_list_stride"}
+    checked = 0
+    for name, (ret, args) in SIGNATURES.items():
+        if ret is not C.c_int or name in not_compute:
+            continue
+        vals = []
+        for a in args:
+            if a is C.c_void_p:
+                vals.append(C.c_void_p(0))
+            elif a in (C.c_int, C.c_long, C.c_longlong, C.c_size_t, C.c_uint):
+                vals.append(0)
+            elif a in (C.c_float, C.c_double):
+                vals.append(0.0)
+            elif isinstance(a, type) and issubclass(a, C.Structure):
+                vals.append(a())
+            else:
+                vals.append(None)                      # typed pointer
+        rc = getattr(lib, name)(*vals)
+        assert rc == (0 if name in empty_ok else -1), (name, rc)
+        checked += 1
+    assert checked >= 30
