@@ -251,3 +251,78 @@ def test_spconv_restatement_equals_dense_conv3d(kind, ks, st, pd):
         p3 = tuple(q // 2 for q in ks) if kind == "subm" else pd
         exp = out_coors[po, 1:] * np.array(s3) - np.array(p3) + np.array([kz, ky, kx])
         assert np.array_equal(coors[pi, 1:], exp) and np.array_equal(coors[pi, 0], out_coors[po, 0])
+
+
+@pytest.mark.parametrize("kind,ks,st,pd", [("subm", (3, 3, 3), (1, 1, 1), (1, 1, 1)), ("spconv", (3, 3, 3), (2, 2, 2), (1, 1, 1)),
+                                           ("spconv", (3, 3, 3), (2, 2, 2), (0, 1, 1)), ("spconv", (3, 1, 1), (2, 1, 1), (0, 0, 0))])
+def test_spconv_backward_restatement_equals_dense_autograd(kind, ks, st, pd):
+    """oracle/spconv_grad_ref.py (oracle of the not-yet-built backward kernels) against an INDEPENDENT implementation: torch autograd
+    through F.conv3d on the densified volume, loss = <out sampled at the output set, G>.  Also the two identities the device design
+    rests on: dgrad == the FORWARD gather run with (G, transposed table, W^T), and for SubM layers the transposed table is the
+    offset-reversed table (no second rulebook).  + eval-mode BN / ReLU backward vs autograd."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import spconv_grad_ref as SG, spconv_ref as S
+    rng = np.random.default_rng(23)
+    B, shape, cin, cout = 2, (9, 14, 12), 4, 6
+    occ = rng.random((B,) + shape) < 0.15
+    coors = np.argwhere(occ).astype(np.int32)
+    feat = rng.standard_normal((len(coors), cin))
+    w = rng.standard_normal(ks + (cin, cout))
+    if kind == "subm":
+        out_coors, s3, p3 = coors, (1, 1, 1), tuple(k // 2 for k in ks)
+    else:
+        out_coors, _ = S.strided_out_coors(coors, shape, ks, st, pd)
+        s3, p3 = st, pd
+    nbr = S.neighbor_table(coors, shape, out_coors, ks, s3, p3)
+    G = rng.standard_normal((len(out_coors), cout))
+    dense = torch.zeros((B, cin) + shape, dtype=torch.float64)
+    dense[coors[:, 0], :, coors[:, 1], coors[:, 2], coors[:, 3]] = torch.from_numpy(feat)
+    dense.requires_grad_(True)
+    wt = torch.from_numpy(w).permute(4, 3, 0, 1, 2).contiguous().requires_grad_(True)
+    out = F.conv3d(dense, wt, None, s3, p3)
+    sampled = out[out_coors[:, 0], :, out_coors[:, 1], out_coors[:, 2], out_coors[:, 3]]
+    (sampled * torch.from_numpy(G)).sum().backward()
+    want_gfeat = dense.grad[coors[:, 0], :, coors[:, 1], coors[:, 2], coors[:, 3]].numpy()
+    want_gw = wt.grad.permute(2, 3, 4, 1, 0).reshape(-1, cin, cout).numpy()
+    wk = w.reshape(-1, cin, cout)
+    gfeat, gw = SG.conv_backward_from_nbr(feat, nbr, wk, G)
+    np.testing.assert_allclose(gfeat, want_gfeat, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(gw, want_gw, rtol=1e-12, atol=1e-12)
+    # dgrad as a forward gather over the transposed table with transposed weights
+    nbr_t = SG.transpose_nbr(nbr, len(coors))
+    np.testing.assert_allclose(S.conv_from_nbr(G, nbr_t, np.ascontiguousarray(wk.transpose(0, 2, 1)), np.float64), want_gfeat, rtol=1e-12, atol=1e-12)
+    if kind == "subm":
+        assert np.array_equal(nbr_t, nbr[:, ::-1])
+    # eval-mode BatchNorm1d + ReLU behind the conv
+    gamma, beta, mean, var = rng.uniform(0.5, 1.5, cout), rng.standard_normal(cout), rng.standard_normal(cout), rng.uniform(0.5, 2.0, cout)
+    x = torch.from_numpy(S.conv_from_nbr(feat, nbr, wk, np.float64)).requires_grad_(True)
+    y = torch.relu((x - torch.from_numpy(mean)) / torch.sqrt(torch.from_numpy(var) + 1e-3) * torch.from_numpy(gamma) + torch.from_numpy(beta))
+    (y * torch.from_numpy(G)).sum().backward()
+    np.testing.assert_allclose(SG.bn_relu_backward(x.detach().numpy(), G, gamma, beta, mean, var), x.grad.numpy(), rtol=1e-12, atol=1e-12)
+
+
+def test_neck_dgrad_restatement_equals_autograd():
+    """oracle/bev_grad_ref.py: the data gradient of every conv family of the SSFA neck written as a FORWARD conv / deconv with re-packed
+    weights (what the device kernels would run) equals torch autograd, the reference's own mechanism."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import bev_grad_ref as BG
+    g = torch.Generator().manual_seed(3)
+    rnd = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)      # noqa: E731
+    for (k, stride, pad, cin, cout) in [(3, 1, 1, 6, 5), (1, 1, 0, 6, 4), (3, 2, 1, 5, 7)]:
+        x = rnd(2, cin, 12, 10).requires_grad_(True)
+        w = rnd(cout, cin, k, k)
+        y = F.conv2d(x, w, None, stride, pad)
+        G = rnd(*y.shape)
+        (y * G).sum().backward()
+        got = BG.conv_dgrad(G, w, stride, pad)
+        assert got.shape == x.shape
+        torch.testing.assert_close(got, x.grad, rtol=1e-12, atol=1e-12)
+    x = rnd(2, 7, 6, 5).requires_grad_(True)
+    wd = rnd(7, 4, 3, 3)
+    y = F.conv_transpose2d(x, wd, None, 2, 1, output_padding=1)
+    assert tuple(y.shape[2:]) == (12, 10)
+    G = rnd(*y.shape)
+    (y * G).sum().backward()
+    torch.testing.assert_close(BG.deconv_dgrad(G, wd), x.grad, rtol=1e-12, atol=1e-12)
