@@ -98,3 +98,18 @@ class ArenaAdamW:
         check(lib.sessd_adamw_step(_p(a.flat), _p(a.grad_flat), _p(self.exp_avg), _p(self.exp_avg_sq), int(a.numel), float(self.lr),
                                    float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.weight_decay), int(self.steps),
                                    _st(a.flat)), "sessd_adamw_step")
+
+
+# ------------------------------------------------------------------------------------------------- data gradients through the forward kernels
+def subm_dgrad_weight(w):
+    """SubMConv3d weight [kz, ky, kx, Cin, Cout] (spconv layout, scn.py:106-131)  ->  [kz, ky, kx, Cout, Cin] such that the FORWARD sparse conv
+    over the SAME rulebook / tile lists, fed with d loss / d out, yields d loss / d in:  W'[k] = W[K-1-k]^T.  (A SubM layer's neighbour
+    table is point-symmetric -- nbr_t[i, k] = nbr[i, K-1-k] -- so the data gradient needs neither a transposed rulebook nor a new kernel;
+    pinned on the CPU by tests/test_train_step.py against oracle/spconv_grad_ref.py, which is pinned to dense autograd.)"""
+    return w.flip(0, 1, 2).transpose(3, 4).contiguous()
+
+
+def conv2d_s1_dgrad_weight(w):
+    """Conv2d weight [Cout, Cin, k, k] of a stride-1 neck layer  ->  [Cin, Cout, k, k], taps flipped: the stride-1 conv (pad k - 1 - p) that
+    maps d loss / d out to d loss / d in (rpn_v1.py:135-210 layers bottom_up_block_0.*, bottom_up_block_1.3 / .6, conv_0, conv_1, trans_*)."""
+    return w.flip(2, 3).transpose(0, 1).contiguous()
